@@ -1,0 +1,117 @@
+"""ctypes binding of libfluidmarch.so (include/fluidmarch.h).  Fails loudly when the CUDA library
+is missing or no sm_100 device is present -- there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libfluidmarch.so")
+
+FR_OK = 0
+FR_PASS_DEPTH, FR_PASS_MARCH, FR_PASS_SHADE, FR_PASS_ALL = 1, 2, 4, 7
+FR_ERR_NO_DEVICE = -3
+
+f32p = C.POINTER(C.c_float)
+u32p = C.POINTER(C.c_uint32)
+u8p = C.POINTER(C.c_uint8)
+vpp = C.POINTER(C.c_void_p)
+
+
+class FrSettings(C.Structure):
+    """fr_settings: POD mirror of VisualizationSettings (reference RayMarcher.h:12-26)."""
+    _fields_ = [("frame", C.c_int32), ("max_steps", C.c_int32), ("step_size", C.c_float),
+                ("iso_density", C.c_float), ("enable_anisotropy", C.c_int32),
+                ("k_n", C.c_float), ("k_r", C.c_float), ("k_s", C.c_float), ("n_eps", C.c_int32),
+                ("bisection_steps", C.c_int32), ("skip_last_pixel", C.c_int32)]
+
+
+class FrCamera(C.Structure):
+    _fields_ = [("view", C.c_float * 16), ("projection", C.c_float * 16),
+                ("inv_projection_view", C.c_float * 16), ("position", C.c_float * 3),
+                ("direction", C.c_float * 3)]
+
+
+class FrFrameInfo(C.Structure):
+    _fields_ = [("num_particles", C.c_uint64), ("h", C.c_float), ("min", C.c_float * 3), ("max", C.c_float * 3),
+                ("grid_dims", C.c_int32 * 3), ("occupied_cells", C.c_uint64),
+                ("search_min", C.c_int32 * 3), ("search_dims", C.c_int32 * 3)]
+
+
+class FrCounters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("pixels", "covered_rays", "hit_rays", "ray_steps", "skip_iterations",
+                                          "candidates", "neighbours", "early_exits", "neighbour_overflow")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class FrTimings(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "grid_ms", "depth_ms", "march_ms", "download_ms")]
+
+    def as_dict(self):
+        return {n: float(getattr(self, n)) for n, _ in self._fields_}
+
+
+# every symbol include/fluidmarch.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("fr_abi_version", C.c_int, []),
+    ("fr_last_error", C.c_char_p, []),
+    ("fr_create", C.c_int, [C.c_int, C.c_int, C.c_int, vpp]),
+    ("fr_resize", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("fr_destroy", None, [C.c_void_p]),
+    ("fr_host_alloc", C.c_int, [C.c_size_t, vpp]),
+    ("fr_host_free", None, [C.c_void_p]),
+    ("fr_upload_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
+    ("fr_build_frame_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
+    ("fr_get_frame_info", C.c_int, [C.c_void_p, C.c_int, C.POINTER(FrFrameInfo)]),
+    ("fr_release_frame", C.c_int, [C.c_void_p, C.c_int]),
+    ("fr_download_frame", C.c_int, [C.c_void_p, C.c_int, f32p, u32p, u32p, u8p]),
+    ("fr_set_settings", C.c_int, [C.c_void_p, C.POINTER(FrSettings)]),
+    ("fr_set_camera", C.c_int, [C.c_void_p, C.POINTER(FrCamera)]),
+    ("fr_set_depth", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("fr_set_tile_partition", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("fr_render_async", C.c_int, [C.c_void_p, C.c_int]),
+    ("fr_is_done", C.c_int, [C.c_void_p]),
+    ("fr_wait", C.c_int, [C.c_void_p]),
+    ("fr_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("fr_device_images", C.c_int, [C.c_void_p, vpp, vpp, vpp, vpp]),
+    ("fr_set_color_target", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("fr_get_counters", C.c_int, [C.c_void_p, C.POINTER(FrCounters)]),
+    ("fr_get_timings", C.c_int, [C.c_void_p, C.POINTER(FrTimings)]),
+    ("fr_get_stream", C.c_int, [C.c_void_p, vpp]),
+    ("fr_query_neighbors", C.c_int, [C.c_void_p, C.c_int, f32p, C.c_size_t, u32p, u32p, C.c_size_t]),
+    ("fr_query_density", C.c_int, [C.c_void_p, C.c_int, f32p, C.c_size_t, f32p, f32p]),
+    ("fr_import_vk_memory_fd", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
+    ("fr_import_vk_semaphores_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+]
+
+_lib = None
+
+
+class FluidMarchError(RuntimeError):
+    pass
+
+
+def load(path: str = LIB_PATH):
+    """Loads the CUDA library; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise FluidMarchError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback.")
+    lib = C.CDLL(path)
+    for name, restype, argtypes in SYMBOLS:
+        fn = getattr(lib, name)   # AttributeError here == header/library mismatch
+        fn.restype = restype
+        fn.argtypes = argtypes
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != FR_OK:
+        msg = load().fr_last_error()
+        raise FluidMarchError(f"{what} failed (rc={rc}): {msg.decode() if msg else ''}")

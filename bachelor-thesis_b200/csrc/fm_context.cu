@@ -1,0 +1,589 @@
+// fm_context.cu -- the C ABI (include/fluidmarch.h): context, memory, stream ordering, hand-off.
+//
+// Host-side replacement of the reference's RayMarcher shell (src/app/AdvancedRenderer/RayMarcher.cpp:64-112:
+// constructor, Prepare, Start, IsDone, Exit) and ThreadPool (src/app/ThreadPool.cpp): "Start" is a kernel
+// launch on the context stream, "IsDone" a cudaEventQuery.  No CPU fallback exists: without a CUDA device
+// fr_create fails with FR_ERR_NO_DEVICE.
+#include "fm_internal.h"
+
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+namespace fm
+{
+
+static thread_local std::string g_error;
+
+void set_error(const std::string& msg) { g_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
+{
+	char buf[512];
+	snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+	g_error = buf;
+	cudaGetLastError();   // clear the sticky-free error state
+	return FR_ERR_CUDA;
+}
+
+static void free_frame(Frame& f)
+{
+	if (f.d_sorted) cudaFree(f.d_sorted);
+	if (f.d_cell_start) cudaFree(f.d_cell_start);
+	if (f.d_grid_counts) cudaFree(f.d_grid_counts);
+	if (f.d_occ_bits) cudaFree(f.d_occ_bits);
+	if (f.d_occupied) cudaFree(f.d_occupied);
+	f = Frame();
+}
+
+static void free_images(Context* c)
+{
+	if (c->d_depth) cudaFree(c->d_depth);
+	if (c->d_pos) cudaFree(c->d_pos);
+	if (c->d_nrm) cudaFree(c->d_nrm);
+	if (c->d_rgba) cudaFree(c->d_rgba);
+	c->d_depth = nullptr; c->d_pos = nullptr; c->d_nrm = nullptr; c->d_rgba = nullptr; c->d_rgba_target = nullptr;
+}
+
+static int alloc_images(Context* c, int w, int h)
+{
+	size_t const npix = (size_t)w * (size_t)h;
+	FM_CUDA(cudaMalloc((void**)&c->d_depth, npix * sizeof(float)));
+	FM_CUDA(cudaMalloc((void**)&c->d_pos, npix * sizeof(float4)));
+	FM_CUDA(cudaMalloc((void**)&c->d_nrm, npix * sizeof(float4)));
+	FM_CUDA(cudaMalloc((void**)&c->d_rgba, npix * sizeof(uchar4)));
+	FM_CUDA(cudaMemsetAsync(c->d_pos, 0, npix * sizeof(float4), c->stream));
+	FM_CUDA(cudaMemsetAsync(c->d_nrm, 0, npix * sizeof(float4), c->stream));
+	FM_CUDA(cudaMemsetAsync(c->d_rgba, 0, npix * sizeof(uchar4), c->stream));
+	c->d_rgba_target = c->d_rgba;
+	c->width = w; c->height = h;
+	c->have_depth = false;
+	return FR_OK;
+}
+
+static Frame* get_frame(Context* c, int frame, bool must_be_valid)
+{
+	if (frame < 0 || (size_t)frame >= c->frames.size() || (must_be_valid && !c->frames[frame].valid))
+	{
+		set_error("frame index does not name an uploaded frame");
+		return nullptr;
+	}
+	return &c->frames[frame];
+}
+
+static int finish_pending(Context* c)
+{
+	if (c->render_pending)
+	{
+		FM_CUDA(cudaEventSynchronize(c->ev_done));
+		c->render_pending = false;
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) c->timings.march_ms = ms;
+	}
+	return FR_OK;
+}
+
+}  // namespace fm
+
+using namespace fm;
+
+struct fr_context : public fm::Context {};
+
+#define FR_CHECK_CTX(ctx)                                                    \
+	do {                                                                     \
+		if (!(ctx)) { fm::set_error("null context"); return FR_ERR_INVALID; } \
+		FM_CUDA(cudaSetDevice((ctx)->device));                               \
+	} while (0)
+
+extern "C" {
+
+int fr_abi_version(void) { return FR_ABI_VERSION; }
+
+const char* fr_last_error(void) { return fm::g_error.c_str(); }
+
+int fr_create(int device, int width, int height, fr_context** out)
+{
+	if (!out || width <= 0 || height <= 0) { set_error("fr_create: bad arguments"); return FR_ERR_INVALID; }
+	*out = nullptr;
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0)
+	{
+		cudaGetLastError();
+		set_error(std::string("fr_create: no CUDA device (") + cudaGetErrorString(e) +
+				  "); fluidmarch has no CPU fallback");
+		return FR_ERR_NO_DEVICE;
+	}
+	if (device < 0 || device >= count) { set_error("fr_create: device index out of range"); return FR_ERR_INVALID; }
+	cudaDeviceProp prop;
+	FM_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+	{
+		set_error("fr_create: device is not sm_100 or newer; the kernels are built for sm_100a only");
+		return FR_ERR_NO_DEVICE;
+	}
+	FM_CUDA(cudaSetDevice(device));
+	fr_context* c = new (std::nothrow) fr_context();
+	if (!c) { set_error("out of host memory"); return FR_ERR_INVALID; }
+	c->device = device;
+	c->sm_count = prop.multiProcessorCount;
+	int rc = FR_OK;
+	do
+	{
+		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		for (auto& ev : c->ev)
+			if (cudaEventCreate(&ev) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (rc) break;
+		if (cudaMalloc((void**)&c->d_gp, sizeof(GridParams)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaMallocHost((void**)&c->h_gp, sizeof(GridParams)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaMallocHost((void**)&c->h_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		rc = alloc_images(c, width, height);
+	} while (0);
+	if (rc != FR_OK)
+	{
+		if (rc == FR_ERR_CUDA && g_error.empty()) cuda_fail(cudaGetLastError(), "fr_create", __FILE__, __LINE__);
+		fr_destroy(c);
+		return rc;
+	}
+	// VisualizationSettings defaults (AdvancedRenderer.cpp:18-28) with the isotropic kernel
+	c->settings.frame = 0;
+	c->settings.max_steps = 128;
+	c->settings.step_size = 0.009f;
+	c->settings.iso_density = 1.0f;
+	c->settings.enable_anisotropy = 0;
+	c->settings.k_n = 0.5f; c->settings.k_r = 2.0f; c->settings.k_s = 2000.0f; c->settings.n_eps = 1;
+	c->have_settings = true;
+	*out = c;
+	return FR_OK;
+}
+
+int fr_resize(fr_context* ctx, int width, int height)
+{
+	FR_CHECK_CTX(ctx);
+	if (width <= 0 || height <= 0) { set_error("fr_resize: bad size"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->render_pending = false;
+	bool const external = ctx->d_rgba_target != ctx->d_rgba;
+	free_images(ctx);
+	int rc = alloc_images(ctx, width, height);
+	if (external) ctx->d_rgba_target = ctx->d_rgba;   // an external target is tied to the old size
+	return rc;
+}
+
+void fr_destroy(fr_context* ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+	for (auto& f : ctx->frames) free_frame(f);
+	free_images(ctx);
+	if (ctx->d_xyz) cudaFree(ctx->d_xyz);
+	if (ctx->d_keys) cudaFree(ctx->d_keys);
+	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
+	if (ctx->d_gp) cudaFree(ctx->d_gp);
+	if (ctx->d_counters) cudaFree(ctx->d_counters);
+	if (ctx->h_gp) cudaFreeHost(ctx->h_gp);
+	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+	if (ctx->ext_wait) cudaDestroyExternalSemaphore(ctx->ext_wait);
+	if (ctx->ext_signal) cudaDestroyExternalSemaphore(ctx->ext_signal);
+	if (ctx->ext_mem) cudaDestroyExternalMemory(ctx->ext_mem);
+	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	if (ctx->stream) cudaStreamDestroy(ctx->stream);
+	delete ctx;
+}
+
+int fr_host_alloc(size_t bytes, void** out)
+{
+	if (!out) { set_error("fr_host_alloc: null out"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaMallocHost(out, bytes ? bytes : 1));
+	return FR_OK;
+}
+
+void fr_host_free(void* p)
+{
+	if (p) cudaFreeHost(p);
+}
+
+// ---- frames --------------------------------------------------------------------------------------
+
+static int frame_slot(fr_context* ctx, int frame, Frame** out)
+{
+	if (frame < 0 || frame > (1 << 20)) { set_error("frame index out of range"); return FR_ERR_INVALID; }
+	if ((size_t)frame >= ctx->frames.size()) ctx->frames.resize((size_t)frame + 1);
+	*out = &ctx->frames[frame];
+	return FR_OK;
+}
+
+int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult)
+{
+	FR_CHECK_CTX(ctx);
+	if (!xyz_host) { set_error("fr_upload_frame: null particle array"); return FR_ERR_INVALID; }
+	if (n == 0) { set_error("fr_upload_frame: a frame needs at least one particle (Frame::ComputeAABB reads m_Particles[0])"); return FR_ERR_INVALID; }
+	Frame* f;
+	int rc = frame_slot(ctx, frame, &f);
+	if (rc) return rc;
+	if ((rc = finish_pending(ctx))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
+	FM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, xyz_host, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+	FM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	rc = build_frame(ctx, f, ctx->d_xyz, n, h, h_ext_mult);
+	if (rc) return rc;
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	float ms = 0.0f;
+	if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timings.upload_ms = ms;
+	if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timings.grid_ms = ms;
+	return FR_OK;
+}
+
+int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult)
+{
+	FR_CHECK_CTX(ctx);
+	if (!xyz_device || n == 0) { set_error("fr_build_frame_device: empty particle array"); return FR_ERR_INVALID; }
+	Frame* f;
+	int rc = frame_slot(ctx, frame, &f);
+	if (rc) return rc;
+	if ((rc = finish_pending(ctx))) return rc;
+	rc = build_frame(ctx, f, xyz_device, n, h, h_ext_mult);
+	if (rc) return rc;
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	float ms = 0.0f;
+	ctx->timings.upload_ms = 0.0f;
+	if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timings.grid_ms = ms;
+	return FR_OK;
+}
+
+int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out)
+{
+	FR_CHECK_CTX(ctx);
+	if (!out) { set_error("fr_get_frame_info: null out"); return FR_ERR_INVALID; }
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	unsigned long long occ = 0;
+	FM_CUDA(cudaMemcpyAsync(&occ, f->d_occupied, sizeof occ, cudaMemcpyDeviceToHost, ctx->stream));
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	memset(out, 0, sizeof *out);
+	out->num_particles = f->n;
+	out->h = f->h;
+	for (int a = 0; a < 3; a++)
+	{
+		out->min[a] = f->gp.mn[a];
+		out->max[a] = f->gp.mx[a];
+		out->grid_dims[a] = f->gp.gdim[a];
+		out->search_min[a] = f->gp.kmin[a];
+		out->search_dims[a] = f->gp.kdim[a];
+	}
+	out->occupied_cells = occ;
+	return FR_OK;
+}
+
+int fr_release_frame(fr_context* ctx, int frame)
+{
+	FR_CHECK_CTX(ctx);
+	Frame* f = get_frame(ctx, frame, false);
+	if (!f) return FR_ERR_INVALID;
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	free_frame(*f);
+	return FR_OK;
+}
+
+int fr_download_frame(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* cell_start,
+					  uint32_t* grid_counts, uint8_t* grid_flags)
+{
+	FR_CHECK_CTX(ctx);
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	cudaStream_t const s = ctx->stream;
+	size_t const cells = (size_t)f->gp.kdim[0] * f->gp.kdim[1] * f->gp.kdim[2];
+	size_t const gcells = (size_t)f->gp.gdim[0] * f->gp.gdim[1] * f->gp.gdim[2];
+	if (sorted_xyzi) FM_CUDA(cudaMemcpyAsync(sorted_xyzi, f->d_sorted, f->n * 16, cudaMemcpyDeviceToHost, s));
+	if (cell_start) FM_CUDA(cudaMemcpyAsync(cell_start, f->d_cell_start, (cells + 1) * 4, cudaMemcpyDeviceToHost, s));
+	if (grid_counts) FM_CUDA(cudaMemcpyAsync(grid_counts, f->d_grid_counts, gcells * 4, cudaMemcpyDeviceToHost, s));
+	std::vector<uint32_t> words;
+	if (grid_flags)
+	{
+		words.resize((gcells + 31) / 32);
+		FM_CUDA(cudaMemcpyAsync(words.data(), f->d_occ_bits, words.size() * 4, cudaMemcpyDeviceToHost, s));
+	}
+	FM_CUDA(cudaStreamSynchronize(s));
+	if (grid_flags)
+		for (size_t c = 0; c < gcells; c++) grid_flags[c] = (uint8_t)((words[c >> 5] >> (c & 31)) & 1u);
+	return FR_OK;
+}
+
+// ---- per-render state ----------------------------------------------------------------------------
+
+int fr_set_settings(fr_context* ctx, const fr_settings* s)
+{
+	FR_CHECK_CTX(ctx);
+	if (!s) { set_error("fr_set_settings: null"); return FR_ERR_INVALID; }
+	if (s->max_steps < 0 || s->bisection_steps < 0 || s->bisection_steps > 64)
+	{
+		set_error("fr_set_settings: max_steps / bisection_steps out of range");
+		return FR_ERR_INVALID;
+	}
+	if (s->enable_anisotropy)
+	{
+		set_error("fr_set_settings: the anisotropic kernel (PerPixel_Anisotropic) is not built yet");
+		return FR_ERR_UNSUPPORTED;
+	}
+	ctx->settings = *s;
+	ctx->have_settings = true;
+	return FR_OK;
+}
+
+int fr_set_camera(fr_context* ctx, const fr_camera* cam)
+{
+	FR_CHECK_CTX(ctx);
+	if (!cam) { set_error("fr_set_camera: null"); return FR_ERR_INVALID; }
+	ctx->camera = *cam;
+	ctx->have_camera = true;
+	return FR_OK;
+}
+
+int fr_set_depth(fr_context* ctx, const float* depth_host)
+{
+	FR_CHECK_CTX(ctx);
+	if (!depth_host) { set_error("fr_set_depth: null"); return FR_ERR_INVALID; }
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	size_t const npix = (size_t)ctx->width * ctx->height;
+	FM_CUDA(cudaMemcpyAsync(ctx->d_depth, depth_host, npix * 4, cudaMemcpyHostToDevice, ctx->stream));
+	ctx->have_depth = true;
+	return FR_OK;
+}
+
+int fr_set_tile_partition(fr_context* ctx, int rank, int world, int tile_w, int tile_h)
+{
+	FR_CHECK_CTX(ctx);
+	if (world < 1 || rank < 0 || rank >= world || tile_w < 32 || tile_h < 8 || tile_w % 32 || tile_h % 8)
+	{
+		set_error("fr_set_tile_partition: need 0 <= rank < world, tile_w a multiple of 32, tile_h a multiple of 8");
+		return FR_ERR_INVALID;
+	}
+	ctx->part_rank = rank; ctx->part_world = world; ctx->part_tw = tile_w; ctx->part_th = tile_h;
+	return FR_OK;
+}
+
+// ---- render ----------------------------------------------------------------------------------------
+
+int fr_render_async(fr_context* ctx, int passes)
+{
+	FR_CHECK_CTX(ctx);
+	if (!(passes & FR_PASS_ALL)) { set_error("fr_render_async: no pass selected"); return FR_ERR_INVALID; }
+	if (!ctx->have_camera) { set_error("fr_render_async: fr_set_camera has not been called"); return FR_ERR_STATE; }
+	Frame* f = get_frame(ctx, ctx->settings.frame, true);
+	if (!f) return FR_ERR_STATE;
+	if ((passes & FR_PASS_MARCH) && !(passes & FR_PASS_DEPTH) && !ctx->have_depth)
+	{
+		set_error("fr_render_async: march without a depth image (call fr_set_depth or include FR_PASS_DEPTH)");
+		return FR_ERR_STATE;
+	}
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	cudaStream_t const s = ctx->stream;
+	if (ctx->ext_wait)
+	{
+		cudaExternalSemaphoreWaitParams wp;
+		memset(&wp, 0, sizeof wp);
+		FM_CUDA(cudaWaitExternalSemaphoresAsync(&ctx->ext_wait, &wp, 1, s));
+	}
+	FM_CUDA(cudaEventRecord(ctx->ev[4], s));
+	if (passes & FR_PASS_DEPTH)
+	{
+		if ((rc = launch_depth_prepass(ctx, *f))) return rc;
+		ctx->have_depth = true;
+	}
+	FM_CUDA(cudaEventRecord(ctx->ev[5], s));
+	if (passes & (FR_PASS_MARCH | FR_PASS_SHADE))
+		if ((rc = launch_march(ctx, *f, (passes & FR_PASS_MARCH) != 0, (passes & FR_PASS_SHADE) != 0))) return rc;
+	FM_CUDA(cudaEventRecord(ctx->ev[6], s));
+	if (ctx->ext_signal)
+	{
+		cudaExternalSemaphoreSignalParams sp;
+		memset(&sp, 0, sizeof sp);
+		FM_CUDA(cudaSignalExternalSemaphoresAsync(&ctx->ext_signal, &sp, 1, s));
+	}
+	FM_CUDA(cudaEventRecord(ctx->ev_done, s));
+	ctx->render_pending = true;
+	return FR_OK;
+}
+
+int fr_is_done(fr_context* ctx)
+{
+	FR_CHECK_CTX(ctx);
+	if (!ctx->render_pending) return 1;
+	cudaError_t const e = cudaEventQuery(ctx->ev_done);
+	if (e == cudaSuccess) return 1;
+	if (e == cudaErrorNotReady) return 0;
+	return cuda_fail(e, "cudaEventQuery", __FILE__, __LINE__);
+}
+
+int fr_wait(fr_context* ctx)
+{
+	FR_CHECK_CTX(ctx);
+	return finish_pending(ctx);
+}
+
+// ---- results -----------------------------------------------------------------------------------------
+
+int fr_download(fr_context* ctx, float* depth, float* positions, float* normals, uint8_t* rgba)
+{
+	FR_CHECK_CTX(ctx);
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	cudaStream_t const s = ctx->stream;
+	size_t const npix = (size_t)ctx->width * ctx->height;
+	FM_CUDA(cudaEventRecord(ctx->ev[7], s));
+	if (depth) FM_CUDA(cudaMemcpyAsync(depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
+	if (positions) FM_CUDA(cudaMemcpyAsync(positions, ctx->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (normals) FM_CUDA(cudaMemcpyAsync(normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (rgba) FM_CUDA(cudaMemcpyAsync(rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaEventRecord(ctx->ev[8], s));
+	FM_CUDA(cudaStreamSynchronize(s));
+	float ms = 0.0f;
+	if (cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]) == cudaSuccess) ctx->timings.download_ms = ms;
+	return FR_OK;
+}
+
+int fr_device_images(fr_context* ctx, void** depth, void** positions, void** normals, void** rgba)
+{
+	FR_CHECK_CTX(ctx);
+	if (depth) *depth = ctx->d_depth;
+	if (positions) *positions = ctx->d_pos;
+	if (normals) *normals = ctx->d_nrm;
+	if (rgba) *rgba = ctx->d_rgba_target;
+	return FR_OK;
+}
+
+int fr_set_color_target(fr_context* ctx, void* rgba_device)
+{
+	FR_CHECK_CTX(ctx);
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	ctx->d_rgba_target = rgba_device ? (uchar4*)rgba_device : ctx->d_rgba;
+	return FR_OK;
+}
+
+int fr_get_counters(fr_context* ctx, fr_counters* out)
+{
+	FR_CHECK_CTX(ctx);
+	if (!out) { set_error("fr_get_counters: null out"); return FR_ERR_INVALID; }
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	FM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, ctx->stream));
+	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	const DeviceCounters& d = *ctx->h_counters;
+	out->pixels = (uint64_t)ctx->width * (uint64_t)ctx->height;
+	out->covered_rays = d.covered_rays;
+	out->hit_rays = d.hit_rays;
+	out->ray_steps = d.ray_steps;
+	out->skip_iterations = d.skip_iterations;
+	out->candidates = d.candidates;
+	out->neighbours = d.neighbours;
+	out->early_exits = d.early_exits;
+	out->neighbour_overflow = d.neighbour_overflow;
+	return FR_OK;
+}
+
+int fr_get_timings(fr_context* ctx, fr_timings* out)
+{
+	FR_CHECK_CTX(ctx);
+	if (!out) { set_error("fr_get_timings: null out"); return FR_ERR_INVALID; }
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	*out = ctx->timings;
+	return FR_OK;
+}
+
+int fr_get_stream(fr_context* ctx, void** stream)
+{
+	FR_CHECK_CTX(ctx);
+	if (!stream) { set_error("fr_get_stream: null out"); return FR_ERR_INVALID; }
+	*stream = (void*)ctx->stream;
+	return FR_OK;
+}
+
+// ---- point queries -------------------------------------------------------------------------------------
+
+int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, size_t m,
+					   uint32_t* counts, uint32_t* ids, size_t cap)
+{
+	FR_CHECK_CTX(ctx);
+	if ((m && (!points_host || !counts))) { set_error("fr_query_neighbors: null array"); return FR_ERR_INVALID; }
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap);
+}
+
+int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad)
+{
+	FR_CHECK_CTX(ctx);
+	if ((m && (!points_host || !density))) { set_error("fr_query_density: null array"); return FR_ERR_INVALID; }
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	return query_density(ctx, *f, points_host, m, density, grad);
+}
+
+// ---- CUDA-Vulkan hand-off ------------------------------------------------------------------------------
+
+int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, size_t offset)
+{
+	FR_CHECK_CTX(ctx);
+	size_t const need = (size_t)ctx->width * ctx->height * 4;
+	if (fd < 0 || offset + need > allocation_bytes)
+	{
+		set_error("fr_import_vk_memory_fd: bad fd or the allocation is smaller than W*H*4 bytes at offset");
+		return FR_ERR_INVALID;
+	}
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if (ctx->ext_mem) { cudaDestroyExternalMemory(ctx->ext_mem); ctx->ext_mem = nullptr; ctx->d_rgba_target = ctx->d_rgba; }
+	cudaExternalMemoryHandleDesc hd;
+	memset(&hd, 0, sizeof hd);
+	hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+	hd.handle.fd = fd;                       // ownership of the fd passes to CUDA on success
+	hd.size = allocation_bytes;
+	FM_CUDA(cudaImportExternalMemory(&ctx->ext_mem, &hd));
+	cudaExternalMemoryBufferDesc bd;
+	memset(&bd, 0, sizeof bd);
+	bd.offset = offset;
+	bd.size = need;
+	void* ptr = nullptr;
+	FM_CUDA(cudaExternalMemoryGetMappedBuffer(&ptr, ctx->ext_mem, &bd));
+	ctx->d_rgba_target = (uchar4*)ptr;
+	return FR_OK;
+}
+
+int fr_import_vk_semaphores_fd(fr_context* ctx, int wait_fd, int signal_fd)
+{
+	FR_CHECK_CTX(ctx);
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if (ctx->ext_wait) { cudaDestroyExternalSemaphore(ctx->ext_wait); ctx->ext_wait = nullptr; }
+	if (ctx->ext_signal) { cudaDestroyExternalSemaphore(ctx->ext_signal); ctx->ext_signal = nullptr; }
+	cudaExternalSemaphoreHandleDesc sd;
+	if (wait_fd >= 0)
+	{
+		memset(&sd, 0, sizeof sd);
+		sd.type = cudaExternalSemaphoreHandleTypeOpaqueFd;
+		sd.handle.fd = wait_fd;
+		FM_CUDA(cudaImportExternalSemaphore(&ctx->ext_wait, &sd));
+	}
+	if (signal_fd >= 0)
+	{
+		memset(&sd, 0, sizeof sd);
+		sd.type = cudaExternalSemaphoreHandleTypeOpaqueFd;
+		sd.handle.fd = signal_fd;
+		FM_CUDA(cudaImportExternalSemaphore(&ctx->ext_signal, &sd));
+	}
+	return FR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,412 @@
+// fm_grid.cu -- GPU build of the per-frame acceleration structures (sm_100a).
+//
+// Replaces Frame::Frame (src/app/Dataset.cpp:9-24): BuildSearch (CompactNSearch hash + z-sort,
+// :49-76), ComputeAABB (:78-92) and BuildDensityGrid (:94-165) with a uniform-grid counting sort:
+//
+//   k_aabb          particle min/max                      reads 12 B/particle
+//   k_grid_params   m_Min/m_Max/dims/cell ranges          (1 thread; exact FP32 ops of the reference)
+//   k_key_count     cell key + histogram (+ occupancy histogram)   reads 12 B, writes 4 B/particle
+//   k_scan_*        exclusive prefix sum over the cell histogram   8 B/cell
+//   k_scatter       counting-sort scatter into float4 SoA           reads 16 B, writes 16 B/particle
+//   k_cell_order    particles of a cell into ascending original index (deterministic sums)
+//   k_flags         OctreeNode::Flag bitmask                        4 B/cell
+//
+// All of it is HBM/L2-bound integer and copy work; nothing here is a contraction.
+#include "fm_internal.h"
+
+#include <math.h>
+
+namespace fm
+{
+
+namespace
+{
+
+constexpr int kThreads = 256;
+
+// order-preserving float <-> uint encoding for atomicMin/atomicMax
+__device__ __forceinline__ uint32_t enc_ordered(float f)
+{
+	uint32_t const u = __float_as_uint(f);
+	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float dec_ordered(uint32_t u)
+{
+	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void k_init_params(GridParams* gp, unsigned long long* occupied)
+{
+	for (int a = 0; a < 3; a++)
+	{
+		gp->raw_min[a] = 0xffffffffu;
+		gp->raw_max[a] = 0u;
+	}
+	*occupied = 0ull;
+}
+
+// Frame::ComputeAABB (Dataset.cpp:78-92): min/max are exact, so any reduction order gives the same bits
+__global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz, uint32_t n, GridParams* gp)
+{
+	float mn[3] = { INFINITY, INFINITY, INFINITY };
+	float mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+		{
+			float const v = __ldg(xyz + 3ull * i + a);
+			mn[a] = fminf(mn[a], v);
+			mx[a] = fmaxf(mx[a], v);
+		}
+	}
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+			mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+		}
+	}
+	__shared__ float s_mn[3][kThreads / 32], s_mx[3][kThreads / 32];
+	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0)
+		for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+	__syncthreads();
+	if (threadIdx.x < 3)
+	{
+		int const a = threadIdx.x;
+		float lo = s_mn[a][0], hi = s_mx[a][0];
+		for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
+		atomicMin(&gp->raw_min[a], enc_ordered(lo));
+		atomicMax(&gp->raw_max[a], enc_ordered(hi));
+	}
+}
+
+__global__ void k_grid_params(GridParams* gp, float h)
+{
+	float const pad = mulr(1.0f, h);                 // padding = 1.0f * ParticleRadius (Dataset.cpp:89)
+	float const cw = mulr(1.0f, h);                  // cellWidth = 1.0f * ParticleRadius (Dataset.cpp:96)
+	float const search_inv = divr(1.0f, h);          // CompactNSearch: inverse cell size in Real
+	gp->cell_width = cw;
+	gp->inv_cell_width = divr(1.0f, cw);             // m_InvCellWidthVec = 1.0f / vec3(cellWidth) (:98)
+	gp->search_inv = search_inv;
+	for (int a = 0; a < 3; a++)
+	{
+		float const lo = dec_ordered(gp->raw_min[a]);
+		float const hi = dec_ordered(gp->raw_max[a]);
+		float const mn = subr(lo, pad);
+		float const mx = addr(hi, pad);
+		gp->mn[a] = mn;
+		gp->mx[a] = mx;
+		gp->gdim[a] = (int32_t)ceilf(divr(subr(mx, mn), cw));   // int32_t(std::ceil(aabb / cellWidth)) (:102-104)
+		int const k0 = search_cell_of(search_inv, lo);           // cell index is monotone in x
+		int const k1 = search_cell_of(search_inv, hi);
+		gp->kmin[a] = k0;
+		gp->kdim[a] = k1 - k0 + 1;
+	}
+}
+
+struct BuildView
+{
+	int3 kmin, kdim;
+	float search_inv;
+	float3 mn;
+	int3 gdim;
+	float inv_cw;
+};
+
+__device__ __forceinline__ uint32_t search_key(const BuildView& b, float x, float y, float z)
+{
+	int const kx = search_cell_of(b.search_inv, x) - b.kmin.x;
+	int const ky = search_cell_of(b.search_inv, y) - b.kmin.y;
+	int const kz = search_cell_of(b.search_inv, z) - b.kmin.z;
+	return ((uint32_t)kx * (uint32_t)b.kdim.y + (uint32_t)ky) * (uint32_t)b.kdim.z + (uint32_t)kz;
+}
+
+// cell key + histograms.  grid_counts follows the "cell-exact" reading of the fork-only
+// find_neighbors_box: a particle counts for the node QueryDensityGrid(particle) returns.
+__global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, BuildView b,
+														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
+														uint32_t* __restrict__ grid_counts)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
+	uint32_t const key = search_key(b, x, y, z);
+	keys[i] = key;
+	atomicAdd(cell_count + key, 1u);
+	// Frame::QueryDensityGrid (Dataset.cpp:26-47)
+	float const fx = floorf(mulr(subr(x, b.mn.x), b.inv_cw));
+	float const fy = floorf(mulr(subr(y, b.mn.y), b.inv_cw));
+	float const fz = floorf(mulr(subr(z, b.mn.z), b.inv_cw));
+	if (fx >= 0.0f && fx < (float)b.gdim.x && fy >= 0.0f && fy < (float)b.gdim.y && fz >= 0.0f && fz < (float)b.gdim.z)
+	{
+		uint32_t const c = (uint32_t)fx + (uint32_t)b.gdim.x * ((uint32_t)fy + (uint32_t)b.gdim.y * (uint32_t)fz);
+		atomicAdd(grid_counts + c, 1u);
+	}
+}
+
+// ---- exclusive scan over m counts, in place: data[i] <- sum(data[0..i)), data[m] <- total ------------
+constexpr int kScanThreads = 512;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
+{
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	uint32_t inc = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1)
+	{
+		uint32_t const t = __shfl_up_sync(0xffffffffu, inc, o);
+		if (lane >= o) inc += t;
+	}
+	if (lane == 31) s_warp[warp] = inc;
+	__syncthreads();
+	if (warp == 0)
+	{
+		uint32_t w = lane < (kScanThreads / 32) ? s_warp[lane] : 0u;
+		uint32_t winc = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			uint32_t const t = __shfl_up_sync(0xffffffffu, winc, o);
+			if (lane >= o) winc += t;
+		}
+		if (lane < (kScanThreads / 32)) s_warp[lane] = winc - w;
+		if (lane == 31) s_warp[32] = winc;
+	}
+	__syncthreads();
+	total = s_warp[32];
+	uint32_t const r = s_warp[warp] + inc - v;
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* __restrict__ data, uint32_t m,
+															 uint32_t* __restrict__ tile_sums)
+{
+	__shared__ uint32_t s_warp[33];
+	uint32_t const base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+	uint32_t v[kScanItems];
+	uint32_t sum = 0;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++)
+	{
+		v[k] = (base + k < m) ? data[base + k] : 0u;
+		sum += v[k];
+	}
+	uint32_t total;
+	uint32_t run = block_exclusive_scan(sum, s_warp, total);
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++)
+	{
+		if (base + k < m) data[base + k] = run;
+		run += v[k];
+	}
+	if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of the tile sums (sequential over chunks of kScanThreads)
+__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t tiles)
+{
+	__shared__ uint32_t s_warp[33];
+	uint32_t carry = 0;
+	for (uint32_t b = 0; b < tiles; b += kScanThreads)
+	{
+		uint32_t const i = b + threadIdx.x;
+		uint32_t const v = i < tiles ? tile_sums[i] : 0u;
+		uint32_t total;
+		uint32_t const r = block_exclusive_scan(v, s_warp, total);
+		if (i < tiles) tile_sums[i] = carry + r;
+		carry += total;
+	}
+	if (threadIdx.x == 0) tile_sums[tiles] = carry;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* __restrict__ data, uint32_t m,
+														   const uint32_t* __restrict__ tile_sums, uint32_t tiles)
+{
+	uint32_t const off = tile_sums[blockIdx.x];
+	uint32_t const base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
+#pragma unroll
+	for (int k = 0; k < kScanItems; k++)
+		if (base + k < m) data[base + k] += off;
+	if (blockIdx.x == 0 && threadIdx.x == 0) data[m] = tile_sums[tiles];
+}
+
+// counting-sort scatter.  cursor[] holds the per-cell counts and is consumed (atomicSub), so no
+// second table is needed; the slot order inside a cell is arbitrary here and fixed by k_cell_order.
+__global__ void __launch_bounds__(kThreads) k_scatter(const float* __restrict__ xyz, uint32_t n,
+													  const uint32_t* __restrict__ keys,
+													  const uint32_t* __restrict__ cell_start,
+													  uint32_t* __restrict__ cursor, float4* __restrict__ sorted)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t const key = keys[i];
+	uint32_t const left = atomicSub(cursor + key, 1u);       // count .. 1
+	uint32_t const pos = cell_start[key] + (left - 1u);
+	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
+	sorted[pos] = make_float4(x, y, z, __uint_as_float(i));
+}
+
+// one thread per cell: insertion sort of the cell's few particles by original index, so that every
+// FP32 sum over a cell runs in the reference's order (ascending point id) and results are
+// reproducible from run to run and from GPU to GPU.
+__global__ void __launch_bounds__(kThreads) k_cell_order(const uint32_t* __restrict__ cell_start, uint32_t cells,
+														 float4* __restrict__ sorted)
+{
+	uint32_t const c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= cells) return;
+	uint32_t const b = cell_start[c], e = cell_start[c + 1];
+	for (uint32_t i = b + 1; i < e; i++)
+	{
+		float4 const v = sorted[i];
+		uint32_t const id = __float_as_uint(v.w);
+		uint32_t j = i;
+		while (j > b)
+		{
+			float4 const u = sorted[j - 1];
+			if (__float_as_uint(u.w) <= id) break;
+			sorted[j] = u;
+			j--;
+		}
+		if (j != i) sorted[j] = v;
+	}
+}
+
+// OctreeNode::Flag (Dataset.cpp:136-164).  The reference sums exp(-1000 * r) * NumParticles over the 27
+// cells; expf(-1000 r) is exactly 0 for r >= 1 and 1 for r = 0, and adding exact zeros changes nothing,
+// so N_c == float(NumParticles of the cell itself).  Flag = N_c * W0 > isoDensity with isoDensity = 1
+// (BuildDensityGrid(1), Dataset.cpp:23).
+__global__ void __launch_bounds__(kThreads) k_flags(const uint32_t* __restrict__ grid_counts, uint32_t cells, float W0,
+													uint32_t* __restrict__ occ_bits, unsigned long long* occupied)
+{
+	uint32_t const c = blockIdx.x * blockDim.x + threadIdx.x;
+	bool flag = false;
+	if (c < cells)
+	{
+		float const rho = mulr((float)grid_counts[c], W0);
+		flag = rho > 1.0f;
+	}
+	uint32_t const word = __ballot_sync(0xffffffffu, flag);
+	if ((threadIdx.x & 31) == 0 && (c >> 5) < ((cells + 31u) >> 5))
+	{
+		occ_bits[c >> 5] = word;
+		if (word) atomicAdd(occupied, (unsigned long long)__popc(word));
+	}
+}
+
+}  // namespace
+
+FrameView make_view(const Frame& f)
+{
+	FrameView v;
+	v.sorted = f.d_sorted;
+	v.cell_start = f.d_cell_start;
+	v.occ_bits = f.d_occ_bits;
+	v.n = (uint32_t)f.n;
+	v.kmin = make_int3(f.gp.kmin[0], f.gp.kmin[1], f.gp.kmin[2]);
+	v.kdim = make_int3(f.gp.kdim[0], f.gp.kdim[1], f.gp.kdim[2]);
+	v.search_inv = f.gp.search_inv;
+	v.mn = make_float3(f.gp.mn[0], f.gp.mn[1], f.gp.mn[2]);
+	v.mx = make_float3(f.gp.mx[0], f.gp.mx[1], f.gp.mx[2]);
+	v.gdim = make_int3(f.gp.gdim[0], f.gp.gdim[1], f.gp.gdim[2]);
+	v.cell_width = f.gp.cell_width;
+	v.inv_cell_width = make_float3(f.gp.inv_cell_width, f.gp.inv_cell_width, f.gp.inv_cell_width);
+	// CubicSplineKernel::CubicSplineKernel (Kernel.cpp:8-14), evaluated in FP32 like the reference
+	float const h = f.h;
+	v.kernel.h = h;
+	v.kernel.h_squared = h * h;
+	v.kernel.h_inv = 1.0f / h;
+	volatile float t = 3.14159265358979323846264338327950288f * h;
+	t = t * h;
+	t = t * h;
+	v.kernel.sig_d = 8.0f / t;
+	return v;
+}
+
+int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
+{
+	if (n == 0 || n > 0x7fffffffull) { set_error("fr_upload_frame: particle count must be in [1, 2^31)"); return FR_ERR_INVALID; }
+	if (!(h > 0.0f)) { set_error("fr_upload_frame: h must be positive"); return FR_ERR_INVALID; }
+	cudaStream_t const s = ctx->stream;
+	uint32_t const n32 = (uint32_t)n;
+	f->valid = false;
+	f->n = n;
+	f->h = h;
+	f->h_ext = h_ext_mult * h;
+
+	FM_CUDA(cudaEventRecord(ctx->ev[2], s));
+	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
+	k_init_params<<<1, 1, 0, s>>>(ctx->d_gp, f->d_occupied);
+	int const aabb_blocks = (int)min((size_t)ctx->sm_count * 8, (n + kThreads - 1) / kThreads);
+	k_aabb<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_gp);
+	k_grid_params<<<1, 1, 0, s>>>(ctx->d_gp, h);
+	FM_CUDA(cudaMemcpyAsync(ctx->h_gp, ctx->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaStreamSynchronize(s));   // table sizes depend on the AABB
+	f->gp = *ctx->h_gp;
+	const GridParams& gp = f->gp;
+	for (int a = 0; a < 3; a++)
+		if (gp.gdim[a] <= 0 || gp.kdim[a] <= 0 || !isfinite(gp.mn[a]) || !isfinite(gp.mx[a]))
+		{
+			set_error("fr_upload_frame: degenerate particle bounds (NaN/inf positions?)");
+			return FR_ERR_INVALID;
+		}
+	uint64_t const cells = (uint64_t)gp.kdim[0] * (uint64_t)gp.kdim[1] * (uint64_t)gp.kdim[2];
+	uint64_t const gcells = (uint64_t)gp.gdim[0] * (uint64_t)gp.gdim[1] * (uint64_t)gp.gdim[2];
+	if (cells >= 0x7fffff00ull || gcells >= 0x7fffff00ull)
+	{
+		set_error("fr_upload_frame: grid too large (extent / h exceeds 2^31 cells)");
+		return FR_ERR_INVALID;
+	}
+	uint32_t const cells32 = (uint32_t)cells, gcells32 = (uint32_t)gcells;
+	uint32_t const occ_words = (gcells32 + 31u) / 32u;
+	uint32_t const tiles = (cells32 + kScanTile - 1) / kScanTile;
+
+	int rc;
+	if ((rc = ensure_capacity(&f->d_sorted, &f->cap_sorted, n))) return rc;
+	if ((rc = ensure_capacity(&f->d_cell_start, &f->cap_cells, (size_t)cells32 + 1))) return rc;
+	if ((rc = ensure_capacity(&f->d_grid_counts, &f->cap_grid, gcells32))) return rc;
+	if ((rc = ensure_capacity(&f->d_occ_bits, &f->cap_occ_words, occ_words))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, n))) return rc;
+	// scan scratch: per-cell cursor copy + tile sums
+	if ((rc = ensure_capacity(&ctx->d_scan_tmp, &ctx->cap_scan_tmp, (size_t)cells32 + tiles + 2))) return rc;
+	uint32_t* const d_cursor = ctx->d_scan_tmp;
+	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
+
+	FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
+	FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, (size_t)gcells32 * 4, s));
+
+	BuildView b;
+	b.kmin = make_int3(gp.kmin[0], gp.kmin[1], gp.kmin[2]);
+	b.kdim = make_int3(gp.kdim[0], gp.kdim[1], gp.kdim[2]);
+	b.search_inv = gp.search_inv;
+	b.mn = make_float3(gp.mn[0], gp.mn[1], gp.mn[2]);
+	b.gdim = make_int3(gp.gdim[0], gp.gdim[1], gp.gdim[2]);
+	b.inv_cw = gp.inv_cell_width;
+
+	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
+	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, b, ctx->d_keys, d_cursor, f->d_grid_counts);
+	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter)
+	FM_CUDA(cudaMemcpyAsync(f->d_cell_start, d_cursor, (size_t)cells32 * 4, cudaMemcpyDeviceToDevice, s));
+	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums);
+	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
+	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums, tiles);
+	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, f->d_sorted);
+	k_cell_order<<<(cells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_cell_start, cells32, f->d_sorted);
+	FrameView const v = make_view(*f);
+	k_flags<<<(gcells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_grid_counts, gcells32, v.kernel.sig_d,
+																	  f->d_occ_bits, f->d_occupied);
+	FM_CUDA(cudaGetLastError());
+	FM_CUDA(cudaEventRecord(ctx->ev[3], s));
+	f->valid = true;
+	return FR_OK;
+}
+
+}  // namespace fm

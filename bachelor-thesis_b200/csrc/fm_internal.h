@@ -1,0 +1,122 @@
+// fm_internal.h -- host-side structures shared by the fluidmarch translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/fluidmarch.h"
+#include "fm_common.cuh"
+
+namespace fm
+{
+
+// written by the device (k_grid_params), read back once per frame upload to size the tables
+struct GridParams
+{
+	float mn[3], mx[3];          // m_Min, m_Max (Dataset.cpp:78-92)
+	int32_t gdim[3];             // density grid W, H, D (Dataset.cpp:102-104)
+	float cell_width;
+	float inv_cell_width;
+	int32_t kmin[3], kdim[3];    // neighbour-search cell range
+	float search_inv;
+	uint32_t raw_min[3], raw_max[3];   // order-preserving encodings used by the AABB atomics
+};
+
+struct Frame
+{
+	bool valid = false;
+	size_t n = 0;
+	float h = 0.0f, h_ext = 0.0f;
+	GridParams gp{};
+	uint64_t occupied = 0;
+	// device buffers (capacities in elements)
+	float4* d_sorted = nullptr;       size_t cap_sorted = 0;
+	uint32_t* d_cell_start = nullptr; size_t cap_cells = 0;     // kdim product + 1
+	uint32_t* d_grid_counts = nullptr; size_t cap_grid = 0;     // gdim product
+	uint32_t* d_occ_bits = nullptr;   size_t cap_occ_words = 0;
+	unsigned long long* d_occupied = nullptr;                   // number of flagged nodes
+};
+
+struct DeviceCounters
+{
+	unsigned long long covered_rays, hit_rays, ray_steps, skip_iterations, candidates, neighbours,
+		early_exits, neighbour_overflow;
+};
+
+struct Context
+{
+	int device = 0;
+	int width = 0, height = 0;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev_done = nullptr;
+	cudaEvent_t ev[10] = {};
+	bool render_pending = false;
+
+	fr_settings settings{};
+	bool have_settings = false;
+	fr_camera camera{};
+	bool have_camera = false;
+	bool have_depth = false;
+	int part_rank = 0, part_world = 1, part_tw = 64, part_th = 64;
+
+	std::vector<Frame> frames;
+
+	// images
+	float* d_depth = nullptr;
+	float4* d_pos = nullptr;
+	float4* d_nrm = nullptr;
+	uchar4* d_rgba = nullptr;
+	uchar4* d_rgba_target = nullptr;   // where the colour pass writes (internal or external)
+	// scratch for frame builds
+	float* d_xyz = nullptr;           size_t cap_xyz = 0;       // staged input particles (n*3)
+	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
+	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
+	GridParams* d_gp = nullptr;
+	DeviceCounters* d_counters = nullptr;
+	GridParams* h_gp = nullptr;        // pinned
+	DeviceCounters* h_counters = nullptr;
+
+	fr_timings timings{};
+	// external interop
+	cudaExternalMemory_t ext_mem = nullptr;
+	cudaExternalSemaphore_t ext_wait = nullptr, ext_signal = nullptr;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FM_CUDA(expr)                                                            \
+	do {                                                                         \
+		cudaError_t _e = (expr);                                                 \
+		if (_e != cudaSuccess) return fm::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+	} while (0)
+
+template <typename T>
+int ensure_capacity(T** ptr, size_t* cap, size_t need)
+{
+	if (need <= *cap && *ptr) return FR_OK;
+	if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
+	size_t const want = need + need / 8 + 64;
+	FM_CUDA(cudaMalloc((void**)ptr, want * sizeof(T)));
+	*cap = want;
+	return FR_OK;
+}
+
+// fm_grid.cu
+int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
+FrameView make_view(const Frame& f);
+// fm_depth.cu
+int launch_depth_prepass(Context* ctx, const Frame& f);
+// fm_march.cu
+int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade);
+// fm_query.cu
+int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
+					uint32_t* ids, size_t cap);
+int query_density(Context* ctx, const Frame& f, const float* points_host, size_t m, float* density, float* grad);
+
+}  // namespace fm

@@ -1,0 +1,137 @@
+// fm_query.cu -- point queries against the built frame, for parity checks of the neighbour search
+// (Dataset::GetNeighbors, src/app/Dataset.cpp:272-280 -> NeighborhoodSearch::find_neighbors) and of the
+// density / gradient sums (RayMarcher.cpp:322-336).  One thread per query point; not a hot path.
+#include "fm_internal.h"
+
+namespace fm
+{
+
+namespace
+{
+
+__global__ void __launch_bounds__(128) k_query_neighbors(FrameView f, const float* __restrict__ pts, uint32_t m,
+														 uint32_t* __restrict__ counts, uint32_t* __restrict__ ids, uint32_t cap)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	float const px = pts[3ull * i], py = pts[3ull * i + 1], pz = pts[3ull * i + 2];
+	int const kx = search_cell_of(f.search_inv, px) - f.kmin.x;
+	int const ky = search_cell_of(f.search_inv, py) - f.kmin.y;
+	int const kz = search_cell_of(f.search_inv, pz) - f.kmin.z;
+	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
+	uint32_t nn = 0;
+	if (z0 <= z1)
+		for (int dx = -1; dx <= 1; dx++)
+		{
+			int const x = kx + dx;
+			if ((unsigned)x >= (unsigned)f.kdim.x) continue;
+			for (int dy = -1; dy <= 1; dy++)
+			{
+				int const y = ky + dy;
+				if ((unsigned)y >= (unsigned)f.kdim.y) continue;
+				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+				uint32_t const b = f.cell_start[base + z0], e = f.cell_start[base + z1 + 1];
+				for (uint32_t j = b; j < e; j++)
+				{
+					float4 const q = f.sorted[j];
+					float const d0 = subr(px, q.x), d1 = subr(py, q.y), d2 = subr(pz, q.z);
+					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+					if (l2 < f.kernel.h_squared)
+					{
+						if (ids && nn < cap) ids[(size_t)i * cap + nn] = __float_as_uint(q.w);
+						nn++;
+					}
+				}
+			}
+		}
+	counts[i] = nn;
+}
+
+__global__ void __launch_bounds__(128) k_query_density(FrameView f, const float* __restrict__ pts, uint32_t m,
+													   float* __restrict__ density, float* __restrict__ grad)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= m) return;
+	float const px = pts[3ull * i], py = pts[3ull * i + 1], pz = pts[3ull * i + 2];
+	int const kx = search_cell_of(f.search_inv, px) - f.kmin.x;
+	int const ky = search_cell_of(f.search_inv, py) - f.kmin.y;
+	int const kz = search_cell_of(f.search_inv, pz) - f.kmin.z;
+	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
+	float rho = 0.0f;
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	if (z0 <= z1)
+		for (int dx = -1; dx <= 1; dx++)
+		{
+			int const x = kx + dx;
+			if ((unsigned)x >= (unsigned)f.kdim.x) continue;
+			for (int dy = -1; dy <= 1; dy++)
+			{
+				int const y = ky + dy;
+				if ((unsigned)y >= (unsigned)f.kdim.y) continue;
+				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+				uint32_t const b = f.cell_start[base + z0], e = f.cell_start[base + z1 + 1];
+				for (uint32_t j = b; j < e; j++)
+				{
+					float4 const q = f.sorted[j];
+					float const d0 = subr(px, q.x), d1 = subr(py, q.y), d2 = subr(pz, q.z);
+					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+					if (l2 < f.kernel.h_squared)
+					{
+						rho = addr(rho, spline_W_inrange(f.kernel, l2));
+						g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+					}
+				}
+			}
+		}
+	density[i] = rho;
+	if (grad) { grad[3ull * i] = g.x; grad[3ull * i + 1] = g.y; grad[3ull * i + 2] = g.z; }
+}
+
+struct DevBuf
+{
+	void* p = nullptr;
+	~DevBuf() { if (p) cudaFree(p); }
+};
+
+}  // namespace
+
+int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
+					uint32_t* ids, size_t cap)
+{
+	if (m == 0) return FR_OK;
+	if (m > 0x7fffffffull || cap > 0xffffffffull) { set_error("fr_query_neighbors: too many points"); return FR_ERR_INVALID; }
+	cudaStream_t const s = ctx->stream;
+	DevBuf dp, dc, di;
+	FM_CUDA(cudaMalloc(&dp.p, m * 12));
+	FM_CUDA(cudaMalloc(&dc.p, m * 4));
+	if (ids && cap) FM_CUDA(cudaMalloc(&di.p, m * cap * 4));
+	FM_CUDA(cudaMemcpyAsync(dp.p, points_host, m * 12, cudaMemcpyHostToDevice, s));
+	k_query_neighbors<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(make_view(f), (const float*)dp.p, (uint32_t)m,
+																 (uint32_t*)dc.p, (uint32_t*)di.p, (uint32_t)cap);
+	FM_CUDA(cudaGetLastError());
+	FM_CUDA(cudaMemcpyAsync(counts, dc.p, m * 4, cudaMemcpyDeviceToHost, s));
+	if (di.p) FM_CUDA(cudaMemcpyAsync(ids, di.p, m * cap * 4, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaStreamSynchronize(s));
+	return FR_OK;
+}
+
+int query_density(Context* ctx, const Frame& f, const float* points_host, size_t m, float* density, float* grad)
+{
+	if (m == 0) return FR_OK;
+	if (m > 0x7fffffffull) { set_error("fr_query_density: too many points"); return FR_ERR_INVALID; }
+	cudaStream_t const s = ctx->stream;
+	DevBuf dp, dd, dg;
+	FM_CUDA(cudaMalloc(&dp.p, m * 12));
+	FM_CUDA(cudaMalloc(&dd.p, m * 4));
+	if (grad) FM_CUDA(cudaMalloc(&dg.p, m * 12));
+	FM_CUDA(cudaMemcpyAsync(dp.p, points_host, m * 12, cudaMemcpyHostToDevice, s));
+	k_query_density<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(make_view(f), (const float*)dp.p, (uint32_t)m,
+															   (float*)dd.p, (float*)dg.p);
+	FM_CUDA(cudaGetLastError());
+	FM_CUDA(cudaMemcpyAsync(density, dd.p, m * 4, cudaMemcpyDeviceToHost, s));
+	if (grad) FM_CUDA(cudaMemcpyAsync(grad, dg.p, m * 12, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaStreamSynchronize(s));
+	return FR_OK;
+}
+
+}  // namespace fm

@@ -1,0 +1,193 @@
+/* fluidmarch.h -- C ABI of the B200-native SPH iso-surface ray-march path (libfluidmarch.so).
+ *
+ * Plain C, `int` status returns (0 = FR_OK, negative = error; text via fr_last_error()),
+ * plain pointers and sizes, no C++ or torch types.  One context per GPU; a context is used from
+ * one host thread at a time; all its work is ordered on one CUDA stream.  There is NO CPU
+ * fallback: every entry point that computes needs an sm_100 device.
+ *
+ * The reference (Fruup/bachelor-thesis, paths relative to its root) has no FFI layer; its seam
+ * for this path is the C++ class RayMarcher used by AdvancedRenderer::Render.  Each entry point
+ * below cites the reference interface it replaces.  A header-compatible `class RayMarcher` over
+ * this ABI lives in bachelor-thesis_b200/host/RayMarcher.h; INTEGRATION.md shows the binding.
+ */
+#ifndef FLUIDMARCH_H
+#define FLUIDMARCH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR_ABI_VERSION 1
+
+enum
+{
+	FR_OK = 0,
+	FR_ERR_INVALID = -1,     /* bad argument */
+	FR_ERR_CUDA = -2,        /* CUDA runtime error (fr_last_error() has the text) */
+	FR_ERR_NO_DEVICE = -3,   /* no usable sm_100 device: the library never falls back to the CPU */
+	FR_ERR_STATE = -4,       /* call order violated (e.g. render before upload/camera) */
+	FR_ERR_UNSUPPORTED = -5  /* feature not built yet (anisotropic path) */
+};
+
+/* passes of fr_render_async, in path order */
+enum
+{
+	FR_PASS_DEPTH = 1,   /* depth pre-pass: replaces CollectRenderData + DepthRenderPass + depth.vert/frag
+	                        (src/app/AdvancedRenderer/AdvancedRenderer.cpp:447-485, DepthRenderPass.cpp:45-87) */
+	FR_PASS_MARCH = 2,   /* RayMarcher::PerPixel_Isotropic (src/app/AdvancedRenderer/RayMarcher.cpp:256-344) */
+	FR_PASS_SHADE = 4,   /* CompositionRenderPass + composition.frag:70-122 */
+	FR_PASS_ALL = 7
+};
+
+typedef struct fr_context fr_context;
+
+/* POD mirror of VisualizationSettings (src/app/AdvancedRenderer/RayMarcher.h:12-26);
+ * defaults: src/app/AdvancedRenderer/AdvancedRenderer.cpp:18-28 */
+typedef struct fr_settings
+{
+	int32_t frame;               /* Frame: index of the uploaded frame to render */
+	int32_t max_steps;           /* MaxSteps   = 128 */
+	float step_size;             /* StepSize   = 0.009 */
+	float iso_density;           /* IsoDensity = 1.0 */
+	int32_t enable_anisotropy;   /* EnableAnisotropy (reference default true; only 0 is built) */
+	float k_n, k_r, k_s;         /* 0.5, 2, 2000 */
+	int32_t n_eps;               /* 1 */
+	/* additions (0 = reference behaviour) */
+	int32_t bisection_steps;     /* >0: refine the hit between the last two samples (north_star item 3);
+	                                0 = parity mode, hit = first sample with density >= iso */
+	int32_t skip_last_pixel;     /* 1: leave pixel W*H-1 untouched like the reference ThreadPool
+	                                (src/app/ThreadPool.cpp:50) */
+} fr_settings;
+
+/* camera inputs the path reads: CameraController3D::{Position,System} and
+ * Camera3D::{View,Projection,InvProjectionView} (src/engine/camera/Camera3D.h:30-32,
+ * CameraController3D.h:22-27).  Matrices are column-major, glm memory order m[col*4+row]. */
+typedef struct fr_camera
+{
+	float view[16];
+	float projection[16];
+	float inv_projection_view[16];
+	float position[3];
+	float direction[3];          /* CameraController3D::System[2] (CompositionRenderPass.cpp:319) */
+} fr_camera;
+
+/* Frame geometry: Frame::{m_Min,m_Max}, DensityGrid::{m_Width,m_Height,m_Depth}
+ * (src/app/Dataset.h:27-35,60-62) */
+typedef struct fr_frame_info
+{
+	uint64_t num_particles;
+	float h;                     /* Dataset::ParticleRadius (SPH support radius) */
+	float min[3], max[3];        /* particle AABB padded by h (Dataset.cpp:78-92) */
+	int32_t grid_dims[3];        /* density grid W, H, D (Dataset.cpp:102-104) */
+	uint64_t occupied_cells;     /* nodes with Flag set (Dataset.cpp:136-164) */
+	int32_t search_min[3];       /* neighbour-search cell range (cells of size h, world origin) */
+	int32_t search_dims[3];
+} fr_frame_info;
+
+typedef struct fr_counters
+{
+	uint64_t pixels;             /* W*H */
+	uint64_t covered_rays;       /* depth != 1 */
+	uint64_t hit_rays;
+	uint64_t ray_steps;          /* density evaluations executed */
+	uint64_t skip_iterations;    /* empty-cell jumps */
+	uint64_t candidates;         /* particles examined (27-cell candidates) */
+	uint64_t neighbours;         /* of those, d^2 < h^2 */
+	uint64_t early_exits;        /* rays stopped after leaving the grid for good (cannot hit) */
+	uint64_t neighbour_overflow; /* samples with more than 8192 neighbours (RayMarcher.cpp:14); must be 0 */
+} fr_counters;
+
+/* device time of the last call of each stage, milliseconds (CUDA events on the context stream) */
+typedef struct fr_timings
+{
+	float upload_ms;             /* host -> device copy of the particle array */
+	float grid_ms;               /* AABB + keys + histogram + scan + scatter + in-cell order + occupancy */
+	float depth_ms;
+	float march_ms;              /* march + normals + shading (fused kernel) */
+	float download_ms;
+} fr_timings;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int fr_abi_version(void);
+const char* fr_last_error(void);
+/* RayMarcher::RayMarcher + the W/H read from Vulkan.SwapchainExtent in Prepare (RayMarcher.cpp:64-69,86-89) */
+int fr_create(int device, int width, int height, fr_context** out);
+int fr_resize(fr_context* ctx, int width, int height);
+/* RayMarcher::Exit (RayMarcher.cpp:71-74) */
+void fr_destroy(fr_context* ctx);
+
+/* pinned host memory for uploads/downloads that should overlap with rendering */
+int fr_host_alloc(size_t bytes, void** out);
+void fr_host_free(void* p);
+
+/* ---- frames: Dataset::ReadFile -> Frames.emplace_back -> Frame::Frame (Dataset.cpp:9-24,292-306) - */
+/* xyz: n packed float3 (glm::vec3 AoS as partio delivers them).  Builds, on the device, the
+ * neighbour search (Frame::BuildSearch), the AABB (ComputeAABB) and the occupancy grid
+ * (BuildDensityGrid).  h = particleRadius, h_ext_mult = particleRadiusMultiplier (assets/config.yml:19-20). */
+int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult);
+/* same, particles already resident in device memory (n packed float3) */
+int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult);
+int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out);
+int fr_release_frame(fr_context* ctx, int frame);
+/* parity access to the built structures (any pointer may be NULL):
+ *   sorted_xyzi    : n * 4 floats, particles in search order, .w = original index (uint32 bits)
+ *   cell_start     : search_dims product + 1 uint32 (exclusive prefix of the per-cell counts)
+ *   grid_counts    : grid_dims product uint32, OctreeNode::NumParticles
+ *   grid_flags     : grid_dims product uint8, OctreeNode::Flag */
+int fr_download_frame(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* cell_start,
+					  uint32_t* grid_counts, uint8_t* grid_flags);
+
+/* ---- per-render state: RayMarcher::Prepare (RayMarcher.cpp:76-100) ------------------------------ */
+int fr_set_settings(fr_context* ctx, const fr_settings* s);
+int fr_set_camera(fr_context* ctx, const fr_camera* cam);
+/* depth supplied by the caller, as Prepare's `float* depth` (W*H floats, row 0 = top, 1.0 = empty);
+ * use it together with passes that omit FR_PASS_DEPTH */
+int fr_set_depth(fr_context* ctx, const float* depth_host);
+/* multi-GPU tile-parallel: this context renders only screen tiles t with t % world == rank
+ * (tiles of tile_w x tile_h pixels, row-major tile index); world = 1 renders everything */
+int fr_set_tile_partition(fr_context* ctx, int rank, int world, int tile_w, int tile_h);
+
+/* ---- render: RayMarcher::Start / IsDone (RayMarcher.cpp:102-112, RayMarcher.h:44) ---------------- */
+int fr_render_async(fr_context* ctx, int passes);
+int fr_is_done(fr_context* ctx);      /* 1 = done, 0 = still running, <0 = error */
+int fr_wait(fr_context* ctx);
+
+/* ---- results ---------------------------------------------------------------------------------- */
+/* host copies (any pointer may be NULL): depth W*H floats; positions/normals W*H*4 floats
+ * (glm::vec4 images of Prepare); rgba W*H*4 bytes, sRGB-encoded R,G,B + linear A.  Waits for the render. */
+int fr_download(fr_context* ctx, float* depth, float* positions, float* normals, uint8_t* rgba);
+/* device pointers of the same images (valid until fr_resize/fr_destroy), for interop / NCCL */
+int fr_device_images(fr_context* ctx, void** depth, void** positions, void** normals, void** rgba);
+/* render the colour image into caller-owned device memory instead (e.g. a torch tensor used as
+ * an NCCL buffer, or imported Vulkan memory); NULL restores the internal image */
+int fr_set_color_target(fr_context* ctx, void* rgba_device);
+int fr_get_counters(fr_context* ctx, fr_counters* out);
+int fr_get_timings(fr_context* ctx, fr_timings* out);
+/* the CUDA stream all work of this context is ordered on (a cudaStream_t) */
+int fr_get_stream(fr_context* ctx, void** stream);
+
+/* ---- point queries (parity of Dataset::GetNeighbors, Dataset.cpp:272-280) ------------------------- */
+/* for each of m query points (packed float3, host): counts[i] = |{j : |x_j - p_i|^2 < h^2}| and, if
+ * ids != NULL, up to cap original particle indices at ids[i*cap ...] in the reference's result order */
+int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, size_t m,
+					   uint32_t* counts, uint32_t* ids, size_t cap);
+/* density = sum_j W(x_j - p_i) (RayMarcher.cpp:322-325) and, if grad != NULL, the un-normalised
+ * sum_j gradW(x_j - p_i) (RayMarcher.cpp:333-336), m*3 floats */
+int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad);
+
+/* ---- CUDA-Vulkan hand-off: replaces BilateralBuffer::CopyToGPU/CopyFromGPU
+ *      (src/app/AdvancedRenderer/BilateralBuffer.cpp:78-134) ------------------------------------------ */
+/* imports VkDeviceMemory exported with VK_KHR_external_memory_fd (opaque fd, linear W*H*4-byte
+ * image or buffer at `offset`) and makes it the colour target */
+int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, size_t offset);
+/* VK_KHR_external_semaphore_fd binary semaphores: the render waits on `wait_fd` (image available)
+ * before writing and signals `signal_fd` when the image is complete; -1 = none */
+int fr_import_vk_semaphores_fd(fr_context* ctx, int wait_fd, int signal_fd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,58 @@
+"""The C-ABI library loads and exports exactly what include/fluidmarch.h declares; error behaviour
+without a device.  No compute calls (CPU suite)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "fluidmarch.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(fr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_and_binding_agree(fm):
+    declared = header_functions()
+    bound = sorted(n for n, _, _ in fm._cabi.SYMBOLS)
+    assert declared == bound
+
+
+def test_library_exports_every_declared_symbol(fm):
+    assert os.path.exists(fm.LIB_PATH), "libfluidmarch.so not built: run __graft_entry__.build()"
+    lib = C.CDLL(fm.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), name
+    assert fm.load().fr_abi_version() == 1
+
+
+def test_struct_layouts(fm):
+    abi = fm._cabi
+    assert C.sizeof(abi.FrSettings) == 11 * 4
+    assert C.sizeof(abi.FrCamera) == (16 * 3 + 6) * 4
+    assert C.sizeof(abi.FrCounters) == 9 * 8
+    assert C.sizeof(abi.FrTimings) == 5 * 4
+
+
+def test_no_cpu_fallback(fm):
+    """without a CUDA device the product path must fail loudly, never compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(fm.FluidMarchError, match="no CUDA device|no CPU fallback"):
+        fm.Context(64, 64)
+
+
+def test_product_does_not_touch_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may use oracle/"""
+    pkg = os.path.join(ROOT, "bachelor-thesis_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, fn), errors="ignore").read()
+                # mentions in comments are fine; including, loading or importing the checker is not
+                bad = re.search(r'#include\s*[<"][^>"]*oracle|dlopen|liboracle\.so|libfluidref\.so|oracle_lib|import\s+oracle', text)
+                assert bad is None, (fn, bad.group(0))

@@ -1,0 +1,349 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (libfluidmarch.so), against the CPU
+oracle on the same inputs and against the golden fixtures generated from the reference.
+
+Parity bar (bit-exact wherever the work is integer/index work or a fixed FP32 sequence):
+  * frame geometry, occupancy counts/flags, per-cell particle sets, neighbour lists: bit-exact
+  * depth pre-pass: bit-exact (fixed FP32 op sequence, order-independent min)
+  * hit mask, hit positions, normals: bit-exact -- the kernel accumulates in the reference's neighbour order,
+    so no epsilon band around the iso threshold is needed (the band allowed by the spec is empty)
+  * RGBA8: +-1 code value on a small fraction of pixels (powf of the sRGB curve is the only non-IEEE op)
+"""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import GOLDEN, golden_camera
+
+pytestmark = pytest.mark.gpu
+scenes = importlib.import_module("bachelor-thesis_b200.scenes")
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def set_cam(ctx, cam):
+    ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+
+
+def search_key(xyz, h, info):
+    inv = np.float32(1.0) / np.float32(h)
+    t = (inv * xyz.astype(np.float32)).astype(np.int32)          # truncation toward zero, like (int)
+    k = np.where(xyz >= 0, t, t - 1) - info["search_min"][None, :]
+    kd = info["search_dims"].astype(np.int64)
+    return (k[:, 0].astype(np.int64) * kd[1] + k[:, 1]) * kd[2] + k[:, 2]
+
+
+@pytest.fixture(scope="module")
+def small():
+    return np.load(os.path.join(GOLDEN, "dambreak8k_160x90.npz"))
+
+
+# ---- (a1-a4) grid build ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,gen", [(8000, "dam"), (64000, "dam"), (5000, "rand"), (1, "rand"), (37, "rand")])
+def test_grid_build_parity(fm, oracle, gpu_ctx_factory, n, gen):
+    xyz = scenes.dam_break(n) if gen == "dam" else scenes.random_block(n, 0.7)
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    g = ctx.download_frame(0)
+    info = g["info"]
+    f = oracle.frame(xyz, 0.1, 2.0)
+    assert info["num_particles"] == len(xyz)
+    assert np.array_equal(bits(info["min"]), bits(f.min)) and np.array_equal(bits(info["max"]), bits(f.max))
+    assert np.array_equal(info["grid_dims"], f.dims)
+    counts, flags = f.grid()
+    assert np.array_equal(g["grid_counts"], counts)
+    assert np.array_equal(g["grid_flags"], flags)
+    assert info["occupied_cells"] == int(flags.sum())
+    # counting sort: a permutation of the input, grouped by cell key, ascending original index inside a cell
+    idx = g["sorted_index"].astype(np.int64)
+    assert np.array_equal(np.sort(idx), np.arange(len(xyz)))
+    assert np.array_equal(bits(g["sorted_xyz"]), bits(xyz[idx]))
+    key = search_key(xyz, 0.1, info)
+    ks = key[idx]
+    assert np.all(np.diff(ks) >= 0)
+    same = np.diff(ks) == 0
+    assert np.all(np.diff(idx)[same] > 0)
+    cells = int(np.prod(info["search_dims"].astype(np.int64)))
+    want_start = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=cells))])
+    assert np.array_equal(g["cell_start"].astype(np.int64), want_start)
+
+
+def test_grid_matches_golden_reference_frame(fm, gpu_ctx_factory, small):
+    """against the Frame the reference itself built (tests/golden, counts in the reference's box reading)"""
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, small["xyz"], float(small["h"]), float(small["mult"]))
+    g = ctx.download_frame(0)
+    assert np.array_equal(bits(g["info"]["min"]), bits(small["frame_min"]))
+    assert np.array_equal(bits(g["info"]["max"]), bits(small["frame_max"]))
+    assert np.array_equal(g["info"]["grid_dims"], small["grid_dims"])
+    # cell-exact vs box reading of find_neighbors_box: only particles within an ulp of a face may move
+    assert (g["grid_counts"] != small["grid_counts"]).sum() <= 8
+    assert (g["grid_flags"] != small["grid_flags"]).sum() <= 4
+
+
+# ---- (a5) neighbour sets ---------------------------------------------------------------------------------
+def test_neighbour_lists_bit_exact(fm, oracle, gpu_ctx_factory, small):
+    xyz = small["xyz"]
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    pts = small["query_points"]
+    counts, ids = ctx.query_neighbors(0, pts, cap=256)
+    off = 0
+    for i, n in enumerate(small["neighbour_len"]):
+        assert counts[i] == n
+        got = xyz[ids[i, :n]]
+        assert np.array_equal(bits(got), bits(small["neighbour_xyz"][off:off + n]))   # reference order, bit for bit
+        off += n
+    # and against brute force as sets, on fresh points (incl. points outside the particle AABB)
+    rng = np.random.default_rng(11)
+    pts = np.concatenate([xyz[rng.integers(0, len(xyz), 300)] + rng.normal(0, 0.06, (300, 3)),
+                          rng.uniform(-3, 3, (50, 3))]).astype(np.float32)
+    counts, ids = ctx.query_neighbors(0, pts, cap=256)
+    h2 = np.float32(0.1) * np.float32(0.1)
+    for i, p in enumerate(pts):
+        d = (p[None, :] - xyz).astype(np.float32)
+        l2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]).astype(np.float32) + d[:, 2] * d[:, 2]
+        want = set(np.nonzero(l2 < h2)[0].tolist())
+        assert counts[i] == len(want)
+        assert set(ids[i, :counts[i]].tolist()) == want
+
+
+def test_density_query_matches_oracle_kernels(fm, oracle, gpu_ctx_factory, small):
+    xyz = small["xyz"]
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    f = oracle.frame(xyz, 0.1, 2.0)
+    perm = f.particles()
+    pts = small["query_points"][:24]
+    rho, grad = ctx.query_density(0, pts)
+    for i, p in enumerate(pts):
+        ids = f.neighbors(p)
+        want = np.float32(0)
+        g = np.zeros(3, np.float32)
+        for j in ids:
+            r = (perm[j] - p).astype(np.float32)
+            want = np.float32(want + oracle.W(0.1, r))
+            g = (g + oracle.gradW(0.1, r)).astype(np.float32)
+        assert bits(rho[i:i + 1])[0] == bits(np.array([want]))[0]
+        assert np.array_equal(bits(grad[i]), bits(g))
+
+
+# ---- (a11) depth pre-pass ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,W,H,cam_name", [(8000, 160, 90, "camera_close_16x9"), (64000, 1280, 720, "camera_default_16x9"),
+                                            (20000, 333, 187, "camera_orbit_a_16x9"), (20000, 320, 180, "camera_orbit_b_16x9")])
+def test_depth_prepass_bit_exact(fm, oracle, gpu_ctx_factory, n, W, H, cam_name):
+    xyz = scenes.dam_break(n)
+    cam = golden_camera(cam_name)
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    set_cam(ctx, cam)
+    ctx.render(fm.FR_PASS_DEPTH)
+    depth, *_ = ctx.download(True, False, False, False)
+    want = oracle.frame(xyz, 0.1, 2.0).depth_prepass(W, H, cam["view"], cam["proj"])
+    assert (want < 1).sum() > 50
+    assert np.array_equal(bits(depth), bits(want))
+
+
+# ---- (a10, a6-a8) the march ---------------------------------------------------------------------------------
+def test_march_matches_golden_reference_output(fm, gpu_ctx_factory, small):
+    """positions / normals the REFERENCE's PerPixel_Isotropic produced (tests/golden), bit for bit"""
+    cam = golden_camera("camera_close_16x9")
+    W, H = int(small["W"]), int(small["H"])
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, small["xyz"], 0.1, 2.0)
+    set_cam(ctx, cam)
+    ctx.set_settings(fm.VisualizationSettings())
+    ctx.set_depth(small["depth"])
+    ctx.render(fm.FR_PASS_MARCH)
+    _, pos, nrm, _ = ctx.download(False, True, True, False)
+    assert np.array_equal(bits(pos), bits(small["positions"]))
+    assert np.array_equal(bits(nrm), bits(small["normals"]))
+    c = ctx.counters()
+    assert c["hit_rays"] == int(small["positions"][..., 3].sum())
+    assert c["neighbour_overflow"] == 0
+
+
+@pytest.mark.parametrize("n,W,H,cam_name,step,iso", [
+    (64000, 1280, 720, "camera_default_16x9", 0.009, 1.0),        # BASELINE config C1
+    (20000, 320, 180, "camera_orbit_a_16x9", 0.009, 1.0),
+    (20000, 333, 187, "camera_orbit_b_16x9", 0.02, 1.0),
+    (8000, 160, 90, "camera_close_16x9", 0.005, 400.0),           # threshold deep inside: many steps per ray
+    (8000, 160, 90, "camera_close_16x9", 0.009, 5000.0),          # never reached: all covered rays miss
+])
+def test_march_bit_exact_vs_oracle(fm, oracle, gpu_ctx_factory, n, W, H, cam_name, step, iso):
+    xyz = scenes.dam_break(n)
+    cam = golden_camera(cam_name)
+    f = oracle.frame(xyz, 0.1, 2.0)
+    depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
+    s = oracle_lib.Settings(step_size=step, iso_density=iso)
+    pos, nrm, band, steps, cnt = f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth)
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    set_cam(ctx, cam)
+    ctx.set_settings(fm.VisualizationSettings(StepSize=step, IsoDensity=iso))
+    ctx.set_depth(depth)
+    ctx.render(fm.FR_PASS_MARCH)
+    _, gpos, gnrm, _ = ctx.download(False, True, True, False)
+    c = ctx.counters()
+    assert c["covered_rays"] == cnt["covered_rays"] and c["hit_rays"] == cnt["hit_rays"]
+    assert np.array_equal(gpos[..., 3], pos[..., 3])                     # hit / miss mask
+    assert np.array_equal(bits(gpos), bits(pos))
+    assert np.array_equal(bits(gnrm), bits(nrm))
+    # the early exit only drops samples that lie outside the grid (density 0)
+    assert c["ray_steps"] <= cnt["ray_steps"]
+    assert c["ray_steps"] >= cnt["ray_steps"] - cnt["steps_outside_grid"]
+    assert c["skip_iterations"] == cnt["skip_iterations"]
+
+
+def test_march_edge_cases(fm, oracle, gpu_ctx_factory):
+    cam = golden_camera("camera_close_16x9")
+    W, H = 61, 35                                                  # not a multiple of the 32x8 CTA footprint
+    xyz = scenes.random_block(4000, 0.5)
+    f = oracle.frame(xyz, 0.1, 2.0)
+    depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    set_cam(ctx, cam)
+    # empty depth image: nothing marched, outputs all zero
+    ctx.set_depth(np.ones((H, W), np.float32))
+    ctx.render(fm.FR_PASS_MARCH)
+    _, p, n, _ = ctx.download(False, True, True, False)
+    assert not p.any() and not n.any() and ctx.counters()["covered_rays"] == 0
+    # ragged size, MaxSteps = 0 and 1
+    for ms in (0, 1, 128):
+        s = oracle_lib.Settings(max_steps=ms)
+        pos, nrm, *_ = f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth)
+        ctx.set_settings(fm.VisualizationSettings(MaxSteps=ms))
+        ctx.set_depth(depth)
+        ctx.render(fm.FR_PASS_MARCH)
+        _, p, n, _ = ctx.download(False, True, True, False)
+        assert np.array_equal(bits(p), bits(pos)) and np.array_equal(bits(n), bits(nrm))
+    # the reference pool never touches the last pixel (ThreadPool.cpp:50)
+    d2 = depth.copy()
+    d2[-1, -1] = d2[d2 < 1].min()
+    ctx.set_settings(fm.VisualizationSettings(SkipLastPixel=True))
+    ctx.set_depth(d2)
+    ctx.render(fm.FR_PASS_MARCH)       # previous outputs stay in place for the skipped pixel
+    _, p2, _, _ = ctx.download(False, True, True, False)
+    assert np.array_equal(bits(p2[-1, -1]), bits(p[-1, -1]))
+
+
+# ---- (a12) shading and the whole pipeline ------------------------------------------------------------------
+def test_full_pipeline_vs_oracle(fm, oracle, gpu_ctx_factory):
+    xyz = scenes.dam_break(64000)
+    cam = golden_camera("camera_default_16x9")
+    W, H = 1280, 720
+    f = oracle.frame(xyz, 0.1, 2.0)
+    depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
+    pos, nrm, *_ = f.march(W, H, oracle_lib.Settings(), cam["inv_proj_view"], cam["position"], depth)
+    cam_dir = cam["system"].reshape(3, 3)[2]
+    color, rgba = oracle.shade(W, H, pos, nrm, cam["inv_proj_view"], cam["position"], cam_dir)
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    set_cam(ctx, cam)
+    ctx.render(fm.FR_PASS_ALL)
+    gd, gp, gn, gc = ctx.download()
+    assert np.array_equal(bits(gd), bits(depth))
+    assert np.array_equal(bits(gp), bits(pos)) and np.array_equal(bits(gn), bits(nrm))
+    diff = np.abs(gc.astype(np.int16) - rgba.astype(np.int16))
+    assert diff.max() <= 1                                         # tolerance: one 8-bit code value
+    assert (diff > 0).mean() < 0.01
+    assert len(np.unique(gc.reshape(-1, 4), axis=0)) > 50          # not a constant image
+
+
+def test_tile_partition_union_is_bit_identical(fm, gpu_ctx_factory):
+    """tile-parallel multi-GPU = pure partitioning: the union of the ranks' tiles equals the 1-GPU image"""
+    xyz = scenes.dam_break(20000)
+    cam = golden_camera("camera_close_16x9")
+    W, H = 640, 360
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    set_cam(ctx, cam)
+    ctx.render(fm.FR_PASS_ALL)
+    full = ctx.download()
+    world = 4
+    acc = [np.zeros_like(a) for a in full]
+    ty, tx = np.meshgrid(np.arange(H) // 64, np.arange(W) // 64, indexing="ij")
+    tile = ty * ((W + 63) // 64) + tx
+    for rank in range(world):
+        c2 = gpu_ctx_factory(W, H)
+        c2.upload_frame(0, xyz, 0.1, 2.0)
+        set_cam(c2, cam)
+        c2.set_tile_partition(rank, world, 64, 64)
+        c2.render(fm.FR_PASS_ALL)
+        part = c2.download()
+        m = (tile % world) == rank
+        for a, p in zip(acc[1:], part[1:]):
+            a[m] = p[m]
+        c2.close()
+    for a, b in zip(acc[1:], full[1:]):
+        assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+# ---- (b) the drop-in seam -------------------------------------------------------------------------------------
+def test_raymarcher_drop_in_protocol(fm, small):
+    """Prepare / Start / IsDone / Exit with caller-owned buffers, as AdvancedRenderer::Render drives it
+    (AdvancedRenderer.cpp:257-298)"""
+    W, H = int(small["W"]), int(small["H"])
+    g = golden_camera("camera_close_16x9")
+
+    class Cam:    # what the engine hands over: CameraController3D with its Camera3D
+        pass
+    ctl, cam = Cam(), Cam()
+    cam.View, cam.Projection, cam.InvProjectionView = g["view"], g["proj"], g["inv_proj_view"]
+    ctl.Camera, ctl.Position, ctl.System = cam, g["position"], g["system"]
+
+    ds = fm.Dataset([small["xyz"]], particleRadius=0.1, particleRadiusMultiplier=2.0)
+    rm = fm.RayMarcher((W, H))
+    positions = np.full((H, W, 4), 9.0, np.float32)
+    normals = np.full((H, W, 4), 9.0, np.float32)
+    rm.Prepare(fm.VisualizationSettings(Frame=0), ctl, ds, positions, normals, small["depth"])
+    rm.Start()
+    import time
+    t0 = time.time()
+    while not rm.IsDone():
+        assert time.time() - t0 < 30
+        time.sleep(0.001)
+    assert np.array_equal(bits(positions), bits(small["positions"]))
+    assert np.array_equal(bits(normals), bits(small["normals"]))
+    rm.Exit()
+
+
+# ---- size-independent properties at the full BASELINE size (C2: 1M particles, 1920x1080) ---------------------
+def test_full_size_properties(fm, gpu_ctx_factory):
+    xyz = scenes.dam_break(1_000_000)
+    cam = golden_camera("camera_default_16x9")
+    W, H = 1920, 1080
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    g = ctx.download_frame(0)
+    assert int(g["grid_counts"].sum()) == len(xyz)                       # every particle counted once
+    assert int(g["cell_start"][-1]) == len(xyz)
+    idx = g["sorted_index"].astype(np.int64)
+    assert np.array_equal(np.sort(idx), np.arange(len(xyz)))             # a permutation
+    ks = search_key(xyz, 0.1, g["info"])[idx]
+    assert np.all(np.diff(ks) >= 0)                                      # sortedness
+    assert np.array_equal(g["grid_flags"], (g["grid_counts"] > 0).astype(np.uint8))
+    set_cam(ctx, cam)
+    ctx.render(fm.FR_PASS_ALL)
+    a = ctx.download()
+    c1 = ctx.counters()
+    ctx.upload_frame(0, xyz[::-1].copy(), 0.1, 2.0)                       # input order must not matter ...
+    ctx.render(fm.FR_PASS_ALL)
+    b = ctx.download()
+    assert np.array_equal(bits(a[0]), bits(b[0]))                        # ... for depth (exact min)
+    assert np.array_equal(a[1][..., 3], b[1][..., 3]) or (a[1][..., 3] != b[1][..., 3]).mean() < 1e-5
+    ctx.upload_frame(0, xyz, 0.1, 2.0)                                   # idempotence: same input, same bits
+    ctx.render(fm.FR_PASS_ALL)
+    c = ctx.download()
+    for x, y in zip(a, c):
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+    assert c1["covered_rays"] > 100_000 and c1["hit_rays"] > 0.8 * c1["covered_rays"]
+    assert c1["neighbour_overflow"] == 0
+    # hits lie on the far side of the seed depth: unprojected hit is never in front of the pre-pass surface
+    hit = a[1][..., 3] == 1
+    assert np.all(np.isfinite(a[1][hit])) and np.all(np.abs(np.linalg.norm(a[2][hit][:, :3], axis=1) - 1) < 1e-3)
