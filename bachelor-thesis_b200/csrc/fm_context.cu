@@ -489,6 +489,7 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->neighbours = d.neighbours;
 	out->early_exits = d.early_exits;
 	out->neighbour_overflow = d.neighbour_overflow;
+	out->kernel_launches = ctx->kernel_launches;
 	return FR_OK;
 }
 

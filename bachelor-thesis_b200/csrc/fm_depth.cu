@@ -142,6 +142,7 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	uint64_t const want_blocks = ((uint64_t)n * 32 + 255) / 256;
 	uint32_t const blocks = (uint32_t)(want_blocks < (uint64_t)ctx->sm_count * 64 ? want_blocks : (uint64_t)ctx->sm_count * 64);
 	k_depth_splat<<<blocks, 256, 0, s>>>(f.d_sorted, n, dp, (uint32_t*)ctx->d_depth);
+	ctx->kernel_launches += 2;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }

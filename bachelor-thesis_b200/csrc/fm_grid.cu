@@ -403,6 +403,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	FrameView const v = make_view(*f);
 	k_flags<<<(gcells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_grid_counts, gcells32, v.kernel.sig_d,
 																	  f->d_occ_bits, f->d_occupied);
+	ctx->kernel_launches += 10;   // init, aabb, params, key_count, 3 x scan, scatter, cell_order, flags
 	FM_CUDA(cudaGetLastError());
 	FM_CUDA(cudaEventRecord(ctx->ev[3], s));
 	f->valid = true;

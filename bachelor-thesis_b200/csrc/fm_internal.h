@@ -82,6 +82,7 @@ struct Context
 	DeviceCounters* h_counters = nullptr;
 
 	fr_timings timings{};
+	uint64_t kernel_launches = 0;      // kernels of this library launched since fr_create
 	// external interop
 	cudaExternalMemory_t ext_mem = nullptr;
 	cudaExternalSemaphore_t ext_wait = nullptr, ext_signal = nullptr;

@@ -319,6 +319,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
 	k_march_shade<<<grid, 256, 0, ctx->stream>>>(make_view(f), mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm,
 												 ctx->d_rgba_target, ctx->d_counters);
+	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }

@@ -108,6 +108,7 @@ int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size
 	FM_CUDA(cudaMemcpyAsync(dp.p, points_host, m * 12, cudaMemcpyHostToDevice, s));
 	k_query_neighbors<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(make_view(f), (const float*)dp.p, (uint32_t)m,
 																 (uint32_t*)dc.p, (uint32_t*)di.p, (uint32_t)cap);
+	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	FM_CUDA(cudaMemcpyAsync(counts, dc.p, m * 4, cudaMemcpyDeviceToHost, s));
 	if (di.p) FM_CUDA(cudaMemcpyAsync(ids, di.p, m * cap * 4, cudaMemcpyDeviceToHost, s));
@@ -127,6 +128,7 @@ int query_density(Context* ctx, const Frame& f, const float* points_host, size_t
 	FM_CUDA(cudaMemcpyAsync(dp.p, points_host, m * 12, cudaMemcpyHostToDevice, s));
 	k_query_density<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(make_view(f), (const float*)dp.p, (uint32_t)m,
 															   (float*)dd.p, (float*)dg.p);
+	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	FM_CUDA(cudaMemcpyAsync(density, dd.p, m * 4, cudaMemcpyDeviceToHost, s));
 	if (grad) FM_CUDA(cudaMemcpyAsync(grad, dg.p, m * 12, cudaMemcpyDeviceToHost, s));

@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the ray-march hot path (BASELINE.json: rays/sec and ms/frame at
+1080p, 1M particles; frames/sec over a sequence at 1-8 GPUs).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
+
+A "step" is one pass of the whole hot path over one synthetic 1M-particle frame at 1920x1080
+(BASELINE.json configs[1]): grid build (neighbour search + AABB + occupancy grid) -> depth pre-pass ->
+ray march + normals + shading.  `value` starts with the particle array resident in HBM; `e2e` runs the
+same step through the C ABI with HOST buffers (pinned): host->device copy of the particles and
+device->host copy of positions, normals and the RGBA image inside the timed region.
+
+N > 1 (torchrun, one rank per GPU): frame-parallel over an animation sequence -- every rank renders its
+own frames, no data-path collective (pure partitioning), `scaling: weak`.  `--mode tiles` instead splits
+ONE frame into interleaved 64x64 screen tiles per rank and gathers the RGBA tiles on rank 0 with NCCL.
+
+Timing: CUDA events on the stream the kernels are launched on (the context stream), L2 flushed between
+steps by zeroing a 512 MiB buffer outside the timed events, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "rays_per_sec_1080p_1M_particles"
+UNIT = "rays/s"
+
+CONFIGS = {
+    # name: (particles, W, H, h, dx)
+    "C1": (64_000, 1280, 720, 0.1, None),
+    "C2": (1_000_000, 1920, 1080, 0.1, None),
+    "C3": (4_000_000, 3840, 2160, 0.063, 0.0315),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_string(cfg_name, n_actual, W, H):
+    return (f"{cfg_name}: dam-break {n_actual} particles, {W}x{H}, default camera (R=10, fov 60), isotropic, "
+            "MaxSteps 128, StepSize 0.009, Iso 1.0")
+
+
+def camera():
+    from conftest import golden_camera
+    return golden_camera("camera_default_16x9")     # reference default: orbit R = 10, fov 60 deg
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region"""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+def reference_step_fn(cfg_name, threads=0):
+    """the reference's CPU path for one frame: Frame::Frame (search + AABB + density grid) + the per-pixel march
+    over all pixels on `threads` host threads.  The depth image is an INPUT of the reference marcher (its
+    GPU raster pass makes it); it is produced once, outside the timed step, by the oracle's restatement."""
+    import oracle_lib
+    n, W, H, h, dx = CONFIGS[cfg_name]
+    fm_scenes = importlib.import_module("bachelor-thesis_b200.scenes")
+    xyz = fm_scenes.dam_break(n, h=h, dx=dx)
+    cam = camera()
+    orc = oracle_lib.Oracle()
+    depth = orc.frame(xyz, h, 2.0).depth_prepass(W, H, cam["view"], cam["proj"])
+    s = oracle_lib.Settings()
+    if oracle_lib.ref_available():
+        ref = oracle_lib.Ref()
+        kind = "reference"
+        nthreads = threads or ref.lib.ref_hardware_threads()
+
+        def step():
+            t0 = time.perf_counter()
+            ds = ref.dataset(xyz, h, 2.0)
+            t1 = time.perf_counter()
+            _, _, march_s = ds.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads)
+            ds.close()
+            return time.perf_counter() - t0, t1 - t0, march_s
+    else:
+        kind = "port"
+        nthreads = threads or orc.lib.fo_get_threads()
+
+        def step():
+            t0 = time.perf_counter()
+            f = orc.frame(xyz, h, 2.0)
+            t1 = time.perf_counter()
+            f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads, want_band=False)
+            t2 = time.perf_counter()
+            return t2 - t0, t1 - t0, t2 - t1
+    return step, kind, nthreads, (n, W, H, len(xyz))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    step, kind, nthreads, (n, W, H, n_actual) = reference_step_fn(args.config)
+    for _ in range(max(0, min(args.warmup, 1))):
+        step()
+    times, builds, marches = [], [], []
+    budget = time.perf_counter() + 240.0
+    for _ in range(args.steps):
+        t, b, m = step()
+        times.append(t); builds.append(b); marches.append(m)
+        if time.perf_counter() > budget:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    value = W * H / (ms * 1e-3)
+    sample = (f"{len(times)} full frames of {args.config} ({n_actual} particles, {W}x{H}): Frame::Frame build "
+              f"{1e3 * sum(builds) / len(builds):.0f} ms + march {1e3 * sum(marches) / len(marches):.0f} ms per frame; "
+              "depth image precomputed (the reference rasterises it on its GPU); neighbour search = API-compatible "
+              "stand-in for the un-vendored CompactNSearch fork")
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_string(args.config, n_actual, W, H),
+                   "step": "Frame::Frame (search + AABB + density grid) + PerPixel_Isotropic over all pixels, host cores"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    fm = importlib.import_module("bachelor-thesis_b200")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    n, W, H, h, dx = CONFIGS[args.config]
+    cam = camera()
+    tiles_mode = args.mode == "tiles" and world > 1
+    # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame)
+    n_frames = 1 if tiles_mode else min(4, args.steps + args.warmup)
+    frames = []
+    for k in range(n_frames):
+        t = 0.6 if tiles_mode else 0.45 + 0.3 * (((k * world + rank) % 240) / 239.0)
+        frames.append(fm.scenes.dam_break(n, h=h, dx=dx, t=t))
+    n_actual = [len(f) for f in frames]
+
+    ctx = fm.Context(W, H, device=local)
+    ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+    ctx.set_settings(fm.VisualizationSettings())
+    if tiles_mode:
+        ctx.set_tile_partition(rank, world, 64, 64)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+
+    d_frames = [torch.from_numpy(f).to(dev) for f in frames]                    # inputs resident in HBM
+    h_frames = [torch.from_numpy(f).pin_memory() for f in frames]               # e2e: pinned host inputs
+    h_pos = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    h_nrm = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
+    gather_buf = None
+    if tiles_mode:
+        rgba_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+        ctx.set_color_target(rgba_dev.data_ptr())
+        gather_buf = [torch.empty_like(rgba_dev) for _ in range(world)] if rank == 0 else None
+    torch.cuda.synchronize()
+
+    def device_step(k):
+        f = k % n_frames
+        ctx.build_frame_device(0, d_frames[f].data_ptr(), n_actual[f], h, 2.0)
+        ctx.render_async(fm.FR_PASS_ALL)
+        if tiles_mode:
+            ctx.wait()
+            # real exchange step of the tile-parallel path: RGBA tiles -> presenting GPU over NVLink
+            dist.gather(rgba_dev, gather_buf, dst=0)
+
+    def e2e_step(k):
+        f = k % n_frames
+        ctx.upload_frame_ptr(0, h_frames[f].data_ptr(), n_actual[f], h, 2.0)
+        ctx.render_async(fm.FR_PASS_ALL)
+        ctx.download_ptrs(positions=h_pos.data_ptr(), normals=h_nrm.data_ptr(), rgba=h_rgba.data_ptr())
+
+    def timed(step_fn, steps, warmup, sampler=None, stage_log=None):
+        for k in range(warmup):
+            step_fn(k)
+        ctx.wait()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+        evs = []
+        wall0 = time.perf_counter()
+        for k in range(steps):
+            if stage_log is not None and k > 0:
+                stage_log.append(ctx.timings())                 # waits for step k-1 (it has to finish anyway)
+            with torch.cuda.stream(stream):
+                flush.zero_()                                   # L2 flush, outside the timed events
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            step_fn(warmup + k)
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            evs.append((e0, e1))
+        ctx.wait()
+        if stage_log is not None:
+            stage_log.append(ctx.timings())
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - wall0
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = sampler.stop() if sampler else None
+        per = [a.elapsed_time(b) for a, b in evs]
+        total_ms = float(sum(per))
+        if world > 1:
+            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            total_ms = float(t.item())
+        return total_ms / steps, per, wall, clocks
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    stage_log = []
+    ctx.wait()
+    launches0 = ctx.counters()["kernel_launches"]
+    ms_step, per_step, wall, clocks = timed(device_step, args.steps, args.warmup, sampler, stage_log)
+    cnt = ctx.counters()                                        # counters of the last step
+    kernel_launches_timed = cnt["kernel_launches"] - launches0 - 13 * args.warmup
+    # per-stage device time (CUDA events on the context stream), averaged over the timed steps
+    tim = {k: float(np.mean([t[k] for t in stage_log])) for k in stage_log[0]}
+    e2e_ms, _, _, _ = timed(e2e_step, args.steps, min(args.warmup, 3))
+    ctx.set_color_target(None) if tiles_mode else None
+
+    units = W * H * (1 if tiles_mode else world)          # rays per step over all ranks
+    value = units / (ms_step * 1e-3)
+    e2e_value = units / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        # dominant kernel by device time
+        dom = "k_depth_splat" if tim["depth_ms"] >= tim["march_ms"] else "k_march_shade"
+        npart = n_actual[(args.warmup + args.steps - 1) % n_frames]
+        if dom == "k_depth_splat":
+            # algorithmic bytes: 16 B/particle read + 4 B/pixel depth written (clear) + 4 B/covered pixel final write
+            alg = 16.0 * npart + 4.0 * W * H + 4.0 * cnt["covered_rays"]
+            dur_ms = tim["depth_ms"]
+            note = "16 B x particles + 4 B x pixels (clear) + 4 B x covered pixels"
+        else:
+            # C_step x 16 B per density evaluation (candidates of the 27-cell query, as any 27-cell
+            # method incl. the CPU reference must examine) + per-pixel outputs 4 (depth) + 32 (pos,nrm) + 4 (rgba)
+            alg = 16.0 * cnt["candidates"] + 40.0 * W * H
+            dur_ms = tim["march_ms"]
+            note = "16 B x candidates examined (incl. the normal pass) + 40 B x pixels"
+        achieved = alg / (dur_ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg, "algorithmic_bytes_def": note,
+                "kernel_ms": dur_ms}
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            step, kind, nthreads, _ = reference_step_fn(args.config)
+            ts = [step() for _ in range(3)]
+            best = min(t[0] for t in ts)
+            cpu = {"value": W * H / best, "unit": UNIT, "cores": nthreads, "kind": kind,
+                   "sample": f"best of 3 full frames of {args.config} on the host cores: Frame::Frame build "
+                             f"{1e3 * min(t[1] for t in ts):.0f} ms + march {1e3 * min(t[2] for t in ts):.0f} ms "
+                             "(depth image precomputed; neighbour search = stand-in for the un-vendored CompactNSearch fork)"}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_string(args.config, npart, W, H),
+                       "step": "grid build + depth pre-pass + march/normals/shade, particles resident in HBM",
+                       "parallelism": ("tile-parallel 64x64 interleaved + NCCL gather" if tiles_mode else f"frame-parallel x{world}"),
+                       "l2": "flushed between steps (512 MiB memset outside the timed events)",
+                       "stage_ms": tim, "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates",
+                                                                         "neighbours", "skip_iterations", "early_exits")},
+                       "covered_rays_per_s": cnt["covered_rays"] * (1 if tiles_mode else world) / (ms_step * 1e-3),
+                       "ray_steps_per_s": cnt["ray_steps"] * (1 if tiles_mode else world) / (ms_step * 1e-3),
+                       "frames_per_s": (1 if tiles_mode else world) / (ms_step * 1e-3),
+                       "wall_s_timed_region": wall},
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
+                    "path": "fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(positions, normals, rgba), pinned host buffers"},
+            "gpu_launches": int(kernel_launches_timed),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(out), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

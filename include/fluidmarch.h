@@ -98,6 +98,7 @@ typedef struct fr_counters
 	uint64_t neighbours;         /* of those, d^2 < h^2 */
 	uint64_t early_exits;        /* rays stopped after leaving the grid for good (cannot hit) */
 	uint64_t neighbour_overflow; /* samples with more than 8192 neighbours (RayMarcher.cpp:14); must be 0 */
+	uint64_t kernel_launches;    /* kernels this context has launched since fr_create (cumulative) */
 } fr_counters;
 
 /* device time of the last call of each stage, milliseconds (CUDA events on the context stream) */

@@ -33,7 +33,7 @@ def test_struct_layouts(fm):
     abi = fm._cabi
     assert C.sizeof(abi.FrSettings) == 11 * 4
     assert C.sizeof(abi.FrCamera) == (16 * 3 + 6) * 4
-    assert C.sizeof(abi.FrCounters) == 9 * 8
+    assert C.sizeof(abi.FrCounters) == 10 * 8
     assert C.sizeof(abi.FrTimings) == 5 * 4
 
 
