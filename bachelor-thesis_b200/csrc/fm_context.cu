@@ -185,6 +185,7 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_xyz) cudaFree(ctx->d_xyz);
 	if (ctx->d_keys) cudaFree(ctx->d_keys);
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
+	if (ctx->d_tile_bound) cudaFree(ctx->d_tile_bound);
 	if (ctx->d_gp) cudaFree(ctx->d_gp);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->h_gp) cudaFreeHost(ctx->h_gp);

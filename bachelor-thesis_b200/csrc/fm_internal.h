@@ -76,6 +76,7 @@ struct Context
 	float* d_xyz = nullptr;           size_t cap_xyz = 0;       // staged input particles (n*3)
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
+	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
 	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;
 	GridParams* h_gp = nullptr;        // pinned
