@@ -7,6 +7,7 @@
 #include "fm_internal.h"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -158,6 +159,7 @@ int fr_create(int device, int width, int height, fr_context** out)
 	c->settings.enable_anisotropy = 0;
 	c->settings.k_n = 0.5f; c->settings.k_r = 2.0f; c->settings.k_s = 2000.0f; c->settings.n_eps = 1;
 	c->have_settings = true;
+	if (const char* e = getenv("FR_DEPTH_REFINE")) c->depth_refine_bounds = e[0] == '1';   // tuning switch, same image either way
 	*out = c;
 	return FR_OK;
 }
@@ -186,6 +188,8 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_keys) cudaFree(ctx->d_keys);
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
 	if (ctx->d_tile_bound) cudaFree(ctx->d_tile_bound);
+	if (ctx->d_splat) cudaFree(ctx->d_splat);
+	if (ctx->d_survivors) cudaFree(ctx->d_survivors);
 	if (ctx->d_gp) cudaFree(ctx->d_gp);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->h_gp) cudaFreeHost(ctx->h_gp);

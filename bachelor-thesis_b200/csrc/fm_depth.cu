@@ -112,15 +112,67 @@ __device__ __forceinline__ bool splat_setup(const DepthParams& dp, float4 p, Spl
 	return true;
 }
 
+// pass 1: per-particle splat parameters -> scratch, and the cheapest useful bound: the tile that contains the
+// disc centre (fully covered whenever the disc radius exceeds the tile diagonal, which is how T is chosen)
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_bounds(const float4* __restrict__ sorted, uint32_t n, DepthParams dp,
-													  uint32_t* __restrict__ tile_bound)
+__global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, uint32_t n, DepthParams dp,
+													float4* __restrict__ splat_a, uint4* __restrict__ splat_b,
+													uint32_t* __restrict__ tile_bound)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	Splat s;
-	if (!splat_setup(dp, __ldg(sorted + i), s)) return;
+	bool const live = splat_setup(dp, __ldg(sorted + i), s);
+	splat_a[i] = make_float4(s.z_c, s.ax, s.bx, s.ay);
+	splat_b[i] = make_uint4(__float_as_uint(s.by), s.near_bits, live ? ((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)) : 0xffffu,
+							live ? ((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)) : 0xffffu);
+	if (!live) return;
+	// tile under the disc centre: u = 0 at ndc_x = bx / ax  ->  pixel = (ndc + 1) * W/2 - 0.5
+	float const pcx = subr(mulr(addr(divr(s.bx, s.ax), 1.0f), dp.half_w), 0.5f);
+	float const pcy = subr(mulr(addr(divr(s.by, s.ay), 1.0f), dp.half_h), 0.5f);
+	if (!(pcx >= 0.0f && pcy >= 0.0f && pcx < (float)dp.W && pcy < (float)dp.H)) return;
+	int const tx = (int)pcx / T, ty = (int)pcy / T;
+	int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
+	int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
+	float const u0 = frag_u((float)px0, dp.two_w_inv, s.ax, s.bx), u1 = frag_u((float)px1, dp.two_w_inv, s.ax, s.bx);
+	float const v0 = frag_u((float)py0, dp.two_h_inv, s.ay, s.by), v1 = frag_u((float)py1, dp.two_h_inv, s.ay, s.by);
+	// largest l2 any pixel of the tile evaluates to (FP32 mul/add are monotone)
+	float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), fmaxf(mulr(v0, v0), mulr(v1, v1)));
+	if (l2 > 1.0f) return;                                // some pixel of the tile is discarded: no bound
+	float const d = frag_depth(dp, s.z_c, l2);
+	uint32_t const bound = __float_as_uint(d) + 8u;       // slack for the non-monotone last bits of the cosine
+	if (bound >= 0x3f800000u) return;
+	uint32_t* const cell = tile_bound + (size_t)ty * dp.tiles_x + tx;
+	if (bound < __ldcg(cell)) atomicMin(cell, bound);
+}
+
+__device__ __forceinline__ bool splat_load(const float4* __restrict__ splat_a, const uint4* __restrict__ splat_b,
+										   uint32_t i, Splat& s)
+{
+	float4 const a = __ldg(splat_a + i);
+	uint4 const b = __ldg(splat_b + i);
+	s.z_c = a.x; s.ax = a.y; s.bx = a.z; s.ay = a.w;
+	s.by = __uint_as_float(b.x); s.near_bits = b.y;
+	s.x0 = (int)(b.z & 0xffffu); s.x1 = (int)(b.z >> 16);
+	s.y0 = (int)(b.w & 0xffffu); s.y1 = (int)(b.w >> 16);
+	return s.x1 >= s.x0;
+}
+
+// pass 2 (optional refinement): every tile the disc covers completely gets the particle's bound.  Only
+// particles that are still in front of the seed bound of their own centre tile take part.
+template <int T>
+__global__ void __launch_bounds__(256) k_depth_bounds(uint32_t n, DepthParams dp, const float4* __restrict__ splat_a,
+													  const uint4* __restrict__ splat_b, uint32_t* __restrict__ tile_bound)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Splat s;
+	if (!splat_load(splat_a, splat_b, i, s)) return;
 	int const tx0 = s.x0 / T, tx1 = s.x1 / T, ty0 = s.y0 / T, ty1 = s.y1 / T;
+	{
+		int const cx = (tx0 + tx1) >> 1, cy = (ty0 + ty1) >> 1;
+		if (s.near_bits >= __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx)) return;
+	}
 	for (int ty = ty0; ty <= ty1; ty++)
 	{
 		int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
@@ -133,11 +185,10 @@ __global__ void __launch_bounds__(256) k_depth_bounds(const float4* __restrict__
 			int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
 			float const u0 = frag_u((float)px0, dp.two_w_inv, s.ax, s.bx);
 			float const u1 = frag_u((float)px1, dp.two_w_inv, s.ax, s.bx);
-			// largest l2 any pixel of the tile evaluates to (FP32 mul/add are monotone)
 			float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), vv);
-			if (l2 > 1.0f) continue;                          // some pixel of the tile is discarded: no bound
+			if (l2 > 1.0f) continue;
 			float const d = frag_depth(dp, s.z_c, l2);
-			uint32_t const bound = __float_as_uint(d) + 8u;   // slack for the non-monotone last bits of the cosine
+			uint32_t const bound = __float_as_uint(d) + 8u;
 			if (bound >= 0x3f800000u) continue;
 			uint32_t* const cell = tile_bound + (size_t)ty * dp.tiles_x + tx;
 			if (bound < __ldcg(cell)) atomicMin(cell, bound);
@@ -145,51 +196,60 @@ __global__ void __launch_bounds__(256) k_depth_bounds(const float4* __restrict__
 	}
 }
 
+// pass 3: keep the particles that can still win a pixel of some tile they overlap (compacted, warp-aggregated)
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_splat(const float4* __restrict__ sorted, uint32_t n, DepthParams dp,
-													 const uint32_t* __restrict__ tile_bound,
-													 uint32_t* __restrict__ depth_bits)
+__global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, const uint4* __restrict__ splat_b,
+													const uint32_t* __restrict__ tile_bound,
+													uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	uint32_t const lane = threadIdx.x & 31u;
+	bool wins = false;
+	if (i < n)
+	{
+		uint4 const b = __ldg(splat_b + i);
+		int const x0 = (int)(b.z & 0xffffu), x1 = (int)(b.z >> 16), y0 = (int)(b.w & 0xffffu), y1 = (int)(b.w >> 16);
+		if (x1 >= x0)
+		{
+			int const tx0 = x0 / T, ty0 = y0 / T, ntx = x1 / T - tx0 + 1, nty = y1 / T - ty0 + 1;
+			for (int ty = 0; ty < nty && !wins; ty++)
+			{
+				const uint32_t* row = tile_bound + (size_t)(ty0 + ty) * dp.tiles_x + tx0;
+				for (int tx = 0; tx < ntx; tx++)
+					if (b.y < __ldg(row + tx)) { wins = true; break; }
+			}
+		}
+	}
+	uint32_t const m = __ballot_sync(0xffffffffu, wins);
+	if (m == 0u) return;
+	uint32_t base = 0;
+	if (lane == 0) base = atomicAdd(n_survivors, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (wins) survivors[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+// pass 4: one warp per surviving particle: lanes re-test the tiles in parallel, then evaluate the fragments of the
+// tiles that are still open, 32 pixels at a time
+template <int T>
+__global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float4* __restrict__ splat_a,
+													 const uint4* __restrict__ splat_b,
+													 const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ n_survivors,
+													 const uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ depth_bits)
 {
 	constexpr int PIX = T * T;                       // pixels per tile
 	constexpr int LPT = PIX < 32 ? PIX : 32;         // lanes working on one tile
 	constexpr int TPR = 32 / LPT;                    // tiles per round
 	constexpr int RPT = PIX / LPT;                   // rounds per tile
 	uint32_t const lane = threadIdx.x & 31u;
-	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-
-	Splat s;
-	bool live = false;
-	if (i < n) live = splat_setup(dp, __ldg(sorted + (dp.reverse ? (n - 1u - i) : i)), s);
-	int tx0 = 0, ty0 = 0, ntx = 0, nty = 0;
-	bool wins = false;
-	if (live)
+	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t const count = __ldg(n_survivors);
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += nwarps)
 	{
-		tx0 = s.x0 / T; ty0 = s.y0 / T;
-		ntx = s.x1 / T - tx0 + 1; nty = s.y1 / T - ty0 + 1;
-		// can this particle still win a pixel of any tile it overlaps?
-		for (int ty = 0; ty < nty && !wins; ty++)
-		{
-			const uint32_t* row = tile_bound + (size_t)(ty0 + ty) * dp.tiles_x + tx0;
-			for (int tx = 0; tx < ntx; tx++)
-				if (s.near_bits < __ldg(row + tx)) { wins = true; break; }
-		}
-	}
-
-	// survivors are processed by the whole warp, one particle at a time
-	uint32_t todo = __ballot_sync(0xffffffffu, wins);
-	while (todo)
-	{
-		int const src = __ffs(todo) - 1;
-		todo &= todo - 1u;
-		float const z_c = __shfl_sync(0xffffffffu, s.z_c, src);
-		float const ax = __shfl_sync(0xffffffffu, s.ax, src), bx = __shfl_sync(0xffffffffu, s.bx, src);
-		float const ay = __shfl_sync(0xffffffffu, s.ay, src), by = __shfl_sync(0xffffffffu, s.by, src);
-		uint32_t const near_bits = __shfl_sync(0xffffffffu, s.near_bits, src);
-		int const bx0 = __shfl_sync(0xffffffffu, s.x0, src), bx1 = __shfl_sync(0xffffffffu, s.x1, src);
-		int const by0 = __shfl_sync(0xffffffffu, s.y0, src), by1 = __shfl_sync(0xffffffffu, s.y1, src);
-		int const ptx0 = bx0 / T, pty0 = by0 / T;
-		int const pntx = bx1 / T - ptx0 + 1;
-		int const ntiles = pntx * (by1 / T - pty0 + 1);
+		Splat s;
+		splat_load(splat_a, splat_b, __ldg(survivors + (dp.reverse ? count - 1u - w : w)), s);
+		int const ptx0 = s.x0 / T, pty0 = s.y0 / T;
+		int const pntx = s.x1 / T - ptx0 + 1;
+		int const ntiles = pntx * (s.y1 / T - pty0 + 1);
 		float const inv_ntx = 1.0f / (float)pntx;
 
 		for (int tb = 0; tb < ntiles; tb += 32)
@@ -199,13 +259,13 @@ __global__ void __launch_bounds__(256) k_depth_splat(const float4* __restrict__ 
 			int trow = (int)(((float)t + 0.5f) * inv_ntx);
 			int tcol = t - trow * pntx;
 			if (tcol < 0) { trow--; tcol += pntx; } else if (tcol >= pntx) { trow++; tcol -= pntx; }
-			bool const alive = t < ntiles && near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
+			bool const alive = t < ntiles && s.near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
 			uint32_t tiles = __ballot_sync(0xffffffffu, alive);
 			int const my_tile_xy = ((pty0 + trow) << 16) | (ptx0 + tcol);
 
 			while (tiles)
 			{
-				// lane group g takes the g-th surviving tile of this batch
+				// lane group g takes the g-th open tile of this batch
 				uint32_t const sel = __fns(tiles, 0, (int)(lane / LPT) + 1);
 #pragma unroll
 				for (int k = 0; k < TPR; k++) tiles &= tiles - 1u;
@@ -217,14 +277,14 @@ __global__ void __launch_bounds__(256) k_depth_splat(const float4* __restrict__ 
 				{
 					int const k = r * LPT + (int)(lane % LPT);
 					int const px = tpx + (k % T), py = tpy + (k / T);
-					if (px < bx0 || px > bx1 || py < by0 || py > by1) continue;
+					if (px < s.x0 || px > s.x1 || py < s.y0 || py > s.y1) continue;
 					uint32_t* const cell = depth_bits + (size_t)py * (size_t)dp.W + (size_t)px;
-					if (near_bits >= __ldcg(cell)) continue;              // cannot win this pixel (L2 read: always fresh)
-					float const u = frag_u((float)px, dp.two_w_inv, ax, bx);
-					float const v = frag_u((float)py, dp.two_h_inv, ay, by);
+					if (s.near_bits >= __ldcg(cell)) continue;            // cannot win this pixel (L2 read: always fresh)
+					float const u = frag_u((float)px, dp.two_w_inv, s.ax, s.bx);
+					float const v = frag_u((float)py, dp.two_h_inv, s.ay, s.by);
 					float const l2 = addr(mulr(u, u), mulr(v, v));
 					if (l2 > 1.0f) continue;                            // depth.frag:22 `if (l2 > 1) discard;`
-					float const d = frag_depth(dp, z_c, l2);
+					float const d = frag_depth(dp, s.z_c, l2);
 					if (!(d < 1.0f)) continue;                          // compare Less against the clear value
 					atomicMin(cell, __float_as_uint(d));
 				}
@@ -234,12 +294,24 @@ __global__ void __launch_bounds__(256) k_depth_splat(const float4* __restrict__ 
 }
 
 template <int T>
-void launch_tiles(Context* ctx, const Frame& f, DepthParams dp, uint32_t* tile_bound)
+int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bounds)
 {
 	uint32_t const n = (uint32_t)f.n;
 	uint32_t const blocks = (n + 255u) / 256u;
-	k_depth_bounds<T><<<blocks, 256, 0, ctx->stream>>>(f.d_sorted, n, dp, tile_bound);
-	k_depth_splat<T><<<blocks, 256, 0, ctx->stream>>>(f.d_sorted, n, dp, tile_bound, (uint32_t*)ctx->d_depth);
+	cudaStream_t const st = ctx->stream;
+	float4* const splat_a = (float4*)ctx->d_splat;
+	uint4* const splat_b = (uint4*)(ctx->d_splat + 4 * (size_t)n);
+	uint32_t* const n_surv = ctx->d_survivors;
+	uint32_t* const surv = ctx->d_survivors + 4;
+	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, dp, splat_a, splat_b, ctx->d_tile_bound);
+	if (refine_bounds) k_depth_bounds<T><<<blocks, 256, 0, st>>>(n, dp, splat_a, splat_b, ctx->d_tile_bound);
+	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, surv, n_surv);
+	uint32_t const want = (n + 7u) / 8u;
+	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
+	k_depth_splat<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
+															 (uint32_t*)ctx->d_depth);
+	ctx->kernel_launches += refine_bounds ? 4 : 3;
+	return FR_OK;
 }
 
 }  // namespace
@@ -285,17 +357,21 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	uint32_t const ntiles = (uint32_t)dp.tiles_x * (uint32_t)dp.tiles_y;
 	int rc;
 	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_splat, &ctx->cap_splat, 8 * f.n))) return rc;            // 2 x 16 B per particle
+	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
+	FM_CUDA(cudaMemsetAsync(ctx->d_survivors, 0, 16, ctx->stream));
 
 	uint32_t const npix = (uint32_t)ctx->width * (uint32_t)ctx->height;
 	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles);
+	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{
-	case 2: launch_tiles<2>(ctx, f, dp, ctx->d_tile_bound); break;
-	case 4: launch_tiles<4>(ctx, f, dp, ctx->d_tile_bound); break;
-	case 8: launch_tiles<8>(ctx, f, dp, ctx->d_tile_bound); break;
-	default: launch_tiles<16>(ctx, f, dp, ctx->d_tile_bound); break;
+	case 2: launch_tiles<2>(ctx, f, dp, refine); break;
+	case 4: launch_tiles<4>(ctx, f, dp, refine); break;
+	case 8: launch_tiles<8>(ctx, f, dp, refine); break;
+	default: launch_tiles<16>(ctx, f, dp, refine); break;
 	}
-	ctx->kernel_launches += 3;
+	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }

@@ -77,6 +77,9 @@ struct Context
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
+	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
+	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
+	bool depth_refine_bounds = true;
 	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;
 	GridParams* h_gp = nullptr;        // pinned
