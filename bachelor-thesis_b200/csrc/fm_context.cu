@@ -189,6 +189,8 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
 	if (ctx->d_tile_bound) cudaFree(ctx->d_tile_bound);
 	if (ctx->d_splat) cudaFree(ctx->d_splat);
+	if (ctx->d_tiles) cudaFree(ctx->d_tiles);
+	if (ctx->d_rayq) cudaFree(ctx->d_rayq);
 	if (ctx->d_survivors) cudaFree(ctx->d_survivors);
 	if (ctx->d_gp) cudaFree(ctx->d_gp);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);

@@ -80,6 +80,9 @@ struct Context
 	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
 	bool depth_refine_bounds = true;
+	uint32_t* d_tiles = nullptr;      size_t cap_tiles = 0;        // march: [0] count, [1] cursor, [2..] covered 8x4 tiles
+	int march_ctas_per_sm = 0;
+	float4* d_rayq = nullptr;         size_t cap_rayq = 0;         // march: ray queues between the phases
 	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;
 	GridParams* h_gp = nullptr;        // pinned

@@ -1,18 +1,29 @@
-// fm_march.cu -- the ray-march kernel with fused normals and shading (sm_100a).
+// fm_march.cu -- the ray-march kernels with fused normals and shading (sm_100a).
 //
 // Replaces RayMarcher::PerPixel_Isotropic (src/app/AdvancedRenderer/RayMarcher.cpp:256-344) together with
 // its callees Frame::QueryDensityGrid (src/app/Dataset.cpp:26-47), Dataset::GetNeighbors (:272-280),
 // CubicSplineKernel::W/gradW (src/app/Kernel.cpp:16-52), intersectAABB (RayMarcher.cpp:51-62), and the
 // fullscreen composition pass (assets/shaders/advanced/composition.frag:37-66,70-122,
 // CompositionRenderPass.cpp:313-321), which only ever reads its own pixel and is therefore fused as the
-// epilogue of the same thread.
+// epilogue of the thread that produced the pixel.
 //
-// Mapping: one warp = one 8x4 pixel tile (lanes = rays), 8 warps per CTA = a 32x8 pixel block.  The rays
-// of a tile are ~1 cell apart (pixel footprint at the default camera distance ~ h/10), so the 9
-// contiguous particle ranges each lane walks are the same addresses across the warp: every LDG.128 of a
-// candidate is a single-sector broadcast served by L1/L2 (the sorted particle array, 16 B/particle,
-// lives in L2: 16 MB at 1M particles).  No neighbour list is materialised; the d^2 < h^2 test and the
-// kernel sum run inline in the reference's accumulation order (see fm_common.cuh: FrameView).
+// Two kernels (the reference's ThreadPool, src/app/ThreadPool.cpp:38-55, hands out single pixels from one
+// atomic counter; most pixels return at once because the depth image says "empty"):
+//
+//   k_classify   every pixel, uniform work: uncovered pixels (depth == 1) get their zero outputs and the
+//                background colour right here; each 8x4 pixel tile with at least one covered pixel is
+//                appended to a work list (one atomic per CTA).
+//   k_march      persistent warps (a multiple of the SM count) pull tiles off the list through one
+//                atomic counter -- the ThreadPool's scheme at warp granularity -- so the expensive rays are
+//                spread over all 148 SMs no matter where the fluid sits on screen.  Warp = one 8x4 tile,
+//                lanes = rays.  The rays of a tile are ~1 cell apart (pixel footprint at the default camera
+//                distance ~ h/10), so the 9 contiguous particle ranges each lane walks are the same
+//                addresses across the warp: every LDG.128 of a candidate is a single-sector broadcast.  Before
+//                a lane walks its 27 cells it issues all 18 range loads and L1 prefetches of the candidate
+//                lines at once, so the walk itself runs out of L1.  No neighbour list is materialised; the
+//                d^2 < h^2 test and the kernel sums run inline in the reference's accumulation order (see
+//                fm_common.cuh: FrameView).  The gradient sum of the normal is accumulated together with the
+//                density on a ray's first sample (where ~95% of the rays seeded by the depth pre-pass hit).
 #include "fm_internal.h"
 
 namespace fm
@@ -38,6 +49,7 @@ struct MarchParams
 	int early_out;
 	int part_rank, part_world, part_tw, part_th, part_tiles_x;
 	int do_march, do_shade;
+	int tiles_x;                      // 8x4 pixel tiles per image row
 };
 
 struct LaneCounters
@@ -45,9 +57,14 @@ struct LaneCounters
 	uint32_t covered, hits, steps, skips, candidates, neighbours, early_exits, overflow;
 };
 
-// density (and optionally the un-normalised gradient sum) at p: Dataset::GetNeighbors + the W / gradW
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+// density (DENS) and/or the un-normalised gradient sum (GRAD) at p: Dataset::GetNeighbors + the W / gradW
 // loops of RayMarcher.cpp:309-336, fused.  Accumulation order == the reference's neighbour order.
-template <bool GRAD>
+template <bool DENS, bool GRAD>
 __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc)
 {
 	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
@@ -59,6 +76,22 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	uint32_t nn = 0;
 	if (z0 <= z1)
 	{
+		// all 18 range bounds in flight at once, then the candidate lines into L1 (128 B = 8 particles)
+		{
+			uint32_t pb[9], pe[9];
+#pragma unroll
+			for (int r = 0; r < 9; r++)
+			{
+				int const x = kx + r / 3 - 1, y = ky + r % 3 - 1;
+				bool const ok = (unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y;
+				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+				pb[r] = ok ? __ldg(f.cell_start + base + z0) : 0u;
+				pe[r] = ok ? __ldg(f.cell_start + base + z1 + 1) : 0u;
+			}
+#pragma unroll
+			for (int r = 0; r < 9; r++)
+				for (uint32_t a = pb[r] & ~7u; a < pe[r]; a += 8u) prefetch_l1(f.sorted + a);
+		}
 #pragma unroll 1
 		for (int dx = -1; dx <= 1; dx++)
 		{
@@ -85,7 +118,7 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 						if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
 						{
 							if (GRAD) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
-							else density = addr(density, spline_W_inrange(f.kernel, l2));
+							if (DENS) density = addr(density, spline_W_inrange(f.kernel, l2));
 						}
 						nn++;
 					}
@@ -124,7 +157,8 @@ __device__ __forceinline__ float srgb_encode(float c)
 {
 	if (!(c > 0.0f)) return 0.0f;
 	if (c >= 1.0f) return 1.0f;
-	return c <= 0.0031308f ? mulr(12.92f, c) : subr(mulr(1.055f, powf(c, 1.0f / 2.4f)), 0.055f);
+	// __powf = ex2(y * lg2(x)) on the SFU: relative error ~1e-6, i.e. < 3e-4 of an 8-bit code value
+	return c <= 0.0031308f ? mulr(12.92f, c) : subr(mulr(1.055f, __powf(c, 1.0f / 2.4f)), 0.055f);
 }
 
 // composition.frag:70-122 for one pixel
@@ -164,19 +198,15 @@ __device__ __forceinline__ uchar4 shade_pixel(const MarchParams& mp, int px, int
 #pragma unroll
 		for (int kk = 0; kk < 4; kk++) color[kk] = addr(mulr(fv, fl[kk]), mulr(amb, diffuse[kk]));
 	}
-	return make_uchar4((unsigned char)unorm8(srgb_encode(color[0])), (unsigned char)unorm8(srgb_encode(color[1])),
-					   (unsigned char)unorm8(srgb_encode(color[2])), (unsigned char)unorm8(color[3]));
+	uint32_t const r8 = unorm8(srgb_encode(color[0]));
+	bool const grey = color[1] == color[0] && color[2] == color[0];   // the floor is grey: one transfer-curve evaluation
+	uint32_t const g8 = grey ? r8 : unorm8(srgb_encode(color[1]));
+	uint32_t const b8 = grey ? r8 : unorm8(srgb_encode(color[2]));
+	return make_uchar4((unsigned char)r8, (unsigned char)g8, (unsigned char)b8, (unsigned char)unorm8(color[3]));
 }
 
-__global__ void __launch_bounds__(256, 3) k_march_shade(FrameView f, MarchParams mp, const float* __restrict__ depth,
-													 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
-													 uchar4* __restrict__ rgba_out, DeviceCounters* __restrict__ counters)
+__device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int py)
 {
-	// warp = 8x4 pixel tile; CTA = 4x2 tiles = 32x8 pixels
-	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int const px = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-	int const py = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3);
-	LaneCounters lc = {};
 	bool active = px < mp.W && py < mp.H;
 	if (active && mp.part_world > 1)
 	{
@@ -185,98 +215,154 @@ __global__ void __launch_bounds__(256, 3) k_march_shade(FrameView f, MarchParams
 	}
 	uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
 	if (active && mp.skip_last_pixel && index == (uint32_t)mp.W * (uint32_t)mp.H - 1u) active = false;   // ThreadPool.cpp:50
+	return active;
+}
 
+// every pixel: background + work list of the 8x4 tiles that hold covered pixels.  CTA = 4x2 tiles = 32x8 pixels.
+__global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* __restrict__ depth,
+												  float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+												  uchar4* __restrict__ rgba_out, uint32_t* __restrict__ tiles,
+												  uint32_t* __restrict__ n_tiles)
+{
+	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int const tx = blockIdx.x * 4 + (warp & 3), ty = blockIdx.y * 2 + (warp >> 2);
+	int const px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+	bool const active = pixel_active(mp, px, py);
+	uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
+	bool covered = false;
 	if (active)
 	{
-		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		if (mp.do_march)
 		{
-			float const z = depth[index];
-			if (z != 1.0f)   // `if (z == 1.0f) return;` (RayMarcher.cpp:264)
+			covered = depth[index] != 1.0f;     // `if (z == 1.0f) return;` (RayMarcher.cpp:264)
+			if (!covered)
 			{
-				lc.covered = 1;
-				// pixel CORNER, not centre (RayMarcher.cpp:268-270)
-				float const cx = subr(mulr((float)px, mp.two_w_inv), 1.0f);
-				float const cy = subr(mulr((float)py, mp.two_h_inv), 1.0f);
-				float wh[4];
-				mat4_mul_vec4(mp.ipv, cx, cy, z, 1.0f, wh);
-				f3 position = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
-				f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
-				f3 const step = scale3(normalize3(sub3(position, cam)), mp.step_size);
-				f3 prev = position;
-
-				for (int i = 0; i < mp.max_steps; i++)
-				{
-					prev = position;
-					position = add3(position, step);
-
-					// empty-space skip (RayMarcher.cpp:282-306); skips do not consume MaxSteps
-					int gx, gy, gz;
-					bool inside;
-					while ((inside = density_cell_of(f, position, gx, gy, gz)) && !density_cell_flag(f, gx, gy, gz))
-					{
-						// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133)
-						f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z),
-											 scale3(mk3((float)gx, (float)gy, (float)gz), f.cell_width));
-						f3 const nmax = add3(nmin, mk3(f.cell_width, f.cell_width, f.cell_width));
-						prev = position;
-						position = add3(intersect_aabb(position, step, nmin, nmax), step);
-						lc.skips++;
-					}
-
-					if (!inside && mp.early_out)
-					{
-						// Outside the density grid every particle is farther than h (the grid is the particle
-						// AABB padded by h), so density is 0 here.  Each coordinate moves monotonically, so a
-						// ray that is outside on an axis and moving away on it can never come back: the
-						// remaining samples of the reference are all misses.  Stop; the result is unchanged.
-						float const rx = floorf(mulr(subr(position.x, f.mn.x), f.inv_cell_width.x));
-						float const ry = floorf(mulr(subr(position.y, f.mn.y), f.inv_cell_width.y));
-						float const rz = floorf(mulr(subr(position.z, f.mn.z), f.inv_cell_width.z));
-						bool const gone =
-							(rx < 0.0f && step.x <= 0.0f) || (rx >= (float)f.gdim.x && step.x >= 0.0f) ||
-							(ry < 0.0f && step.y <= 0.0f) || (ry >= (float)f.gdim.y && step.y >= 0.0f) ||
-							(rz < 0.0f && step.z <= 0.0f) || (rz >= (float)f.gdim.z && step.z >= 0.0f);
-						if (gone) { lc.early_exits = 1; break; }
-					}
-
-					f3 grad;
-					float const density = eval_density<false>(f, position, grad, lc);
-					lc.steps++;
-
-					if (density >= mp.iso)   // RayMarcher.cpp:327
-					{
-						// optional refinement (north_star item 3; not in the reference): bisect between the last
-						// sample below the threshold and the hit sample
-						f3 lo = prev, hi = position;
-						for (int b = 0; b < mp.bisection_steps; b++)
-						{
-							f3 const mid = scale3(add3(lo, hi), 0.5f);
-							float const dm = eval_density<false>(f, mid, grad, lc);
-							lc.steps++;
-							if (dm >= mp.iso) hi = mid; else lo = mid;
-						}
-						position = hi;
-						P = make_float4(position.x, position.y, position.z, 1.0f);
-						eval_density<true>(f, position, grad, lc);
-						f3 const n = normalize3(grad);   // glm::normalize(normal) (RayMarcher.cpp:338)
-						N = make_float4(n.x, n.y, n.z, 1.0f);
-						lc.hits = 1;
-						break;
-					}
-				}
+				float4 const zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // RayMarcher.cpp:262-263
+				pos_out[index] = zero;
+				nrm_out[index] = zero;
+				if (mp.do_shade) rgba_out[index] = shade_pixel(mp, px, py, zero, zero);
 			}
-			pos_out[index] = P;
-			nrm_out[index] = N;
 		}
-		else if (mp.do_shade)
-		{
-			P = pos_out[index];
-			N = nrm_out[index];
-		}
-		if (mp.do_shade) rgba_out[index] = shade_pixel(mp, px, py, P, N);
+		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
 	}
+	if (!mp.do_march) return;
+	__shared__ uint32_t s_any[8];
+	__shared__ uint32_t s_base;
+	bool const any = __any_sync(0xffffffffu, covered);
+	if (lane == 0) s_any[warp] = any ? 1u : 0u;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t c = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) c += s_any[w];
+		s_base = c ? atomicAdd(n_tiles, c) : 0u;
+	}
+	__syncthreads();
+	if (any && lane == 0)
+	{
+		uint32_t slot = s_base;
+		for (int w = 0; w < warp; w++) slot += s_any[w];
+		tiles[slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
+	}
+}
 
+__device__ __forceinline__ void add_counts(LaneCounters& a, const LaneCounters& b)
+{
+	a.candidates += b.candidates; a.neighbours += b.neighbours; a.overflow += b.overflow;
+}
+
+// one `position += step` with the empty-space skip of RayMarcher.cpp:279-306 (skips do not consume MaxSteps).
+// Returns true when the ray has left the density grid for good, i.e. this and all later samples are misses:
+// outside the grid every particle is farther than h (the grid is the particle AABB padded by h), so the
+// density is 0 there; each coordinate moves monotonically, so a ray that is outside on an axis and moving
+// away on it can never come back.  Stopping there leaves the result unchanged.
+__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, f3& position, f3& prev,
+										uint32_t& skips)
+{
+	prev = position;
+	position = add3(position, step);
+	int gx, gy, gz;
+	bool inside;
+	while ((inside = density_cell_of(f, position, gx, gy, gz)) && !density_cell_flag(f, gx, gy, gz))
+	{
+		// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133)
+		f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z), scale3(mk3((float)gx, (float)gy, (float)gz), f.cell_width));
+		f3 const nmax = add3(nmin, mk3(f.cell_width, f.cell_width, f.cell_width));
+		prev = position;
+		position = add3(intersect_aabb(position, step, nmin, nmax), step);
+		skips++;
+	}
+	if (!inside && mp.early_out)
+	{
+		float const rx = floorf(mulr(subr(position.x, f.mn.x), f.inv_cell_width.x));
+		float const ry = floorf(mulr(subr(position.y, f.mn.y), f.inv_cell_width.y));
+		float const rz = floorf(mulr(subr(position.z, f.mn.z), f.inv_cell_width.z));
+		return (rx < 0.0f && step.x <= 0.0f) || (rx >= (float)f.gdim.x && step.x >= 0.0f) ||
+			   (ry < 0.0f && step.y <= 0.0f) || (ry >= (float)f.gdim.y && step.y >= 0.0f) ||
+			   (rz < 0.0f && step.z <= 0.0f) || (rz >= (float)f.gdim.z && step.z >= 0.0f);
+	}
+	return false;
+}
+
+// the sample at `position` reached the threshold (RayMarcher.cpp:327-341): optional bisection, normal
+__device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams& mp, f3 prev, f3 position, bool have_grad,
+										   f3 grad, LaneCounters& lc, float4& P, float4& N)
+{
+	// optional refinement (north_star item 3; not in the reference): bisect between the last sample below the
+	// threshold and the hit sample
+	f3 lo = prev, hi = position;
+	for (int b = 0; b < mp.bisection_steps; b++)
+	{
+		f3 const mid = scale3(add3(lo, hi), 0.5f);
+		f3 unused;
+		float const dm = eval_density<true, false>(f, mid, unused, lc);
+		lc.steps++;
+		if (dm >= mp.iso) hi = mid; else lo = mid;
+	}
+	P = make_float4(hi.x, hi.y, hi.z, 1.0f);
+	if (!have_grad || mp.bisection_steps > 0) eval_density<false, true>(f, hi, grad, lc);
+	f3 const n = normalize3(grad);   // glm::normalize(normal) (RayMarcher.cpp:338)
+	N = make_float4(n.x, n.y, n.z, 1.0f);
+	lc.hits++;
+}
+
+// ---- ray queues between the three march phases -----------------------------------------------------------
+// A ray that is not finished by a phase is handed on as 32 bytes: (position.xyz, pixel index) (step.xyz, samples taken)
+struct RayQueues
+{
+	float4* q1;              // rays left after the first sample -> k_march_long
+	uint32_t* ctl;           // [0] tiles listed [1] tile cursor [2] |q1| [3] q1 cursor
+};
+
+__device__ __forceinline__ void push_rays(bool want, float4* __restrict__ q, uint32_t* __restrict__ n, uint32_t index,
+										  f3 position, f3 step, int i)
+{
+	uint32_t const m = __ballot_sync(0xffffffffu, want);
+	if (m == 0u) return;
+	int const lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(m) - 1) base = atomicAdd(n, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	if (want)
+	{
+		uint32_t const slot = base + __popc(m & ((1u << lane) - 1u));
+		q[2 * (size_t)slot] = make_float4(position.x, position.y, position.z, __uint_as_float(index));
+		q[2 * (size_t)slot + 1] = make_float4(step.x, step.y, step.z, __int_as_float(i));
+	}
+}
+
+__device__ __forceinline__ void write_pixel(const MarchParams& mp, uint32_t index, float4 P, float4 N,
+											float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+											uchar4* __restrict__ rgba_out)
+{
+	pos_out[index] = P;
+	nrm_out[index] = N;
+	if (mp.do_shade) rgba_out[index] = shade_pixel(mp, (int)(index % (uint32_t)mp.W), (int)(index / (uint32_t)mp.W), P, N);
+}
+
+__device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCounters* __restrict__ counters)
+{
 	// per-warp counter reduction, one atomic per counter per warp
 	uint32_t vals[8] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow };
 	unsigned long long* dst = reinterpret_cast<unsigned long long*>(counters);
@@ -284,8 +370,142 @@ __global__ void __launch_bounds__(256, 3) k_march_shade(FrameView f, MarchParams
 	for (int k = 0; k < 8; k++)
 	{
 		uint32_t const s = __reduce_add_sync(0xffffffffu, vals[k]);
-		if (lane == 0 && s) atomicAdd(dst + k, (unsigned long long)s);
+		if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst + k, (unsigned long long)s);
 	}
+}
+
+// phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
+// together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
+__global__ void __launch_bounds__(256, 3) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
+														 RayQueues rq, DeviceCounters* __restrict__ counters)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	LaneCounters lc = {};
+	uint32_t const count = __ldcg(rq.ctl + 0);
+	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
+
+	for (;;)
+	{
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(rq.ctl + 1, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= count) break;
+		uint32_t const txy = __ldg(tiles + t);
+		int const px = (int)(txy & 0xffffu) * 8 + (lane & 7), py = (int)(txy >> 16) * 4 + (lane >> 3);
+		uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
+		bool covered = pixel_active(mp, px, py);
+		float z = 1.0f;
+		if (covered) { z = depth[index]; covered = z != 1.0f; }   // uncovered pixels were finished by k_classify
+
+		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		f3 position = mk3(0.0f, 0.0f, 0.0f), step = position;
+		bool more = false;
+		if (covered)
+		{
+			lc.covered++;
+			// pixel CORNER, not centre (RayMarcher.cpp:268-270)
+			float const cx = subr(mulr((float)px, mp.two_w_inv), 1.0f);
+			float const cy = subr(mulr((float)py, mp.two_h_inv), 1.0f);
+			float wh[4];
+			mat4_mul_vec4(mp.ipv, cx, cy, z, 1.0f, wh);
+			position = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
+			step = scale3(normalize3(sub3(position, cam)), mp.step_size);
+			f3 prev = position;
+			if (mp.max_steps > 0)
+			{
+				if (advance(f, mp, step, position, prev, lc.skips)) lc.early_exits++;
+				else
+				{
+					bool const fused = mp.bisection_steps == 0;
+					f3 grad;
+					float const density = fused ? eval_density<true, true>(f, position, grad, lc)
+												: eval_density<true, false>(f, position, grad, lc);
+					lc.steps++;
+					if (density >= mp.iso) finish_hit(f, mp, prev, position, fused, grad, lc, P, N);   // RayMarcher.cpp:327
+					else if (mp.max_steps > 1)
+					{
+						// most rays that miss here are silhouette rays about to leave the grid: settle them now
+						f3 p2 = position, prev2 = position;
+						uint32_t skips2 = 0;
+						if (advance(f, mp, step, p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
+						else more = true;      // (the queue keeps the state before this advance)
+					}
+				}
+			}
+		}
+		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
+		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+	}
+	flush_counters(lc, counters);
+}
+
+// phase B: the few rays that are left (about 0.3% at the default settings: rays that enter the fluid through a
+// sparse region, and silhouette rays that graze it for up to MaxSteps samples).  One ray per warp, lanes = samples:
+// 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
+// densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
+// and not counted.
+__global__ void __launch_bounds__(256, 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
+														RayQueues rq, DeviceCounters* __restrict__ counters)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	LaneCounters lc = {};
+	uint32_t const count = __ldcg(rq.ctl + 2);
+	for (;;)
+	{
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(rq.ctl + 3, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= count) break;
+		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
+		f3 cur = mk3(a.x, a.y, a.z);
+		f3 const rstep = mk3(b.x, b.y, b.z);
+		uint32_t const index = __float_as_uint(a.w);
+		int ri = __float_as_int(b.w);
+		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
+		for (;;)
+		{
+			// every lane walks the same 32 positions and keeps its own (uniform control flow)
+			f3 my_pos = cur, my_prev = cur, prv = cur;
+			uint32_t skips = 0, my_skips = 0;
+			int n_valid = 32;
+			bool gone = false;
+			for (int k = 0; k < 32; k++)
+			{
+				if (ri + k >= mp.max_steps) { n_valid = k; break; }
+				if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = true; break; }
+				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
+			}
+			LaneCounters tc = {};
+			f3 unused;
+			float const density = lane < n_valid ? eval_density<true, false>(f, my_pos, unused, tc) : 0.0f;
+			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
+			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
+			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
+			if (hits)
+			{
+				if (lane == kstar)
+				{
+					lc.skips += my_skips;
+					finish_hit(f, mp, my_prev, my_pos, false, unused, lc, P, N);
+				}
+				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
+				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
+				N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
+				N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
+				break;
+			}
+			if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
+			ri += n_valid;
+			if (gone || ri >= mp.max_steps) break;
+		}
+		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+	}
+	flush_counters(lc, counters);
 }
 
 }  // namespace
@@ -315,11 +535,39 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	mp.do_march = do_march ? 1 : 0;
 	mp.do_shade = do_shade ? 1 : 0;
 
-	FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), ctx->stream));
+	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
+	mp.tiles_x = tiles_x;
+	size_t const npix = (size_t)ctx->width * ctx->height;
+	int rc;
+	if ((rc = ensure_capacity(&ctx->d_tiles, &ctx->cap_tiles, (size_t)tiles_x * tiles_y + 8))) return rc;
+	if (do_march && (rc = ensure_capacity(&ctx->d_rayq, &ctx->cap_rayq, 2 * npix))) return rc;   // 32 B per pixel
+	RayQueues rq;
+	rq.ctl = ctx->d_tiles;
+	rq.q1 = ctx->d_rayq;
+	uint32_t* const tiles = ctx->d_tiles + 8;
+	cudaStream_t const st = ctx->stream;
+	FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));
+	FM_CUDA(cudaMemsetAsync(ctx->d_tiles, 0, 32, st));
 	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
-	k_march_shade<<<grid, 256, 0, ctx->stream>>>(make_view(f), mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm,
-												 ctx->d_rgba_target, ctx->d_counters);
+	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
 	ctx->kernel_launches += 1;
+	if (do_march)
+	{
+		// persistent: as many CTAs as stay resident (occupancy of this build), never more warps than tiles
+		if (ctx->march_ctas_per_sm == 0)
+		{
+			int nb = 0;
+			FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first, 256, 0));
+			ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
+		}
+		uint32_t const max_ctas = (uint32_t)((tiles_x * tiles_y + 7) / 8);
+		uint32_t ctas = (uint32_t)(ctx->sm_count * ctx->march_ctas_per_sm);
+		if (ctas > max_ctas) ctas = max_ctas;
+		FrameView const fv = make_view(f);
+		k_march_first<<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+		k_march_long<<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+		ctx->kernel_launches += 2;
+	}
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }
