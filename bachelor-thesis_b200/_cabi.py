@@ -23,7 +23,7 @@ class FrSettings(C.Structure):
     _fields_ = [("frame", C.c_int32), ("max_steps", C.c_int32), ("step_size", C.c_float),
                 ("iso_density", C.c_float), ("enable_anisotropy", C.c_int32),
                 ("k_n", C.c_float), ("k_r", C.c_float), ("k_s", C.c_float), ("n_eps", C.c_int32),
-                ("bisection_steps", C.c_int32), ("skip_last_pixel", C.c_int32)]
+                ("bisection_steps", C.c_int32), ("skip_last_pixel", C.c_int32), ("fast_normals", C.c_int32)]
 
 
 class FrCamera(C.Structure):
@@ -41,14 +41,15 @@ class FrFrameInfo(C.Structure):
 class FrCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("pixels", "covered_rays", "hit_rays", "ray_steps", "skip_iterations",
                                           "candidates", "neighbours", "early_exits", "neighbour_overflow",
-                                          "kernel_launches")]
+                                          "kernel_launches", "first_candidates", "queued_rays")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
 class FrTimings(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("upload_ms", "grid_ms", "depth_ms", "march_ms", "download_ms")]
+    _fields_ = [(n, C.c_float) for n in ("upload_ms", "grid_ms", "depth_ms", "march_ms", "download_ms",
+                                          "classify_ms", "march_first_ms", "march_long_ms")]
 
     def as_dict(self):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}

@@ -82,6 +82,12 @@ static int finish_pending(Context* c)
 		float ms = 0.0f;
 		if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
 		if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) c->timings.march_ms = ms;
+		if (c->march_timed)
+		{
+			if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[10]) == cudaSuccess) c->timings.classify_ms = ms;
+			if (cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]) == cudaSuccess) c->timings.march_first_ms = ms;
+			if (cudaEventElapsedTime(&ms, c->ev[11], c->ev[6]) == cudaSuccess) c->timings.march_long_ms = ms;
+		}
 	}
 	return FR_OK;
 }
@@ -408,7 +414,8 @@ int fr_render_async(fr_context* ctx, int passes)
 		ctx->have_depth = true;
 	}
 	FM_CUDA(cudaEventRecord(ctx->ev[5], s));
-	if (passes & (FR_PASS_MARCH | FR_PASS_SHADE))
+	ctx->march_timed = (passes & (FR_PASS_MARCH | FR_PASS_SHADE)) != 0;
+	if (ctx->march_timed)
 		if ((rc = launch_march(ctx, *f, (passes & FR_PASS_MARCH) != 0, (passes & FR_PASS_SHADE) != 0))) return rc;
 	FM_CUDA(cudaEventRecord(ctx->ev[6], s));
 	if (ctx->ext_signal)
@@ -497,6 +504,8 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->early_exits = d.early_exits;
 	out->neighbour_overflow = d.neighbour_overflow;
 	out->kernel_launches = ctx->kernel_launches;
+	out->first_candidates = d.first_candidates;
+	out->queued_rays = d.queued_rays;
 	return FR_OK;
 }
 

@@ -45,6 +45,8 @@ struct DeviceCounters
 {
 	unsigned long long covered_rays, hit_rays, ray_steps, skip_iterations, candidates, neighbours,
 		early_exits, neighbour_overflow;
+	unsigned long long first_candidates;   // snapshot of `candidates` after k_march_first
+	unsigned long long queued_rays;
 };
 
 struct Context
@@ -54,8 +56,9 @@ struct Context
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
-	cudaEvent_t ev[10] = {};
+	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
+	bool march_timed = false;
 
 	fr_settings settings{};
 	bool have_settings = false;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 
 // density (DENS) and/or the un-normalised gradient sum (GRAD) at p: Dataset::GetNeighbors + the W / gradW
 // loops of RayMarcher.cpp:309-336, fused.  Accumulation order == the reference's neighbour order.
-template <bool DENS, bool GRAD>
+template <bool DENS, bool GRAD, bool FAST = false>
 __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc)
 {
 	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
@@ -117,7 +117,12 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 					{
 						if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
 						{
-							if (GRAD) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+							if (GRAD && !FAST) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+							if (GRAD && FAST)
+							{
+								float const c = spline_gradW_coeff_fast(f.kernel, l2, mulr(sqrtr(l2), f.kernel.h_inv));
+								g.x = fmaf(c, -d0, g.x); g.y = fmaf(c, -d1, g.y); g.z = fmaf(c, -d2, g.z);
+							}
 							if (DENS) density = addr(density, spline_W_inrange(f.kernel, l2));
 						}
 						nn++;
@@ -306,6 +311,7 @@ __device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& m
 }
 
 // the sample at `position` reached the threshold (RayMarcher.cpp:327-341): optional bisection, normal
+template <bool FAST>
 __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams& mp, f3 prev, f3 position, bool have_grad,
 										   f3 grad, LaneCounters& lc, float4& P, float4& N)
 {
@@ -321,7 +327,7 @@ __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams
 		if (dm >= mp.iso) hi = mid; else lo = mid;
 	}
 	P = make_float4(hi.x, hi.y, hi.z, 1.0f);
-	if (!have_grad || mp.bisection_steps > 0) eval_density<false, true>(f, hi, grad, lc);
+	if (!have_grad || mp.bisection_steps > 0) eval_density<false, true, FAST>(f, hi, grad, lc);
 	f3 const n = normalize3(grad);   // glm::normalize(normal) (RayMarcher.cpp:338)
 	N = make_float4(n.x, n.y, n.z, 1.0f);
 	lc.hits++;
@@ -376,6 +382,7 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 
 // phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
 // together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
+template <bool FAST>
 __global__ void __launch_bounds__(256, 3) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
@@ -421,10 +428,10 @@ __global__ void __launch_bounds__(256, 3) k_march_first(FrameView f, MarchParams
 				{
 					bool const fused = mp.bisection_steps == 0;
 					f3 grad;
-					float const density = fused ? eval_density<true, true>(f, position, grad, lc)
+					float const density = fused ? eval_density<true, true, FAST>(f, position, grad, lc)
 												: eval_density<true, false>(f, position, grad, lc);
 					lc.steps++;
-					if (density >= mp.iso) finish_hit(f, mp, prev, position, fused, grad, lc, P, N);   // RayMarcher.cpp:327
+					if (density >= mp.iso) finish_hit<FAST>(f, mp, prev, position, fused, grad, lc, P, N);   // RayMarcher.cpp:327
 					else if (mp.max_steps > 1)
 					{
 						// most rays that miss here are silhouette rays about to leave the grid: settle them now
@@ -447,6 +454,7 @@ __global__ void __launch_bounds__(256, 3) k_march_first(FrameView f, MarchParams
 // 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
+template <bool FAST>
 __global__ void __launch_bounds__(256, 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
@@ -491,7 +499,7 @@ __global__ void __launch_bounds__(256, 3) k_march_long(FrameView f, MarchParams 
 				if (lane == kstar)
 				{
 					lc.skips += my_skips;
-					finish_hit(f, mp, my_prev, my_pos, false, unused, lc, P, N);
+					finish_hit<FAST>(f, mp, my_prev, my_pos, false, unused, lc, P, N);
 				}
 				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
 				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
@@ -551,23 +559,34 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
 	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
 	ctx->kernel_launches += 1;
+	FM_CUDA(cudaEventRecord(ctx->ev[10], st));
 	if (do_march)
 	{
 		// persistent: as many CTAs as stay resident (occupancy of this build), never more warps than tiles
 		if (ctx->march_ctas_per_sm == 0)
 		{
 			int nb = 0;
-			FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first, 256, 0));
+			FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false>, 256, 0));
 			ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
 		}
 		uint32_t const max_ctas = (uint32_t)((tiles_x * tiles_y + 7) / 8);
 		uint32_t ctas = (uint32_t)(ctx->sm_count * ctx->march_ctas_per_sm);
 		if (ctas > max_ctas) ctas = max_ctas;
 		FrameView const fv = make_view(f);
-		k_march_first<<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
-		k_march_long<<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+		if (ctx->settings.fast_normals)
+			k_march_first<true><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+		else
+			k_march_first<false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+		FM_CUDA(cudaEventRecord(ctx->ev[11], st));
+		FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->first_candidates, &ctx->d_counters->candidates, 8, cudaMemcpyDeviceToDevice, st));
+		FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->queued_rays, rq.ctl + 2, 4, cudaMemcpyDeviceToDevice, st));
+		if (ctx->settings.fast_normals)
+			k_march_long<true><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+		else
+			k_march_long<false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		ctx->kernel_launches += 2;
 	}
+	else FM_CUDA(cudaEventRecord(ctx->ev[11], st));
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }

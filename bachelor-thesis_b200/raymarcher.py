@@ -33,11 +33,12 @@ class VisualizationSettings:
     # additions, 0 = reference behaviour
     BisectionSteps: int = 0
     SkipLastPixel: bool = False
+    FastNormals: bool = False
 
     def to_c(self) -> abi.FrSettings:
         return abi.FrSettings(self.Frame, self.MaxSteps, self.StepSize, self.IsoDensity,
                               1 if self.EnableAnisotropy else 0, self.k_n, self.k_r, self.k_s, self.N_eps,
-                              self.BisectionSteps, 1 if self.SkipLastPixel else 0)
+                              self.BisectionSteps, 1 if self.SkipLastPixel else 0, 1 if self.FastNormals else 0)
 
 
 def _ptr(a, ctype=C.c_void_p):

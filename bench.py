@@ -13,7 +13,8 @@ device->host copy of positions, normals and the RGBA image inside the timed regi
 
 N > 1 (torchrun, one rank per GPU): frame-parallel over an animation sequence -- every rank renders its
 own frames, no data-path collective (pure partitioning), `scaling: weak`.  `--mode tiles` instead splits
-ONE frame into interleaved 64x64 screen tiles per rank and gathers the RGBA tiles on rank 0 with NCCL.
+ONE frame into interleaved 64x64 screen tiles per rank and gathers the RGBA tiles on rank 0 with NCCL
+(bachelor-thesis_b200/multigpu.py; `scaling: strong`).
 
 Timing: CUDA events on the stream the kernels are launched on (the context stream), L2 flushed between
 steps by zeroing a 512 MiB buffer outside the timed events, max over ranks.
@@ -54,6 +55,17 @@ def load_peaks():
             d = json.load(f)
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_ncu_stats(cfg_name, kernel):
+    """per-launch ncu figures of the dominant kernel for this workload (profiles/ncu_stats.json, written from the
+    committed ncu captures by tools/ncu_summary.py); {} when there is no capture for it"""
+    path = os.path.join(ROOT, "profiles", "ncu_stats.json")
+    try:
+        with open(path) as f:
+            return json.load(f).get(cfg_name, {}).get(kernel, {})
+    except Exception:
+        return {}
 
 
 def workload_string(cfg_name, n_actual, W, H):
@@ -215,7 +227,6 @@ def run_b200(args):
 
     ctx = fm.Context(W, H, device=local)
     ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
-    ctx.set_settings(fm.VisualizationSettings())
     if tiles_mode:
         ctx.set_tile_partition(rank, world, 64, 64)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
@@ -226,11 +237,12 @@ def run_b200(args):
     h_nrm = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
     h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
-    gather_buf = None
+    mg = importlib.import_module("bachelor-thesis_b200.multigpu")
     if tiles_mode:
         rgba_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
         ctx.set_color_target(rgba_dev.data_ptr())
-        gather_buf = [torch.empty_like(rgba_dev) for _ in range(world)] if rank == 0 else None
+        owner = torch.from_numpy(mg.tile_owner_map(W, H, world, 64, 64)).to(dev)
+    ctx.set_settings(fm.VisualizationSettings(FastNormals=args.fast_normals))
     torch.cuda.synchronize()
 
     def device_step(k):
@@ -239,10 +251,18 @@ def run_b200(args):
         ctx.render_async(fm.FR_PASS_ALL)
         if tiles_mode:
             ctx.wait()
-            # real exchange step of the tile-parallel path: RGBA tiles -> presenting GPU over NVLink
-            dist.gather(rgba_dev, gather_buf, dst=0)
+            # real exchange step of the tile-parallel path: RGBA tiles -> presenting GPU over NVLink, merged there
+            mg.gather_tiles(rgba_dev, rank, world, owner, dst=0)
 
     def e2e_step(k):
+        # what a host application calls per frame: particles (host) -> finished colour image (host)
+        f = k % n_frames
+        ctx.upload_frame_ptr(0, h_frames[f].data_ptr(), n_actual[f], h, 2.0)
+        ctx.render_async(fm.FR_PASS_ALL)
+        ctx.download_ptrs(rgba=h_rgba.data_ptr())
+
+    def e2e_refproto_step(k):
+        # the reference's RayMarcher protocol: positions and normals also come back to the host (Prepare's buffers)
         f = k % n_frames
         ctx.upload_frame_ptr(0, h_frames[f].data_ptr(), n_actual[f], h, 2.0)
         ctx.render_async(fm.FR_PASS_ALL)
@@ -300,6 +320,7 @@ def run_b200(args):
     # per-stage device time (CUDA events on the context stream), averaged over the timed steps
     tim = {k: float(np.mean([t[k] for t in stage_log])) for k in stage_log[0]}
     e2e_ms, _, _, _ = timed(e2e_step, args.steps, min(args.warmup, 3))
+    e2e_ref_ms, _, _, _ = timed(e2e_refproto_step, max(3, args.steps // 2), 2)
     ctx.set_color_target(None) if tiles_mode else None
 
     units = W * H * (1 if tiles_mode else world)          # rays per step over all ranks
@@ -308,24 +329,32 @@ def run_b200(args):
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # dominant kernel by device time
-        dom = "k_depth_splat" if tim["depth_ms"] >= tim["march_ms"] else "k_march_shade"
         npart = n_actual[(args.warmup + args.steps - 1) % n_frames]
-        if dom == "k_depth_splat":
-            # algorithmic bytes: 16 B/particle read + 4 B/pixel depth written (clear) + 4 B/covered pixel final write
-            alg = 16.0 * npart + 4.0 * W * H + 4.0 * cnt["covered_rays"]
-            dur_ms = tim["depth_ms"]
-            note = "16 B x particles + 4 B x pixels (clear) + 4 B x covered pixels"
+        # per-kernel device times of the stages (CUDA events on the context stream, averaged over the timed steps)
+        stages = {"grid build (10 kernels)": tim["grid_ms"], "depth pre-pass (5 kernels)": tim["depth_ms"],
+                  "k_classify": tim["classify_ms"], "k_march_first": tim["march_first_ms"], "k_march_long": tim["march_long_ms"]}
+        dom = "k_march_first" if tim["march_first_ms"] >= tim["depth_ms"] else "depth pre-pass (5 kernels)"
+        if dom == "k_march_first":
+            # C_step x 16 B per density evaluation (the candidates of the 27-cell query, which any 27-cell
+            # method incl. the CPU reference must examine) + per covered pixel 4 (depth) + 32 (pos, nrm) + 4 (rgba)
+            alg = 16.0 * cnt["first_candidates"] + 40.0 * cnt["covered_rays"]
+            dur_ms = tim["march_first_ms"]
+            note = "16 B x candidates examined by the first sample of every covered ray + 40 B x covered pixels"
         else:
-            # C_step x 16 B per density evaluation (candidates of the 27-cell query, as any 27-cell
-            # method incl. the CPU reference must examine) + per-pixel outputs 4 (depth) + 32 (pos,nrm) + 4 (rgba)
-            alg = 16.0 * cnt["candidates"] + 40.0 * W * H
-            dur_ms = tim["march_ms"]
-            note = "16 B x candidates examined (incl. the normal pass) + 40 B x pixels"
+            alg = 16.0 * npart + 4.0 * W * H + 4.0 * cnt["covered_rays"] + 32.0 * npart
+            dur_ms = tim["depth_ms"]
+            note = "16 B x particles + 32 B x particles (splat records) + 4 B x pixels (clear) + 4 B x covered pixels"
         achieved = alg / (dur_ms * 1e-3) / 1e9
+        ncu = load_ncu_stats(args.config, dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes": alg, "algorithmic_bytes_def": note,
-                "kernel_ms": dur_ms}
+                "traffic": ncu.get("dram_bytes"), "peak_source": peak_src, "algorithmic_bytes": alg,
+                "algorithmic_bytes_def": note, "kernel_ms": dur_ms, "kernel_share_of_step": dur_ms / ms_step,
+                "stage_ms": stages,
+                "note": "the path is FP32-issue bound, not HBM bound (DESIGN.md 3.5): compulsory HBM traffic of the frame is "
+                        "~0.1 GB; `frac` is SURVEY 8(d)'s algorithmic-bytes figure against the HBM peak",
+                "ncu": ncu}
+        if ncu.get("warp_instructions") and clocks and clocks.get("sm_mhz"):
+            roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * clocks["sm_mhz"] * 1e6 * dur_ms * 1e-3)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             step, kind, nthreads, _ = reference_step_fn(args.config)
@@ -343,6 +372,7 @@ def run_b200(args):
                        "step": "grid build + depth pre-pass + march/normals/shade, particles resident in HBM",
                        "parallelism": ("tile-parallel 64x64 interleaved + NCCL gather" if tiles_mode else f"frame-parallel x{world}"),
                        "l2": "flushed between steps (512 MiB memset outside the timed events)",
+                       "normals": "fast (FMA + approximate reciprocal, ~1e-6)" if args.fast_normals else "bit-exact with the reference",
                        "stage_ms": tim, "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates",
                                                                          "neighbours", "skip_iterations", "early_exits")},
                        "covered_rays_per_s": cnt["covered_rays"] * (1 if tiles_mode else world) / (ms_step * 1e-3),
@@ -351,8 +381,11 @@ def run_b200(args):
                        "wall_s_timed_region": wall},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
-                    "path": "fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(positions, normals, rgba), pinned host buffers"},
+                    "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * 4),
+                    "path": "fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(rgba), pinned host buffers",
+                    "reference_protocol": {"value": units / (e2e_ref_ms * 1e-3), "ms_per_step": e2e_ref_ms,
+                                           "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
+                                           "path": "same, plus positions and normals copied back as RayMarcher::Prepare's host buffers expect"}},
             "gpu_launches": int(kernel_launches_timed),
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -372,6 +405,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

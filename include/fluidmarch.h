@@ -60,6 +60,11 @@ typedef struct fr_settings
 	                                0 = parity mode, hit = first sample with density >= iso */
 	int32_t skip_last_pixel;     /* 1: leave pixel W*H-1 untouched like the reference ThreadPool
 	                                (src/app/ThreadPool.cpp:50) */
+	int32_t fast_normals;        /* 1: the density-gradient sum of the normal (RayMarcher.cpp:333-338) is evaluated as
+	                                sum c_i * r_i with c_i = -+6 sig poly(q) / (|r|^2 h), FMA + approximate reciprocal,
+	                                instead of the reference's per-component IEEE divisions (Kernel.cpp:43-51).
+	                                Hit mask and positions are unaffected (bit-exact); normals agree to ~1e-6.
+	                                0 = normals bit-identical to the reference */
 } fr_settings;
 
 /* camera inputs the path reads: CameraController3D::{Position,System} and
@@ -99,6 +104,8 @@ typedef struct fr_counters
 	uint64_t early_exits;        /* rays stopped after leaving the grid for good (cannot hit) */
 	uint64_t neighbour_overflow; /* samples with more than 8192 neighbours (RayMarcher.cpp:14); must be 0 */
 	uint64_t kernel_launches;    /* kernels this context has launched since fr_create (cumulative) */
+	uint64_t first_candidates;   /* share of `candidates` examined by k_march_first (first sample of every ray) */
+	uint64_t queued_rays;        /* rays that needed more than the first sample (handled by k_march_long) */
 } fr_counters;
 
 /* device time of the last call of each stage, milliseconds (CUDA events on the context stream) */
@@ -107,8 +114,11 @@ typedef struct fr_timings
 	float upload_ms;             /* host -> device copy of the particle array */
 	float grid_ms;               /* AABB + keys + histogram + scan + scatter + in-cell order + occupancy */
 	float depth_ms;
-	float march_ms;              /* march + normals + shading (fused kernel) */
+	float march_ms;              /* classify + march + normals + shading (sum of the three below) */
 	float download_ms;
+	float classify_ms;           /* k_classify: background pixels + tile work list */
+	float march_first_ms;        /* k_march_first: first sample of every covered ray (density + gradient), shading */
+	float march_long_ms;         /* k_march_long: the rays that need more samples */
 } fr_timings;
 
 /* ---- lifetime ------------------------------------------------------------------------------- */
