@@ -192,6 +192,7 @@ void fr_destroy(fr_context* ctx)
 	free_images(ctx);
 	if (ctx->d_xyz) cudaFree(ctx->d_xyz);
 	if (ctx->d_keys) cudaFree(ctx->d_keys);
+	if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
 	if (ctx->d_tile_bound) cudaFree(ctx->d_tile_bound);
 	if (ctx->d_splat) cudaFree(ctx->d_splat);
@@ -546,6 +547,13 @@ int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
 	return query_density(ctx, *f, points_host, m, density, grad);
+}
+
+int fr_selftest_division(fr_context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches)
+{
+	FR_CHECK_CTX(ctx);
+	if (!mismatches) { set_error("fr_selftest_division: null out"); return FR_ERR_INVALID; }
+	return selftest_division(ctx, n, seed, mismatches);
 }
 
 // ---- CUDA-Vulkan hand-off ------------------------------------------------------------------------------

@@ -8,7 +8,7 @@
 //   k_key_count     cell key + histogram (+ occupancy histogram)   reads 12 B, writes 4 B/particle
 //   k_scan_*        exclusive prefix sum over the cell histogram   8 B/cell
 //   k_scatter       counting-sort scatter into float4 SoA           reads 16 B, writes 16 B/particle
-//   k_cell_order    particles of a cell into ascending original index (deterministic sums)
+//   k_cell_order    particles of a cell into ascending original index (deterministic sums)   reads 16+ B, writes 16 B/particle
 //   k_flags         OctreeNode::Flag bitmask                        4 B/cell
 //
 // All of it is HBM/L2-bound integer and copy work; nothing here is a contraction.
@@ -255,29 +255,22 @@ __global__ void __launch_bounds__(kThreads) k_scatter(const float* __restrict__ 
 	sorted[pos] = make_float4(x, y, z, __uint_as_float(i));
 }
 
-// one thread per cell: insertion sort of the cell's few particles by original index, so that every
-// FP32 sum over a cell runs in the reference's order (ascending point id) and results are
-// reproducible from run to run and from GPU to GPU.
-__global__ void __launch_bounds__(kThreads) k_cell_order(const uint32_t* __restrict__ cell_start, uint32_t cells,
-														 float4* __restrict__ sorted)
+// one thread per particle slot: the final place of a particle inside its cell is its rank by original index
+// (number of cell mates with a smaller index), so that every FP32 sum over a cell runs in the reference's order
+// (ascending point id) and results are reproducible from run to run and from GPU to GPU.  `unordered` holds the
+// cell's particles in arrival order of the scatter atomics.
+__global__ void __launch_bounds__(kThreads) k_cell_order(const float4* __restrict__ unordered, uint32_t n, BuildView b,
+														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
 {
-	uint32_t const c = blockIdx.x * blockDim.x + threadIdx.x;
-	if (c >= cells) return;
-	uint32_t const b = cell_start[c], e = cell_start[c + 1];
-	for (uint32_t i = b + 1; i < e; i++)
-	{
-		float4 const v = sorted[i];
-		uint32_t const id = __float_as_uint(v.w);
-		uint32_t j = i;
-		while (j > b)
-		{
-			float4 const u = sorted[j - 1];
-			if (__float_as_uint(u.w) <= id) break;
-			sorted[j] = u;
-			j--;
-		}
-		if (j != i) sorted[j] = v;
-	}
+	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	float4 const v = __ldg(unordered + s);
+	uint32_t const id = __float_as_uint(v.w);
+	uint32_t const key = search_key(b, v.x, v.y, v.z);
+	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
+	uint32_t rank = 0;
+	for (uint32_t t = cb; t < ce; t++) rank += __float_as_uint(__ldg(&unordered[t].w)) < id ? 1u : 0u;
+	sorted[cb + rank] = v;
 }
 
 // OctreeNode::Flag (Dataset.cpp:136-164).  The reference sums exp(-1000 * r) * NumParticles over the 27
@@ -375,6 +368,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	if ((rc = ensure_capacity(&f->d_grid_counts, &f->cap_grid, gcells32))) return rc;
 	if ((rc = ensure_capacity(&f->d_occ_bits, &f->cap_occ_words, occ_words))) return rc;
 	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, n))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_sort_tmp, &ctx->cap_sort_tmp, n))) return rc;
 	// scan scratch: per-cell cursor copy + tile sums
 	if ((rc = ensure_capacity(&ctx->d_scan_tmp, &ctx->cap_scan_tmp, (size_t)cells32 + tiles + 2))) return rc;
 	uint32_t* const d_cursor = ctx->d_scan_tmp;
@@ -398,8 +392,8 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums);
 	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums, tiles);
-	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, f->d_sorted);
-	k_cell_order<<<(cells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_cell_start, cells32, f->d_sorted);
+	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_sort_tmp);
+	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start, f->d_sorted);
 	FrameView const v = make_view(*f);
 	k_flags<<<(gcells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_grid_counts, gcells32, v.kernel.sig_d,
 																	  f->d_occ_bits, f->d_occupied);

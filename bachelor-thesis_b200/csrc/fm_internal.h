@@ -78,6 +78,7 @@ struct Context
 	// scratch for frame builds
 	float* d_xyz = nullptr;           size_t cap_xyz = 0;       // staged input particles (n*3)
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
+	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // counting sort output before the in-cell ordering
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
 	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
@@ -129,5 +130,6 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade);
 int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
 					uint32_t* ids, size_t cap);
 int query_density(Context* ctx, const Frame& f, const float* points_host, size_t m, float* density, float* grad);
+int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
 }  // namespace fm

@@ -315,16 +315,24 @@ template <bool FAST>
 __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams& mp, f3 prev, f3 position, bool have_grad,
 										   f3 grad, LaneCounters& lc, float4& P, float4& N)
 {
-	// optional refinement (north_star item 3; not in the reference): bisect between the last sample below the
-	// threshold and the hit sample
+	// optional refinement (north_star item 3; not in the reference): bisect between the position before the last
+	// advance and the hit sample.  That position was never sampled when the hit is the ray's first sample or follows
+	// an empty-cell jump, so it is sampled first: without a sign change there is no bracket and the hit stays where
+	// the reference puts it.
 	f3 lo = prev, hi = position;
-	for (int b = 0; b < mp.bisection_steps; b++)
+	if (mp.bisection_steps > 0)
 	{
-		f3 const mid = scale3(add3(lo, hi), 0.5f);
 		f3 unused;
-		float const dm = eval_density<true, false>(f, mid, unused, lc);
+		float const d_lo = eval_density<true, false>(f, lo, unused, lc);
 		lc.steps++;
-		if (dm >= mp.iso) hi = mid; else lo = mid;
+		if (d_lo < mp.iso)
+			for (int b = 0; b < mp.bisection_steps; b++)
+			{
+				f3 const mid = scale3(add3(lo, hi), 0.5f);
+				float const dm = eval_density<true, false>(f, mid, unused, lc);
+				lc.steps++;
+				if (dm >= mp.iso) hi = mid; else lo = mid;
+			}
 	}
 	P = make_float4(hi.x, hi.y, hi.z, 1.0f);
 	if (!have_grad || mp.bisection_steps > 0) eval_density<false, true, FAST>(f, hi, grad, lc);

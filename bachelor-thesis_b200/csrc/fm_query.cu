@@ -93,7 +93,69 @@ struct DevBuf
 	~DevBuf() { if (p) cudaFree(p); }
 };
 
+// self-test of the arithmetic shortcuts that claim bit-identity with the plain IEEE operations
+// (fm_common.cuh: divs3_shared, rcpr): pseudo-random operands over the whole magnitude range the guard admits and
+// beyond it, every result compared bit for bit with __fdiv_rn.
+__device__ __forceinline__ uint32_t mix32(uint64_t& st)
+{
+	st = st * 6364136223846793005ull + 1442695040888963407ull;
+	uint32_t x = (uint32_t)(st >> 32);
+	x ^= x >> 15; x *= 0x2c1b3c6du; x ^= x >> 12; x *= 0x297a2d39u; x ^= x >> 15;
+	return x;
+}
+
+__device__ __forceinline__ float random_operand(uint64_t& st, int mode)
+{
+	uint32_t const m = mix32(st);
+	uint32_t const sign = m & 0x80000000u;
+	uint32_t const frac = m & 0x007fffffu;
+	uint32_t e;
+	if (mode == 0) e = 127u - (mix32(st) % 30u);               // the march's range: |x| in (1e-9, 1]
+	else if (mode == 1) e = 127u - 64u + (mix32(st) % 128u);   // around and across the guard (2^-60 .. 2^60)
+	else e = mix32(st) % 256u;                                 // anything: zeros, denormals, infinities, NaNs
+	return __uint_as_float(sign | (e << 23) | frac);
+}
+
+__global__ void __launch_bounds__(256) k_selftest_division(uint64_t per_thread, uint64_t seed, unsigned long long* mismatches)
+{
+	uint64_t st = seed + (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9e3779b97f4a7c15ull;
+	unsigned long long bad = 0;
+	for (uint64_t it = 0; it < per_thread; it++)
+	{
+		int const mode = (int)(it % 3);
+		f3 const a = mk3(random_operand(st, mode), random_operand(st, mode), random_operand(st, mode));
+		float const d = random_operand(st, mode);
+		f3 const q = divs3_shared(a, d);
+		f3 const w = mk3(divr(a.x, d), divr(a.y, d), divr(a.z, d));
+		// NaNs compare by class only (the payload of a generated NaN is unspecified either way)
+		bad += (__float_as_uint(q.x) != __float_as_uint(w.x) && !(isnan(q.x) && isnan(w.x))) ? 1 : 0;
+		bad += (__float_as_uint(q.y) != __float_as_uint(w.y) && !(isnan(q.y) && isnan(w.y))) ? 1 : 0;
+		bad += (__float_as_uint(q.z) != __float_as_uint(w.z) && !(isnan(q.z) && isnan(w.z))) ? 1 : 0;
+		float const r1 = rcpr(d), r2 = divr(1.0f, d);
+		bad += (__float_as_uint(r1) != __float_as_uint(r2) && !(isnan(r1) && isnan(r2))) ? 1 : 0;
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace
+
+int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches)
+{
+	cudaStream_t const s = ctx->stream;
+	DevBuf dm;
+	FM_CUDA(cudaMalloc(&dm.p, 8));
+	FM_CUDA(cudaMemsetAsync(dm.p, 0, 8, s));
+	unsigned const blocks = (unsigned)ctx->sm_count * 8;
+	uint64_t const per_thread = (n + (uint64_t)blocks * 256 - 1) / ((uint64_t)blocks * 256);
+	k_selftest_division<<<blocks, 256, 0, s>>>(per_thread, seed, (unsigned long long*)dm.p);
+	ctx->kernel_launches += 1;
+	FM_CUDA(cudaGetLastError());
+	unsigned long long h = 0;
+	FM_CUDA(cudaMemcpyAsync(&h, dm.p, 8, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaStreamSynchronize(s));
+	*mismatches = h;
+	return FR_OK;
+}
 
 int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
 					uint32_t* ids, size_t cap)

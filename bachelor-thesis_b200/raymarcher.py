@@ -217,6 +217,12 @@ class Context:
         return rho, grad
 
 
+    def selftest_division(self, n: int = 1 << 26, seed: int = 1) -> int:
+        bad = C.c_uint64(0)
+        check(self.lib.fr_selftest_division(self.h, n, seed, C.byref(bad)), "fr_selftest_division")
+        return int(bad.value)
+
+
 class Dataset:
     """Mirror of the reference Dataset (src/app/Dataset.h:67-105): a sequence of particle frames sharing one
     support radius.  ``Frames[i]`` are (N_i, 3) float32 arrays; uploading a frame builds its search grid,

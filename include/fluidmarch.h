@@ -189,6 +189,10 @@ int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, siz
  * sum_j gradW(x_j - p_i) (RayMarcher.cpp:333-336), m*3 floats */
 int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad);
 
+/* device self-test of the shortcuts that claim bit-identity with IEEE division (shared-reciprocal quotients of
+ * gradW, Kernel.cpp:43): n pseudo-random operand sets, *mismatches must come back 0 */
+int fr_selftest_division(fr_context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
+
 /* ---- CUDA-Vulkan hand-off: replaces BilateralBuffer::CopyToGPU/CopyFromGPU
  *      (src/app/AdvancedRenderer/BilateralBuffer.cpp:78-134) ------------------------------------------ */
 /* imports VkDeviceMemory exported with VK_KHR_external_memory_fd (opaque fd, linear W*H*4-byte

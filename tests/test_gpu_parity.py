@@ -277,11 +277,16 @@ def test_bisection_refines_toward_the_camera(fm, oracle, gpu_ctx_factory):
     d0 = np.linalg.norm(p0[hit][:, :3] - campos, axis=1)
     d1 = np.linalg.norm(p1[hit][:, :3] - campos, axis=1)
     assert np.all(d1 <= d0 + 1e-5)                                         # moved toward the camera (or stayed)
-    assert np.median(d0 - d1) > 0.0005 and np.percentile(d0 - d1, 90) <= 0.009 * 1.001   # by at most one StepSize
+    # ... by at most the last advance: one StepSize, or StepSize + the empty cell the ray skipped right before the
+    # hit (the reference's skip is not conservative: neighbours of an empty cell reach into it, RayMarcher.cpp:282-306)
+    assert np.max(d0 - d1) <= 0.009 + 0.1 * np.sqrt(3.0) + 1e-4
+    moved = (d0 - d1) > 1e-6                                               # rays with a bracketed sign change
+    assert moved.sum() > 20
     rho, _ = ctx.query_density(0, p1[hit][:, :3], want_grad=False)
-    assert np.all(rho >= 1.0)                                             # still on / inside the iso-surface
     rho0, _ = ctx.query_density(0, p0[hit][:, :3], want_grad=False)
-    assert np.mean(rho - 1.0) < 0.25 * np.mean(rho0 - 1.0)                # and much closer to it
+    assert np.all(rho >= 1.0)                                             # still on / inside the iso-surface
+    assert np.median(rho[moved]) < 1.05 and np.median(rho0[moved]) > 2.0   # and now right at it
+    assert np.array_equal(bits(p1[hit][~moved]), bits(p0[hit][~moved]))   # no bracket: the reference's hit, bit for bit
     assert np.all(np.abs(np.linalg.norm(n1[hit][:, :3], axis=1) - 1) < 1e-3)
 
 
