@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libfluidmarch.so")
+LIB_PATH = os.environ.get("FLUIDMARCH_LIB") or os.path.join(HERE, "libfluidmarch.so")   # override: A/B builds of the kernels
 
 FR_OK = 0
 FR_PASS_DEPTH, FR_PASS_MARCH, FR_PASS_SHADE, FR_PASS_ALL = 1, 2, 4, 7
