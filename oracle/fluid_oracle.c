@@ -101,7 +101,7 @@ static inline void mat4_mul_vec4(const float* m, const float v[4], float out[4])
 	}
 }
 
-int fo_abi_version(void) { return 1; }
+int fo_abi_version(void) { return 2; }
 
 /* ------------------------------------------------------------------------------------- */
 /* Kernel.cpp                                                                            */
@@ -201,6 +201,8 @@ float fo_cos_half_pi(float s)
 	p = p * x2 + 1.0f;
 	return p;
 }
+
+#include "fluid_oracle_aniso.inc"
 
 /* ------------------------------------------------------------------------------------- */
 /* neighbour search: restatement of CompactNSearch as used by Dataset.cpp                */
@@ -522,6 +524,7 @@ void fo_frame_info(const fo_frame* f, float mn[3], float mx[3], int32_t dims[3])
 }
 
 void fo_frame_particles(const fo_frame* f, float* xyz) { memcpy(xyz, f->particles, f->n * 12); }
+void fo_frame_particles_ext(const fo_frame* f, float* xyz) { memcpy(xyz, f->particles_ext, f->n * 12); }
 
 void fo_frame_grid(const fo_frame* f, uint32_t* counts, uint8_t* flags)
 {
@@ -657,6 +660,8 @@ typedef struct
 {
 	uint32_t ids[FO_MAX_NEIGHBORS];
 	v3 rel[FO_MAX_NEIGHBORS];    /* ThreadLocals::NeighborPositions_Rel (RayMarcher.cpp:16-23) */
+	v3 abs_ext[FO_MAX_NEIGHBORS]; /* ThreadLocals::NeighborPositions_AbsExt */
+	float weights[FO_MAX_NEIGHBORS];
 } march_locals;
 
 static void march_pixel_isotropic(const fo_frame* f, int32_t W, const fo_settings* s,
@@ -740,6 +745,93 @@ static void march_pixel_isotropic(const fo_frame* f, int32_t W, const fo_setting
 	if (steps) steps[index] = nsteps;
 }
 
+/* RayMarcher::PerPixel_Anisotropic (RayMarcher.cpp:346-423) */
+static void march_pixel_anisotropic(const fo_frame* f, int32_t W, const fo_settings* s,
+									float two_w_inv, float two_h_inv, const float* ipv, v3 cam,
+									const float* depth, float* pos4, float* nrm4, float* band, uint32_t* steps,
+									uint32_t index, march_locals* loc, fo_counters* c)
+{
+	float const z = depth[index];
+	memset(pos4 + 4 * (size_t)index, 0, 16);
+	memset(nrm4 + 4 * (size_t)index, 0, 16);
+	if (band) band[index] = INFINITY;
+	if (steps) steps[index] = 0;
+	if (z == 1.0f) return;
+	c->covered_rays++;
+
+	float const clip[4] = { (float)(index % (uint32_t)W) * two_w_inv - 1.0f,
+							(float)(index / (uint32_t)W) * two_h_inv - 1.0f, z, 1.0f };
+	float wh[4];
+	mat4_mul_vec4(ipv, clip, wh);
+	v3 position = v3_divs(v3_make(wh[0], wh[1], wh[2]), wh[3]);
+	v3 const step = v3_scale(v3_normalize(v3_sub(position, cam)), s->step_size);
+	float band_min = INFINITY;
+	uint32_t nsteps = 0;
+	aniso_kernel const ak = aniso_make(f->h);            /* Dataset::m_AnisotropicKernel(ParticleRadius) */
+	float const h2 = f->h * f->h;                        /* ParticleRadius * ParticleRadius (RayMarcher.cpp:393) */
+	float const particle_radius_inv = 1.0f / f->h;       /* Dataset::ParticleRadiusInv */
+
+	for (int i = 0; i < s->max_steps; i++)
+	{
+		position = v3_add(position, step);
+
+		int64_t cell;
+		while ((cell = frame_query_cell(f, position)) >= 0 && !f->flags[cell])
+		{
+			int32_t const cx = (int32_t)(cell % f->gw);
+			int32_t const cy = (int32_t)((cell / f->gw) % f->gh);
+			int32_t const cz = (int32_t)(cell / ((int64_t)f->gw * f->gh));
+			v3 const nmin = v3_add(f->mn, v3_scale(v3_make((float)cx, (float)cy, (float)cz), f->cell_width));
+			v3 const nmax = v3_add(nmin, v3_make(f->cell_width, f->cell_width, f->cell_width));
+			position = v3_add(intersect_aabb(position, step, nmin, nmax), step);
+			c->skip_iterations++;
+		}
+
+		/* Dataset::GetNeighborsExt (Dataset.cpp:282-290): the r = h_ext search over m_ParticlesExt */
+		float const q[3] = { position.x, position.y, position.z };
+		ns_result res = { loc->ids, FO_MAX_NEIGHBORS, 0, 0 };
+		ns_query(&f->search_ext, f->particles_ext, q, &res);
+		uint32_t const n_ext = res.count < FO_MAX_NEIGHBORS ? (uint32_t)res.count : FO_MAX_NEIGHBORS;
+		uint32_t nn = 0;
+		for (uint32_t k = 0; k < n_ext; k++)
+		{
+			const float* xb = f->particles_ext + 3 * (size_t)loc->ids[k];
+			loc->abs_ext[k] = v3_make(xb[0], xb[1], xb[2]);
+			v3 const r = v3_sub(loc->abs_ext[k], position);
+			if (v3_dot(r, r) < h2) loc->rel[nn++] = r;
+		}
+		c->candidates += res.candidates;
+		c->neighbours += nn;
+		c->ray_steps++;
+		if (cell < 0) c->steps_outside_grid++;
+		nsteps++;
+
+		float G[3][3];
+		an_wpca(f->h_ext, particle_radius_inv, s, position, loc->abs_ext, n_ext, loc->weights, G);
+		float const detG = an_det3(G);
+		float density = 0.0f;
+		for (uint32_t k = 0; k < nn; k++) density += aniso_W(&ak, G, detG, loc->rel[k]);
+
+		float const dist = fabsf(density - s->iso_density);
+		if (dist < band_min) band_min = dist;
+
+		if (density >= s->iso_density)
+		{
+			float* P = pos4 + 4 * (size_t)index;
+			P[0] = position.x; P[1] = position.y; P[2] = position.z; P[3] = 1.0f;
+			v3 normal = v3_make(0.0f, 0.0f, 0.0f);
+			for (uint32_t k = 0; k < nn; k++) normal = v3_add(normal, aniso_gradW(&ak, G, detG, loc->rel[k]));
+			normal = v3_normalize(normal);
+			float* N = nrm4 + 4 * (size_t)index;
+			N[0] = normal.x; N[1] = normal.y; N[2] = normal.z; N[3] = 1.0f;
+			c->hit_rays++;
+			break;
+		}
+	}
+	if (band) band[index] = band_min;
+	if (steps) steps[index] = nsteps;
+}
+
 typedef struct
 {
 	const fo_frame* f; int32_t W; const fo_settings* s;
@@ -753,8 +845,14 @@ static void march_body(int64_t begin, int64_t end, int tid, void* vctx)
 	march_ctx* c = (march_ctx*)vctx;
 	march_locals* loc = (march_locals*)malloc(sizeof(march_locals));
 	for (int64_t i = begin; i < end; i++)
-		march_pixel_isotropic(c->f, c->W, c->s, c->two_w_inv, c->two_h_inv, c->ipv, c->cam, c->depth,
-							  c->pos4, c->nrm4, c->band, c->steps, (uint32_t)i, loc, &c->per_thread[tid]);
+	{
+		if (c->s->anisotropic)
+			march_pixel_anisotropic(c->f, c->W, c->s, c->two_w_inv, c->two_h_inv, c->ipv, c->cam, c->depth,
+									c->pos4, c->nrm4, c->band, c->steps, (uint32_t)i, loc, &c->per_thread[tid]);
+		else
+			march_pixel_isotropic(c->f, c->W, c->s, c->two_w_inv, c->two_h_inv, c->ipv, c->cam, c->depth,
+								  c->pos4, c->nrm4, c->band, c->steps, (uint32_t)i, loc, &c->per_thread[tid]);
+	}
 	free(loc);
 }
 
@@ -764,7 +862,6 @@ int fo_march(const fo_frame* f, int32_t W, int32_t H, const fo_settings* s,
 			 int threads)
 {
 	if (!f || !s || W <= 0 || H <= 0) return -1;
-	if (s->anisotropic) return -3;   /* PerPixel_Anisotropic: SURVEY.md 8 row f1, not restated yet */
 	march_ctx* c = (march_ctx*)calloc(1, sizeof(march_ctx));
 	c->f = f; c->W = W; c->s = s;
 	c->two_w_inv = 2.0f / (float)W;   /* RayMarcher.cpp:88-89 */

@@ -96,6 +96,27 @@ int fo_march(const fo_frame* f, int32_t W, int32_t H, const fo_settings* s,
 			 float* pos4, float* nrm4, float* band, uint32_t* steps, fo_counters* counters,
 			 int threads);
 
+/* ---- anisotropic path (RayMarcher.cpp:114-254,346-423; Kernel.cpp:55-125); fluid_oracle_aniso.inc ------ */
+/* fo_march runs PerPixel_Anisotropic when fo_settings.anisotropic != 0 */
+void fo_frame_particles_ext(const fo_frame* f, float* xyz);     /* m_ParticlesExt after its Morton permutation */
+/* Eigen::SelfAdjointEigenSolver<Matrix3f>::computeDirect; c9/evecs9 column-major, lower triangle of c9 read */
+int fo_eigen3(const float c9[9], float evals3[3], float evecs9[9]);
+/* RayMarcher::WPCA; nbr_xyz = N absolute neighbour positions in list order; g9 = glm::mat3 G, column-major */
+void fo_wpca(float h, float h_ext, const fo_settings* s, const float particle[3], const float* nbr_xyz, uint32_t N, float g9[9]);
+float fo_det3(const float g9[9]);                               /* glm::determinant(mat3) */
+float fo_aniso_W(float h, const float g9[9], float detG, const float r[3]);               /* Kernel.cpp:63-82 */
+void fo_aniso_gradW(float h, const float g9[9], float detG, const float r[3], float out[3]); /* Kernel.cpp:84-107 */
+float fo_cubic_W(float h, const float r[3]);                    /* CubicKernel::W, Kernel.cpp:117-125 */
+/* glibc 2.39 atan2f / sinf / cosf restated op for op (what computeDirect's std::atan2/cos/sin resolve to in the
+ * oracle/_ref build); fo_set_trig_libm(1) makes the eigen solver call libm itself instead */
+float fo_atan2f(float y, float x);
+float fo_sinf(float x);
+float fo_cosf(float x);
+void fo_set_trig_libm(int on);
+/* brute-force comparison of the three restatements with libm: returns the number of mismatching results.
+ * which: 0 sinf, 1 cosf over every float in [lo, hi]; 2 atan2f over `count` pseudo-random (y >= 0, x) pairs */
+uint64_t fo_trig_selftest(int which, float lo, float hi, uint64_t count, uint32_t seed);
+
 /* ---- shading (composition.frag:37-66,70-122, CompositionRenderPass.cpp:313-321) ------- */
 /* color4 (optional): linear RGBA floats.  rgba8 (optional): sRGB-encoded bytes in R,G,B,A order
  * (alpha linear), what a B8G8R8A8_SRGB / R8G8B8A8_SRGB attachment stores. */

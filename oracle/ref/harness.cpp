@@ -60,7 +60,7 @@ constexpr size_t kLocalsBytes = 256 * 1024;
 
 extern "C" {
 
-int ref_abi_version() { return 1; }
+int ref_abi_version() { return 2; }
 
 // ---- kernels (Kernel.cpp) ----------------------------------------------------------------
 float ref_W(float h, const float* r)
@@ -271,6 +271,75 @@ double ref_march(void* p, int frame, int W, int H,
 	work();
 	for (auto& t : pool) t.join();
 	return now_s() - t0;
+}
+
+// ---- anisotropic path probes (RayMarcher.cpp:114-254, Kernel.cpp:55-125) ----------------------------
+// Eigen::SelfAdjointEigenSolver<Matrix3f>::computeDirect on a symmetric matrix given column-major (9 floats);
+// only the lower triangle is read, as in RayMarcher::WPCA (RayMarcher.cpp:179-181).
+int ref_eigen3(const float* c9, float* evals3, float* evecs9)
+{
+	Eigen::Matrix3f C;
+	for (int c = 0; c < 3; c++)
+		for (int r = 0; r < 3; r++) C(r, c) = c9[3 * c + r];
+	Eigen::SelfAdjointEigenSolver<Eigen::Matrix3f> solver;
+	solver.computeDirect(C);
+	Eigen::Vector3f const S = solver.eigenvalues();
+	Eigen::Matrix3f const R = solver.eigenvectors();
+	for (int k = 0; k < 3; k++) evals3[k] = S[k];
+	for (int c = 0; c < 3; c++)
+		for (int r = 0; r < 3; r++) evecs9[3 * c + r] = R(r, c);
+	return solver.info() == Eigen::Success ? 0 : 1;
+}
+
+// RayMarcher::WPCA itself.  nbr_xyz: N absolute neighbour positions in list order.  g9: glm::mat3 G, column-major.
+void ref_wpca(void* p, float k_n, float k_r, float k_s, int N_eps, const float* particle, const float* nbr_xyz,
+			  uint32_t N, float* g9)
+{
+	RefDataset* r = static_cast<RefDataset*>(p);
+	if (!r->marcher) r->marcher = new RayMarcher();
+	RayMarcher& m = *r->marcher;
+	m.m_Dataset = &r->ds;
+	m.m_Settings.k_n = k_n; m.m_Settings.k_r = k_r; m.m_Settings.k_s = k_s; m.m_Settings.N_eps = N_eps;
+	glm::mat3 G(0.0f);
+	m.WPCA(glm::vec3(particle[0], particle[1], particle[2]), reinterpret_cast<const glm::vec3*>(nbr_xyz), N, G, false);
+	std::memcpy(g9, &G[0][0], 36);
+}
+
+float ref_det3(const float* g9)
+{
+	glm::mat3 G;
+	std::memcpy(&G[0][0], g9, 36);
+	return glm::determinant(G);
+}
+
+float ref_aniso_W(float h, const float* g9, float detG, const float* r)
+{
+	AnisotropicKernel k(h);
+	glm::mat3 G;
+	std::memcpy(&G[0][0], g9, 36);
+	return k.W(G, detG, glm::vec3(r[0], r[1], r[2]));
+}
+
+void ref_aniso_gradW(float h, const float* g9, float detG, const float* r, float* out)
+{
+	AnisotropicKernel k(h);
+	glm::mat3 G;
+	std::memcpy(&G[0][0], g9, 36);
+	glm::vec3 g = k.gradW(G, detG, glm::vec3(r[0], r[1], r[2]));
+	out[0] = g.x; out[1] = g.y; out[2] = g.z;
+}
+
+float ref_cubic_W(float h, const float* r)
+{
+	CubicKernel k(h);
+	return k.W(glm::vec3(r[0], r[1], r[2]));
+}
+
+// particles of the r = h_ext search after ITS Morton permutation (Frame::m_ParticlesExt, Dataset.cpp:65-75)
+void ref_frame_particles_ext(void* p, int f, float* out_xyz)
+{
+	Frame& fr = static_cast<RefDataset*>(p)->ds.Frames[f];
+	std::memcpy(out_xyz, fr.m_ParticlesExt.data(), fr.m_ParticlesExt.size() * 12);
 }
 
 int ref_hardware_threads() { return int(std::thread::hardware_concurrency()); }

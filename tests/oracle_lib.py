@@ -93,6 +93,57 @@ class Oracle:
         L.fo_set_threads.argtypes = [C.c_int]
         L.fo_set_count_mode.argtypes = [C.c_int]
         L.fo_get_threads.restype = C.c_int
+        # anisotropic path
+        L.fo_frame_particles_ext.argtypes = [C.c_void_p, f32p]
+        L.fo_eigen3.argtypes = [f32p, f32p, f32p]
+        L.fo_wpca.argtypes = [C.c_float, C.c_float, C.POINTER(FoSettings), f32p, f32p, C.c_uint32, f32p]
+        L.fo_det3.restype = C.c_float
+        L.fo_det3.argtypes = [f32p]
+        L.fo_aniso_W.restype = C.c_float
+        L.fo_aniso_W.argtypes = [C.c_float, f32p, C.c_float, f32p]
+        L.fo_aniso_gradW.argtypes = [C.c_float, f32p, C.c_float, f32p, f32p]
+        L.fo_cubic_W.restype = C.c_float
+        L.fo_cubic_W.argtypes = [C.c_float, f32p]
+        for fn in (L.fo_sinf, L.fo_cosf):
+            fn.restype = C.c_float
+            fn.argtypes = [C.c_float]
+        L.fo_atan2f.restype = C.c_float
+        L.fo_atan2f.argtypes = [C.c_float, C.c_float]
+        L.fo_set_trig_libm.argtypes = [C.c_int]
+        L.fo_trig_selftest.restype = C.c_uint64
+        L.fo_trig_selftest.argtypes = [C.c_int, C.c_float, C.c_float, C.c_uint64, C.c_uint32]
+
+    # anisotropic path (RayMarcher.cpp:114-254, Kernel.cpp:55-125)
+    def eigen3(self, c9):
+        c9 = _f32(c9).reshape(9)
+        ev, vec = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        self.lib.fo_eigen3(_fp(c9), _fp(ev), _fp(vec))
+        return ev, vec
+
+    def wpca(self, h, h_ext, settings, particle, nbr_xyz):
+        particle, nbr_xyz = _f32(particle), _f32(nbr_xyz).reshape(-1, 3)
+        g = np.zeros(9, np.float32)
+        s = settings.fo()
+        self.lib.fo_wpca(h, h_ext, C.byref(s), _fp(particle), _fp(nbr_xyz), nbr_xyz.shape[0], _fp(g))
+        return g
+
+    def det3(self, g9):
+        g9 = _f32(g9)
+        return np.float32(self.lib.fo_det3(_fp(g9)))
+
+    def aniso_W(self, h, g9, det, r):
+        g9, r = _f32(g9), _f32(r)
+        return np.float32(self.lib.fo_aniso_W(h, _fp(g9), float(det), _fp(r)))
+
+    def aniso_gradW(self, h, g9, det, r):
+        g9, r = _f32(g9), _f32(r)
+        out = np.zeros(3, np.float32)
+        self.lib.fo_aniso_gradW(h, _fp(g9), float(det), _fp(r), _fp(out))
+        return out
+
+    def cubic_W(self, h, r):
+        r = _f32(r)
+        return np.float32(self.lib.fo_cubic_W(h, _fp(r)))
 
     # kernels
     def W0(self, h):
@@ -157,6 +208,11 @@ class OracleFrame:
     def particles(self):
         out = np.zeros((self.n, 3), np.float32)
         self.L.fo_frame_particles(self.ptr, _fp(out))
+        return out
+
+    def particles_ext(self):
+        out = np.zeros((self.n, 3), np.float32)
+        self.L.fo_frame_particles_ext(self.ptr, _fp(out))
         return out
 
     def grid(self):
@@ -236,6 +292,43 @@ class Ref:
                                 C.c_float, C.c_float, C.c_float, C.c_int, f32p, f32p, f32p, f32p, f32p,
                                 C.c_int, C.c_int]
         L.ref_hardware_threads.restype = C.c_int
+        L.ref_abi_version.restype = C.c_int
+        self.has_aniso = L.ref_abi_version() >= 2
+        if self.has_aniso:
+            L.ref_eigen3.argtypes = [f32p, f32p, f32p]
+            L.ref_wpca.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, f32p, f32p, C.c_uint32, f32p]
+            L.ref_det3.restype = C.c_float
+            L.ref_det3.argtypes = [f32p]
+            L.ref_aniso_W.restype = C.c_float
+            L.ref_aniso_W.argtypes = [C.c_float, f32p, C.c_float, f32p]
+            L.ref_aniso_gradW.argtypes = [C.c_float, f32p, C.c_float, f32p, f32p]
+            L.ref_cubic_W.restype = C.c_float
+            L.ref_cubic_W.argtypes = [C.c_float, f32p]
+            L.ref_frame_particles_ext.argtypes = [C.c_void_p, C.c_int, f32p]
+
+    def eigen3(self, c9):
+        c9 = _f32(c9).reshape(9)
+        ev, vec = np.zeros(3, np.float32), np.zeros(9, np.float32)
+        self.lib.ref_eigen3(_fp(c9), _fp(ev), _fp(vec))
+        return ev, vec
+
+    def det3(self, g9):
+        g9 = _f32(g9)
+        return np.float32(self.lib.ref_det3(_fp(g9)))
+
+    def aniso_W(self, h, g9, det, r):
+        g9, r = _f32(g9), _f32(r)
+        return np.float32(self.lib.ref_aniso_W(h, _fp(g9), float(det), _fp(r)))
+
+    def aniso_gradW(self, h, g9, det, r):
+        g9, r = _f32(g9), _f32(r)
+        out = np.zeros(3, np.float32)
+        self.lib.ref_aniso_gradW(h, _fp(g9), float(det), _fp(r), _fp(out))
+        return out
+
+    def cubic_W(self, h, r):
+        r = _f32(r)
+        return np.float32(self.lib.ref_cubic_W(h, _fp(r)))
 
     def W(self, h, r):
         r = _f32(r)
@@ -289,6 +382,18 @@ class RefDataset:
         out = np.zeros((self.n, 3), np.float32)
         self.L.ref_frame_particles(self.ptr, 0, _fp(out))
         return out
+
+    def particles_ext(self):
+        out = np.zeros((self.n, 3), np.float32)
+        self.L.ref_frame_particles_ext(self.ptr, 0, _fp(out))
+        return out
+
+    def wpca(self, settings, particle, nbr_xyz):
+        particle, nbr_xyz = _f32(particle), _f32(nbr_xyz).reshape(-1, 3)
+        g = np.zeros(9, np.float32)
+        s = settings
+        self.L.ref_wpca(self.ptr, s.k_n, s.k_r, s.k_s, s.n_eps, _fp(particle), _fp(nbr_xyz), nbr_xyz.shape[0], _fp(g))
+        return g
 
     def grid(self):
         ncell = int(np.prod(self.dims.astype(np.int64)))
