@@ -35,6 +35,8 @@ static void free_frame(Frame& f)
 	if (f.d_grid_counts) cudaFree(f.d_grid_counts);
 	if (f.d_occ_bits) cudaFree(f.d_occ_bits);
 	if (f.d_occupied) cudaFree(f.d_occupied);
+	if (f.d_sorted_ext) cudaFree(f.d_sorted_ext);
+	if (f.d_cell_start_ext) cudaFree(f.d_cell_start_ext);
 	f = Frame();
 }
 
@@ -342,10 +344,10 @@ int fr_set_settings(fr_context* ctx, const fr_settings* s)
 		set_error("fr_set_settings: max_steps / bisection_steps out of range");
 		return FR_ERR_INVALID;
 	}
-	if (s->enable_anisotropy)
+	if (s->enable_anisotropy && s->n_eps < 0)
 	{
-		set_error("fr_set_settings: the anisotropic kernel (PerPixel_Anisotropic) is not built yet");
-		return FR_ERR_UNSUPPORTED;
+		set_error("fr_set_settings: n_eps must not be negative");
+		return FR_ERR_INVALID;
 	}
 	ctx->settings = *s;
 	ctx->have_settings = true;
@@ -402,6 +404,8 @@ int fr_render_async(fr_context* ctx, int passes)
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
 	cudaStream_t const s = ctx->stream;
+	// Frame::m_SearchExt (the reference builds it in Frame::Frame; here on the frame's first anisotropic render)
+	if ((passes & FR_PASS_MARCH) && ctx->settings.enable_anisotropy && (rc = build_frame_ext(ctx, f))) return rc;
 	if (ctx->ext_wait)
 	{
 		cudaExternalSemaphoreWaitParams wp;
@@ -537,7 +541,54 @@ int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, siz
 	if ((m && (!points_host || !counts))) { set_error("fr_query_neighbors: null array"); return FR_ERR_INVALID; }
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
-	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap);
+	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap, false);
+}
+
+int fr_query_neighbors_ext(fr_context* ctx, int frame, const float* points_host, size_t m,
+						   uint32_t* counts, uint32_t* ids, size_t cap)
+{
+	FR_CHECK_CTX(ctx);
+	if ((m && (!points_host || !counts))) { set_error("fr_query_neighbors_ext: null array"); return FR_ERR_INVALID; }
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if ((rc = build_frame_ext(ctx, f))) return rc;
+	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap, true);
+}
+
+int fr_query_anisotropic(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad, float* g9)
+{
+	FR_CHECK_CTX(ctx);
+	if ((m && (!points_host || !density))) { set_error("fr_query_anisotropic: null array"); return FR_ERR_INVALID; }
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if ((rc = build_frame_ext(ctx, f))) return rc;
+	return query_aniso(ctx, *f, ctx->settings, points_host, m, density, grad, g9);
+}
+
+int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* cell_start, int32_t search_min[3],
+						  int32_t search_dims[3])
+{
+	FR_CHECK_CTX(ctx);
+	Frame* f = get_frame(ctx, frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if ((rc = build_frame_ext(ctx, f))) return rc;
+	cudaStream_t const s = ctx->stream;
+	size_t const cells = (size_t)f->kdim_ext[0] * f->kdim_ext[1] * f->kdim_ext[2];
+	if (sorted_xyzi) FM_CUDA(cudaMemcpyAsync(sorted_xyzi, f->d_sorted_ext, f->n * 16, cudaMemcpyDeviceToHost, s));
+	if (cell_start) FM_CUDA(cudaMemcpyAsync(cell_start, f->d_cell_start_ext, (cells + 1) * 4, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaStreamSynchronize(s));
+	for (int a = 0; a < 3; a++)
+	{
+		if (search_min) search_min[a] = f->kmin_ext[a];
+		if (search_dims) search_dims[a] = f->kdim_ext[a];
+	}
+	return FR_OK;
 }
 
 int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad)

@@ -15,6 +15,7 @@
 #include "fm_internal.h"
 
 #include <math.h>
+#include <string.h>
 
 namespace fm
 {
@@ -273,6 +274,30 @@ __global__ void __launch_bounds__(kThreads) k_cell_order(const float4* __restric
 	sorted[cb + rank] = v;
 }
 
+// ---- second search structure (r = h_ext) from the already sorted particles ----------------------------------------
+__global__ void __launch_bounds__(kThreads) k_key_count4(const float4* __restrict__ src, uint32_t n, BuildView b,
+														 uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float4 const v = __ldg(src + i);
+	uint32_t const key = search_key(b, v.x, v.y, v.z);
+	keys[i] = key;
+	atomicAdd(cell_count + key, 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) k_scatter4(const float4* __restrict__ src, uint32_t n,
+													   const uint32_t* __restrict__ keys,
+													   const uint32_t* __restrict__ cell_start,
+													   uint32_t* __restrict__ cursor, float4* __restrict__ out)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uint32_t const key = keys[i];
+	uint32_t const left = atomicSub(cursor + key, 1u);
+	out[cell_start[key] + (left - 1u)] = __ldg(src + i);
+}
+
 // OctreeNode::Flag (Dataset.cpp:136-164).  The reference sums exp(-1000 * r) * NumParticles over the 27
 // cells; expf(-1000 r) is exactly 0 for r >= 1 and 1 for r = 0, and adding exact zeros changes nothing,
 // so N_c == float(NumParticles of the cell itself).  Flag = N_c * W0 > isoDensity with isoDensity = 1
@@ -321,7 +346,86 @@ FrameView make_view(const Frame& f)
 	t = t * h;
 	t = t * h;
 	v.kernel.sig_d = 8.0f / t;
+	v.sorted_ext = f.ext_valid ? f.d_sorted_ext : nullptr;
+	v.cell_start_ext = f.ext_valid ? f.d_cell_start_ext : nullptr;
+	v.kmin_ext = make_int3(f.kmin_ext[0], f.kmin_ext[1], f.kmin_ext[2]);
+	v.kdim_ext = make_int3(f.kdim_ext[0], f.kdim_ext[1], f.kdim_ext[2]);
+	v.search_inv_ext = f.search_inv_ext;
+	v.h_ext = f.h_ext;
+	v.h_ext_squared = f.h_ext * f.h_ext;
+	v.aniso_sig = 8.0f / 3.14159265358979323846264338327950288f;
 	return v;
+}
+
+static float host_dec_ordered(uint32_t u)
+{
+	uint32_t const b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+	float f;
+	memcpy(&f, &b, 4);
+	return f;
+}
+
+// CompactNSearch cell_index on the host (IEEE single multiply, truncation): the same bits as search_cell_of
+static int host_search_cell_of(float inv, float x)
+{
+	volatile float const m = inv * x;
+	int const t = (int)m;
+	return x >= 0.0f ? t : t - 1;
+}
+
+// Frame::BuildSearch, second half (Dataset.cpp:65-75): the r = h_ext search over a copy of the particles.  Built from
+// the h-sorted array (positions + original index), so the raw upload does not have to stay resident; inside a cell
+// particles end up in ascending original index like in the reference's Morton-sorted copy.
+int build_frame_ext(Context* ctx, Frame* f)
+{
+	if (f->ext_valid) return FR_OK;
+	if (!f->valid) { set_error("build_frame_ext: frame not built"); return FR_ERR_STATE; }
+	if (!(f->h_ext > 0.0f)) { set_error("anisotropic path: h_ext must be positive (particleRadiusMultiplier)"); return FR_ERR_INVALID; }
+	cudaStream_t const s = ctx->stream;
+	uint32_t const n32 = (uint32_t)f->n;
+	volatile float inv_v = 1.0f / f->h_ext;
+	float const inv = inv_v;
+	f->search_inv_ext = inv;
+	uint64_t cells = 1;
+	for (int a = 0; a < 3; a++)
+	{
+		int const k0 = host_search_cell_of(inv, host_dec_ordered(f->gp.raw_min[a]));
+		int const k1 = host_search_cell_of(inv, host_dec_ordered(f->gp.raw_max[a]));
+		f->kmin_ext[a] = k0;
+		f->kdim_ext[a] = k1 - k0 + 1;
+		cells *= (uint64_t)f->kdim_ext[a];
+	}
+	if (cells >= 0x7fffff00ull) { set_error("build_frame_ext: grid too large"); return FR_ERR_INVALID; }
+	uint32_t const cells32 = (uint32_t)cells;
+	uint32_t const tiles = (cells32 + kScanTile - 1) / kScanTile;
+	int rc;
+	if ((rc = ensure_capacity(&f->d_sorted_ext, &f->cap_sorted_ext, f->n))) return rc;
+	if ((rc = ensure_capacity(&f->d_cell_start_ext, &f->cap_cells_ext, (size_t)cells32 + 1))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, f->n))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_sort_tmp, &ctx->cap_sort_tmp, f->n))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_scan_tmp, &ctx->cap_scan_tmp, (size_t)cells32 + tiles + 2))) return rc;
+	uint32_t* const d_cursor = ctx->d_scan_tmp;
+	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
+	FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
+	BuildView b;
+	b.kmin = make_int3(f->kmin_ext[0], f->kmin_ext[1], f->kmin_ext[2]);
+	b.kdim = make_int3(f->kdim_ext[0], f->kdim_ext[1], f->kdim_ext[2]);
+	b.search_inv = inv;
+	b.mn = make_float3(0.0f, 0.0f, 0.0f);
+	b.gdim = make_int3(0, 0, 0);
+	b.inv_cw = 0.0f;
+	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
+	k_key_count4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, b, ctx->d_keys, d_cursor);
+	FM_CUDA(cudaMemcpyAsync(f->d_cell_start_ext, d_cursor, (size_t)cells32 * 4, cudaMemcpyDeviceToDevice, s));
+	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums);
+	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
+	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums, tiles);
+	k_scatter4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, ctx->d_keys, f->d_cell_start_ext, d_cursor, ctx->d_sort_tmp);
+	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start_ext, f->d_sorted_ext);
+	ctx->kernel_launches += 6;
+	FM_CUDA(cudaGetLastError());
+	f->ext_valid = true;
+	return FR_OK;
 }
 
 int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
@@ -331,6 +435,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	cudaStream_t const s = ctx->stream;
 	uint32_t const n32 = (uint32_t)n;
 	f->valid = false;
+	f->ext_valid = false;
 	f->n = n;
 	f->h = h;
 	f->h_ext = h_ext_mult * h;

@@ -39,6 +39,12 @@ struct Frame
 	uint32_t* d_grid_counts = nullptr; size_t cap_grid = 0;     // gdim product
 	uint32_t* d_occ_bits = nullptr;   size_t cap_occ_words = 0;
 	unsigned long long* d_occupied = nullptr;                   // number of flagged nodes
+	// Frame::m_SearchExt (r = h_ext), built on demand by build_frame_ext
+	bool ext_valid = false;
+	int32_t kmin_ext[3] = {}, kdim_ext[3] = {};
+	float search_inv_ext = 0.0f;
+	float4* d_sorted_ext = nullptr;       size_t cap_sorted_ext = 0;
+	uint32_t* d_cell_start_ext = nullptr; size_t cap_cells_ext = 0;
 };
 
 struct DeviceCounters
@@ -85,7 +91,7 @@ struct Context
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
 	bool depth_refine_bounds = true;
 	uint32_t* d_tiles = nullptr;      size_t cap_tiles = 0;        // march: [0] count, [1] cursor, [2..] covered 8x4 tiles
-	int march_ctas_per_sm = 0;
+	int march_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
 	float4* d_rayq = nullptr;         size_t cap_rayq = 0;         // march: ray queues between the phases
 	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;
@@ -121,14 +127,21 @@ int ensure_capacity(T** ptr, size_t* cap, size_t need)
 
 // fm_grid.cu
 int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
+int build_frame_ext(Context* ctx, Frame* f);      // no-op when already built
 FrameView make_view(const Frame& f);
 // fm_depth.cu
 int launch_depth_prepass(Context* ctx, const Frame& f);
 // fm_march.cu
 int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade);
+// fm_aniso.cu (the one translation unit compiled with -fmad=false)
+struct MarchLaunch;
+int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml);
+int march_occupancy_aniso(int* blocks_per_sm);
+int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float* points_host, size_t m, float* density,
+				float* grad, float* g9);
 // fm_query.cu
 int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
-					uint32_t* ids, size_t cap);
+					uint32_t* ids, size_t cap, bool ext);
 int query_density(Context* ctx, const Frame& f, const float* points_host, size_t m, float* density, float* grad);
 int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 

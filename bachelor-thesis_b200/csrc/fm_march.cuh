@@ -1,0 +1,771 @@
+// fm_march.cu -- the ray-march kernels with fused normals and shading (sm_100a).
+//
+// Replaces RayMarcher::PerPixel_Isotropic (src/app/AdvancedRenderer/RayMarcher.cpp:256-344) together with
+// its callees Frame::QueryDensityGrid (src/app/Dataset.cpp:26-47), Dataset::GetNeighbors (:272-280),
+// CubicSplineKernel::W/gradW (src/app/Kernel.cpp:16-52), intersectAABB (RayMarcher.cpp:51-62), and the
+// fullscreen composition pass (assets/shaders/advanced/composition.frag:37-66,70-122,
+// CompositionRenderPass.cpp:313-321), which only ever reads its own pixel and is therefore fused as the
+// epilogue of the thread that produced the pixel.
+//
+// Two kernels (the reference's ThreadPool, src/app/ThreadPool.cpp:38-55, hands out single pixels from one
+// atomic counter; most pixels return at once because the depth image says "empty"):
+//
+//   k_classify   every pixel, uniform work: uncovered pixels (depth == 1) get their zero outputs and the
+//                background colour right here; each 8x4 pixel tile with at least one covered pixel is
+//                appended to a work list (one atomic per CTA).
+//   k_march      persistent warps (a multiple of the SM count) pull tiles off the list through one
+//                atomic counter -- the ThreadPool's scheme at warp granularity -- so the expensive rays are
+//                spread over all 148 SMs no matter where the fluid sits on screen.  Warp = one 8x4 tile,
+//                lanes = rays.  The rays of a tile are ~1 cell apart (pixel footprint at the default camera
+//                distance ~ h/10), so the 9 contiguous particle ranges each lane walks are the same
+//                addresses across the warp: every LDG.128 of a candidate is a single-sector broadcast.  Before
+//                a lane walks its 27 cells it issues all 18 range loads and L1 prefetches of the candidate
+//                lines at once, so the walk itself runs out of L1.  No neighbour list is materialised; the
+//                d^2 < h^2 test and the kernel sums run inline in the reference's accumulation order (see
+//                fm_common.cuh: FrameView).  The gradient sum of the normal is accumulated together with the
+//                density on a ray's first sample (where ~95% of the rays seeded by the depth pre-pass hit).
+//
+// This header holds the device code of the march; it is compiled twice: fm_march.cu instantiates the isotropic
+// kernels (ANISO = false), fm_aniso.cu -- the one translation unit built with -fmad=false -DFM_NO_FMAD, because the
+// anisotropic arithmetic (fm_aniso.cuh) is written as plain C expressions -- instantiates PerPixel_Anisotropic
+// (RayMarcher.cpp:346-423, ANISO = true).  Stepping, empty-space skip, queues, hit epilogue and shading are shared.
+#pragma once
+
+#include "fm_internal.h"
+#ifdef FM_NO_FMAD
+#include "fm_aniso.cuh"
+#endif
+
+namespace fm
+{
+
+// everything the host needs to launch the two march kernels (filled by launch_march)
+struct MarchParams
+{
+	int W, H;
+	float two_w_inv, two_h_inv;       // m_TwoWidthInv, m_TwoHeightInv (RayMarcher.cpp:88-89)
+	float inv_w, inv_h;
+	float ipv[16];                    // m_InvProjectionView
+	float cam[3];                     // m_CameraPosition
+	float dir[3];                     // Uniforms.CameraDirection
+	int max_steps;
+	float step_size, iso;
+	int bisection_steps;
+	int skip_last_pixel;
+	int early_out;
+	float early_margin;               // cells a sample must lie beyond the grid before the ray is stopped
+	int part_rank, part_world, part_tw, part_th, part_tiles_x;
+	int do_march, do_shade;
+	int tiles_x;                      // 8x4 pixel tiles per image row
+	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
+	uint32_t n_eps;
+};
+
+struct RayQueues
+{
+	float4* q1;              // rays left after the first sample -> k_march_long
+	uint32_t* ctl;           // [0] tiles listed [1] tile cursor [2] |q1| [3] q1 cursor
+};
+
+struct MarchLaunch
+{
+	FrameView fv;
+	MarchParams mp;
+	RayQueues rq;
+	const uint32_t* tiles;
+	uint32_t ctas;
+	bool fast_normals;
+};
+
+namespace
+{
+
+constexpr int kMaxNeighbors = 2 * 4096;   // MAX_NEIGHBORS (RayMarcher.cpp:14)
+
+struct LaneCounters
+{
+	uint32_t covered, hits, steps, skips, candidates, neighbours, early_exits, overflow;
+};
+
+__device__ __forceinline__ void prefetch_l1(const void* p)
+{
+	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+}
+
+// density (DENS) and/or the un-normalised gradient sum (GRAD) at p: Dataset::GetNeighbors + the W / gradW
+// loops of RayMarcher.cpp:309-336, fused.  Accumulation order == the reference's neighbour order.
+template <bool DENS, bool GRAD, bool FAST = false>
+__device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc)
+{
+	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
+	int const ky = search_cell_of(f.search_inv, p.y) - f.kmin.y;
+	int const kz = search_cell_of(f.search_inv, p.z) - f.kmin.z;
+	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
+	float density = 0.0f;
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t nn = 0;
+	if (z0 <= z1)
+	{
+		// all 18 range bounds in flight at once, then the candidate lines into L1 (128 B = 8 particles)
+		{
+			uint32_t pb[9], pe[9];
+#pragma unroll
+			for (int r = 0; r < 9; r++)
+			{
+				int const x = kx + r / 3 - 1, y = ky + r % 3 - 1;
+				bool const ok = (unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y;
+				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+				pb[r] = ok ? __ldg(f.cell_start + base + z0) : 0u;
+				pe[r] = ok ? __ldg(f.cell_start + base + z1 + 1) : 0u;
+			}
+#pragma unroll
+			for (int r = 0; r < 9; r++)
+				for (uint32_t a = pb[r] & ~7u; a < pe[r]; a += 8u) prefetch_l1(f.sorted + a);
+		}
+#pragma unroll 1
+		for (int dx = -1; dx <= 1; dx++)
+		{
+			int const x = kx + dx;
+			if ((unsigned)x >= (unsigned)f.kdim.x) continue;
+#pragma unroll 1
+			for (int dy = -1; dy <= 1; dy++)
+			{
+				int const y = ky + dy;
+				if ((unsigned)y >= (unsigned)f.kdim.y) continue;
+				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+				uint32_t const b = __ldg(f.cell_start + base + z0);
+				uint32_t const e = __ldg(f.cell_start + base + z1 + 1);
+				lc.candidates += e - b;
+#pragma unroll 4
+				for (uint32_t j = b; j < e; j++)
+				{
+					float4 const q = __ldg(f.sorted + j);
+					// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to right); l2 < r2
+					float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
+					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+					if (l2 < f.kernel.h_squared)
+					{
+						if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
+						{
+							if (GRAD && !FAST) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+							if (GRAD && FAST)
+							{
+								float const c = spline_gradW_coeff_fast(f.kernel, l2, mulr(sqrtr(l2), f.kernel.h_inv));
+								g.x = fmaf(c, -d0, g.x); g.y = fmaf(c, -d1, g.y); g.z = fmaf(c, -d2, g.z);
+							}
+							if (DENS) density = addr(density, spline_W_inrange(f.kernel, l2));
+						}
+						nn++;
+					}
+				}
+			}
+		}
+	}
+	lc.neighbours += nn;
+	if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
+	grad = g;
+	return density;
+}
+
+#ifdef FM_NO_FMAD
+// ---- the anisotropic sample: Dataset::GetNeighborsExt + WPCA + AnisotropicKernel sums (RayMarcher.cpp:380-403) -------
+// The reference materialises the 2h neighbour list (positions), its h-subset and the WPCA weights in 8192-entry thread
+// locals.  Here nothing is materialised: the 27 cells of the r = h_ext search are walked three times in the
+// reference's list order -- (1) weights, weight sum, weighted mean; (2) covariance about that mean; (3) kernel sum over
+// the h-subset with the finished G -- each pass recomputing membership and weight with the same operations, hence the
+// same bits.  Pass 3 (and the gradient pass of a hit) only visits the cells that can hold a particle within h.
+struct CellBox { int x0, x1, y0, y1, z0, z1; };
+
+// cells (relative to kmin_ext, clamped to the table and to the query's own 3x3x3 block) that can hold a particle
+// within `reach` of p on every axis: the cell index is monotone in the coordinate
+__device__ __forceinline__ CellBox ext_box(const FrameView& f, f3 p, float reach)
+{
+	CellBox b;
+	int const cx = search_cell_of(f.search_inv_ext, p.x), cy = search_cell_of(f.search_inv_ext, p.y),
+		cz = search_cell_of(f.search_inv_ext, p.z);
+	b.x0 = max(max(search_cell_of(f.search_inv_ext, p.x - reach), cx - 1) - f.kmin_ext.x, 0);
+	b.x1 = min(min(search_cell_of(f.search_inv_ext, p.x + reach), cx + 1) - f.kmin_ext.x, f.kdim_ext.x - 1);
+	b.y0 = max(max(search_cell_of(f.search_inv_ext, p.y - reach), cy - 1) - f.kmin_ext.y, 0);
+	b.y1 = min(min(search_cell_of(f.search_inv_ext, p.y + reach), cy + 1) - f.kmin_ext.y, f.kdim_ext.y - 1);
+	b.z0 = max(max(search_cell_of(f.search_inv_ext, p.z - reach), cz - 1) - f.kmin_ext.z, 0);
+	b.z1 = min(min(search_cell_of(f.search_inv_ext, p.z + reach), cz + 1) - f.kmin_ext.z, f.kdim_ext.z - 1);
+	return b;
+}
+
+// the query's whole 3x3x3 block (NeighborhoodSearch::find_neighbors)
+__device__ __forceinline__ CellBox ext_box_full(const FrameView& f, f3 p)
+{
+	CellBox b;
+	int const cx = search_cell_of(f.search_inv_ext, p.x) - f.kmin_ext.x, cy = search_cell_of(f.search_inv_ext, p.y) - f.kmin_ext.y,
+		cz = search_cell_of(f.search_inv_ext, p.z) - f.kmin_ext.z;
+	// a sample far outside the table must not overflow cx +- 1
+	int const big = 1 << 29;
+	int const sx = min(max(cx, -big), big), sy = min(max(cy, -big), big), sz = min(max(cz, -big), big);
+	b.x0 = max(sx - 1, 0); b.x1 = min(sx + 1, f.kdim_ext.x - 1);
+	b.y0 = max(sy - 1, 0); b.y1 = min(sy + 1, f.kdim_ext.y - 1);
+	b.z0 = max(sz - 1, 0); b.z1 = min(sz + 1, f.kdim_ext.z - 1);
+	return b;
+}
+
+// visits the particles of the box in the reference's result order (x, then y, then z cells; ascending id inside a
+// cell); returns the number of particles visited
+template <typename Visit>
+__device__ __forceinline__ uint32_t walk_ext(const FrameView& f, const CellBox& b, Visit&& visit)
+{
+	uint32_t visited = 0;
+	if (b.z0 > b.z1) return 0;
+#pragma unroll 1
+	for (int x = b.x0; x <= b.x1; x++)
+	{
+#pragma unroll 1
+		for (int y = b.y0; y <= b.y1; y++)
+		{
+			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim_ext.y + (uint32_t)y) * (uint32_t)f.kdim_ext.z;
+			uint32_t const jb = __ldg(f.cell_start_ext + base + b.z0);
+			uint32_t const je = __ldg(f.cell_start_ext + base + b.z1 + 1);
+			visited += je - jb;
+#pragma unroll 2
+			for (uint32_t j = jb; j < je; j++) visit(__ldg(f.sorted_ext + j));
+		}
+	}
+	return visited;
+}
+
+struct AnisoSample
+{
+	aniso::Mat3 G;
+	float detG;
+};
+
+__device__ __forceinline__ aniso::Kernel aniso_kernel_of(const FrameView& f)
+{
+	aniso::Kernel k;
+	k.h = f.kernel.h; k.h_squared = f.kernel.h_squared; k.h_inv = f.kernel.h_inv; k.sig = f.aniso_sig;
+	return k;
+}
+
+// G and det G at p (RayMarcher::WPCA over GetNeighborsExt(p), RayMarcher.cpp:380-400); returns the number of 2h neighbours
+__device__ __forceinline__ uint32_t aniso_wpca(const FrameView& f, const MarchParams& mp, f3 p, AnisoSample& as, LaneCounters& lc)
+{
+	CellBox const full = ext_box_full(f, p);
+	float wsum = 0.0f;
+	f3 mean = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t n_ext = 0;
+	lc.candidates += walk_ext(f, full, [&](float4 q) {
+		// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2; l2 < r2.  CubicKernel::W takes dot(r, r) of
+		// r = xb - x, which is the same sum of the same squares
+		float const d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
+		float const l2 = d0 * d0 + d1 * d1 + d2 * d2;
+		if (l2 < f.h_ext_squared)
+		{
+			if (n_ext < (uint32_t)kMaxNeighbors)
+			{
+				float const w = aniso::cubic_W(f.h_ext, f.search_inv_ext, l2);
+				wsum += w;
+				mean.x += w * q.x; mean.y += w * q.y; mean.z += w * q.z;
+			}
+			n_ext++;
+		}
+	});
+	if (n_ext > (uint32_t)kMaxNeighbors) { lc.overflow++; n_ext = (uint32_t)kMaxNeighbors; }
+	float const inv_wsum = 1.0f / wsum;
+	mean.x *= inv_wsum; mean.y *= inv_wsum; mean.z *= inv_wsum;
+	aniso::Sym3 C = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+	uint32_t n2 = 0;
+	walk_ext(f, full, [&](float4 q) {
+		float const d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
+		float const l2 = d0 * d0 + d1 * d1 + d2 * d2;
+		if (l2 < f.h_ext_squared)
+		{
+			if (n2 < (uint32_t)kMaxNeighbors)
+			{
+				float const w = aniso::cubic_W(f.h_ext, f.search_inv_ext, l2);
+				float const x0 = q.x - mean.x, x1 = q.y - mean.y, x2 = q.z - mean.z;
+				float const w0 = w * x0, w1 = w * x1, w2 = w * x2;
+				C.m00 += w0 * x0;
+				C.m10 += w1 * x0; C.m11 += w1 * x1;
+				C.m20 += w2 * x0; C.m21 += w2 * x1; C.m22 += w2 * x2;
+			}
+			n2++;
+		}
+	});
+	C.m00 *= inv_wsum; C.m10 *= inv_wsum; C.m11 *= inv_wsum; C.m20 *= inv_wsum; C.m21 *= inv_wsum; C.m22 *= inv_wsum;
+	aniso::Settings st;
+	st.k_n = mp.k_n; st.k_r = mp.k_r; st.k_s = mp.k_s; st.n_eps = mp.n_eps;
+	aniso::wpca_G(C, n_ext, st, f.kernel.h_inv, as.G);
+	as.detG = aniso::det3(as.G);
+	return n_ext;
+}
+
+// density at p (RayMarcher.cpp:380-403); leaves G, det G in `as` for the hit epilogue
+__device__ __forceinline__ float aniso_density(const FrameView& f, const MarchParams& mp, f3 p, AnisoSample& as, LaneCounters& lc)
+{
+	uint32_t const n_ext = aniso_wpca(f, mp, p, as, lc);
+	if (n_ext == 0) return 0.0f;      // no 2h neighbour, hence no h neighbour: the kernel sum is empty
+	aniso::Kernel const ak = aniso_kernel_of(f);
+	CellBox const near = ext_box(f, p, f.kernel.h * 1.01f);
+	float density = 0.0f;
+	uint32_t nn = 0;
+	walk_ext(f, near, [&](float4 q) {
+		f3 const r = mk3(q.x - p.x, q.y - p.y, q.z - p.z);
+		float const rr = (r.x * r.x + r.y * r.y) + r.z * r.z;           // glm::dot(r, r) (RayMarcher.cpp:392)
+		if (rr < f.kernel.h_squared)
+		{
+			density += aniso::W(ak, as.G, as.detG, r);
+			nn++;
+		}
+	});
+	lc.neighbours += nn;
+	return density;
+}
+
+// un-normalised normal of a hit at p (RayMarcher.cpp:411-414)
+__device__ __forceinline__ f3 aniso_gradient(const FrameView& f, f3 p, const AnisoSample& as)
+{
+	aniso::Kernel const ak = aniso_kernel_of(f);
+	CellBox const near = ext_box(f, p, f.kernel.h * 1.01f);
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	walk_ext(f, near, [&](float4 q) {
+		f3 const r = mk3(q.x - p.x, q.y - p.y, q.z - p.z);
+		float const rr = (r.x * r.x + r.y * r.y) + r.z * r.z;
+		if (rr < f.kernel.h_squared)
+		{
+			f3 const t = aniso::gradW(ak, as.G, as.detG, r);
+			g.x += t.x; g.y += t.y; g.z += t.z;
+		}
+	});
+	return g;
+}
+#endif   // FM_NO_FMAD
+
+// ---- one sample of either flavour ------------------------------------------------------------------------------------
+// what a density evaluation leaves behind for the hit epilogue
+template <bool ANISO> struct SampleState;
+template <> struct SampleState<false> { f3 grad; bool have_grad; };
+#ifdef FM_NO_FMAD
+template <> struct SampleState<true> { AnisoSample as; };
+#endif
+
+// WITH_GRAD (isotropic only): accumulate the gradient sum together with the density
+template <bool ANISO, bool WITH_GRAD, bool FAST>
+__device__ __forceinline__ float sample_density(const FrameView& f, const MarchParams& mp, f3 p, SampleState<ANISO>& st, LaneCounters& lc)
+{
+	if constexpr (ANISO)
+	{
+#ifdef FM_NO_FMAD
+		return aniso_density(f, mp, p, st.as, lc);
+#else
+		return 0.0f;
+#endif
+	}
+	else
+	{
+		st.have_grad = WITH_GRAD;
+		return eval_density<true, WITH_GRAD, FAST>(f, p, st.grad, lc);
+	}
+}
+
+template <bool ANISO, bool FAST>
+__device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleState<ANISO>& st, LaneCounters& lc)
+{
+	if constexpr (ANISO)
+	{
+#ifdef FM_NO_FMAD
+		return aniso_gradient(f, p, st.as);
+#else
+		return mk3(0.0f, 0.0f, 0.0f);
+#endif
+	}
+	else
+	{
+		if (!st.have_grad) eval_density<false, true, FAST>(f, p, st.grad, lc);
+		return st.grad;
+	}
+}
+
+// sampleFloor (composition.frag:37-46)
+__device__ __forceinline__ void sample_floor(f3 a, f3 r, float out[4])
+{
+	float const sN = subr(-1.0f, a.y);                         // FLOOR_HEIGHT - a.y
+	f3 const b = add3(a, divs3(scale3(r, sN), r.y));           // a + r * (..) / r.y, left to right
+	float const mx = subr(b.x, mulr(2.0f, floorf(divr(b.x, 2.0f))));   // mod(b.x, 2)
+	float const mz = subr(b.z, mulr(2.0f, floorf(divr(b.z, 2.0f))));
+	float const fx = (1.0f < mx) ? 0.0f : 1.0f;                // step(m, 1)
+	float const fy = (1.0f < mz) ? 0.0f : 1.0f;
+	float const g = addr(0.25f, divr(addr(fx, fy), 4.0f));
+	out[0] = g; out[1] = g; out[2] = g; out[3] = 0.5f;
+}
+
+__device__ __forceinline__ uint32_t unorm8(float x)
+{
+	if (!(x > 0.0f)) return 0u;      // also NaN
+	if (x >= 1.0f) return 255u;
+	return (uint32_t)(addr(mulr(x, 255.0f), 0.5f));
+}
+
+// linear -> sRGB, applied by the B8G8R8A8_SRGB swapchain attachment on write (RendererInit2.cpp:50)
+__device__ __forceinline__ float srgb_encode(float c)
+{
+	if (!(c > 0.0f)) return 0.0f;
+	if (c >= 1.0f) return 1.0f;
+	// __powf = ex2(y * lg2(x)) on the SFU: relative error ~1e-6, i.e. < 3e-4 of an 8-bit code value
+	return c <= 0.0031308f ? mulr(12.92f, c) : subr(mulr(1.055f, __powf(c, 1.0f / 2.4f)), 0.055f);
+}
+
+// composition.frag:70-122 for one pixel
+__device__ __forceinline__ uchar4 shade_pixel(const MarchParams& mp, int px, int py, float4 P, float4 N)
+{
+	float const u = divr(addr((float)px, 0.5f), (float)mp.W);   // fullscreen.vert UV at the pixel centre
+	float const v = divr(addr((float)py, 0.5f), (float)mp.H);
+	// viewRay() (composition.frag:59-66): a far-plane POINT used as a direction
+	float wh[4];
+	mat4_mul_vec4(mp.ipv, subr(mulr(2.0f, u), 1.0f), subr(mulr(2.0f, v), 1.0f), 1.0f, 1.0f, wh);
+	f3 const view_ray = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
+	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
+	float color[4];
+	if (P.w == 0.0f)
+	{
+		float fl[4];
+		sample_floor(cam, view_ray, fl);
+#pragma unroll
+		for (int k = 0; k < 4; k++) color[k] = mulr(0.75f, fl[k]);
+	}
+	else
+	{
+		f3 const world = mk3(P.x, P.y, P.z);
+		f3 const normal = mk3(N.x, N.y, N.z);
+		// refract(I, N, eta): k = 1 - eta^2 (1 - dot(N,I)^2); k < 0 ? 0 : eta*I - (eta*dot(N,I) + sqrt(k))*N
+		f3 const I = normalize3(view_ray);
+		float const eta = 1.333f;
+		float const dotNI = dot3(normal, I);
+		float const k = subr(1.0f, mulr(mulr(eta, eta), subr(1.0f, mulr(dotNI, dotNI))));
+		f3 refracted = mk3(0.0f, 0.0f, 0.0f);
+		if (k >= 0.0f) refracted = sub3(scale3(I, eta), scale3(normal, addr(mulr(eta, dotNI), sqrtr(k))));
+		float fl[4];
+		sample_floor(world, refracted, fl);
+		float const fv = -dot3(mk3(mp.dir[0], mp.dir[1], mp.dir[2]), normal);
+		float const amb = subr(addr(0.15f, 1.0f), mulr(fv, fv));
+		float const diffuse[4] = { 120.0f / 255.0f, 185.0f / 255.0f, 255.0f / 255.0f, 255.0f / 255.0f };
+#pragma unroll
+		for (int kk = 0; kk < 4; kk++) color[kk] = addr(mulr(fv, fl[kk]), mulr(amb, diffuse[kk]));
+	}
+	uint32_t const r8 = unorm8(srgb_encode(color[0]));
+	bool const grey = color[1] == color[0] && color[2] == color[0];   // the floor is grey: one transfer-curve evaluation
+	uint32_t const g8 = grey ? r8 : unorm8(srgb_encode(color[1]));
+	uint32_t const b8 = grey ? r8 : unorm8(srgb_encode(color[2]));
+	return make_uchar4((unsigned char)r8, (unsigned char)g8, (unsigned char)b8, (unsigned char)unorm8(color[3]));
+}
+
+__device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int py)
+{
+	bool active = px < mp.W && py < mp.H;
+	if (active && mp.part_world > 1)
+	{
+		int const tile = (py / mp.part_th) * mp.part_tiles_x + (px / mp.part_tw);
+		active = (tile % mp.part_world) == mp.part_rank;
+	}
+	uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
+	if (active && mp.skip_last_pixel && index == (uint32_t)mp.W * (uint32_t)mp.H - 1u) active = false;   // ThreadPool.cpp:50
+	return active;
+}
+
+// every pixel: background + work list of the 8x4 tiles that hold covered pixels.  CTA = 4x2 tiles = 32x8 pixels.
+__global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* __restrict__ depth,
+												  float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+												  uchar4* __restrict__ rgba_out, uint32_t* __restrict__ tiles,
+												  uint32_t* __restrict__ n_tiles)
+{
+	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int const tx = blockIdx.x * 4 + (warp & 3), ty = blockIdx.y * 2 + (warp >> 2);
+	int const px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+	bool const active = pixel_active(mp, px, py);
+	uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
+	bool covered = false;
+	if (active)
+	{
+		if (mp.do_march)
+		{
+			covered = depth[index] != 1.0f;     // `if (z == 1.0f) return;` (RayMarcher.cpp:264)
+			if (!covered)
+			{
+				float4 const zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // RayMarcher.cpp:262-263
+				pos_out[index] = zero;
+				nrm_out[index] = zero;
+				if (mp.do_shade) rgba_out[index] = shade_pixel(mp, px, py, zero, zero);
+			}
+		}
+		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
+	}
+	if (!mp.do_march) return;
+	__shared__ uint32_t s_any[8];
+	__shared__ uint32_t s_base;
+	bool const any = __any_sync(0xffffffffu, covered);
+	if (lane == 0) s_any[warp] = any ? 1u : 0u;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t c = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) c += s_any[w];
+		s_base = c ? atomicAdd(n_tiles, c) : 0u;
+	}
+	__syncthreads();
+	if (any && lane == 0)
+	{
+		uint32_t slot = s_base;
+		for (int w = 0; w < warp; w++) slot += s_any[w];
+		tiles[slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
+	}
+}
+
+__device__ __forceinline__ void add_counts(LaneCounters& a, const LaneCounters& b)
+{
+	a.candidates += b.candidates; a.neighbours += b.neighbours; a.overflow += b.overflow;
+}
+
+// one `position += step` with the empty-space skip of RayMarcher.cpp:279-306 (skips do not consume MaxSteps).
+// Returns true when the ray has left the density grid for good, i.e. this and all later samples are misses:
+// outside the grid every particle is farther than h (the grid is the particle AABB padded by h), so the
+// density is 0 there; each coordinate moves monotonically, so a ray that is outside on an axis and moving
+// away on it can never come back.  Stopping there leaves the result unchanged.
+__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, f3& position, f3& prev,
+										uint32_t& skips)
+{
+	prev = position;
+	position = add3(position, step);
+	int gx, gy, gz;
+	bool inside;
+	while ((inside = density_cell_of(f, position, gx, gy, gz)) && !density_cell_flag(f, gx, gy, gz))
+	{
+		// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133)
+		f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z), scale3(mk3((float)gx, (float)gy, (float)gz), f.cell_width));
+		f3 const nmax = add3(nmin, mk3(f.cell_width, f.cell_width, f.cell_width));
+		prev = position;
+		position = add3(intersect_aabb(position, step, nmin, nmax), step);
+		skips++;
+	}
+	if (!inside && mp.early_out)
+	{
+		float const rx = floorf(mulr(subr(position.x, f.mn.x), f.inv_cell_width.x));
+		float const ry = floorf(mulr(subr(position.y, f.mn.y), f.inv_cell_width.y));
+		float const rz = floorf(mulr(subr(position.z, f.mn.z), f.inv_cell_width.z));
+		float const m = mp.early_margin;
+		return (rx < -m && step.x <= 0.0f) || (rx >= (float)f.gdim.x + m && step.x >= 0.0f) ||
+			   (ry < -m && step.y <= 0.0f) || (ry >= (float)f.gdim.y + m && step.y >= 0.0f) ||
+			   (rz < -m && step.z <= 0.0f) || (rz >= (float)f.gdim.z + m && step.z >= 0.0f);
+	}
+	return false;
+}
+
+// the sample at `position` reached the threshold (RayMarcher.cpp:327-341 / :405-417): optional bisection, normal
+template <bool ANISO, bool FAST>
+__device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams& mp, f3 prev, f3 position,
+										   SampleState<ANISO>& st, LaneCounters& lc, float4& P, float4& N)
+{
+	// optional refinement (north_star item 3; not in the reference): bisect between the position before the last
+	// advance and the hit sample.  That position was never sampled when the hit is the ray's first sample or follows
+	// an empty-cell jump, so it is sampled first: without a sign change there is no bracket and the hit stays where
+	// the reference puts it.
+	f3 lo = prev, hi = position;
+	if (mp.bisection_steps > 0)
+	{
+		SampleState<ANISO> tmp;
+		float const d_lo = sample_density<ANISO, false, false>(f, mp, lo, tmp, lc);
+		lc.steps++;
+		if (d_lo < mp.iso)
+			for (int b = 0; b < mp.bisection_steps; b++)
+			{
+				f3 const mid = scale3(add3(lo, hi), 0.5f);
+				float const dm = sample_density<ANISO, false, false>(f, mp, mid, tmp, lc);
+				lc.steps++;
+				if (dm >= mp.iso) { hi = mid; st = tmp; } else lo = mid;
+			}
+	}
+	P = make_float4(hi.x, hi.y, hi.z, 1.0f);
+	f3 const n = normalize3(sample_gradient<ANISO, FAST>(f, hi, st, lc));   // glm::normalize(normal) (RayMarcher.cpp:338)
+	N = make_float4(n.x, n.y, n.z, 1.0f);
+	lc.hits++;
+}
+
+// ---- ray queues between the three march phases -----------------------------------------------------------
+// A ray that is not finished by a phase is handed on as 32 bytes: (position.xyz, pixel index) (step.xyz, samples taken)
+__device__ __forceinline__ void push_rays(bool want, float4* __restrict__ q, uint32_t* __restrict__ n, uint32_t index,
+										  f3 position, f3 step, int i)
+{
+	uint32_t const m = __ballot_sync(0xffffffffu, want);
+	if (m == 0u) return;
+	int const lane = threadIdx.x & 31;
+	uint32_t base = 0;
+	if (lane == __ffs(m) - 1) base = atomicAdd(n, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	if (want)
+	{
+		uint32_t const slot = base + __popc(m & ((1u << lane) - 1u));
+		q[2 * (size_t)slot] = make_float4(position.x, position.y, position.z, __uint_as_float(index));
+		q[2 * (size_t)slot + 1] = make_float4(step.x, step.y, step.z, __int_as_float(i));
+	}
+}
+
+__device__ __forceinline__ void write_pixel(const MarchParams& mp, uint32_t index, float4 P, float4 N,
+											float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+											uchar4* __restrict__ rgba_out)
+{
+	pos_out[index] = P;
+	nrm_out[index] = N;
+	if (mp.do_shade) rgba_out[index] = shade_pixel(mp, (int)(index % (uint32_t)mp.W), (int)(index / (uint32_t)mp.W), P, N);
+}
+
+__device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCounters* __restrict__ counters)
+{
+	// per-warp counter reduction, one atomic per counter per warp
+	uint32_t vals[8] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow };
+	unsigned long long* dst = reinterpret_cast<unsigned long long*>(counters);
+#pragma unroll
+	for (int k = 0; k < 8; k++)
+	{
+		uint32_t const s = __reduce_add_sync(0xffffffffu, vals[k]);
+		if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst + k, (unsigned long long)s);
+	}
+}
+
+// phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
+// together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
+template <bool FAST, bool ANISO>
+__global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
+														 RayQueues rq, DeviceCounters* __restrict__ counters)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	LaneCounters lc = {};
+	uint32_t const count = __ldcg(rq.ctl + 0);
+	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
+
+	for (;;)
+	{
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(rq.ctl + 1, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= count) break;
+		uint32_t const txy = __ldg(tiles + t);
+		int const px = (int)(txy & 0xffffu) * 8 + (lane & 7), py = (int)(txy >> 16) * 4 + (lane >> 3);
+		uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
+		bool covered = pixel_active(mp, px, py);
+		float z = 1.0f;
+		if (covered) { z = depth[index]; covered = z != 1.0f; }   // uncovered pixels were finished by k_classify
+
+		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+		f3 position = mk3(0.0f, 0.0f, 0.0f), step = position;
+		bool more = false;
+		if (covered)
+		{
+			lc.covered++;
+			// pixel CORNER, not centre (RayMarcher.cpp:268-270)
+			float const cx = subr(mulr((float)px, mp.two_w_inv), 1.0f);
+			float const cy = subr(mulr((float)py, mp.two_h_inv), 1.0f);
+			float wh[4];
+			mat4_mul_vec4(mp.ipv, cx, cy, z, 1.0f, wh);
+			position = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
+			step = scale3(normalize3(sub3(position, cam)), mp.step_size);
+			f3 prev = position;
+			if (mp.max_steps > 0)
+			{
+				if (advance(f, mp, step, position, prev, lc.skips)) lc.early_exits++;
+				else
+				{
+					// isotropic: the gradient sum rides along with the density on this sample (unless bisection moves the hit)
+					SampleState<ANISO> st;
+					float const density = (!ANISO && mp.bisection_steps == 0)
+						? sample_density<ANISO, true, FAST>(f, mp, position, st, lc)
+						: sample_density<ANISO, false, false>(f, mp, position, st, lc);
+					lc.steps++;
+					if (density >= mp.iso) finish_hit<ANISO, FAST>(f, mp, prev, position, st, lc, P, N);   // RayMarcher.cpp:327
+					else if (mp.max_steps > 1)
+					{
+						// most rays that miss here are silhouette rays about to leave the grid: settle them now
+						f3 p2 = position, prev2 = position;
+						uint32_t skips2 = 0;
+						if (advance(f, mp, step, p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
+						else more = true;      // (the queue keeps the state before this advance)
+					}
+				}
+			}
+		}
+		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
+		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+	}
+	flush_counters(lc, counters);
+}
+
+// phase B: the few rays that are left (about 0.3% at the default settings: rays that enter the fluid through a
+// sparse region, and silhouette rays that graze it for up to MaxSteps samples).  One ray per warp, lanes = samples:
+// 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
+// densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
+// and not counted.
+template <bool FAST, bool ANISO>
+__global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
+														RayQueues rq, DeviceCounters* __restrict__ counters)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	LaneCounters lc = {};
+	uint32_t const count = __ldcg(rq.ctl + 2);
+	for (;;)
+	{
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(rq.ctl + 3, 1u);
+		t = __shfl_sync(FULL, t, 0);
+		if (t >= count) break;
+		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
+		f3 cur = mk3(a.x, a.y, a.z);
+		f3 const rstep = mk3(b.x, b.y, b.z);
+		uint32_t const index = __float_as_uint(a.w);
+		int ri = __float_as_int(b.w);
+		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
+		for (;;)
+		{
+			// every lane walks the same 32 positions and keeps its own (uniform control flow)
+			f3 my_pos = cur, my_prev = cur, prv = cur;
+			uint32_t skips = 0, my_skips = 0;
+			int n_valid = 32;
+			bool gone = false;
+			for (int k = 0; k < 32; k++)
+			{
+				if (ri + k >= mp.max_steps) { n_valid = k; break; }
+				if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = true; break; }
+				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
+			}
+			LaneCounters tc = {};
+			SampleState<ANISO> st;
+			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc) : 0.0f;
+			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
+			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
+			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
+			if (hits)
+			{
+				if (lane == kstar)
+				{
+					lc.skips += my_skips;
+					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, P, N);
+				}
+				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
+				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
+				N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
+				N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
+				break;
+			}
+			if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
+			ri += n_valid;
+			if (gone || ri >= mp.max_steps) break;
+		}
+		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+	}
+	flush_counters(lc, counters);
+}
+
+
+}  // namespace
+
+}  // namespace fm

@@ -9,15 +9,25 @@ namespace fm
 namespace
 {
 
-__global__ void __launch_bounds__(128) k_query_neighbors(FrameView f, const float* __restrict__ pts, uint32_t m,
+// the search to query: Frame::m_Search (r = h) or Frame::m_SearchExt (r = h_ext)
+struct SearchView
+{
+	const float4* sorted;
+	const uint32_t* cell_start;
+	int3 kmin, kdim;
+	float search_inv, r2;
+};
+
+__global__ void __launch_bounds__(128) k_query_neighbors(SearchView f, const float* __restrict__ pts, uint32_t m,
 														 uint32_t* __restrict__ counts, uint32_t* __restrict__ ids, uint32_t cap)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= m) return;
 	float const px = pts[3ull * i], py = pts[3ull * i + 1], pz = pts[3ull * i + 2];
-	int const kx = search_cell_of(f.search_inv, px) - f.kmin.x;
-	int const ky = search_cell_of(f.search_inv, py) - f.kmin.y;
-	int const kz = search_cell_of(f.search_inv, pz) - f.kmin.z;
+	int const big = 1 << 29;
+	int const kx = min(max(search_cell_of(f.search_inv, px) - f.kmin.x, -big), big);
+	int const ky = min(max(search_cell_of(f.search_inv, py) - f.kmin.y, -big), big);
+	int const kz = min(max(search_cell_of(f.search_inv, pz) - f.kmin.z, -big), big);
 	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
 	uint32_t nn = 0;
 	if (z0 <= z1)
@@ -36,7 +46,7 @@ __global__ void __launch_bounds__(128) k_query_neighbors(FrameView f, const floa
 					float4 const q = f.sorted[j];
 					float const d0 = subr(px, q.x), d1 = subr(py, q.y), d2 = subr(pz, q.z);
 					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
-					if (l2 < f.kernel.h_squared)
+					if (l2 < f.r2)
 					{
 						if (ids && nn < cap) ids[(size_t)i * cap + nn] = __float_as_uint(q.w);
 						nn++;
@@ -158,7 +168,7 @@ int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatc
 }
 
 int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
-					uint32_t* ids, size_t cap)
+					uint32_t* ids, size_t cap, bool ext)
 {
 	if (m == 0) return FR_OK;
 	if (m > 0x7fffffffull || cap > 0xffffffffull) { set_error("fr_query_neighbors: too many points"); return FR_ERR_INVALID; }
@@ -168,7 +178,19 @@ int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size
 	FM_CUDA(cudaMalloc(&dc.p, m * 4));
 	if (ids && cap) FM_CUDA(cudaMalloc(&di.p, m * cap * 4));
 	FM_CUDA(cudaMemcpyAsync(dp.p, points_host, m * 12, cudaMemcpyHostToDevice, s));
-	k_query_neighbors<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(make_view(f), (const float*)dp.p, (uint32_t)m,
+	FrameView const fv = make_view(f);
+	SearchView sv;
+	if (ext)
+	{
+		sv.sorted = fv.sorted_ext; sv.cell_start = fv.cell_start_ext; sv.kmin = fv.kmin_ext; sv.kdim = fv.kdim_ext;
+		sv.search_inv = fv.search_inv_ext; sv.r2 = fv.h_ext_squared;
+	}
+	else
+	{
+		sv.sorted = fv.sorted; sv.cell_start = fv.cell_start; sv.kmin = fv.kmin; sv.kdim = fv.kdim;
+		sv.search_inv = fv.search_inv; sv.r2 = fv.kernel.h_squared;
+	}
+	k_query_neighbors<<<(unsigned)((m + 127) / 128), 128, 0, s>>>(sv, (const float*)dp.p, (uint32_t)m,
 																 (uint32_t*)dc.p, (uint32_t*)di.p, (uint32_t)cap);
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());

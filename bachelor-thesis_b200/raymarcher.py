@@ -25,7 +25,7 @@ class VisualizationSettings:
     MaxSteps: int = 128
     StepSize: float = 0.009
     IsoDensity: float = 1.0
-    EnableAnisotropy: bool = False     # reference default is True; the isotropic path is the one built
+    EnableAnisotropy: bool = False     # the reference's default is True (AdvancedRenderer.cpp:23); north_star's headline path is the isotropic one
     k_n: float = 0.5
     k_r: float = 2.0
     k_s: float = 2000.0
@@ -198,14 +198,42 @@ class Context:
         return s.value or 0
 
     # point queries ---------------------------------------------------------------------------------
-    def query_neighbors(self, frame: int, points, cap: int = 256):
+    def query_neighbors(self, frame: int, points, cap: int = 256, ext: bool = False):
+        """Dataset::GetNeighbors (ext=False, r = h) / GetNeighborsExt (ext=True, r = h_ext): counts and original ids"""
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
         m = pts.shape[0]
         counts = np.zeros(m, np.uint32)
         ids = np.zeros((m, cap), np.uint32) if cap else None
-        check(self.lib.fr_query_neighbors(self.h, frame, _ptr(pts, abi.f32p), m, _ptr(counts, abi.u32p),
-                                          _ptr(ids, abi.u32p), cap), "fr_query_neighbors")
+        fn = self.lib.fr_query_neighbors_ext if ext else self.lib.fr_query_neighbors
+        check(fn(self.h, frame, _ptr(pts, abi.f32p), m, _ptr(counts, abi.u32p), _ptr(ids, abi.u32p), cap),
+              "fr_query_neighbors_ext" if ext else "fr_query_neighbors")
         return counts, ids
+
+    def query_anisotropic(self, frame: int, points, want_grad=True):
+        """per point: WPCA's G (9 floats, glm::mat3 column-major), the anisotropic density and gradient sums"""
+        pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)
+        m = pts.shape[0]
+        rho = np.zeros(m, np.float32)
+        grad = np.zeros((m, 3), np.float32) if want_grad else None
+        g9 = np.zeros((m, 9), np.float32)
+        check(self.lib.fr_query_anisotropic(self.h, frame, _ptr(pts, abi.f32p), m, _ptr(rho, abi.f32p),
+                                            _ptr(grad, abi.f32p), _ptr(g9, abi.f32p)), "fr_query_anisotropic")
+        return rho, grad, g9
+
+    def download_frame_ext(self, frame: int):
+        """the r = h_ext search (Frame::m_SearchExt): sorted (n, 4) xyz + original id bits, cell_start, kmin, kdim"""
+        info = self.frame_info(frame)
+        n = int(info["num_particles"])
+        kmin = np.zeros(3, np.int32)
+        kdim = np.zeros(3, np.int32)
+        i32p = C.POINTER(C.c_int32)
+        check(self.lib.fr_download_frame_ext(self.h, frame, None, None, kmin.ctypes.data_as(i32p),
+                                             kdim.ctypes.data_as(i32p)), "fr_download_frame_ext")
+        sorted_ = np.zeros((n, 4), np.float32)
+        cell_start = np.zeros(int(np.prod(kdim.astype(np.int64))) + 1, np.uint32)
+        check(self.lib.fr_download_frame_ext(self.h, frame, _ptr(sorted_, abi.f32p), _ptr(cell_start, abi.u32p),
+                                             None, None), "fr_download_frame_ext")
+        return sorted_, cell_start, kmin, kdim
 
     def query_density(self, frame: int, points, want_grad=True):
         pts = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FR_ABI_VERSION 1
+#define FR_ABI_VERSION 2
 
 enum
 {
@@ -29,7 +29,7 @@ enum
 	FR_ERR_CUDA = -2,        /* CUDA runtime error (fr_last_error() has the text) */
 	FR_ERR_NO_DEVICE = -3,   /* no usable sm_100 device: the library never falls back to the CPU */
 	FR_ERR_STATE = -4,       /* call order violated (e.g. render before upload/camera) */
-	FR_ERR_UNSUPPORTED = -5  /* feature not built yet (anisotropic path) */
+	FR_ERR_UNSUPPORTED = -5  /* reserved: a feature this build does not have */
 };
 
 /* passes of fr_render_async, in path order */
@@ -37,7 +37,8 @@ enum
 {
 	FR_PASS_DEPTH = 1,   /* depth pre-pass: replaces CollectRenderData + DepthRenderPass + depth.vert/frag
 	                        (src/app/AdvancedRenderer/AdvancedRenderer.cpp:447-485, DepthRenderPass.cpp:45-87) */
-	FR_PASS_MARCH = 2,   /* RayMarcher::PerPixel_Isotropic (src/app/AdvancedRenderer/RayMarcher.cpp:256-344) */
+	FR_PASS_MARCH = 2,   /* RayMarcher::PerPixel_Isotropic (src/app/AdvancedRenderer/RayMarcher.cpp:256-344) or, with
+	                        fr_settings.enable_anisotropy, PerPixel_Anisotropic (:346-423) */
 	FR_PASS_SHADE = 4,   /* CompositionRenderPass + composition.frag:70-122 */
 	FR_PASS_ALL = 7
 };
@@ -52,8 +53,8 @@ typedef struct fr_settings
 	int32_t max_steps;           /* MaxSteps   = 128 */
 	float step_size;             /* StepSize   = 0.009 */
 	float iso_density;           /* IsoDensity = 1.0 */
-	int32_t enable_anisotropy;   /* EnableAnisotropy (reference default true; only 0 is built) */
-	float k_n, k_r, k_s;         /* 0.5, 2, 2000 */
+	int32_t enable_anisotropy;   /* EnableAnisotropy: 0 = PerPixel_Isotropic, 1 = PerPixel_Anisotropic (reference default) */
+	float k_n, k_r, k_s;         /* WPCA eigenvalue clamps 0.5, 2, 2000 (RayMarcher.cpp:227-238) */
 	int32_t n_eps;               /* 1 */
 	/* additions (0 = reference behaviour) */
 	int32_t bisection_steps;     /* >0: refine the hit between the last two samples (north_star item 3);
@@ -188,6 +189,19 @@ int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, siz
 /* density = sum_j W(x_j - p_i) (RayMarcher.cpp:322-325) and, if grad != NULL, the un-normalised
  * sum_j gradW(x_j - p_i) (RayMarcher.cpp:333-336), m*3 floats */
 int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad);
+
+/* ---- anisotropic path probes (parity of Dataset::GetNeighborsExt, RayMarcher::WPCA, AnisotropicKernel) ------ */
+/* like fr_query_neighbors for the r = h_ext search (Dataset.cpp:282-290): |x_j - p_i|^2 < h_ext^2 */
+int fr_query_neighbors_ext(fr_context* ctx, int frame, const float* points_host, size_t m,
+						   uint32_t* counts, uint32_t* ids, size_t cap);
+/* per point: G = WPCA(p, GetNeighborsExt(p)) with the k_n/k_r/k_s/n_eps of fr_set_settings (g9: m*9 floats, glm::mat3
+ * column-major, RayMarcher.cpp:114-254), density = sum W(G, det G, r) over the h-subset (:402-403) and the
+ * un-normalised sum of gradW (:411-414, m*3 floats).  grad and g9 may be NULL */
+int fr_query_anisotropic(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad, float* g9);
+/* the r = h_ext search structure (Frame::m_SearchExt / m_ParticlesExt, Dataset.cpp:65-75), layout as fr_download_frame;
+ * any pointer may be NULL.  Built on first use. */
+int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* cell_start, int32_t search_min[3],
+						  int32_t search_dims[3]);
 
 /* device self-test of the shortcuts that claim bit-identity with IEEE division (shared-reciprocal quotients of
  * gradW, Kernel.cpp:43): n pseudo-random operand sets, *mismatches must come back 0 */
