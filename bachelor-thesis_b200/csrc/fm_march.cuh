@@ -95,7 +95,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 // density (DENS) and/or the un-normalised gradient sum (GRAD) at p: Dataset::GetNeighbors + the W / gradW
 // loops of RayMarcher.cpp:309-336, fused.  Accumulation order == the reference's neighbour order.
 template <bool DENS, bool GRAD, bool FAST = false>
-__device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc)
+__device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc, bool on = true)
 {
 	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
 	int const ky = search_cell_of(f.search_inv, p.y) - f.kmin.y;
@@ -104,7 +104,7 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	float density = 0.0f;
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t nn = 0;
-	if (z0 <= z1)
+	if (z0 <= z1 && on)
 	{
 		// all 18 range bounds in flight at once, then the candidate lines into L1 (128 B = 8 particles)
 		{
@@ -348,12 +348,13 @@ template <> struct SampleState<true> { AnisoSample as; };
 
 // WITH_GRAD (isotropic only): accumulate the gradient sum together with the density
 template <bool ANISO, bool WITH_GRAD, bool FAST>
-__device__ __forceinline__ float sample_density(const FrameView& f, const MarchParams& mp, f3 p, SampleState<ANISO>& st, LaneCounters& lc)
+__device__ __forceinline__ float sample_density(const FrameView& f, const MarchParams& mp, f3 p, SampleState<ANISO>& st, LaneCounters& lc,
+												bool on = true)
 {
 	if constexpr (ANISO)
 	{
 #ifdef FM_NO_FMAD
-		return aniso_density(f, mp, p, st.as, lc);
+		return on ? aniso_density(f, mp, p, st.as, lc) : 0.0f;
 #else
 		return 0.0f;
 #endif
@@ -361,7 +362,7 @@ __device__ __forceinline__ float sample_density(const FrameView& f, const MarchP
 	else
 	{
 		st.have_grad = WITH_GRAD;
-		return eval_density<true, WITH_GRAD, FAST>(f, p, st.grad, lc);
+		return eval_density<true, WITH_GRAD, FAST>(f, p, st.grad, lc, on);
 	}
 }
 
@@ -656,8 +657,8 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f,
 		if (covered) { z = depth[index]; covered = z != 1.0f; }   // uncovered pixels were finished by k_classify
 
 		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-		f3 position = mk3(0.0f, 0.0f, 0.0f), step = position;
-		bool more = false;
+		f3 position = mk3(0.0f, 0.0f, 0.0f), step = position, prev = position;
+		bool more = false, sample = false;
 		if (covered)
 		{
 			lc.covered++;
@@ -668,30 +669,38 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f,
 			mat4_mul_vec4(mp.ipv, cx, cy, z, 1.0f, wh);
 			position = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
 			step = scale3(normalize3(sub3(position, cam)), mp.step_size);
-			f3 prev = position;
+			prev = position;
 			if (mp.max_steps > 0)
 			{
 				if (advance(f, mp, step, position, prev, lc.skips)) lc.early_exits++;
-				else
-				{
-					// isotropic: the gradient sum rides along with the density on this sample (unless bisection moves the hit)
-					SampleState<ANISO> st;
-					float const density = (!ANISO && mp.bisection_steps == 0)
-						? sample_density<ANISO, true, FAST>(f, mp, position, st, lc)
-						: sample_density<ANISO, false, false>(f, mp, position, st, lc);
-					lc.steps++;
-					if (density >= mp.iso) finish_hit<ANISO, FAST>(f, mp, prev, position, st, lc, P, N);   // RayMarcher.cpp:327
-					else if (mp.max_steps > 1)
-					{
-						// most rays that miss here are silhouette rays about to leave the grid: settle them now
-						f3 p2 = position, prev2 = position;
-						uint32_t skips2 = 0;
-						if (advance(f, mp, step, p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
-						else more = true;      // (the queue keeps the state before this advance)
-					}
-				}
+				else sample = true;
 			}
 		}
+		// The empty-space skip loop of `advance` ends after a different number of iterations per lane, and the compiler
+		// only reconverges at the end of the enclosing branch: without this barrier the warp walks the 27 cells below in
+		// ~1.8 separate groups of lanes (ncu r01 s6: 16.5 active threads per instruction).  From here on the lanes run in
+		// lock step again; lanes without a sample walk empty ranges.
+		__syncwarp();
+		// isotropic: the gradient sum rides along with the density on this sample (unless bisection moves the hit)
+		SampleState<ANISO> st;
+		float const density = (!ANISO && mp.bisection_steps == 0)
+			? sample_density<ANISO, true, FAST>(f, mp, position, st, lc, sample)
+			: sample_density<ANISO, false, false>(f, mp, position, st, lc, sample);
+		__syncwarp();
+		if (sample)
+		{
+			lc.steps++;
+			if (density >= mp.iso) finish_hit<ANISO, FAST>(f, mp, prev, position, st, lc, P, N);   // RayMarcher.cpp:327
+			else if (mp.max_steps > 1)
+			{
+				// most rays that miss here are silhouette rays about to leave the grid: settle them now
+				f3 p2 = position, prev2 = position;
+				uint32_t skips2 = 0;
+				if (advance(f, mp, step, p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
+				else more = true;      // (the queue keeps the state before this advance)
+			}
+		}
+		__syncwarp();
 		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
 		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
 	}
