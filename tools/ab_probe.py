@@ -8,4 +8,4 @@ for name in sorted(os.listdir(os.path.join(ROOT, "build_variants"))):
         continue
     env = dict(os.environ, FLUIDMARCH_LIB=lib)
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_step.py"), cfg, "6"], env=env, capture_output=True, text=True)
-    print(name, out.stdout.strip().split("{'pixels'")[0][:400], out.stderr[-300:] if out.returncode else "", flush=True)
+    print(name, out.stdout.strip().split("{'pixels'")[0][:400], out.stderr[-400:], flush=True)
