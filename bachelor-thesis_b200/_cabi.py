@@ -55,6 +55,13 @@ class FrTimings(C.Structure):
         return {n: float(getattr(self, n)) for n, _ in self._fields_}
 
 
+class FrSeqJob(C.Structure):
+    """fr_seq_job: one frame of a sequence (particles in, host images out)."""
+    _fields_ = [("xyz", C.c_void_p), ("n", C.c_uint64), ("h", C.c_float), ("h_ext_mult", C.c_float),
+                ("xyz_on_device", C.c_int32), ("passes", C.c_int32),
+                ("depth", C.c_void_p), ("positions", C.c_void_p), ("normals", C.c_void_p), ("rgba", C.c_void_p)]
+
+
 # every symbol include/fluidmarch.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("fr_abi_version", C.c_int, []),
@@ -90,6 +97,17 @@ SYMBOLS = [
     ("fr_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("fr_import_vk_memory_fd", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
     ("fr_import_vk_semaphores_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("fr_seq_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vpp]),
+    ("fr_seq_destroy", None, [C.c_void_p]),
+    ("fr_seq_lanes", C.c_int, [C.c_void_p]),
+    ("fr_seq_context", C.c_int, [C.c_void_p, C.c_int, vpp]),
+    ("fr_seq_set_camera", C.c_int, [C.c_void_p, C.POINTER(FrCamera)]),
+    ("fr_seq_set_settings", C.c_int, [C.c_void_p, C.POINTER(FrSettings)]),
+    ("fr_seq_submit", C.c_int64, [C.c_void_p, C.POINTER(FrSeqJob)]),
+    ("fr_seq_wait", C.c_int, [C.c_void_p, C.c_int64]),
+    ("fr_seq_drain", C.c_int, [C.c_void_p]),
+    ("fr_seq_timer_begin", C.c_int, [C.c_void_p]),
+    ("fr_seq_timer_end", C.c_int, [C.c_void_p, f32p]),
 ]
 
 _lib = None

@@ -98,7 +98,6 @@ static int finish_pending(Context* c)
 
 using namespace fm;
 
-struct fr_context : public fm::Context {};
 
 #define FR_CHECK_CTX(ctx)                                                    \
 	do {                                                                     \

@@ -146,3 +146,6 @@ int query_density(Context* ctx, const Frame& f, const float* points_host, size_t
 int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
 }  // namespace fm
+
+// the opaque handle of the C ABI
+struct fr_context : public fm::Context {};

@@ -1,0 +1,266 @@
+// fm_sequence.cu -- frame pipeline over several contexts of one GPU (fr_seq_* of include/fluidmarch.h).
+//
+// The reference renders an animation one frame at a time: AdvancedRenderer::Render starts a march, polls IsDone once
+// per UI frame and only then advances `Frame` (src/app/AdvancedRenderer/AdvancedRenderer.cpp:257-298); its only
+// parallelism is the pixel ThreadPool (src/app/ThreadPool.cpp:38-55).  On the GPU a single frame leaves gaps no kernel
+// can fill by itself: the host round trip that sizes the grid tables, one-CTA scan steps, the tail of the persistent
+// march where the last tiles and the few long rays run on a mostly idle machine, and -- end to end -- the PCIe copies
+// of the particles in and the image out.  A sequence keeps `lanes` frames in flight instead: one fr_context (own
+// stream, own images and scratch) and one host worker thread per lane; frame k goes to lane k % lanes.  Kernels of
+// different lanes overlap wherever SMs are free and the copy engines run beside them, so the gaps of one frame are
+// filled with the next frame's work.  Every frame is still rendered by exactly the single-context code path, hence
+// bit-identical to fr_render_async on one context (tests/test_gpu_sequence.py).
+#include "fm_internal.h"
+
+#include <condition_variable>
+#include <mutex>
+#include <new>
+#include <thread>
+#include <vector>
+
+using namespace fm;
+
+namespace
+{
+
+struct Lane
+{
+	fr_context* ctx = nullptr;
+	std::thread worker;
+	std::mutex m;
+	std::condition_variable cv;
+	bool has_job = false, busy = false, quit = false;
+	fr_seq_job job{};
+	int64_t ticket = -1;           // ticket of the job in `job` / being worked on
+	int64_t done_ticket = -1;      // last ticket finished on this lane
+	int done_status = FR_OK;
+	std::string done_error;
+	cudaEvent_t ev_end = nullptr;
+};
+
+}  // namespace
+
+struct fr_sequence
+{
+	int device = 0;
+	std::vector<Lane*> lanes;
+	int64_t next_ticket = 0;
+	int first_error = FR_OK;
+	std::string first_error_text;
+	std::mutex err_m;
+	cudaEvent_t ev_begin = nullptr;
+	uint64_t frames_done = 0;
+};
+
+namespace
+{
+
+// device -> host copies of the requested images behind the render, then the lane's end-of-frame event (the timer
+// reads it), then wait
+int finish_job(Lane* ln, const fr_seq_job& job)
+{
+	Context* const c = ln->ctx;
+	cudaStream_t const s = c->stream;
+	size_t const npix = (size_t)c->width * c->height;
+	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, c->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
+	if (job.positions) FM_CUDA(cudaMemcpyAsync(job.positions, c->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, c->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, c->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
+	FM_CUDA(cudaEventRecord(ln->ev_end, s));
+	int const rc = fr_wait(ln->ctx);
+	if (rc) return rc;
+	FM_CUDA(cudaEventSynchronize(ln->ev_end));
+	return FR_OK;
+}
+
+void lane_main(fr_sequence* seq, Lane* ln)
+{
+	cudaSetDevice(seq->device);
+	for (;;)
+	{
+		fr_seq_job job;
+		int64_t ticket;
+		{
+			std::unique_lock<std::mutex> lk(ln->m);
+			ln->cv.wait(lk, [&] { return ln->has_job || ln->quit; });
+			if (!ln->has_job && ln->quit) return;
+			job = ln->job;
+			ticket = ln->ticket;
+			ln->has_job = false;
+			ln->busy = true;
+		}
+		int rc;
+		if (job.xyz_on_device) rc = fr_build_frame_device(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
+		else rc = fr_upload_frame(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
+		if (rc == FR_OK) rc = fr_render_async(ln->ctx, job.passes ? job.passes : FR_PASS_ALL);
+		if (rc == FR_OK) rc = finish_job(ln, job);
+		std::string err;
+		if (rc != FR_OK) err = fr_last_error();      // thread-local text of this worker
+		{
+			std::lock_guard<std::mutex> lk(ln->m);
+			ln->busy = false;
+			ln->done_ticket = ticket;
+			ln->done_status = rc;
+			ln->done_error = err;
+		}
+		if (rc != FR_OK)
+		{
+			std::lock_guard<std::mutex> lk(seq->err_m);
+			if (seq->first_error == FR_OK) { seq->first_error = rc; seq->first_error_text = err; }
+		}
+		ln->cv.notify_all();
+	}
+}
+
+int wait_lane_idle(Lane* ln)
+{
+	std::unique_lock<std::mutex> lk(ln->m);
+	ln->cv.wait(lk, [&] { return !ln->has_job && !ln->busy; });
+	return ln->done_status;
+}
+
+}  // namespace
+
+extern "C" {
+
+int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** out)
+{
+	if (!out || lanes < 1 || lanes > 16) { set_error("fr_seq_create: lanes must be in [1, 16]"); return FR_ERR_INVALID; }
+	*out = nullptr;
+	fr_sequence* seq = new (std::nothrow) fr_sequence();
+	if (!seq) { set_error("out of host memory"); return FR_ERR_INVALID; }
+	seq->device = device;
+	for (int k = 0; k < lanes; k++)
+	{
+		Lane* ln = new (std::nothrow) Lane();
+		if (!ln) { fr_seq_destroy(seq); set_error("out of host memory"); return FR_ERR_INVALID; }
+		seq->lanes.push_back(ln);
+		int const rc = fr_create(device, width, height, &ln->ctx);
+		if (rc != FR_OK) { fr_seq_destroy(seq); return rc; }
+		if (cudaEventCreate(&ln->ev_end) != cudaSuccess) { fr_seq_destroy(seq); return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__); }
+	}
+	if (cudaEventCreate(&seq->ev_begin) != cudaSuccess) { fr_seq_destroy(seq); return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__); }
+	for (Lane* ln : seq->lanes) ln->worker = std::thread(lane_main, seq, ln);
+	*out = seq;
+	return FR_OK;
+}
+
+void fr_seq_destroy(fr_sequence* seq)
+{
+	if (!seq) return;
+	for (Lane* ln : seq->lanes)
+	{
+		if (ln->worker.joinable())
+		{
+			{ std::lock_guard<std::mutex> lk(ln->m); ln->quit = true; }
+			ln->cv.notify_all();
+			ln->worker.join();
+		}
+		cudaSetDevice(seq->device);
+		if (ln->ev_end) cudaEventDestroy(ln->ev_end);
+		if (ln->ctx) fr_destroy(ln->ctx);
+		delete ln;
+	}
+	if (seq->ev_begin) cudaEventDestroy(seq->ev_begin);
+	delete seq;
+}
+
+int fr_seq_lanes(fr_sequence* seq) { return seq ? (int)seq->lanes.size() : FR_ERR_INVALID; }
+
+int fr_seq_context(fr_sequence* seq, int lane, fr_context** out)
+{
+	if (!seq || !out || lane < 0 || (size_t)lane >= seq->lanes.size()) { set_error("fr_seq_context: bad lane"); return FR_ERR_INVALID; }
+	*out = seq->lanes[lane]->ctx;
+	return FR_OK;
+}
+
+int fr_seq_drain(fr_sequence* seq)
+{
+	if (!seq) { set_error("null sequence"); return FR_ERR_INVALID; }
+	for (Lane* ln : seq->lanes) wait_lane_idle(ln);
+	std::lock_guard<std::mutex> lk(seq->err_m);
+	int const rc = seq->first_error;
+	if (rc != FR_OK) set_error(seq->first_error_text);
+	seq->first_error = FR_OK;
+	seq->first_error_text.clear();
+	return rc;
+}
+
+int fr_seq_set_camera(fr_sequence* seq, const fr_camera* cam)
+{
+	int rc = fr_seq_drain(seq);
+	if (rc) return rc;
+	for (Lane* ln : seq->lanes)
+		if ((rc = fr_set_camera(ln->ctx, cam))) return rc;
+	return FR_OK;
+}
+
+int fr_seq_set_settings(fr_sequence* seq, const fr_settings* s)
+{
+	int rc = fr_seq_drain(seq);
+	if (rc) return rc;
+	if (!s) { set_error("fr_seq_set_settings: null settings"); return FR_ERR_INVALID; }
+	fr_settings t = *s;
+	t.frame = 0;                     // every lane keeps its current frame in slot 0
+	for (Lane* ln : seq->lanes)
+		if ((rc = fr_set_settings(ln->ctx, &t))) return rc;
+	return FR_OK;
+}
+
+int64_t fr_seq_submit(fr_sequence* seq, const fr_seq_job* job)
+{
+	if (!seq || !job || !job->xyz || job->n == 0) { set_error("fr_seq_submit: bad job"); return FR_ERR_INVALID; }
+	int64_t const ticket = seq->next_ticket++;
+	Lane* ln = seq->lanes[(size_t)(ticket % (int64_t)seq->lanes.size())];
+	{
+		std::unique_lock<std::mutex> lk(ln->m);
+		ln->cv.wait(lk, [&] { return !ln->has_job && !ln->busy; });    // the lane's previous frame (ticket - lanes) is out
+		ln->job = *job;
+		ln->ticket = ticket;
+		ln->has_job = true;
+	}
+	ln->cv.notify_all();
+	return ticket;
+}
+
+int fr_seq_wait(fr_sequence* seq, int64_t ticket)
+{
+	if (!seq || ticket < 0 || ticket >= seq->next_ticket) { set_error("fr_seq_wait: unknown ticket"); return FR_ERR_INVALID; }
+	Lane* ln = seq->lanes[(size_t)(ticket % (int64_t)seq->lanes.size())];
+	std::unique_lock<std::mutex> lk(ln->m);
+	ln->cv.wait(lk, [&] { return ln->done_ticket >= ticket; });
+	if (ln->done_ticket == ticket && ln->done_status != FR_OK) { set_error(ln->done_error); return ln->done_status; }
+	return FR_OK;
+}
+
+// device time of everything submitted between the two calls: begin is recorded on lane 0's stream with every lane
+// idle; every lane records an event behind the last copy of each of its frames; the result is the latest of them
+int fr_seq_timer_begin(fr_sequence* seq)
+{
+	int rc = fr_seq_drain(seq);
+	if (rc) return rc;
+	FM_CUDA(cudaSetDevice(seq->device));
+	FM_CUDA(cudaDeviceSynchronize());
+	FM_CUDA(cudaEventRecord(seq->ev_begin, seq->lanes[0]->ctx->stream));
+	return FR_OK;
+}
+
+int fr_seq_timer_end(fr_sequence* seq, float* ms)
+{
+	int rc = fr_seq_drain(seq);
+	if (rc) return rc;
+	if (!ms) { set_error("fr_seq_timer_end: null out"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaSetDevice(seq->device));
+	float best = 0.0f;
+	for (Lane* ln : seq->lanes)
+	{
+		if (ln->done_ticket < 0) continue;        // lane never used: its event was never recorded
+		float t = 0.0f;
+		FM_CUDA(cudaEventElapsedTime(&t, seq->ev_begin, ln->ev_end));
+		if (t > best) best = t;
+	}
+	*ms = best;
+	return FR_OK;
+}
+
+}  // extern "C"

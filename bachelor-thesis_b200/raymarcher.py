@@ -251,6 +251,89 @@ class Context:
         return int(bad.value)
 
 
+class _LaneContext(Context):
+    """A lane's context inside a Sequence: owned by the sequence, read-only use (counters, timings, frame info)."""
+
+    def __init__(self, lib, handle, width, height, device):
+        self.lib, self.h, self.width, self.height, self.device = lib, handle, width, height, device
+
+    def close(self):
+        self.h = None
+
+    __del__ = close
+
+
+class Sequence:
+    """fr_seq_*: `lanes` frames of an animation in flight on one GPU (the autoplay loop of AdvancedRenderer::Render,
+    reference AdvancedRenderer.cpp:275-298, pipelined).  Frame k renders on lane k % lanes."""
+
+    def __init__(self, width: int, height: int, lanes: int = 2, device: int = 0):
+        self.lib = abi.load()
+        self.width, self.height, self.device = int(width), int(height), device
+        h = C.c_void_p()
+        check(self.lib.fr_seq_create(device, self.width, self.height, lanes, C.byref(h)), "fr_seq_create")
+        self.h = h
+        self.lanes = lanes
+        self._keep = {}          # ticket -> arrays that must outlive the job
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.fr_seq_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def context(self, lane: int) -> Context:
+        c = C.c_void_p()
+        check(self.lib.fr_seq_context(self.h, lane, C.byref(c)), "fr_seq_context")
+        return _LaneContext(self.lib, c, self.width, self.height, self.device)
+
+    def set_camera(self, view, projection, inv_projection_view, position, direction):
+        cam = _camera_struct(view, projection, inv_projection_view, position, direction)
+        check(self.lib.fr_seq_set_camera(self.h, C.byref(cam)), "fr_seq_set_camera")
+
+    def set_settings(self, s: VisualizationSettings):
+        cs = s.to_c()
+        check(self.lib.fr_seq_set_settings(self.h, C.byref(cs)), "fr_seq_set_settings")
+
+    def submit_ptrs(self, xyz_ptr: int, n: int, h: float = 0.1, h_ext_mult: float = 2.0, on_device: bool = False,
+                    passes: int = FR_PASS_ALL, depth: int = 0, positions: int = 0, normals: int = 0, rgba: int = 0) -> int:
+        job = abi.FrSeqJob(xyz_ptr, n, h, h_ext_mult, 1 if on_device else 0, passes, depth or None, positions or None,
+                           normals or None, rgba or None)
+        t = self.lib.fr_seq_submit(self.h, C.byref(job))
+        if t < 0:
+            check(int(t), "fr_seq_submit")
+        return int(t)
+
+    def submit(self, xyz, h: float = 0.1, h_ext_mult: float = 2.0, want=("rgba",), passes: int = FR_PASS_ALL):
+        """numpy in, numpy out: returns (ticket, dict of output arrays that are valid after wait(ticket))"""
+        xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        H, W = self.height, self.width
+        shapes = dict(depth=((H, W), np.float32), positions=((H, W, 4), np.float32), normals=((H, W, 4), np.float32),
+                      rgba=((H, W, 4), np.uint8))
+        out = {k: np.zeros(*shapes[k]) for k in want}
+        t = self.submit_ptrs(xyz.ctypes.data, xyz.shape[0], h, h_ext_mult, False, passes,
+                             **{k: v.ctypes.data for k, v in out.items()})
+        self._keep[t] = (xyz, out)
+        return t, out
+
+    def wait(self, ticket: int):
+        check(self.lib.fr_seq_wait(self.h, ticket), "fr_seq_wait")
+        self._keep.pop(ticket, None)
+
+    def drain(self):
+        check(self.lib.fr_seq_drain(self.h), "fr_seq_drain")
+        self._keep.clear()
+
+    def timer_begin(self):
+        check(self.lib.fr_seq_timer_begin(self.h), "fr_seq_timer_begin")
+
+    def timer_end(self) -> float:
+        ms = C.c_float()
+        check(self.lib.fr_seq_timer_end(self.h, C.byref(ms)), "fr_seq_timer_end")
+        return float(ms.value)
+
+
 class Dataset:
     """Mirror of the reference Dataset (src/app/Dataset.h:67-105): a sequence of particle frames sharing one
     support radius.  ``Frames[i]`` are (N_i, 3) float32 arrays; uploading a frame builds its search grid,

@@ -7,9 +7,12 @@
 
 A "step" is one pass of the whole hot path over one synthetic 1M-particle frame at 1920x1080
 (BASELINE.json configs[1]): grid build (neighbour search + AABB + occupancy grid) -> depth pre-pass ->
-ray march + normals + shading.  `value` starts with the particle array resident in HBM; `e2e` runs the
+ray march + normals + shading.  `value` starts with the particle arrays resident in HBM; `e2e` runs the
 same step through the C ABI with HOST buffers (pinned): host->device copy of the particles and
-device->host copy of positions, normals and the RGBA image inside the timed region.
+device->host copy of the RGBA image inside the timed region (`e2e.reference_protocol`: positions and
+normals too).  Both go through the sequence API (fr_seq_*, --lanes frames in flight per GPU; K steps are
+one timed region); `config.latency_ms_per_frame`, the per-stage times and the roofline kernel time come
+from one frame at a time on one context with L2 flushed between steps.
 
 N > 1 (torchrun, one rank per GPU): frame-parallel over an animation sequence -- every rank renders its
 own frames, no data-path collective (pure partitioning), `scaling: weak`.  `--mode tiles` instead splits
@@ -250,35 +253,54 @@ def run_b200(args):
 
     n, W, H, h, dx = CONFIGS[args.config]
     cam = camera()
+    cam_args = (cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
     tiles_mode = args.mode == "tiles" and world > 1
-    # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame)
-    n_frames = 1 if tiles_mode else min(4, args.steps + args.warmup)
+    lanes = 1 if tiles_mode else max(1, args.lanes)
+    # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame).  Enough
+    # distinct frames that the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush)
+    n_frames = 1 if tiles_mode else max(4, min(24, -(-150_000_000 // (12 * n))))
     frames = []
     for k in range(n_frames):
         t = 0.6 if tiles_mode else 0.45 + 0.3 * (((k * world + rank) % 240) / 239.0)
         frames.append(fm.scenes.dam_break(n, h=h, dx=dx, t=t))
     n_actual = [len(f) for f in frames]
+    settings = fm.VisualizationSettings(FastNormals=args.fast_normals)
 
     ctx = fm.Context(W, H, device=local)
-    ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+    ctx.set_camera(*cam_args)
     if tiles_mode:
         ctx.set_tile_partition(rank, world, 64, 64)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     d_frames = [torch.from_numpy(f).to(dev) for f in frames]                    # inputs resident in HBM
     h_frames = [torch.from_numpy(f).pin_memory() for f in frames]               # e2e: pinned host inputs
-    h_pos = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    h_nrm = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
-    h_rgba = torch.empty((H, W, 4), dtype=torch.uint8).pin_memory()
+    n_out = max(2, lanes)
+    h_pos = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(n_out)]
+    h_nrm = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(n_out)]
+    h_rgba = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
     mg = importlib.import_module("bachelor-thesis_b200.multigpu")
     if tiles_mode:
         rgba_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
         ctx.set_color_target(rgba_dev.data_ptr())
         owner = torch.from_numpy(mg.tile_owner_map(W, H, world, 64, 64)).to(dev)
-    ctx.set_settings(fm.VisualizationSettings(FastNormals=args.fast_normals))
+    ctx.set_settings(settings)
     torch.cuda.synchronize()
 
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return ms
+
+    # ---- one frame at a time on one context: per-frame latency, per-stage device times, the roofline kernel -----
     def device_step(k):
         f = k % n_frames
         ctx.build_frame_device(0, d_frames[f].data_ptr(), n_actual[f], h, 2.0)
@@ -288,29 +310,12 @@ def run_b200(args):
             # real exchange step of the tile-parallel path: RGBA tiles -> presenting GPU over NVLink, merged there
             mg.gather_tiles(rgba_dev, rank, world, owner, dst=0)
 
-    def e2e_step(k):
-        # what a host application calls per frame: particles (host) -> finished colour image (host)
-        f = k % n_frames
-        ctx.upload_frame_ptr(0, h_frames[f].data_ptr(), n_actual[f], h, 2.0)
-        ctx.render_async(fm.FR_PASS_ALL)
-        ctx.download_ptrs(rgba=h_rgba.data_ptr())
-
-    def e2e_refproto_step(k):
-        # the reference's RayMarcher protocol: positions and normals also come back to the host (Prepare's buffers)
-        f = k % n_frames
-        ctx.upload_frame_ptr(0, h_frames[f].data_ptr(), n_actual[f], h, 2.0)
-        ctx.render_async(fm.FR_PASS_ALL)
-        ctx.download_ptrs(positions=h_pos.data_ptr(), normals=h_nrm.data_ptr(), rgba=h_rgba.data_ptr())
-
-    def timed(step_fn, steps, warmup, sampler=None, stage_log=None):
+    def timed_serial(step_fn, steps, warmup, sampler=None, stage_log=None):
         for k in range(warmup):
             step_fn(k)
         ctx.wait()
         launches_before = ctx.counters()["kernel_launches"]
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
         if sampler:
             sampler.start()
         evs = []
@@ -332,30 +337,78 @@ def run_b200(args):
             stage_log.append(ctx.timings())
         torch.cuda.synchronize()
         wall = time.perf_counter() - wall0
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        sync_all()
         clocks = sampler.stop() if sampler else None
-        per = [a.elapsed_time(b) for a, b in evs]
-        total_ms = float(sum(per))
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        timed.launches = ctx.counters()["kernel_launches"] - launches_before
-        return total_ms / steps, per, wall, clocks
+        total_ms = max_over_ranks(float(sum(a.elapsed_time(b) for a, b in evs)))
+        timed_serial.launches = ctx.counters()["kernel_launches"] - launches_before
+        return total_ms / steps, wall, clocks
 
     sampler = ClockSampler(local) if rank == 0 else None
     stage_log = []
     ctx.wait()
-    ms_step, per_step, wall, clocks = timed(device_step, args.steps, args.warmup, sampler, stage_log)
+    serial_ms, serial_wall, serial_clocks = timed_serial(device_step, args.steps, args.warmup,
+                                                         sampler if tiles_mode else None, stage_log)
     cnt = ctx.counters()                                        # counters of the last step
-    kernel_launches_timed = timed.launches                       # kernels of libfluidmarch.so inside the timed region
-    # per-stage device time (CUDA events on the context stream), averaged over the timed steps
+    serial_launches = timed_serial.launches
     tim = {k: float(np.mean([t[k] for t in stage_log])) for k in stage_log[0]}
-    e2e_ms, _, _, _ = timed(e2e_step, args.steps, min(args.warmup, 3))
-    e2e_ref_ms, _, _, _ = timed(e2e_refproto_step, max(3, args.steps // 2), 2)
-    ctx.set_color_target(None) if tiles_mode else None
+
+    # ---- the sequence: `lanes` frames in flight (fr_seq_*), K steps timed as one region --------------------------
+    def timed_sequence(seq, submit, steps, warmup, sampler=None):
+        lane_ctx = [seq.context(l) for l in range(lanes)]
+        for k in range(warmup):
+            submit(k)
+        seq.drain()
+        before = sum(c.counters()["kernel_launches"] for c in lane_ctx)
+        sync_all()
+        if sampler:
+            sampler.start()
+        wall0 = time.perf_counter()
+        seq.timer_begin()
+        for k in range(steps):
+            submit(warmup + k)
+        ms = seq.timer_end()                                    # drains; CUDA events, latest lane
+        wall = time.perf_counter() - wall0
+        sync_all()
+        clocks = sampler.stop() if sampler else None
+        timed_sequence.launches = sum(c.counters()["kernel_launches"] for c in lane_ctx) - before
+        return max_over_ranks(ms) / steps, wall, clocks
+
+    if tiles_mode:
+        ms_step, wall, clocks, kernel_launches_timed = serial_ms, serial_wall, serial_clocks, serial_launches
+        ctx.set_color_target(None)
+
+        def e2e_tiles(k):
+            ctx.upload_frame_ptr(0, h_frames[0].data_ptr(), n_actual[0], h, 2.0)
+            ctx.render_async(fm.FR_PASS_ALL)
+            ctx.download_ptrs(rgba=h_rgba[0].data_ptr())
+        e2e_ms, _, _ = timed_serial(e2e_tiles, args.steps, 3)
+        e2e_ref_ms = None
+    else:
+        seq = fm.Sequence(W, H, lanes=lanes, device=local)
+        seq.set_camera(*cam_args)
+        seq.set_settings(settings)
+
+        def submit_device(k):
+            f = k % n_frames
+            seq.submit_ptrs(d_frames[f].data_ptr(), n_actual[f], h, 2.0, on_device=True)
+
+        def submit_e2e(k):
+            # what a host application calls per frame: particles (pinned host) -> finished colour image (pinned host)
+            f = k % n_frames
+            seq.submit_ptrs(h_frames[f].data_ptr(), n_actual[f], h, 2.0, rgba=h_rgba[k % n_out].data_ptr())
+
+        def submit_e2e_refproto(k):
+            # the reference's RayMarcher protocol: positions and normals also come back to the host (Prepare's buffers)
+            f = k % n_frames
+            o = k % n_out
+            seq.submit_ptrs(h_frames[f].data_ptr(), n_actual[f], h, 2.0, positions=h_pos[o].data_ptr(),
+                            normals=h_nrm[o].data_ptr(), rgba=h_rgba[o].data_ptr())
+
+        ms_step, wall, clocks = timed_sequence(seq, submit_device, args.steps, args.warmup, sampler)
+        kernel_launches_timed = timed_sequence.launches
+        e2e_ms, _, _ = timed_sequence(seq, submit_e2e, args.steps, max(3, min(args.warmup, 6)))
+        e2e_ref_ms, _, _ = timed_sequence(seq, submit_e2e_refproto, max(4, args.steps // 2), 3)
+        seq.close()
 
     units = W * H * (1 if tiles_mode else world)          # rays per step over all ranks
     value = units / (ms_step * 1e-3)
@@ -364,7 +417,7 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = load_peaks()
         npart = n_actual[(args.warmup + args.steps - 1) % n_frames]
-        # per-kernel device times of the stages (CUDA events on the context stream, averaged over the timed steps)
+        # per-kernel device times of the stages (CUDA events on the context stream, one frame at a time, L2 flushed)
         stages = {"grid build (10 kernels)": tim["grid_ms"], "depth pre-pass (5 kernels)": tim["depth_ms"],
                   "k_classify": tim["classify_ms"], "k_march_first": tim["march_first_ms"], "k_march_long": tim["march_long_ms"]}
         # dominant KERNEL (not stage): the depth stage is five kernels, the largest of which (k_depth_splat) is ~43% of the
@@ -384,10 +437,11 @@ def run_b200(args):
         ncu = load_ncu_stats(args.config, dom)
         roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": ncu.get("dram_bytes"), "peak_source": peak_src, "algorithmic_bytes": alg,
-                "algorithmic_bytes_def": note, "kernel_ms": dur_ms, "kernel_share_of_step": dur_ms / ms_step,
+                "algorithmic_bytes_def": note, "kernel_ms": dur_ms, "kernel_share_of_step": dur_ms / serial_ms,
                 "stage_ms": stages,
-                "note": "the path is FP32-issue bound, not HBM bound (DESIGN.md 3.5): compulsory HBM traffic of the frame is "
-                        "~0.1 GB; `frac` is SURVEY 8(d)'s algorithmic-bytes figure against the HBM peak",
+                "note": "kernel_ms is the kernel's CUDA-event time with one frame in flight and L2 flushed; the path is "
+                        "FP32-issue bound, not HBM bound (DESIGN.md 3.5): compulsory HBM traffic of the frame is ~0.1 GB; "
+                        "`frac` is SURVEY 8(d)'s algorithmic-bytes figure against the HBM peak",
                 "ncu": ncu}
         if ncu.get("warp_instructions") and clocks and clocks.get("sm_mhz"):
             roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * clocks["sm_mhz"] * 1e6 * dur_ms * 1e-3)
@@ -400,15 +454,31 @@ def run_b200(args):
                    "sample": f"best of 3 full frames of {args.config} on the host cores: Frame::Frame build "
                              f"{1e3 * min(t[1] for t in ts):.0f} ms + march {1e3 * min(t[2] for t in ts):.0f} ms "
                              "(depth image precomputed; neighbour search = stand-in for the un-vendored CompactNSearch fork)"}
+        if tiles_mode:
+            par = "tile-parallel 64x64 interleaved + NCCL gather"
+            l2 = "flushed between steps (512 MiB memset outside the timed events)"
+        else:
+            par = f"frame-parallel x{world}, {lanes} frames in flight per GPU (fr_seq_*)"
+            l2 = (f"inputs larger than L2: {n_frames} distinct frames of {12 * npart / 1e6:.1f} MB cycled "
+                  f"({n_frames * 12 * npart / 1e6:.0f} MB of particles, + {lanes} x {W * H * 40 / 1e6:.0f} MB of images); "
+                  "latency_ms_per_frame / stage_ms: L2 flushed between steps (512 MiB memset outside the timed events)")
+        e2e = {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * 4),
+               "path": ("fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(rgba), pinned host buffers" if tiles_mode else
+                        f"fr_seq_submit(host xyz -> host rgba), pinned host buffers, {lanes} frames in flight")}
+        if e2e_ref_ms is not None:
+            e2e["reference_protocol"] = {"value": units / (e2e_ref_ms * 1e-3), "ms_per_step": e2e_ref_ms,
+                                         "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
+                                         "path": "same, plus positions and normals copied back as RayMarcher::Prepare's host buffers expect"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if tiles_mode else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_string(args.config, npart, W, H),
-                       "step": "grid build + depth pre-pass + march/normals/shade, particles resident in HBM",
-                       "parallelism": ("tile-parallel 64x64 interleaved + NCCL gather" if tiles_mode else f"frame-parallel x{world}"),
-                       "l2": "flushed between steps (512 MiB memset outside the timed events)",
+                       "step": "grid build + depth pre-pass + march/normals/shade of one frame, particles resident in HBM",
+                       "parallelism": par, "l2": l2,
                        "normals": "fast (FMA + approximate reciprocal, ~1e-6)" if args.fast_normals else "bit-exact with the reference",
+                       "latency_ms_per_frame": serial_ms,
                        "stage_ms": tim, "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates",
                                                                          "neighbours", "skip_iterations", "early_exits")},
                        "covered_rays_per_s": cnt["covered_rays"] * (1 if tiles_mode else world) / (ms_step * 1e-3),
@@ -416,12 +486,7 @@ def run_b200(args):
                        "frames_per_s": (1 if tiles_mode else world) / (ms_step * 1e-3),
                        "wall_s_timed_region": wall},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
-                    "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * 4),
-                    "path": "fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(rgba), pinned host buffers",
-                    "reference_protocol": {"value": units / (e2e_ref_ms * 1e-3), "ms_per_step": e2e_ref_ms,
-                                           "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
-                                           "path": "same, plus positions and normals copied back as RayMarcher::Prepare's host buffers expect"}},
+            "e2e": e2e,
             "gpu_launches": int(kernel_launches_timed),
             "roofline": roof,
             "cpu_baseline": cpu,
@@ -435,11 +500,12 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()

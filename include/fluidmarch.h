@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FR_ABI_VERSION 2
+#define FR_ABI_VERSION 3
 
 enum
 {
@@ -215,6 +215,44 @@ int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, siz
 /* VK_KHR_external_semaphore_fd binary semaphores: the render waits on `wait_fd` (image available)
  * before writing and signals `signal_fd` when the image is complete; -1 = none */
 int fr_import_vk_semaphores_fd(fr_context* ctx, int wait_fd, int signal_fd);
+
+/* ---- frame sequences: the autoplay loop of AdvancedRenderer::Render (src/app/AdvancedRenderer/AdvancedRenderer.cpp:
+ *      275-298: wait for the march, then Frame++) with `lanes` frames in flight on one GPU -------------------------------
+ * One fr_context (own stream, images, scratch) and one host worker thread per lane; frame k is rendered on lane
+ * k % lanes by the same code path as fr_upload_frame -> fr_render_async -> fr_download, so results are bit-identical;
+ * kernels and PCIe copies of different frames overlap.  Calls on one fr_sequence come from one host thread. */
+typedef struct fr_sequence fr_sequence;
+
+typedef struct fr_seq_job
+{
+	const float* xyz;            /* n packed float3: Frame::m_Particles as partio delivers them (Dataset.cpp:292-303) */
+	uint64_t n;
+	float h, h_ext_mult;         /* particleRadius, particleRadiusMultiplier */
+	int32_t xyz_on_device;       /* 0: host memory (pinned for overlap), 1: device memory */
+	int32_t passes;              /* FR_PASS_* mask, 0 = FR_PASS_ALL */
+	/* host outputs (pinned for overlap), any may be NULL: as fr_download */
+	float* depth;
+	float* positions;
+	float* normals;
+	uint8_t* rgba;
+} fr_seq_job;
+
+int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** out);
+void fr_seq_destroy(fr_sequence* seq);
+int fr_seq_lanes(fr_sequence* seq);
+/* the context of a lane (counters, timings, frame info of the lane's last frame); do not render on it directly */
+int fr_seq_context(fr_sequence* seq, int lane, fr_context** out);
+/* applied to every lane (waits for the frames in flight) */
+int fr_seq_set_camera(fr_sequence* seq, const fr_camera* cam);
+int fr_seq_set_settings(fr_sequence* seq, const fr_settings* s);
+/* queues one frame; blocks while the frame's lane is still busy with frame ticket - lanes.  Returns the ticket
+ * (0, 1, 2, ...) or a negative error.  The job's buffers must stay valid until the ticket is done */
+int64_t fr_seq_submit(fr_sequence* seq, const fr_seq_job* job);
+int fr_seq_wait(fr_sequence* seq, int64_t ticket);      /* status of that frame */
+int fr_seq_drain(fr_sequence* seq);                     /* waits for everything; first error since the last drain */
+/* device time (CUDA events) of everything submitted between begin and end, milliseconds */
+int fr_seq_timer_begin(fr_sequence* seq);
+int fr_seq_timer_end(fr_sequence* seq, float* ms);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(fm):
     lib = C.CDLL(fm.LIB_PATH)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert fm.load().fr_abi_version() == 2
+    assert fm.load().fr_abi_version() == 3
 
 
 def test_struct_layouts(fm):

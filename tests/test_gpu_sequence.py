@@ -1,0 +1,111 @@
+"""fr_seq_*: several frames in flight on one GPU must give, frame for frame, the bits of the single-context path
+(and therefore of the oracle); tickets, drain, error propagation, timer."""
+import numpy as np
+import pytest
+
+import oracle_lib
+from conftest import golden_camera
+
+pytestmark = pytest.mark.gpu
+
+W, H = 320, 180
+
+
+def u(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def frames(fm, k):
+    return [fm.scenes.dam_break(6000 + 700 * i, t=0.3 + 0.1 * i) for i in range(k)]
+
+
+def setup(obj, cam, fm, **settings):
+    obj.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+    obj.set_settings(fm.VisualizationSettings(**settings))
+
+
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_sequence_matches_single_context_bit_for_bit(fm, gpu_ctx_factory, lanes):
+    cam = golden_camera("camera_close_16x9")
+    fs = frames(fm, 7)
+    ctx = gpu_ctx_factory(W, H)
+    setup(ctx, cam, fm)
+    want = []
+    for xyz in fs:
+        ctx.upload_frame(0, xyz, 0.1, 2.0)
+        ctx.render(fm.FR_PASS_ALL)
+        want.append(ctx.download())
+    seq = fm.Sequence(W, H, lanes=lanes)
+    try:
+        setup(seq, cam, fm)
+        jobs = [seq.submit(xyz, 0.1, 2.0, want=("depth", "positions", "normals", "rgba")) for xyz in fs]
+        assert [t for t, _ in jobs] == list(range(len(fs)))
+        for (t, out), (d, p, n, c) in zip(jobs, want):
+            seq.wait(t)
+            assert np.array_equal(u(out["depth"]), u(d))
+            assert np.array_equal(u(out["positions"]), u(p))
+            assert np.array_equal(u(out["normals"]), u(n))
+            assert np.array_equal(out["rgba"], c)
+        seq.drain()
+    finally:
+        seq.close()
+
+
+def test_sequence_frame_matches_oracle(fm, oracle):
+    cam = golden_camera("camera_close_16x9")
+    fs = frames(fm, 3)
+    seq = fm.Sequence(W, H, lanes=2)
+    try:
+        setup(seq, cam, fm)
+        jobs = [seq.submit(xyz, 0.1, 2.0, want=("depth", "positions", "normals")) for xyz in fs]
+        seq.drain()
+        xyz, (_, out) = fs[2], jobs[2]
+        f = oracle.frame(xyz, 0.1, 2.0)
+        depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
+        pos, nrm, *_ = f.march(W, H, oracle_lib.Settings(), cam["inv_proj_view"], cam["position"], depth)
+        assert np.array_equal(u(out["depth"]), u(depth))
+        assert np.array_equal(u(out["positions"]), u(pos))
+        assert np.array_equal(u(out["normals"]), u(nrm))
+    finally:
+        seq.close()
+
+
+def test_sequence_device_inputs_timer_and_lane_contexts(fm):
+    import torch
+    cam = golden_camera("camera_close_16x9")
+    fs = frames(fm, 4)
+    dev = [torch.from_numpy(f).cuda() for f in fs]
+    seq = fm.Sequence(W, H, lanes=2)
+    try:
+        setup(seq, cam, fm)
+        seq.timer_begin()
+        for k in range(8):
+            seq.submit_ptrs(dev[k % 4].data_ptr(), len(fs[k % 4]), 0.1, 2.0, on_device=True)
+        ms = seq.timer_end()
+        assert 0.0 < ms < 1000.0
+        # lane l rendered frames l, l + 2, ...: its context still holds the last of them
+        for lane in range(2):
+            c = seq.context(lane)
+            assert c.frame_info(0)["num_particles"] == len(fs[(6 + lane) % 4])
+            assert c.counters()["hit_rays"] > 100
+    finally:
+        seq.close()
+
+
+def test_sequence_reports_job_errors(fm):
+    cam = golden_camera("camera_close_16x9")
+    seq = fm.Sequence(W, H, lanes=2)
+    try:
+        setup(seq, cam, fm)
+        bad = np.full((10, 3), np.nan, np.float32)          # degenerate bounds -> FR_ERR_INVALID from the frame build
+        t, _ = seq.submit(bad)
+        with pytest.raises(fm.FluidMarchError, match="degenerate|bounds"):
+            seq.wait(t)
+        with pytest.raises(fm.FluidMarchError):
+            seq.drain()
+        seq.drain()                                           # the error is reported once
+        t, out = seq.submit(frames(fm, 1)[0])
+        seq.wait(t)
+        assert out["rgba"].any()
+    finally:
+        seq.close()
