@@ -92,10 +92,44 @@ __device__ __forceinline__ void prefetch_l1(const void* p)
 	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
 }
 
+#ifndef FM_LIST_CAP
+#define FM_LIST_CAP 32                    // in-range candidates a lane collects before it evaluates them
+#endif
+constexpr int kListCap = FM_LIST_CAP;
+constexpr int kListWords = kListCap * 32;  // shared-memory words per warp: list[k * 32 + lane]
+
+// one neighbour (d = p - x_j, l2 = |d|^2 < h^2) into the running sums, in the reference's list order
+template <bool DENS, bool GRAD, bool FAST>
+__device__ __forceinline__ void add_neighbour(const FrameView& f, float d0, float d1, float d2, float l2, float& density, f3& g,
+											  uint32_t& nn)
+{
+	if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
+	{
+		if (GRAD && !FAST) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+		if (GRAD && FAST)
+		{
+			float const c = spline_gradW_coeff_fast(f.kernel, l2, mulr(sqrtr(l2), f.kernel.h_inv));
+			g.x = fmaf(c, -d0, g.x); g.y = fmaf(c, -d1, g.y); g.z = fmaf(c, -d2, g.z);
+		}
+		if (DENS) density = addr(density, spline_W_inrange(f.kernel, l2));
+	}
+	nn++;
+}
+
 // density (DENS) and/or the un-normalised gradient sum (GRAD) at p: Dataset::GetNeighbors + the W / gradW
 // loops of RayMarcher.cpp:309-336, fused.  Accumulation order == the reference's neighbour order.
-template <bool DENS, bool GRAD, bool FAST = false>
-__device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc, bool on = true)
+//
+// Two passes per lane, like the reference's "collect the neighbour list, then sum over it" but without leaving the SM:
+// (1) the candidate walk -- load, distance, compare -- appends the indices of the in-range particles to the lane's
+// column of a shared-memory list; this loop has no expensive branch in it, so the loads of several candidates are in
+// flight at once and all lanes stay active; (2) the kernel sums run over the list.  With the sums inline in the walk
+// a warp spent half of its kernel-evaluation slots idle (ncu r01j: 15.4 of 32 lanes active in W / gradW, because
+// every lane has its own in-range subset of the shared candidates).  A lane whose list fills up evaluates it and
+// resumes the walk where it stopped, so any neighbour count works; the order of the sums is unchanged.
+// `list` = this lane's column (stride 32 words); WARP: the whole warp calls together (re-converge between the passes).
+template <bool DENS, bool GRAD, bool FAST = false, bool WARP = false>
+__device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad, LaneCounters& lc, uint32_t* __restrict__ list,
+											  bool on = true)
 {
 	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
 	int const ky = search_cell_of(f.search_inv, p.y) - f.kmin.y;
@@ -104,40 +138,46 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	float density = 0.0f;
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t nn = 0;
-	if (z0 <= z1 && on)
+	bool const walk = z0 <= z1 && on;
+	if (walk)
 	{
 		// all 18 range bounds in flight at once, then the candidate lines into L1 (128 B = 8 particles)
-		{
-			uint32_t pb[9], pe[9];
+		uint32_t pb[9], pe[9];
 #pragma unroll
-			for (int r = 0; r < 9; r++)
+		for (int r = 0; r < 9; r++)
+		{
+			int const x = kx + r / 3 - 1, y = ky + r % 3 - 1;
+			bool const ok = (unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y;
+			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+			pb[r] = ok ? __ldg(f.cell_start + base + z0) : 0u;
+			pe[r] = ok ? __ldg(f.cell_start + base + z1 + 1) : 0u;
+		}
+#pragma unroll
+		for (int r = 0; r < 9; r++)
+			for (uint32_t a = pb[r] & ~7u; a < pe[r]; a += 8u) prefetch_l1(f.sorted + a);
+	}
+	int r0 = 0;              // where the walk resumes after a full list: range r0, particle j0
+	uint32_t j0 = 0;
+	bool resume = false;
+	for (;;)
+	{
+		uint32_t cnt = 0;
+		bool full = false;
+		if (walk)
+		{
+#pragma unroll 1
+			for (int r = r0; r < 9 && !full; r++)
 			{
 				int const x = kx + r / 3 - 1, y = ky + r % 3 - 1;
-				bool const ok = (unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y;
-				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
-				pb[r] = ok ? __ldg(f.cell_start + base + z0) : 0u;
-				pe[r] = ok ? __ldg(f.cell_start + base + z1 + 1) : 0u;
-			}
-#pragma unroll
-			for (int r = 0; r < 9; r++)
-				for (uint32_t a = pb[r] & ~7u; a < pe[r]; a += 8u) prefetch_l1(f.sorted + a);
-		}
-#pragma unroll 1
-		for (int dx = -1; dx <= 1; dx++)
-		{
-			int const x = kx + dx;
-			if ((unsigned)x >= (unsigned)f.kdim.x) continue;
-#pragma unroll 1
-			for (int dy = -1; dy <= 1; dy++)
-			{
-				int const y = ky + dy;
-				if ((unsigned)y >= (unsigned)f.kdim.y) continue;
+				if ((unsigned)x >= (unsigned)f.kdim.x || (unsigned)y >= (unsigned)f.kdim.y) continue;
 				uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
 				uint32_t const b = __ldg(f.cell_start + base + z0);
 				uint32_t const e = __ldg(f.cell_start + base + z1 + 1);
-				lc.candidates += e - b;
+				uint32_t j = b;
+				if (resume && r == r0) j = j0;       // this range was counted when the walk first entered it
+				else lc.candidates += e - b;
 #pragma unroll 4
-				for (uint32_t j = b; j < e; j++)
+				for (; j < e; j++)
 				{
 					float4 const q = __ldg(f.sorted + j);
 					// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to right); l2 < r2
@@ -145,21 +185,28 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
 					if (l2 < f.kernel.h_squared)
 					{
-						if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
-						{
-							if (GRAD && !FAST) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
-							if (GRAD && FAST)
-							{
-								float const c = spline_gradW_coeff_fast(f.kernel, l2, mulr(sqrtr(l2), f.kernel.h_inv));
-								g.x = fmaf(c, -d0, g.x); g.y = fmaf(c, -d1, g.y); g.z = fmaf(c, -d2, g.z);
-							}
-							if (DENS) density = addr(density, spline_W_inrange(f.kernel, l2));
-						}
-						nn++;
+						if (cnt == (uint32_t)kListCap) { full = true; resume = true; r0 = r; j0 = j; break; }
+						list[cnt * 32u] = j;
+						cnt++;
 					}
 				}
 			}
 		}
+		if (WARP) __syncwarp();
+#pragma unroll 1
+		for (uint32_t k = 0; k < cnt; k++)
+		{
+			float4 const q = __ldg(f.sorted + list[k * 32u]);
+			float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
+			float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+			add_neighbour<DENS, GRAD, FAST>(f, d0, d1, d2, l2, density, g, nn);
+		}
+		if (WARP)
+		{
+			if (!__any_sync(0xffffffffu, full)) break;      // the warp stays together while any lane has more to walk
+			if (!full) r0 = 9;
+		}
+		else if (!full) break;
 	}
 	lc.neighbours += nn;
 	if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
@@ -347,9 +394,9 @@ template <> struct SampleState<true> { AnisoSample as; };
 #endif
 
 // WITH_GRAD (isotropic only): accumulate the gradient sum together with the density
-template <bool ANISO, bool WITH_GRAD, bool FAST>
+template <bool ANISO, bool WITH_GRAD, bool FAST, bool WARP = false>
 __device__ __forceinline__ float sample_density(const FrameView& f, const MarchParams& mp, f3 p, SampleState<ANISO>& st, LaneCounters& lc,
-												bool on = true)
+												uint32_t* __restrict__ list, bool on = true)
 {
 	if constexpr (ANISO)
 	{
@@ -362,12 +409,13 @@ __device__ __forceinline__ float sample_density(const FrameView& f, const MarchP
 	else
 	{
 		st.have_grad = WITH_GRAD;
-		return eval_density<true, WITH_GRAD, FAST>(f, p, st.grad, lc, on);
+		return eval_density<true, WITH_GRAD, FAST, WARP>(f, p, st.grad, lc, list, on);
 	}
 }
 
 template <bool ANISO, bool FAST>
-__device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleState<ANISO>& st, LaneCounters& lc)
+__device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleState<ANISO>& st, LaneCounters& lc,
+											  uint32_t* __restrict__ list)
 {
 	if constexpr (ANISO)
 	{
@@ -379,7 +427,7 @@ __device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleSt
 	}
 	else
 	{
-		if (!st.have_grad) eval_density<false, true, FAST>(f, p, st.grad, lc);
+		if (!st.have_grad) eval_density<false, true, FAST>(f, p, st.grad, lc, list);
 		return st.grad;
 	}
 }
@@ -561,7 +609,7 @@ __device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& m
 // the sample at `position` reached the threshold (RayMarcher.cpp:327-341 / :405-417): optional bisection, normal
 template <bool ANISO, bool FAST>
 __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams& mp, f3 prev, f3 position,
-										   SampleState<ANISO>& st, LaneCounters& lc, float4& P, float4& N)
+										   SampleState<ANISO>& st, LaneCounters& lc, uint32_t* __restrict__ list, float4& P, float4& N)
 {
 	// optional refinement (north_star item 3; not in the reference): bisect between the position before the last
 	// advance and the hit sample.  That position was never sampled when the hit is the ray's first sample or follows
@@ -571,19 +619,19 @@ __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams
 	if (mp.bisection_steps > 0)
 	{
 		SampleState<ANISO> tmp;
-		float const d_lo = sample_density<ANISO, false, false>(f, mp, lo, tmp, lc);
+		float const d_lo = sample_density<ANISO, false, false>(f, mp, lo, tmp, lc, list);
 		lc.steps++;
 		if (d_lo < mp.iso)
 			for (int b = 0; b < mp.bisection_steps; b++)
 			{
 				f3 const mid = scale3(add3(lo, hi), 0.5f);
-				float const dm = sample_density<ANISO, false, false>(f, mp, mid, tmp, lc);
+				float const dm = sample_density<ANISO, false, false>(f, mp, mid, tmp, lc, list);
 				lc.steps++;
 				if (dm >= mp.iso) { hi = mid; st = tmp; } else lo = mid;
 			}
 	}
 	P = make_float4(hi.x, hi.y, hi.z, 1.0f);
-	f3 const n = normalize3(sample_gradient<ANISO, FAST>(f, hi, st, lc));   // glm::normalize(normal) (RayMarcher.cpp:338)
+	f3 const n = normalize3(sample_gradient<ANISO, FAST>(f, hi, st, lc, list));   // glm::normalize(normal) (RayMarcher.cpp:338)
 	N = make_float4(n.x, n.y, n.z, 1.0f);
 	lc.hits++;
 }
@@ -639,6 +687,8 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f,
 {
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
+	__shared__ uint32_t s_list[ANISO ? 1 : 8 * kListWords];      // in-range candidate lists, one column per lane
+	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 0);
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
@@ -684,13 +734,13 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f,
 		// isotropic: the gradient sum rides along with the density on this sample (unless bisection moves the hit)
 		SampleState<ANISO> st;
 		float const density = (!ANISO && mp.bisection_steps == 0)
-			? sample_density<ANISO, true, FAST>(f, mp, position, st, lc, sample)
-			: sample_density<ANISO, false, false>(f, mp, position, st, lc, sample);
+			? sample_density<ANISO, true, FAST, true>(f, mp, position, st, lc, list, sample)
+			: sample_density<ANISO, false, false, true>(f, mp, position, st, lc, list, sample);
 		__syncwarp();
 		if (sample)
 		{
 			lc.steps++;
-			if (density >= mp.iso) finish_hit<ANISO, FAST>(f, mp, prev, position, st, lc, P, N);   // RayMarcher.cpp:327
+			if (density >= mp.iso) finish_hit<ANISO, FAST>(f, mp, prev, position, st, lc, list, P, N);   // RayMarcher.cpp:327
 			else if (mp.max_steps > 1)
 			{
 				// most rays that miss here are silhouette rays about to leave the grid: settle them now
@@ -719,6 +769,8 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_long(FrameView f, 
 {
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
+	__shared__ uint32_t s_list[ANISO ? 1 : 8 * kListWords];
+	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 2);
 	for (;;)
@@ -748,7 +800,7 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_long(FrameView f, 
 			}
 			LaneCounters tc = {};
 			SampleState<ANISO> st;
-			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc) : 0.0f;
+			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
 			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
 			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
 			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
@@ -757,7 +809,7 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_long(FrameView f, 
 				if (lane == kstar)
 				{
 					lc.skips += my_skips;
-					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, P, N);
+					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, list, P, N);
 				}
 				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
 				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
