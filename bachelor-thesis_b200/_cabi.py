@@ -59,7 +59,13 @@ class FrSeqJob(C.Structure):
     """fr_seq_job: one frame of a sequence (particles in, host images out)."""
     _fields_ = [("xyz", C.c_void_p), ("n", C.c_uint64), ("h", C.c_float), ("h_ext_mult", C.c_float),
                 ("xyz_on_device", C.c_int32), ("passes", C.c_int32),
-                ("depth", C.c_void_p), ("positions", C.c_void_p), ("normals", C.c_void_p), ("rgba", C.c_void_p)]
+                ("depth", C.c_void_p), ("positions", C.c_void_p), ("normals", C.c_void_p), ("rgba", C.c_void_p),
+                ("bgeo_path", C.c_char_p), ("bmp_path", C.c_char_p)]
+
+
+class FrBgeoInfo(C.Structure):
+    _fields_ = [("num_particles", C.c_uint64), ("record_words", C.c_uint32), ("compressed", C.c_int32),
+                ("data_offset", C.c_uint64), ("file_bytes", C.c_uint64)]
 
 
 # every symbol include/fluidmarch.h declares: (name, restype, argtypes)
@@ -97,6 +103,13 @@ SYMBOLS = [
     ("fr_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("fr_import_vk_memory_fd", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
     ("fr_import_vk_semaphores_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    ("fr_bgeo_probe", C.c_int, [C.c_char_p, C.POINTER(FrBgeoInfo)]),
+    ("fr_bgeo_read", C.c_int, [C.c_char_p, f32p, C.c_uint64, C.POINTER(C.c_uint64)]),
+    ("fr_bgeo_write", C.c_int, [C.c_char_p, f32p, C.c_uint64, C.c_int]),
+    ("fr_dataset_count", C.c_int, [C.c_char_p, C.c_char_p, C.c_int]),
+    ("fr_upload_frame_bgeo", C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_float, C.c_float]),
+    ("fr_encode_bmp", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    ("fr_write_bmp", C.c_int, [C.c_void_p, C.c_char_p]),
     ("fr_seq_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vpp]),
     ("fr_seq_destroy", None, [C.c_void_p]),
     ("fr_seq_lanes", C.c_int, [C.c_void_p]),

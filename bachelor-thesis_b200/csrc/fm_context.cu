@@ -192,6 +192,10 @@ void fr_destroy(fr_context* ctx)
 	for (auto& f : ctx->frames) free_frame(f);
 	free_images(ctx);
 	if (ctx->d_xyz) cudaFree(ctx->d_xyz);
+	if (ctx->d_raw) cudaFree(ctx->d_raw);
+	if (ctx->d_bmp) cudaFree(ctx->d_bmp);
+	if (ctx->h_bmp) cudaFreeHost(ctx->h_bmp);
+	if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
 	if (ctx->d_keys) cudaFree(ctx->d_keys);
 	if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);

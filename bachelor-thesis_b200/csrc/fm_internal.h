@@ -83,6 +83,10 @@ struct Context
 	uchar4* d_rgba_target = nullptr;   // where the colour pass writes (internal or external)
 	// scratch for frame builds
 	float* d_xyz = nullptr;           size_t cap_xyz = 0;       // staged input particles (n*3)
+	unsigned char* h_stage = nullptr; size_t cap_stage = 0;     // pinned: a particle file as read from disk (fm_bgeo.cu)
+	uint32_t* d_raw = nullptr;        size_t cap_raw = 0;       // the file's big-endian point block on the device
+	uchar4* d_bmp = nullptr;          size_t cap_bmp = 0;       // recording: B G R A rows bottom-up (fm_record.cu)
+	uint8_t* h_bmp = nullptr;         size_t cap_bmp_host = 0;  // pinned: header + pixels of one .bmp
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
 	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // counting sort output before the in-cell ordering
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
@@ -139,6 +143,8 @@ int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml);
 int march_occupancy_aniso(int* blocks_per_sm);
 int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float* points_host, size_t m, float* density,
 				float* grad, float* g9);
+// fm_bgeo.cu
+int stage_bgeo(Context* ctx, const char* path, size_t* n_out);
 // fm_query.cu
 int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size_t m, uint32_t* counts,
 					uint32_t* ids, size_t cap, bool ext);

@@ -31,6 +31,7 @@ struct Lane
 	std::condition_variable cv;
 	bool has_job = false, busy = false, quit = false;
 	fr_seq_job job{};
+	std::string path, bmp;         // copies of job.bgeo_path, job.bmp_path
 	int64_t ticket = -1;           // ticket of the job in `job` / being worked on
 	int64_t done_ticket = -1;      // last ticket finished on this lane
 	int done_status = FR_OK;
@@ -79,21 +80,26 @@ void lane_main(fr_sequence* seq, Lane* ln)
 	for (;;)
 	{
 		fr_seq_job job;
+		std::string path, bmp;
 		int64_t ticket;
 		{
 			std::unique_lock<std::mutex> lk(ln->m);
 			ln->cv.wait(lk, [&] { return ln->has_job || ln->quit; });
 			if (!ln->has_job && ln->quit) return;
 			job = ln->job;
+			path = ln->path;
+			bmp = ln->bmp;
 			ticket = ln->ticket;
 			ln->has_job = false;
 			ln->busy = true;
 		}
 		int rc;
-		if (job.xyz_on_device) rc = fr_build_frame_device(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
+		if (job.bgeo_path) rc = fr_upload_frame_bgeo(ln->ctx, 0, path.c_str(), job.h, job.h_ext_mult);   // decode on this lane
+		else if (job.xyz_on_device) rc = fr_build_frame_device(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
 		else rc = fr_upload_frame(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
 		if (rc == FR_OK) rc = fr_render_async(ln->ctx, job.passes ? job.passes : FR_PASS_ALL);
 		if (rc == FR_OK) rc = finish_job(ln, job);
+		if (rc == FR_OK && job.bmp_path) rc = fr_write_bmp(ln->ctx, bmp.c_str());      // recording (Renderer.cpp:400-409)
 		std::string err;
 		if (rc != FR_OK) err = fr_last_error();      // thread-local text of this worker
 		{
@@ -209,13 +215,15 @@ int fr_seq_set_settings(fr_sequence* seq, const fr_settings* s)
 
 int64_t fr_seq_submit(fr_sequence* seq, const fr_seq_job* job)
 {
-	if (!seq || !job || !job->xyz || job->n == 0) { set_error("fr_seq_submit: bad job"); return FR_ERR_INVALID; }
+	if (!seq || !job || (!job->bgeo_path && (!job->xyz || job->n == 0))) { set_error("fr_seq_submit: bad job"); return FR_ERR_INVALID; }
 	int64_t const ticket = seq->next_ticket++;
 	Lane* ln = seq->lanes[(size_t)(ticket % (int64_t)seq->lanes.size())];
 	{
 		std::unique_lock<std::mutex> lk(ln->m);
 		ln->cv.wait(lk, [&] { return !ln->has_job && !ln->busy; });    // the lane's previous frame (ticket - lanes) is out
 		ln->job = *job;
+		ln->path = job->bgeo_path ? job->bgeo_path : "";
+		ln->bmp = job->bmp_path ? job->bmp_path : "";
 		ln->ticket = ticket;
 		ln->has_job = true;
 	}

@@ -11,6 +11,7 @@ All compute happens in libfluidmarch.so on the GPU; nothing here has a CPU fallb
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -86,6 +87,10 @@ class Context:
 
     def upload_frame_ptr(self, frame: int, host_ptr: int, n: int, h: float = 0.1, h_ext_mult: float = 2.0):
         check(self.lib.fr_upload_frame(self.h, frame, C.c_void_p(host_ptr), n, h, h_ext_mult), "fr_upload_frame")
+
+    def upload_frame_bgeo(self, frame: int, path: str, h: float = 0.1, h_ext_mult: float = 2.0):
+        """the frame straight from a classic .bgeo file (decoded on the GPU)"""
+        check(self.lib.fr_upload_frame_bgeo(self.h, frame, os.fsencode(path), h, h_ext_mult), "fr_upload_frame_bgeo")
 
     def build_frame_device(self, frame: int, dev_ptr: int, n: int, h: float = 0.1, h_ext_mult: float = 2.0):
         check(self.lib.fr_build_frame_device(self.h, frame, C.c_void_p(dev_ptr), n, h, h_ext_mult),
@@ -179,6 +184,17 @@ class Context:
         check(self.lib.fr_device_images(self.h, C.byref(d), C.byref(p), C.byref(n), C.byref(c)), "fr_device_images")
         return dict(depth=d.value, positions=p.value, normals=n.value, rgba=c.value)
 
+    def encode_bmp(self) -> bytes:
+        """the colour image of the last render as the reference's screenshot file (Renderer::_Screenshot)"""
+        n = C.c_size_t()
+        check(self.lib.fr_encode_bmp(self.h, None, 0, C.byref(n)), "fr_encode_bmp")
+        buf = np.zeros(n.value, np.uint8)
+        check(self.lib.fr_encode_bmp(self.h, buf.ctypes.data, n.value, C.byref(n)), "fr_encode_bmp")
+        return buf.tobytes()
+
+    def write_bmp(self, path: str):
+        check(self.lib.fr_write_bmp(self.h, os.fsencode(path)), "fr_write_bmp")
+
     def set_color_target(self, dev_ptr: int | None):
         check(self.lib.fr_set_color_target(self.h, C.c_void_p(dev_ptr) if dev_ptr else None), "fr_set_color_target")
 
@@ -251,6 +267,34 @@ class Context:
         return int(bad.value)
 
 
+def bgeo_probe(path: str) -> dict:
+    """header of a classic .bgeo file (fr_bgeo_probe)"""
+    info = abi.FrBgeoInfo()
+    check(abi.load().fr_bgeo_probe(os.fsencode(path), C.byref(info)), "fr_bgeo_probe")
+    return {n: int(getattr(info, n)) for n, _ in info._fields_}
+
+
+def bgeo_read(path: str) -> np.ndarray:
+    """positions of a classic .bgeo file as (N, 3) float32 -- what Dataset::ReadFile keeps (reference Dataset.cpp:292-306)"""
+    lib = abi.load()
+    n = C.c_uint64()
+    check(lib.fr_bgeo_read(os.fsencode(path), None, 0, C.byref(n)), "fr_bgeo_read")
+    xyz = np.zeros((int(n.value), 3), np.float32)
+    if n.value:
+        check(lib.fr_bgeo_read(os.fsencode(path), _ptr(xyz, abi.f32p), n.value, C.byref(n)), "fr_bgeo_read")
+    return xyz
+
+
+def bgeo_write(path: str, xyz, compressed: bool = False):
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    check(abi.load().fr_bgeo_write(os.fsencode(path), _ptr(xyz, abi.f32p), xyz.shape[0], 1 if compressed else 0), "fr_bgeo_write")
+
+
+def dataset_count(prefix: str, suffix: str, count: int = -1) -> int:
+    """files <prefix>1<suffix>, <prefix>2<suffix>, ... that exist (Dataset::Dataset, reference Dataset.cpp:186-203)"""
+    return int(abi.load().fr_dataset_count(os.fsencode(prefix), os.fsencode(suffix), count))
+
+
 class _LaneContext(Context):
     """A lane's context inside a Sequence: owned by the sequence, read-only use (counters, timings, frame info)."""
 
@@ -297,9 +341,11 @@ class Sequence:
         check(self.lib.fr_seq_set_settings(self.h, C.byref(cs)), "fr_seq_set_settings")
 
     def submit_ptrs(self, xyz_ptr: int, n: int, h: float = 0.1, h_ext_mult: float = 2.0, on_device: bool = False,
-                    passes: int = FR_PASS_ALL, depth: int = 0, positions: int = 0, normals: int = 0, rgba: int = 0) -> int:
-        job = abi.FrSeqJob(xyz_ptr, n, h, h_ext_mult, 1 if on_device else 0, passes, depth or None, positions or None,
-                           normals or None, rgba or None)
+                    passes: int = FR_PASS_ALL, depth: int = 0, positions: int = 0, normals: int = 0, rgba: int = 0,
+                    bgeo_path: str | None = None, bmp_path: str | None = None) -> int:
+        job = abi.FrSeqJob(xyz_ptr or None, n, h, h_ext_mult, 1 if on_device else 0, passes, depth or None, positions or None,
+                           normals or None, rgba or None, os.fsencode(bgeo_path) if bgeo_path else None,
+                           os.fsencode(bmp_path) if bmp_path else None)
         t = self.lib.fr_seq_submit(self.h, C.byref(job))
         if t < 0:
             check(int(t), "fr_seq_submit")
@@ -315,6 +361,16 @@ class Sequence:
         t = self.submit_ptrs(xyz.ctypes.data, xyz.shape[0], h, h_ext_mult, False, passes,
                              **{k: v.ctypes.data for k, v in out.items()})
         self._keep[t] = (xyz, out)
+        return t, out
+
+    def submit_file(self, path: str, h: float = 0.1, h_ext_mult: float = 2.0, want=("rgba",), passes: int = FR_PASS_ALL):
+        """a frame from a .bgeo file, read and decoded on the lane that renders it"""
+        H, W = self.height, self.width
+        shapes = dict(depth=((H, W), np.float32), positions=((H, W, 4), np.float32), normals=((H, W, 4), np.float32),
+                      rgba=((H, W, 4), np.uint8))
+        out = {k: np.zeros(*shapes[k]) for k in want}
+        t = self.submit_ptrs(0, 0, h, h_ext_mult, False, passes, bgeo_path=path, **{k: v.ctypes.data for k, v in out.items()})
+        self._keep[t] = (None, out)
         return t, out
 
     def wait(self, ticket: int):

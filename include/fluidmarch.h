@@ -216,6 +216,35 @@ int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, siz
  * before writing and signals `signal_fd` when the image is complete; -1 = none */
 int fr_import_vk_semaphores_fd(fr_context* ctx, int wait_fd, int signal_fd);
 
+/* ---- particle files: Dataset::Dataset's file loop, Partio::read and Dataset::ReadFile (src/app/Dataset.cpp:169-227,
+ *      292-306; classic .bgeo version 5, vendor/partio/src/io/BGEO.cpp:200-290, optionally gzip'd) ----------------------- */
+typedef struct fr_bgeo_info
+{
+	uint64_t num_particles;
+	uint32_t record_words;       /* 32-bit words per point record: x y z w + the file's other point attributes */
+	int32_t compressed;          /* 1: the file is a gzip member */
+	uint64_t data_offset;        /* byte offset of the point block in the (uncompressed) file */
+	uint64_t file_bytes;         /* size on disk */
+} fr_bgeo_info;
+int fr_bgeo_probe(const char* path, fr_bgeo_info* out);
+/* positions ("position" attribute, what Dataset::ReadFile keeps) as packed float3 into host memory; xyz may be NULL
+ * to query *n only */
+int fr_bgeo_read(const char* path, float* xyz, uint64_t capacity, uint64_t* n);
+/* writes a positions-only file, byte for byte what partio's writeBGEO emits for such a particle set */
+int fr_bgeo_write(const char* path, const float* xyz, uint64_t n, int compressed);
+/* number of files <prefix>1<suffix>, <prefix>2<suffix>, ... that exist, at most count (count < 0: no limit) */
+int fr_dataset_count(const char* prefix, const char* suffix, int count);
+/* fr_upload_frame straight from a file: the point block goes to the GPU as it lies in the file, the big-endian
+ * swap and the record -> packed xyz gather are a kernel in front of the frame build */
+int fr_upload_frame_bgeo(fr_context* ctx, int frame, const char* path, float h, float h_ext_mult);
+
+/* ---- recording: Renderer::_Screenshot (src/engine/renderer/Renderer.cpp:326-415: swapchain -> linear image -> host
+ *      R/B swizzle -> stbi_write_bmp(name, W, H, 4, data)), once per frame while g_Recording (AdvancedRenderer.cpp:283-297)
+ * The colour image of the last render as that .bmp, byte for byte what stb_image_write emits for the same pixels
+ * (file header + BITMAPV4HEADER, 32 bpp BI_BITFIELDS, rows bottom-up, B G R A); swizzle + flip run on the device. */
+int fr_encode_bmp(fr_context* ctx, uint8_t* out, size_t capacity, size_t* bytes);   /* out may be NULL: *bytes only */
+int fr_write_bmp(fr_context* ctx, const char* path);
+
 /* ---- frame sequences: the autoplay loop of AdvancedRenderer::Render (src/app/AdvancedRenderer/AdvancedRenderer.cpp:
  *      275-298: wait for the march, then Frame++) with `lanes` frames in flight on one GPU -------------------------------
  * One fr_context (own stream, images, scratch) and one host worker thread per lane; frame k is rendered on lane
@@ -235,6 +264,9 @@ typedef struct fr_seq_job
 	float* positions;
 	float* normals;
 	uint8_t* rgba;
+	const char* bgeo_path;       /* non-NULL: the frame is this particle file (fr_upload_frame_bgeo on the lane's worker:
+	                                files of different lanes are read and decoded in parallel); xyz / n are ignored */
+	const char* bmp_path;        /* non-NULL: the finished frame is also written there as fr_write_bmp does (recording) */
 } fr_seq_job;
 
 int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** out);

@@ -25,6 +25,13 @@
 
 #include <chrono>
 #include <thread>
+#include <Partio.h>
+// the vendored copy calls MSVC's two-argument-template sprintf_s in its .hdr writer (not on this path)
+#define sprintf_s(buf, ...) snprintf(buf, sizeof(buf), __VA_ARGS__)
+#define STB_IMAGE_WRITE_IMPLEMENTATION
+#define STB_IMAGE_WRITE_STATIC
+#include <stb_image_write.h>   // the reference's vendored copy (vendor/stb_image)
+#undef sprintf_s
 
 RefExtentStub& RefExtentStub::GetInstance()
 {
@@ -60,7 +67,7 @@ constexpr size_t kLocalsBytes = 256 * 1024;
 
 extern "C" {
 
-int ref_abi_version() { return 2; }
+int ref_abi_version() { return 4; }
 
 // ---- kernels (Kernel.cpp) ----------------------------------------------------------------
 float ref_W(float h, const float* r)
@@ -343,5 +350,58 @@ void ref_frame_particles_ext(void* p, int f, float* out_xyz)
 }
 
 int ref_hardware_threads() { return int(std::thread::hardware_concurrency()); }
+
+// ---- screenshot file: the save step of Renderer::_Screenshot (Renderer.cpp:400-409) after its R/B swizzle, i.e.
+// stbi_write_bmp(filename, W, H, 4, rgba) with the reference's vendored stb_image_write
+int ref_write_bmp(const char* path, int w, int h, const unsigned char* rgba)
+{
+	return stbi_write_bmp(path, w, h, 4, rgba);
+}
+
+// ---- particle files through the reference's vendored partio (Dataset.cpp:209-220, 292-306) -------------------------
+// positions of a file exactly as Dataset::ReadFile takes them (before Frame::BuildSearch permutes them); returns the
+// particle count or -1
+long ref_partio_read(const char* path, float* out_xyz, size_t cap)
+{
+	Partio::ParticlesDataMutable* file = Partio::read(path);
+	if (!file) return -1;
+	Partio::ParticleAttribute attr;
+	file->attributeInfo("position", attr);
+	long const n = file->numParticles();
+	for (long i = 0; i < n && size_t(i) < cap; i++)
+		std::memcpy(out_xyz + 3 * i, file->data<float>(attr, int(i)), 12);
+	file->release();
+	return n;
+}
+
+// writes a file with partio's own writer.  extras: bit 0 = "velocity" (vector 3), bit 1 = "id" (int 1),
+// bit 2 = "density" (float 1) in front of everything else, bit 3 = an indexed-string attribute "kind"
+int ref_partio_write(const char* path, const float* xyz, size_t n, int extras, int compressed)
+{
+	Partio::ParticlesDataMutable* p = Partio::create();
+	Partio::ParticleAttribute dens, pos, vel, id, kind;
+	if (extras & 4) dens = p->addAttribute("density", Partio::FLOAT, 1);
+	pos = p->addAttribute("position", Partio::VECTOR, 3);
+	if (extras & 1) vel = p->addAttribute("velocity", Partio::VECTOR, 3);
+	if (extras & 2) id = p->addAttribute("id", Partio::INT, 1);
+	if (extras & 8)
+	{
+		kind = p->addAttribute("kind", Partio::INDEXEDSTR, 1);
+		p->registerIndexedStr(kind, "fluid");
+		p->registerIndexedStr(kind, "boundary-particle");
+	}
+	p->addParticles(int(n));
+	for (size_t i = 0; i < n; i++)
+	{
+		std::memcpy(p->dataWrite<float>(pos, int(i)), xyz + 3 * i, 12);
+		if (extras & 1) { float* v = p->dataWrite<float>(vel, int(i)); v[0] = float(i); v[1] = -1.5f; v[2] = xyz[3 * i] * 2.0f; }
+		if (extras & 2) p->dataWrite<int>(id, int(i))[0] = int(i) * 7 + 1;
+		if (extras & 4) p->dataWrite<float>(dens, int(i))[0] = 1000.0f + float(i);
+		if (extras & 8) p->dataWrite<int>(kind, int(i))[0] = int(i & 1);
+	}
+	Partio::write(path, *p, compressed != 0);
+	p->release();
+	return 0;
+}
 
 }  // extern "C"

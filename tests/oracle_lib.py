@@ -294,6 +294,14 @@ class Ref:
         L.ref_hardware_threads.restype = C.c_int
         L.ref_abi_version.restype = C.c_int
         self.has_aniso = L.ref_abi_version() >= 2
+        self.has_partio = L.ref_abi_version() >= 3
+        self.has_bmp = L.ref_abi_version() >= 4
+        if self.has_bmp:
+            L.ref_write_bmp.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p]
+        if self.has_partio:
+            L.ref_partio_read.restype = C.c_long
+            L.ref_partio_read.argtypes = [C.c_char_p, f32p, C.c_size_t]
+            L.ref_partio_write.argtypes = [C.c_char_p, f32p, C.c_size_t, C.c_int, C.c_int]
         if self.has_aniso:
             L.ref_eigen3.argtypes = [f32p, f32p, f32p]
             L.ref_wpca.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_int, f32p, f32p, C.c_uint32, f32p]
@@ -305,6 +313,25 @@ class Ref:
             L.ref_cubic_W.restype = C.c_float
             L.ref_cubic_W.argtypes = [C.c_float, f32p]
             L.ref_frame_particles_ext.argtypes = [C.c_void_p, C.c_int, f32p]
+
+    def write_bmp(self, path, rgba):
+        """stbi_write_bmp(path, W, H, 4, rgba) of the reference's vendored stb (Renderer.cpp:400-409)"""
+        rgba = np.ascontiguousarray(rgba, np.uint8)
+        h, w = rgba.shape[:2]
+        return self.lib.ref_write_bmp(os.fsencode(path), w, h, rgba.ctypes.data)
+
+    def partio_read(self, path):
+        """positions of a particle file through the reference's vendored partio (Dataset.cpp:209-220, 292-306)"""
+        n = self.lib.ref_partio_read(os.fsencode(path), None, 0)
+        if n < 0:
+            return None
+        out = np.zeros((n, 3), np.float32)
+        self.lib.ref_partio_read(os.fsencode(path), _fp(out), n)
+        return out
+
+    def partio_write(self, path, xyz, extras=0, compressed=False):
+        xyz = _f32(xyz).reshape(-1, 3)
+        self.lib.ref_partio_write(os.fsencode(path), _fp(xyz), xyz.shape[0], extras, 1 if compressed else 0)
 
     def eigen3(self, c9):
         c9 = _f32(c9).reshape(9)

@@ -5,11 +5,11 @@ cd "$(dirname "$0")/.."
 NAME=$1; EXTRA=$2
 D=build_variants/$NAME; mkdir -p $D
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $EXTRA"
-for f in fm_context fm_grid fm_depth fm_march fm_query fm_sequence; do
+for f in fm_context fm_grid fm_depth fm_march fm_query fm_sequence fm_bgeo fm_record; do
   /usr/local/cuda/bin/nvcc $FLAGS -c bachelor-thesis_b200/csrc/$f.cu -o $D/$f.o &
 done
 /usr/local/cuda/bin/nvcc $FLAGS -fmad=false -DFM_NO_FMAD -c bachelor-thesis_b200/csrc/fm_aniso.cu -o $D/fm_aniso.o &
 wait
-/usr/local/cuda/bin/nvcc -shared -o $D/libfluidmarch.so $D/*.o -lpthread
+/usr/local/cuda/bin/nvcc -shared -o $D/libfluidmarch.so $D/*.o -lpthread -lz
 rm -f $D/*.o
 echo built $D/libfluidmarch.so
