@@ -18,12 +18,13 @@
 //                spread over all 148 SMs no matter where the fluid sits on screen.  Warp = one 8x4 tile,
 //                lanes = rays.  The rays of a tile are ~1 cell apart (pixel footprint at the default camera
 //                distance ~ h/10), so the 9 contiguous particle ranges each lane walks are the same
-//                addresses across the warp: every LDG.128 of a candidate is a single-sector broadcast.  Before
-//                a lane walks its 27 cells it issues all 18 range loads and L1 prefetches of the candidate
-//                lines at once, so the walk itself runs out of L1.  No neighbour list is materialised; the
-//                d^2 < h^2 test and the kernel sums run inline in the reference's accumulation order (see
-//                fm_common.cuh: FrameView).  The gradient sum of the normal is accumulated together with the
-//                density on a ray's first sample (where ~95% of the rays seeded by the depth pre-pass hit).
+//                addresses across the warp: every LDG.128 of a candidate is a single-sector broadcast out of L1.
+//                No neighbour list leaves the SM: the d^2 < h^2 walk collects the in-range candidates of each
+//                lane in shared memory and the kernel sums run over that list in the reference's accumulation
+//                order (eval_density; fm_common.cuh: FrameView).  The gradient sum of the normal is accumulated
+//                together with the density on a ray's first sample (where ~94% of the rays seeded by the depth
+//                pre-pass hit).  (An explicit L1 prefetch of the candidate lines in front of the walk cost more
+//                issue slots and registers than it saved once the walk loop had no branch in it: r01p.)
 //
 // This header holds the device code of the march; it is compiled twice: fm_march.cu instantiates the isotropic
 // kernels (ANISO = false), fm_aniso.cu -- the one translation unit built with -fmad=false -DFM_NO_FMAD, because the
@@ -87,11 +88,13 @@ struct LaneCounters
 	uint32_t covered, hits, steps, skips, candidates, neighbours, early_exits, overflow;
 };
 
-__device__ __forceinline__ void prefetch_l1(const void* p)
-{
-	asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-}
-
+#ifndef FM_MARCH_MINBLOCKS
+#define FM_MARCH_MINBLOCKS 4              // resident 256-thread CTAs per SM k_march_first is compiled for (64 registers)
+#endif
+#ifndef FM_WALK_UNROLL
+#define FM_WALK_UNROLL 1
+#endif
+constexpr int kWalkUnroll = FM_WALK_UNROLL;   // candidates per iteration of the walk loop
 #ifndef FM_LIST_CAP
 #define FM_LIST_CAP 32                    // in-range candidates a lane collects before it evaluates them
 #endif
@@ -139,23 +142,6 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t nn = 0;
 	bool const walk = z0 <= z1 && on;
-	if (walk)
-	{
-		// all 18 range bounds in flight at once, then the candidate lines into L1 (128 B = 8 particles)
-		uint32_t pb[9], pe[9];
-#pragma unroll
-		for (int r = 0; r < 9; r++)
-		{
-			int const x = kx + r / 3 - 1, y = ky + r % 3 - 1;
-			bool const ok = (unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y;
-			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
-			pb[r] = ok ? __ldg(f.cell_start + base + z0) : 0u;
-			pe[r] = ok ? __ldg(f.cell_start + base + z1 + 1) : 0u;
-		}
-#pragma unroll
-		for (int r = 0; r < 9; r++)
-			for (uint32_t a = pb[r] & ~7u; a < pe[r]; a += 8u) prefetch_l1(f.sorted + a);
-	}
 	int r0 = 0;              // where the walk resumes after a full list: range r0, particle j0
 	uint32_t j0 = 0;
 	bool resume = false;
@@ -176,7 +162,7 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 				uint32_t j = b;
 				if (resume && r == r0) j = j0;       // this range was counted when the walk first entered it
 				else lc.candidates += e - b;
-#pragma unroll 4
+#pragma unroll (kWalkUnroll)
 				for (; j < e; j++)
 				{
 					float4 const q = __ldg(f.sorted + j);
@@ -680,7 +666,7 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 // phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
 // together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+__global__ void __launch_bounds__(256, ANISO ? 2 : FM_MARCH_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
