@@ -196,11 +196,28 @@ __global__ void __launch_bounds__(256) k_depth_bounds(uint32_t n, DepthParams dp
 	}
 }
 
-// pass 3: keep the particles that can still win a pixel of some tile they overlap (compacted, warp-aggregated)
+// coarse level of the tile bounds: the maximum over every 4 x 4 block of tiles.  A particle whose nearest possible
+// depth is not in front of that maximum cannot win any tile of the block.
+constexpr int kCoarse = 4;
+
+__global__ void __launch_bounds__(256) k_depth_coarse(const uint32_t* __restrict__ tile_bound, int tiles_x, int tiles_y,
+													  uint32_t* __restrict__ coarse, int cx, int cy)
+{
+	int const b = blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= cx * cy) return;
+	int const bx = b % cx, by = b / cx;
+	uint32_t m = 0u;
+	for (int y = by * kCoarse; y < min((by + 1) * kCoarse, tiles_y); y++)
+		for (int x = bx * kCoarse; x < min((bx + 1) * kCoarse, tiles_x); x++) m = max(m, __ldg(tile_bound + (size_t)y * tiles_x + x));
+	coarse[b] = m;
+}
+
+// pass 3: keep the particles that can still win a pixel of some tile they overlap (compacted, warp-aggregated).
+// Interior particles -- almost all of them -- are settled by the few coarse blocks their box touches.
 template <int T>
 __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, const uint4* __restrict__ splat_b,
-													const uint32_t* __restrict__ tile_bound,
-													uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
+													const uint32_t* __restrict__ tile_bound, const uint32_t* __restrict__ coarse,
+													int coarse_x, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t const lane = threadIdx.x & 31u;
@@ -211,13 +228,20 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, 
 		int const x0 = (int)(b.z & 0xffffu), x1 = (int)(b.z >> 16), y0 = (int)(b.w & 0xffffu), y1 = (int)(b.w >> 16);
 		if (x1 >= x0)
 		{
-			int const tx0 = x0 / T, ty0 = y0 / T, ntx = x1 / T - tx0 + 1, nty = y1 / T - ty0 + 1;
-			for (int ty = 0; ty < nty && !wins; ty++)
-			{
-				const uint32_t* row = tile_bound + (size_t)(ty0 + ty) * dp.tiles_x + tx0;
-				for (int tx = 0; tx < ntx; tx++)
-					if (b.y < __ldg(row + tx)) { wins = true; break; }
-			}
+			int const tx0 = x0 / T, ty0 = y0 / T, tx1 = x1 / T, ty1 = y1 / T;
+			for (int by = ty0 / kCoarse; by <= ty1 / kCoarse && !wins; by++)
+				for (int bx = tx0 / kCoarse; bx <= tx1 / kCoarse && !wins; bx++)
+				{
+					if (b.y >= __ldg(coarse + (size_t)by * coarse_x + bx)) continue;
+					int const fy0 = max(ty0, by * kCoarse), fy1 = min(ty1, by * kCoarse + kCoarse - 1);
+					int const fx0 = max(tx0, bx * kCoarse), fx1 = min(tx1, bx * kCoarse + kCoarse - 1);
+					for (int ty = fy0; ty <= fy1 && !wins; ty++)
+					{
+						const uint32_t* row = tile_bound + (size_t)ty * dp.tiles_x;
+						for (int tx = fx0; tx <= fx1; tx++)
+							if (b.y < __ldg(row + tx)) { wins = true; break; }
+					}
+				}
 		}
 	}
 	uint32_t const m = __ballot_sync(0xffffffffu, wins);
@@ -241,8 +265,10 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 	constexpr int TPR = 32 / LPT;                    // tiles per round
 	constexpr int RPT = PIX / LPT;                   // rounds per tile
 	uint32_t const lane = threadIdx.x & 31u;
+	uint32_t const count = __ldcg(n_survivors);
+	// (survivors are dealt out statically: one atomic ticket per warp costs more than the imbalance it removes,
+	// 9 472 warps on one counter -- r01q)
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
-	uint32_t const count = __ldg(n_survivors);
 	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += nwarps)
 	{
 		Splat s;
@@ -305,12 +331,15 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	uint32_t* const surv = ctx->d_survivors + 4;
 	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, dp, splat_a, splat_b, ctx->d_tile_bound);
 	if (refine_bounds) k_depth_bounds<T><<<blocks, 256, 0, st>>>(n, dp, splat_a, splat_b, ctx->d_tile_bound);
-	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, surv, n_surv);
+	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
+	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
+	k_depth_coarse<<<(cx * cy + 255) / 256, 256, 0, st>>>(ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy);
+	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv);
 	uint32_t const want = (n + 7u) / 8u;
 	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	k_depth_splat<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
 															 (uint32_t*)ctx->d_depth);
-	ctx->kernel_launches += refine_bounds ? 4 : 3;
+	ctx->kernel_launches += refine_bounds ? 5 : 4;
 	return FR_OK;
 }
 
@@ -356,7 +385,8 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	dp.tiles_y = (ctx->height + T - 1) / T;
 	uint32_t const ntiles = (uint32_t)dp.tiles_x * (uint32_t)dp.tiles_y;
 	int rc;
-	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles))) return rc;
+	size_t const ncoarse = (size_t)((dp.tiles_x + kCoarse - 1) / kCoarse) * ((dp.tiles_y + kCoarse - 1) / kCoarse);
+	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles + ncoarse))) return rc;   // tiles + coarse blocks
 	if ((rc = ensure_capacity(&ctx->d_splat, &ctx->cap_splat, 8 * f.n))) return rc;            // 2 x 16 B per particle
 	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
 	FM_CUDA(cudaMemsetAsync(ctx->d_survivors, 0, 16, ctx->stream));
