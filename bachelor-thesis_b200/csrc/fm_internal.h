@@ -123,7 +123,7 @@ int ensure_capacity(T** ptr, size_t* cap, size_t need)
 {
 	if (need <= *cap && *ptr) return FR_OK;
 	if (*ptr) { cudaFree(*ptr); *ptr = nullptr; *cap = 0; }
-	size_t const want = need + need / 8 + 64;
+	size_t const want = need + need / 4 + 64;     // head-room: a spreading fluid grows its tables frame by frame
 	FM_CUDA(cudaMalloc((void**)ptr, want * sizeof(T)));
 	*cap = want;
 	return FR_OK;

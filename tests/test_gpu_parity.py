@@ -199,6 +199,40 @@ def test_march_bit_exact_vs_oracle(fm, oracle, gpu_ctx_factory, n, W, H, cam_nam
     assert c["skip_iterations"] == cnt["skip_iterations"]
 
 
+# BASELINE config C5: smoothing-radius sweep (neighbour count ~20 .. ~120 at fixed dx) and step-size sweep with
+# MaxSteps scaled to keep MaxSteps * StepSize = 1.152, at a size the oracle finishes in seconds
+@pytest.mark.parametrize("ratio,step_div", [(1.68, 11), (1.93, 20), (2.29, 5), (2.67, 11), (3.06, 11), (3.06, 5), (3.9, 11)])
+def test_march_sweep_c5_bit_exact(fm, oracle, gpu_ctx_factory, ratio, step_div):
+    dx = 0.05
+    h = float(np.float32(ratio * dx))
+    step = float(np.float32(h / step_div))
+    max_steps = int(round(1.152 / step))
+    W, H = 240, 135
+    xyz = scenes.dam_break(24000, h=h, dx=dx)
+    cam = golden_camera("camera_close_16x9")
+    f = oracle.frame(xyz, h, 2.0)
+    depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
+    s = oracle_lib.Settings(step_size=step, max_steps=max_steps)
+    pos, nrm, band, steps, cnt = f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth)
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, h, 2.0)
+    set_cam(ctx, cam)
+    ctx.set_settings(fm.VisualizationSettings(StepSize=step, MaxSteps=max_steps))
+    ctx.render(fm.FR_PASS_DEPTH | fm.FR_PASS_MARCH)
+    gdepth, gpos, gnrm, _ = ctx.download(True, True, True, False)
+    c = ctx.counters()
+    assert np.array_equal(bits(gdepth), bits(depth))
+    assert c["covered_rays"] == cnt["covered_rays"] and c["hit_rays"] == cnt["hit_rays"] and c["hit_rays"] > 500
+    assert np.array_equal(bits(gpos), bits(pos))
+    assert np.array_equal(bits(gnrm), bits(nrm))
+    assert c["neighbour_overflow"] == 0
+    # the sweep is about the neighbour count: ~ (4/3) pi ratio^3 in the interior, about half of it at the surface
+    per_sample = c["neighbours"] / max(c["ray_steps"], 1)
+    assert 0.2 * 4.19 * ratio ** 3 < per_sample < 1.1 * 4.19 * ratio ** 3
+    if ratio >= 3.0:
+        assert per_sample > 40          # more than one shared-memory list (32 entries) per sample: the resume path ran
+
+
 def test_march_edge_cases(fm, oracle, gpu_ctx_factory):
     cam = golden_camera("camera_close_16x9")
     W, H = 61, 35                                                  # not a multiple of the 32x8 CTA footprint
