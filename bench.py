@@ -505,7 +505,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
-    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
+    ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()
