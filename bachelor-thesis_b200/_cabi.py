@@ -92,6 +92,9 @@ SYMBOLS = [
     ("fr_download", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("fr_device_images", C.c_int, [C.c_void_p, vpp, vpp, vpp, vpp]),
     ("fr_set_color_target", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("fr_ipc_export_color", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("fr_ipc_open_color_target", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("fr_ipc_close_color_target", C.c_int, [C.c_void_p]),
     ("fr_get_counters", C.c_int, [C.c_void_p, C.POINTER(FrCounters)]),
     ("fr_get_timings", C.c_int, [C.c_void_p, C.POINTER(FrTimings)]),
     ("fr_get_stream", C.c_int, [C.c_void_p, vpp]),

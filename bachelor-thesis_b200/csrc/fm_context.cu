@@ -192,6 +192,7 @@ void fr_destroy(fr_context* ctx)
 	for (auto& f : ctx->frames) free_frame(f);
 	free_images(ctx);
 	if (ctx->d_xyz) cudaFree(ctx->d_xyz);
+	if (ctx->peer_rgba) cudaIpcCloseMemHandle(ctx->peer_rgba);
 	if (ctx->d_raw) cudaFree(ctx->d_raw);
 	if (ctx->d_bmp) cudaFree(ctx->d_bmp);
 	if (ctx->h_bmp) cudaFreeHost(ctx->h_bmp);
@@ -490,6 +491,52 @@ int fr_set_color_target(fr_context* ctx, void* rgba_device)
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
 	ctx->d_rgba_target = rgba_device ? (uchar4*)rgba_device : ctx->d_rgba;
+	return FR_OK;
+}
+
+// ---- tile-parallel over peer memory ---------------------------------------------------------------------------
+// The presenting GPU exports its colour image; every other rank opens it and renders its own screen tiles straight
+// into it: the shading epilogue's stores travel over NVLink / NVSwitch, there is no separate gather.
+int fr_ipc_export_color(fr_context* ctx, fr_ipc_handle* out)
+{
+	FR_CHECK_CTX(ctx);
+	if (!out) { set_error("fr_ipc_export_color: null out"); return FR_ERR_INVALID; }
+	static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(fr_ipc_handle), "fr_ipc_handle too small");
+	cudaIpcMemHandle_t h;
+	FM_CUDA(cudaIpcGetMemHandle(&h, ctx->d_rgba));          // the internal image is its own cudaMalloc allocation
+	memset(out, 0, sizeof *out);
+	memcpy(out->bytes, &h, sizeof h);
+	return FR_OK;
+}
+
+int fr_ipc_open_color_target(fr_context* ctx, const fr_ipc_handle* handle)
+{
+	FR_CHECK_CTX(ctx);
+	if (!handle) { set_error("fr_ipc_open_color_target: null handle"); return FR_ERR_INVALID; }
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if (ctx->peer_rgba) { cudaIpcCloseMemHandle(ctx->peer_rgba); ctx->peer_rgba = nullptr; ctx->d_rgba_target = ctx->d_rgba; }
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle->bytes, sizeof h);
+	void* p = nullptr;
+	FM_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+	ctx->peer_rgba = p;
+	ctx->d_rgba_target = (uchar4*)p;
+	return FR_OK;
+}
+
+int fr_ipc_close_color_target(fr_context* ctx)
+{
+	FR_CHECK_CTX(ctx);
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if (ctx->peer_rgba)
+	{
+		FM_CUDA(cudaStreamSynchronize(ctx->stream));
+		FM_CUDA(cudaIpcCloseMemHandle(ctx->peer_rgba));
+		ctx->peer_rgba = nullptr;
+		ctx->d_rgba_target = ctx->d_rgba;
+	}
 	return FR_OK;
 }
 

@@ -45,7 +45,33 @@ struct DepthParams
 	float two_w_inv, two_h_inv, half_w, half_h;
 	int reverse;
 	int tiles_x, tiles_y;
+	// tile-parallel multi-GPU (fr_set_tile_partition): only pixels of this rank's screen tiles are needed.  The
+	// partition tile size is a multiple of 64 and every hi-Z tile / coarse block size divides 64, so a hi-Z tile or
+	// coarse block has exactly one owner
+	int part_rank, part_world, part_sw, part_sh, part_tiles_x;     // tile width / height = 1 << part_sw / part_sh
 };
+
+__device__ __forceinline__ bool tile_owned(const DepthParams& dp, int tx, int ty)
+{
+	return (uint32_t)(ty * dp.part_tiles_x + tx) % (uint32_t)dp.part_world == (uint32_t)dp.part_rank;
+}
+
+// does this rank own the partition tile that holds pixel (px, py)?
+__device__ __forceinline__ bool pixel_owned(const DepthParams& dp, int px, int py)
+{
+	if (dp.part_world <= 1) return true;
+	return tile_owned(dp, px >> dp.part_sw, py >> dp.part_sh);
+}
+
+// does the pixel box touch any partition tile of this rank?
+__device__ __forceinline__ bool box_owned(const DepthParams& dp, int x0, int y0, int x1, int y1)
+{
+	if (dp.part_world <= 1) return true;
+	for (int ty = y0 >> dp.part_sh; ty <= (y1 >> dp.part_sh); ty++)
+		for (int tx = x0 >> dp.part_sw; tx <= (x1 >> dp.part_sw); tx++)
+			if (tile_owned(dp, tx, ty)) return true;
+	return false;
+}
 
 // everything the fragment evaluation needs about one particle
 struct Splat
@@ -122,7 +148,8 @@ __global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ s
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	Splat s;
-	bool const live = splat_setup(dp, __ldg(sorted + i), s);
+	bool live = splat_setup(dp, __ldg(sorted + i), s);
+	if (live && !box_owned(dp, s.x0, s.y0, s.x1, s.y1)) live = false;      // cannot touch a pixel this rank renders
 	splat_a[i] = make_float4(s.z_c, s.ax, s.bx, s.ay);
 	splat_b[i] = make_uint4(__float_as_uint(s.by), s.near_bits, live ? ((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)) : 0xffffu,
 							live ? ((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)) : 0xffffu);
@@ -183,6 +210,7 @@ __global__ void __launch_bounds__(256) k_depth_bounds(uint32_t n, DepthParams dp
 		for (int tx = tx0; tx <= tx1; tx++)
 		{
 			int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
+			if (!pixel_owned(dp, px0, py0)) continue;
 			float const u0 = frag_u((float)px0, dp.two_w_inv, s.ax, s.bx);
 			float const u1 = frag_u((float)px1, dp.two_w_inv, s.ax, s.bx);
 			float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), vv);
@@ -232,6 +260,7 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, 
 			for (int by = ty0 / kCoarse; by <= ty1 / kCoarse && !wins; by++)
 				for (int bx = tx0 / kCoarse; bx <= tx1 / kCoarse && !wins; bx++)
 				{
+					if (!pixel_owned(dp, bx * kCoarse * T, by * kCoarse * T)) continue;
 					if (b.y >= __ldg(coarse + (size_t)by * coarse_x + bx)) continue;
 					int const fy0 = max(ty0, by * kCoarse), fy1 = min(ty1, by * kCoarse + kCoarse - 1);
 					int const fx0 = max(tx0, bx * kCoarse), fx1 = min(tx1, bx * kCoarse + kCoarse - 1);
@@ -285,7 +314,8 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 			int trow = (int)(((float)t + 0.5f) * inv_ntx);
 			int tcol = t - trow * pntx;
 			if (tcol < 0) { trow--; tcol += pntx; } else if (tcol >= pntx) { trow++; tcol -= pntx; }
-			bool const alive = t < ntiles && s.near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
+			bool const alive = t < ntiles && pixel_owned(dp, (ptx0 + tcol) * T, (pty0 + trow) * T) &&
+				s.near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
 			uint32_t tiles = __ballot_sync(0xffffffffu, alive);
 			int const my_tile_xy = ((pty0 + trow) << 16) | (ptx0 + tcol);
 
@@ -371,6 +401,16 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	float const adx = fabsf(d[0]), ady = fabsf(d[1]), adz = fabsf(d[2]);
 	float const dom = (adz >= adx && adz >= ady) ? d[2] : (adx >= ady ? d[0] : d[1]);
 	dp.reverse = dom < 0.0f ? 1 : 0;
+	// the pre-pass is partitioned with the march when every hi-Z tile / coarse block (<= 64 px) has one owner (tile
+	// sizes that are powers of two >= 64);
+	// otherwise every rank computes the whole depth image (same result on the pixels it uses)
+	auto pow2 = [](int v) { return v >= 64 && (v & (v - 1)) == 0; };
+	bool const part_ok = ctx->part_world > 1 && pow2(ctx->part_tw) && pow2(ctx->part_th);
+	dp.part_rank = ctx->part_rank; dp.part_world = part_ok ? ctx->part_world : 1;
+	dp.part_sw = 0; dp.part_sh = 0;
+	while ((1 << dp.part_sw) < ctx->part_tw) dp.part_sw++;
+	while ((1 << dp.part_sh) < ctx->part_th) dp.part_sh++;
+	dp.part_tiles_x = (ctx->width + ctx->part_tw - 1) / ctx->part_tw;
 
 	// tile size from the projected disc radius at the centre of the particle AABB (a tuning choice only:
 	// every T gives the same image)

@@ -81,6 +81,7 @@ struct Context
 	float4* d_nrm = nullptr;
 	uchar4* d_rgba = nullptr;
 	uchar4* d_rgba_target = nullptr;   // where the colour pass writes (internal or external)
+	void* peer_rgba = nullptr;         // another process's colour image opened through CUDA IPC (tile-parallel)
 	// scratch for frame builds
 	float* d_xyz = nullptr;           size_t cap_xyz = 0;       // staged input particles (n*3)
 	unsigned char* h_stage = nullptr; size_t cap_stage = 0;     // pinned: a particle file as read from disk (fm_bgeo.cu)

@@ -198,6 +198,19 @@ class Context:
     def set_color_target(self, dev_ptr: int | None):
         check(self.lib.fr_set_color_target(self.h, C.c_void_p(dev_ptr) if dev_ptr else None), "fr_set_color_target")
 
+    def ipc_export_color(self) -> bytes:
+        """64-byte handle of this context's colour image for the other processes of the box (fr_ipc_export_color)"""
+        buf = (C.c_ubyte * 64)()
+        check(self.lib.fr_ipc_export_color(self.h, buf), "fr_ipc_export_color")
+        return bytes(buf)
+
+    def ipc_open_color_target(self, handle: bytes):
+        buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+        check(self.lib.fr_ipc_open_color_target(self.h, buf), "fr_ipc_open_color_target")
+
+    def ipc_close_color_target(self):
+        check(self.lib.fr_ipc_close_color_target(self.h), "fr_ipc_close_color_target")
+
     def counters(self) -> dict:
         c = abi.FrCounters()
         check(self.lib.fr_get_counters(self.h, C.byref(c)), "fr_get_counters")

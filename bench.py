@@ -269,7 +269,7 @@ def run_b200(args):
     ctx = fm.Context(W, H, device=local)
     ctx.set_camera(*cam_args)
     if tiles_mode:
-        ctx.set_tile_partition(rank, world, 64, 64)
+        ctx.set_tile_partition(rank, world, args.tile, args.tile)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     d_frames = [torch.from_numpy(f).to(dev) for f in frames]                    # inputs resident in HBM
@@ -280,10 +280,17 @@ def run_b200(args):
     h_rgba = [torch.empty((H, W, 4), dtype=torch.uint8).pin_memory() for _ in range(n_out)]
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)               # > 126 MB L2
     mg = importlib.import_module("bachelor-thesis_b200.multigpu")
-    if tiles_mode:
+    peer_mode = tiles_mode and args.gather == "peer"
+    if peer_mode:
+        # the presenting GPU's colour image is every rank's colour target (CUDA IPC, NVLink peer stores): no gather
+        handle = [ctx.ipc_export_color() if rank == 0 else None]
+        dist.broadcast_object_list(handle, src=0)
+        if rank != 0:
+            ctx.ipc_open_color_target(handle[0])
+    elif tiles_mode:
         rgba_dev = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
         ctx.set_color_target(rgba_dev.data_ptr())
-        owner = torch.from_numpy(mg.tile_owner_map(W, H, world, 64, 64)).to(dev)
+        owner = torch.from_numpy(mg.tile_owner_map(W, H, world, args.tile, args.tile)).to(dev)
     ctx.set_settings(settings)
     torch.cuda.synchronize()
 
@@ -305,9 +312,12 @@ def run_b200(args):
         f = k % n_frames
         ctx.build_frame_device(0, d_frames[f].data_ptr(), n_actual[f], h, 2.0)
         ctx.render_async(fm.FR_PASS_ALL)
-        if tiles_mode:
+        if peer_mode:
             ctx.wait()
-            # real exchange step of the tile-parallel path: RGBA tiles -> presenting GPU over NVLink, merged there
+            dist.barrier()                   # every rank's tiles have landed in the presenter's image
+        elif tiles_mode:
+            ctx.wait()
+            # exchange step of the tile-parallel path as a collective: RGBA tiles -> presenting GPU, merged there
             mg.gather_tiles(rgba_dev, rank, world, owner, dst=0)
 
     def timed_serial(step_fn, steps, warmup, sampler=None, stage_log=None):
@@ -375,7 +385,12 @@ def run_b200(args):
 
     if tiles_mode:
         ms_step, wall, clocks, kernel_launches_timed = serial_ms, serial_wall, serial_clocks, serial_launches
-        ctx.set_color_target(None)
+        if peer_mode:
+            dist.barrier()
+            if rank != 0:
+                ctx.ipc_close_color_target()
+        else:
+            ctx.set_color_target(None)
 
         def e2e_tiles(k):
             ctx.upload_frame_ptr(0, h_frames[0].data_ptr(), n_actual[0], h, 2.0)
@@ -455,7 +470,8 @@ def run_b200(args):
                              f"{1e3 * min(t[1] for t in ts):.0f} ms + march {1e3 * min(t[2] for t in ts):.0f} ms "
                              "(depth image precomputed; neighbour search = stand-in for the un-vendored CompactNSearch fork)"}
         if tiles_mode:
-            par = "tile-parallel 64x64 interleaved + NCCL gather"
+            par = (f"tile-parallel {args.tile}x{args.tile} interleaved, every rank's shading epilogue stores its tiles into the presenting GPU's image "
+                   "over NVLink peer memory (CUDA IPC), barrier" if peer_mode else f"tile-parallel {args.tile}x{args.tile} interleaved + NCCL gather")
             l2 = "flushed between steps (512 MiB memset outside the timed events)"
         else:
             par = f"frame-parallel x{world}, {lanes} frames in flight per GPU (fr_seq_*)"
@@ -506,6 +522,9 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
     ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
+    ap.add_argument("--tile", type=int, default=128, help="--mode tiles: partition tile size in pixels (multiple of 64)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="--mode tiles: peer = ranks render into the presenter's image over NVLink peer memory; nccl = gather collective")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()

@@ -176,6 +176,14 @@ int fr_device_images(fr_context* ctx, void** depth, void** positions, void** nor
 /* render the colour image into caller-owned device memory instead (e.g. a torch tensor used as
  * an NCCL buffer, or imported Vulkan memory); NULL restores the internal image */
 int fr_set_color_target(fr_context* ctx, void* rgba_device);
+/* tile-parallel without a gather: the presenting process exports its internal colour image, every other process
+ * (one per GPU of the box) opens it as its colour target and renders its tiles (fr_set_tile_partition) straight into
+ * the presenter's memory over NVLink / NVSwitch peer access.  The presenter reads the image once all ranks have
+ * finished (fr_wait on each + a barrier of the host's choice).  The reference has no counterpart (single GPU). */
+typedef struct fr_ipc_handle { unsigned char bytes[64]; } fr_ipc_handle;
+int fr_ipc_export_color(fr_context* ctx, fr_ipc_handle* out);
+int fr_ipc_open_color_target(fr_context* ctx, const fr_ipc_handle* handle);
+int fr_ipc_close_color_target(fr_context* ctx);      /* back to the internal image */
 int fr_get_counters(fr_context* ctx, fr_counters* out);
 int fr_get_timings(fr_context* ctx, fr_timings* out);
 /* the CUDA stream all work of this context is ordered on (a cudaStream_t) */

@@ -369,10 +369,10 @@ def test_tile_partition_union_is_bit_identical(fm, gpu_ctx_factory):
         c2.render(fm.FR_PASS_ALL)
         part = c2.download()
         m = (tile % world) == rank
-        for a, p in zip(acc[1:], part[1:]):
+        for a, p in zip(acc, part):            # depth too: the pre-pass of a rank is complete on the pixels it owns
             a[m] = p[m]
         c2.close()
-    for a, b in zip(acc[1:], full[1:]):
+    for a, b in zip(acc, full):
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
 
 
