@@ -116,6 +116,7 @@ SYMBOLS = [
     ("fr_seq_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vpp]),
     ("fr_seq_destroy", None, [C.c_void_p]),
     ("fr_seq_lanes", C.c_int, [C.c_void_p]),
+    ("fr_seq_set_yielding", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_seq_context", C.c_int, [C.c_void_p, C.c_int, vpp]),
     ("fr_seq_set_camera", C.c_int, [C.c_void_p, C.POINTER(FrCamera)]),
     ("fr_seq_set_settings", C.c_int, [C.c_void_p, C.POINTER(FrSettings)]),
@@ -144,6 +145,8 @@ def load(path: str = LIB_PATH):
             "(nvcc, sm_100a).  There is no CPU fallback.")
     lib = C.CDLL(path)
     for name, restype, argtypes in SYMBOLS:
+        if os.environ.get("FLUIDMARCH_AB") and not hasattr(lib, name):
+            continue              # A/B runs against an older build (tools/ab_bench.sh); never set in tests or the bench
         fn = getattr(lib, name)   # AttributeError here == header/library mismatch
         fn.restype = restype
         fn.argtypes = argtypes

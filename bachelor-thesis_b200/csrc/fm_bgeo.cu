@@ -238,7 +238,7 @@ int stage_bgeo(Context* ctx, const char* path, size_t* n_out)
 	int rc = ensure_pinned(ctx, fsize + 16);
 	if (rc) { close(fd); return rc; }
 	// the previous upload from this staging buffer must have left it
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	size_t got = 0;
 	while (got < fsize)
 	{
@@ -386,8 +386,9 @@ int fr_upload_frame_bgeo(fr_context* ctx, int frame, const char* path, float h, 
 	if (rc) return rc;
 	FM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 	rc = fr_build_frame_device(ctx, frame, ctx->d_xyz, n, h, h_ext_mult);
+	if (rc == FR_OK && ctx->build_timed) ctx->build_timed = 2;      // upload_ms = file block copy + decode
 	float ms = 0.0f;
-	if (rc == FR_OK && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timings.upload_ms = ms;
+	if (rc == FR_OK && !ctx->blocking_sync && cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timings.upload_ms = ms;
 	return rc;
 }
 

@@ -6,6 +6,7 @@
 // fr_create fails with FR_ERR_NO_DEVICE.
 #include "fm_internal.h"
 
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -26,6 +27,59 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line)
 	g_error = buf;
 	cudaGetLastError();   // clear the sticky-free error state
 	return FR_ERR_CUDA;
+}
+
+// cuStreamWriteValue32: a stream memory operation -- executed by the front end when the stream gets there, no SM
+// and no copy engine involved, so it is not held up by other lanes' persistent kernels the way a signalling kernel
+// is.  Fetched through the runtime so the library does not link libcuda (it must load on machines without a driver).
+typedef int (*StreamWriteValue32Fn)(cudaStream_t, unsigned long long, uint32_t, unsigned int);
+static StreamWriteValue32Fn stream_write_value32()
+{
+	static StreamWriteValue32Fn fn = [] {
+		void* p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+		{
+			cudaGetLastError();
+			p = nullptr;
+		}
+		return (StreamWriteValue32Fn)p;
+	}();
+	return fn;
+}
+
+int stream_sync(Context* c)
+{
+	// the lanes of a sequence: a word in mapped pinned memory, written behind everything on the stream, polled
+	// without entering the driver
+	if (c->blocking_sync && c->h_sync_flag)
+	{
+		StreamWriteValue32Fn const write32 = stream_write_value32();
+		uint32_t const seq = ++c->sync_seq;
+		if (!write32 || write32(c->stream, (unsigned long long)(uintptr_t)c->d_sync_flag, seq, 0u) != 0)
+		{
+			FM_CUDA(cudaStreamSynchronize(c->stream));
+			return FR_OK;
+		}
+		volatile uint32_t* const flag = c->h_sync_flag;
+		uint32_t spins = 0;
+		while ((int32_t)(*flag - seq) < 0)
+		{
+			if ((++spins & 63u) == 0u)
+			{
+				sched_yield();
+				if ((spins & 0xfffffu) == 0u)       // every ~million polls: has the stream failed?
+				{
+					cudaError_t const e = cudaStreamQuery(c->stream);
+					if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "cudaStreamQuery", __FILE__, __LINE__);
+				}
+			}
+			else __builtin_ia32_pause();
+		}
+		return FR_OK;
+	}
+	FM_CUDA(cudaStreamSynchronize(c->stream));
+	return FR_OK;
 }
 
 static void free_frame(Frame& f)
@@ -75,12 +129,24 @@ static Frame* get_frame(Context* c, int frame, bool must_be_valid)
 	return &c->frames[frame];
 }
 
+// upload / grid build times of the last frame build, once its events have completed
+static void read_build_timings(Context* c)
+{
+	float ms = 0.0f;
+	if (c->build_timed == 2) { if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timings.upload_ms = ms; }
+	else if (c->build_timed == 1) c->timings.upload_ms = 0.0f;
+	if (c->build_timed && cudaEventElapsedTime(&ms, c->ev[2], c->ev[3]) == cudaSuccess) c->timings.grid_ms = ms;
+	c->build_timed = 0;
+}
+
 static int finish_pending(Context* c)
 {
 	if (c->render_pending)
 	{
-		FM_CUDA(cudaEventSynchronize(c->ev_done));
+		if (c->blocking_sync) { int const rc = stream_sync(c); if (rc) return rc; }     // ev_done is the last thing on the stream
+		else FM_CUDA(cudaEventSynchronize(c->ev_done));
 		c->render_pending = false;
+		read_build_timings(c);
 		float ms = 0.0f;
 		if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
 		if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) c->timings.march_ms = ms;
@@ -142,6 +208,9 @@ int fr_create(int device, int width, int height, fr_context** out)
 	{
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaHostAlloc((void**)&c->h_sync_flag, 64, cudaHostAllocMapped) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		*c->h_sync_flag = 0u;
+		if (cudaHostGetDevicePointer((void**)&c->d_sync_flag, (void*)c->h_sync_flag, 0) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		for (auto& ev : c->ev)
 			if (cudaEventCreate(&ev) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (rc) break;
@@ -175,7 +244,7 @@ int fr_resize(fr_context* ctx, int width, int height)
 {
 	FR_CHECK_CTX(ctx);
 	if (width <= 0 || height <= 0) { set_error("fr_resize: bad size"); return FR_ERR_INVALID; }
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	ctx->render_pending = false;
 	bool const external = ctx->d_rgba_target != ctx->d_rgba;
 	free_images(ctx);
@@ -214,6 +283,7 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->ext_mem) cudaDestroyExternalMemory(ctx->ext_mem);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	if (ctx->h_sync_flag) cudaFreeHost((void*)ctx->h_sync_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
 }
@@ -255,10 +325,11 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 	FM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
 	rc = build_frame(ctx, f, ctx->d_xyz, n, h, h_ext_mult);
 	if (rc) return rc;
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
-	float ms = 0.0f;
-	if (cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]) == cudaSuccess) ctx->timings.upload_ms = ms;
-	if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timings.grid_ms = ms;
+	ctx->build_timed = 2;
+	// (the copy out of xyz_host is complete: build_frame waits for the grid parameters behind it)
+	if (ctx->blocking_sync) return FR_OK;       // a lane goes straight on to the render; timings are read when the frame is done
+	{ int const src = stream_sync(ctx); if (src) return src; }
+	read_build_timings(ctx);
 	return FR_OK;
 }
 
@@ -272,10 +343,10 @@ int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, s
 	if ((rc = finish_pending(ctx))) return rc;
 	rc = build_frame(ctx, f, xyz_device, n, h, h_ext_mult);
 	if (rc) return rc;
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
-	float ms = 0.0f;
-	ctx->timings.upload_ms = 0.0f;
-	if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) ctx->timings.grid_ms = ms;
+	ctx->build_timed = 1;
+	if (ctx->blocking_sync) return FR_OK;
+	{ int const src = stream_sync(ctx); if (src) return src; }
+	read_build_timings(ctx);
 	return FR_OK;
 }
 
@@ -287,7 +358,7 @@ int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out)
 	if (!f) return FR_ERR_STATE;
 	unsigned long long occ = 0;
 	FM_CUDA(cudaMemcpyAsync(&occ, f->d_occupied, sizeof occ, cudaMemcpyDeviceToHost, ctx->stream));
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	memset(out, 0, sizeof *out);
 	out->num_particles = f->n;
 	out->h = f->h;
@@ -308,7 +379,7 @@ int fr_release_frame(fr_context* ctx, int frame)
 	FR_CHECK_CTX(ctx);
 	Frame* f = get_frame(ctx, frame, false);
 	if (!f) return FR_ERR_INVALID;
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	free_frame(*f);
 	return FR_OK;
 }
@@ -331,7 +402,7 @@ int fr_download_frame(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* 
 		words.resize((gcells + 31) / 32);
 		FM_CUDA(cudaMemcpyAsync(words.data(), f->d_occ_bits, words.size() * 4, cudaMemcpyDeviceToHost, s));
 	}
-	FM_CUDA(cudaStreamSynchronize(s));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	if (grid_flags)
 		for (size_t c = 0; c < gcells; c++) grid_flags[c] = (uint8_t)((words[c >> 5] >> (c & 31)) & 1u);
 	return FR_OK;
@@ -469,7 +540,7 @@ int fr_download(fr_context* ctx, float* depth, float* positions, float* normals,
 	if (normals) FM_CUDA(cudaMemcpyAsync(normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (rgba) FM_CUDA(cudaMemcpyAsync(rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
 	FM_CUDA(cudaEventRecord(ctx->ev[8], s));
-	FM_CUDA(cudaStreamSynchronize(s));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	float ms = 0.0f;
 	if (cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]) == cudaSuccess) ctx->timings.download_ms = ms;
 	return FR_OK;
@@ -532,7 +603,7 @@ int fr_ipc_close_color_target(fr_context* ctx)
 	if (rc) return rc;
 	if (ctx->peer_rgba)
 	{
-		FM_CUDA(cudaStreamSynchronize(ctx->stream));
+		{ int const src = stream_sync(ctx); if (src) return src; }
 		FM_CUDA(cudaIpcCloseMemHandle(ctx->peer_rgba));
 		ctx->peer_rgba = nullptr;
 		ctx->d_rgba_target = ctx->d_rgba;
@@ -547,7 +618,7 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
 	FM_CUDA(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(DeviceCounters), cudaMemcpyDeviceToHost, ctx->stream));
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	const DeviceCounters& d = *ctx->h_counters;
 	out->pixels = (uint64_t)ctx->width * (uint64_t)ctx->height;
 	out->covered_rays = d.covered_rays;
@@ -632,7 +703,7 @@ int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32
 	size_t const cells = (size_t)f->kdim_ext[0] * f->kdim_ext[1] * f->kdim_ext[2];
 	if (sorted_xyzi) FM_CUDA(cudaMemcpyAsync(sorted_xyzi, f->d_sorted_ext, f->n * 16, cudaMemcpyDeviceToHost, s));
 	if (cell_start) FM_CUDA(cudaMemcpyAsync(cell_start, f->d_cell_start_ext, (cells + 1) * 4, cudaMemcpyDeviceToHost, s));
-	FM_CUDA(cudaStreamSynchronize(s));
+	{ int const src = stream_sync(ctx); if (src) return src; }
 	for (int a = 0; a < 3; a++)
 	{
 		if (search_min) search_min[a] = f->kmin_ext[a];

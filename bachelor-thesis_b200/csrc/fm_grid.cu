@@ -447,7 +447,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	k_aabb<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_gp);
 	k_grid_params<<<1, 1, 0, s>>>(ctx->d_gp, h);
 	FM_CUDA(cudaMemcpyAsync(ctx->h_gp, ctx->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
-	FM_CUDA(cudaStreamSynchronize(s));   // table sizes depend on the AABB
+	{ int const src = stream_sync(ctx); if (src) return src; }   // table sizes depend on the AABB
 	f->gp = *ctx->h_gp;
 	const GridParams& gp = f->gp;
 	for (int a = 0; a < 3; a++)

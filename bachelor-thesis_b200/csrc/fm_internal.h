@@ -62,9 +62,21 @@ struct Context
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
+	// Host waits.  By default a thread waits inside the driver (cudaStreamSynchronize spins: lowest latency, best
+	// throughput while every waiting thread has a core of its own -- 0.296 ms per C2 frame at 6 lanes).  When the host
+	// is oversubscribed (8 ranks x 6 lanes on a 32-core box: 0.47 ms) the lanes of a sequence can instead append a
+	// stream memory operation (cuStreamWriteValue32) that writes a sequence number into mapped pinned memory and
+	// poll that word, yielding the core between polls (0.42 ms there; 0.33 ms on an idle host), fr_seq_set_yielding.
+	// Also tried (r01u): sleeping on a blocking-sync event (0.43 ms on an idle host: wake-up latency), polling
+	// cudaEventQuery (0.33), a signalling kernel (waits for an SM behind the other lanes' persistent kernels).
+	bool blocking_sync = false;
+	volatile uint32_t* h_sync_flag = nullptr;
+	uint32_t* d_sync_flag = nullptr;
+	uint32_t sync_seq = 0;
 	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
 	bool march_timed = false;
+	int build_timed = 0;               // 1 / 2: grid (and upload) events of a frame build wait to be read
 
 	fr_settings settings{};
 	bool have_settings = false;
@@ -111,6 +123,7 @@ struct Context
 };
 
 void set_error(const std::string& msg);
+int stream_sync(Context* c);          // waits for everything on c->stream (see Context::blocking_sync)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define FM_CUDA(expr)                                                            \

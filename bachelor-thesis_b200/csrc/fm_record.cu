@@ -68,8 +68,7 @@ int fr_encode_bmp(fr_context* ctx, uint8_t* out, size_t capacity, size_t* bytes)
 	FM_CUDA(cudaGetLastError());
 	FM_CUDA(cudaMemcpyAsync(out + kBmpHeader, ctx->d_bmp, (size_t)W * H * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	bmp_header(out, W, H);
-	FM_CUDA(cudaStreamSynchronize(ctx->stream));
-	return FR_OK;
+	return stream_sync(ctx);
 }
 
 int fr_write_bmp(fr_context* ctx, const char* path)

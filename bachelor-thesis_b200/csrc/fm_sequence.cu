@@ -12,6 +12,8 @@
 // bit-identical to fr_render_async on one context (tests/test_gpu_sequence.py).
 #include "fm_internal.h"
 
+#include <stdlib.h>
+
 #include <condition_variable>
 #include <mutex>
 #include <new>
@@ -70,8 +72,8 @@ int finish_job(Lane* ln, const fr_seq_job& job)
 	FM_CUDA(cudaEventRecord(ln->ev_end, s));
 	int const rc = fr_wait(ln->ctx);
 	if (rc) return rc;
-	FM_CUDA(cudaEventSynchronize(ln->ev_end));
-	return FR_OK;
+	if (!(job.depth || job.positions || job.normals || job.rgba)) return FR_OK;     // nothing behind the render
+	return stream_sync(ln->ctx);
 }
 
 void lane_main(fr_sequence* seq, Lane* ln)
@@ -169,6 +171,14 @@ void fr_seq_destroy(fr_sequence* seq)
 	}
 	if (seq->ev_begin) cudaEventDestroy(seq->ev_begin);
 	delete seq;
+}
+
+int fr_seq_set_yielding(fr_sequence* seq, int on)
+{
+	int const rc = fr_seq_drain(seq);
+	if (rc) return rc;
+	for (Lane* ln : seq->lanes) ln->ctx->blocking_sync = on != 0;
+	return FR_OK;
 }
 
 int fr_seq_lanes(fr_sequence* seq) { return seq ? (int)seq->lanes.size() : FR_ERR_INVALID; }

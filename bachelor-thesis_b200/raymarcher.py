@@ -340,6 +340,10 @@ class Sequence:
 
     __del__ = close
 
+    def set_yielding(self, on: bool):
+        """lane workers poll pinned memory and yield the core instead of spinning in the driver (oversubscribed hosts)"""
+        check(self.lib.fr_seq_set_yielding(self.h, 1 if on else 0), "fr_seq_set_yielding")
+
     def context(self, lane: int) -> Context:
         c = C.c_void_p()
         check(self.lib.fr_seq_context(self.h, lane, C.byref(c)), "fr_seq_context")

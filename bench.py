@@ -89,6 +89,9 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index = index
+        # NVML queries go through the driver and disturb concurrent kernel launches: at 1 kHz the pipelined arm
+        # (6 lanes launching ~120 kernels per frame time) became erratic (0.30 .. 0.66 ms per frame, r01u)
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "4")) * 1e-3
         self.sm, self.mx, self.reasons = [], [], set()
         self.running = False
         self.thread = None
@@ -125,7 +128,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 break
-            time.sleep(0.001)
+            time.sleep(self.period)
 
     def _poll_smi(self):
         while self.running:
@@ -255,7 +258,11 @@ def run_b200(args):
     cam = camera()
     cam_args = (cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
     tiles_mode = args.mode == "tiles" and world > 1
-    lanes = 1 if tiles_mode else max(1, args.lanes)
+    # frames in flight per GPU: every lane has a host worker that waits for its GPU work on a core of its own, so no
+    # more lanes than this rank's share of the host cores carries (8 ranks on a 32-core box: 3)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    cores = os.cpu_count() or 8
+    lanes = 1 if tiles_mode else max(1, args.lanes if args.lanes > 0 else min(6, max(2, cores // max(local_world, 1) - 1)))
     # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame).  Enough
     # distinct frames that the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush)
     n_frames = 1 if tiles_mode else max(4, min(24, -(-150_000_000 // (12 * n))))
@@ -353,7 +360,7 @@ def run_b200(args):
         timed_serial.launches = ctx.counters()["kernel_launches"] - launches_before
         return total_ms / steps, wall, clocks
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     stage_log = []
     ctx.wait()
     serial_ms, serial_wall, serial_clocks = timed_serial(device_step, args.steps, args.warmup,
@@ -494,7 +501,7 @@ def run_b200(args):
                        "step": "grid build + depth pre-pass + march/normals/shade of one frame, particles resident in HBM",
                        "parallelism": par, "l2": l2,
                        "normals": "fast (FMA + approximate reciprocal, ~1e-6)" if args.fast_normals else "bit-exact with the reference",
-                       "latency_ms_per_frame": serial_ms,
+                       "latency_ms_per_frame": serial_ms, "host_cores": cores,
                        "stage_ms": tim, "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates",
                                                                          "neighbours", "skip_iterations", "early_exits")},
                        "covered_rays_per_s": cnt["covered_rays"] * (1 if tiles_mode else world) / (ms_step * 1e-3),
@@ -516,12 +523,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
-    ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
+    ap.add_argument("--lanes", type=int, default=0,
+                    help="frames in flight per GPU (fr_seq_create); 0 = min(6, host cores per rank - 1); 1 = one frame at a time")
     ap.add_argument("--tile", type=int, default=128, help="--mode tiles: partition tile size in pixels (multiple of 64)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="--mode tiles: peer = ranks render into the presenter's image over NVLink peer memory; nccl = gather collective")

@@ -280,6 +280,10 @@ typedef struct fr_seq_job
 int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** out);
 void fr_seq_destroy(fr_sequence* seq);
 int fr_seq_lanes(fr_sequence* seq);
+/* how the lane workers wait for the GPU: 0 (default) inside the driver, one busy core per waiting lane -- fastest while
+ * (lanes + 1) x processes <= host cores; 1: poll a word in pinned memory and yield the core between polls, for
+ * oversubscribed hosts */
+int fr_seq_set_yielding(fr_sequence* seq, int on);
 /* the context of a lane (counters, timings, frame info of the lane's last frame); do not render on it directly */
 int fr_seq_context(fr_sequence* seq, int lane, fr_context** out);
 /* applied to every lane (waits for the frames in flight) */

@@ -24,8 +24,8 @@ def setup(obj, cam, fm, **settings):
     obj.set_settings(fm.VisualizationSettings(**settings))
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 3])
-def test_sequence_matches_single_context_bit_for_bit(fm, gpu_ctx_factory, lanes):
+@pytest.mark.parametrize("lanes,yielding", [(1, False), (2, False), (3, False), (3, True)])
+def test_sequence_matches_single_context_bit_for_bit(fm, gpu_ctx_factory, lanes, yielding):
     cam = golden_camera("camera_close_16x9")
     fs = frames(fm, 7)
     ctx = gpu_ctx_factory(W, H)
@@ -38,6 +38,7 @@ def test_sequence_matches_single_context_bit_for_bit(fm, gpu_ctx_factory, lanes)
     seq = fm.Sequence(W, H, lanes=lanes)
     try:
         setup(seq, cam, fm)
+        seq.set_yielding(yielding)          # how the lane workers wait for the GPU; results must not depend on it
         jobs = [seq.submit(xyz, 0.1, 2.0, want=("depth", "positions", "normals", "rgba")) for xyz in fs]
         assert [t for t, _ in jobs] == list(range(len(fs)))
         for (t, out), (d, p, n, c) in zip(jobs, want):
