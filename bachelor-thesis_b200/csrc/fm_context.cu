@@ -157,6 +157,12 @@ static int finish_pending(Context* c)
 			if (cudaEventElapsedTime(&ms, c->ev[11], c->ev[6]) == cudaSuccess) c->timings.march_long_ms = ms;
 		}
 	}
+	else if (c->build_timed)       // a frame build without a render behind it
+	{
+		int const rc = stream_sync(c);
+		if (rc) return rc;
+		read_build_timings(c);
+	}
 	return FR_OK;
 }
 
@@ -326,10 +332,9 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 	rc = build_frame(ctx, f, ctx->d_xyz, n, h, h_ext_mult);
 	if (rc) return rc;
 	ctx->build_timed = 2;
-	// (the copy out of xyz_host is complete: build_frame waits for the grid parameters behind it)
-	if (ctx->blocking_sync) return FR_OK;       // a lane goes straight on to the render; timings are read when the frame is done
-	{ int const src = stream_sync(ctx); if (src) return src; }
-	read_build_timings(ctx);
+	// The copy out of xyz_host is complete (build_frame waits for the grid parameters behind it); the rest of the
+	// build is left on the stream, so a render can be queued right behind it.  Its times are read when the host
+	// next waits for the stream (fr_wait / fr_download / fr_get_timings).
 	return FR_OK;
 }
 
@@ -344,10 +349,7 @@ int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, s
 	rc = build_frame(ctx, f, xyz_device, n, h, h_ext_mult);
 	if (rc) return rc;
 	ctx->build_timed = 1;
-	if (ctx->blocking_sync) return FR_OK;
-	{ int const src = stream_sync(ctx); if (src) return src; }
-	read_build_timings(ctx);
-	return FR_OK;
+	return FR_OK;                  // xyz_device must stay valid until the host next waits for this context
 }
 
 int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out)

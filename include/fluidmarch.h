@@ -138,9 +138,11 @@ void fr_host_free(void* p);
 /* ---- frames: Dataset::ReadFile -> Frames.emplace_back -> Frame::Frame (Dataset.cpp:9-24,292-306) - */
 /* xyz: n packed float3 (glm::vec3 AoS as partio delivers them).  Builds, on the device, the
  * neighbour search (Frame::BuildSearch), the AABB (ComputeAABB) and the occupancy grid
- * (BuildDensityGrid).  h = particleRadius, h_ext_mult = particleRadiusMultiplier (assets/config.yml:19-20). */
+ * (BuildDensityGrid).  h = particleRadius, h_ext_mult = particleRadiusMultiplier (assets/config.yml:19-20).
+ * Returns once xyz_host has been consumed; the rest of the build stays queued on the context's stream. */
 int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult);
-/* same, particles already resident in device memory (n packed float3) */
+/* same, particles already resident in device memory (n packed float3); the build is left on the context's stream:
+ * xyz_device must stay valid and unchanged until the host next waits for the context (fr_wait, fr_download, ...) */
 int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult);
 int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out);
 int fr_release_frame(fr_context* ctx, int frame);
