@@ -258,11 +258,10 @@ def run_b200(args):
     cam = camera()
     cam_args = (cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
     tiles_mode = args.mode == "tiles" and world > 1
-    # frames in flight per GPU: every lane has a host worker that waits for its GPU work on a core of its own, so no
-    # more lanes than this rank's share of the host cores carries (8 ranks on a 32-core box: 3)
+    # frames in flight per GPU; every lane has a host worker thread (see --wait)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     cores = os.cpu_count() or 8
-    lanes = 1 if tiles_mode else max(1, args.lanes if args.lanes > 0 else min(6, max(2, cores // max(local_world, 1) - 1)))
+    lanes = 1 if tiles_mode else max(1, args.lanes)
     # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame).  Enough
     # distinct frames that the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush)
     n_frames = 1 if tiles_mode else max(4, min(24, -(-150_000_000 // (12 * n))))
@@ -407,6 +406,9 @@ def run_b200(args):
         e2e_ref_ms = None
     else:
         seq = fm.Sequence(W, H, lanes=lanes, device=local)
+        # lane workers wait inside the driver unless the host is oversubscribed ((lanes + 1) threads per rank)
+        yielding = args.wait == "yield" or (args.wait == "auto" and (lanes + 1) * local_world > cores)
+        seq.set_yielding(yielding)
         seq.set_camera(*cam_args)
         seq.set_settings(settings)
 
@@ -481,7 +483,8 @@ def run_b200(args):
                    "over NVLink peer memory (CUDA IPC), barrier" if peer_mode else f"tile-parallel {args.tile}x{args.tile} interleaved + NCCL gather")
             l2 = "flushed between steps (512 MiB memset outside the timed events)"
         else:
-            par = f"frame-parallel x{world}, {lanes} frames in flight per GPU (fr_seq_*)"
+            par = (f"frame-parallel x{world}, {lanes} frames in flight per GPU (fr_seq_*), lane workers "
+                   f"{'poll pinned memory and yield' if yielding else 'wait in the driver'} ({cores} host cores)")
             l2 = (f"inputs larger than L2: {n_frames} distinct frames of {12 * npart / 1e6:.1f} MB cycled "
                   f"({n_frames * 12 * npart / 1e6:.0f} MB of particles, + {lanes} x {W * H * 40 / 1e6:.0f} MB of images); "
                   "latency_ms_per_frame / stage_ms: L2 flushed between steps (512 MiB memset outside the timed events)")
@@ -528,8 +531,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
-    ap.add_argument("--lanes", type=int, default=0,
-                    help="frames in flight per GPU (fr_seq_create); 0 = min(6, host cores per rank - 1); 1 = one frame at a time")
+    ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
+    ap.add_argument("--wait", default="auto", choices=["auto", "spin", "yield"], help="how lane workers wait for the GPU (fr_seq_set_yielding)")
     ap.add_argument("--tile", type=int, default=128, help="--mode tiles: partition tile size in pixels (multiple of 64)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="--mode tiles: peer = ranks render into the presenter's image over NVLink peer memory; nccl = gather collective")
