@@ -53,9 +53,7 @@ int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml)
 		k_march_first<true, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
 	else
 		k_march_first<false, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
-	FM_CUDA(cudaEventRecord(ctx->ev[11], st));
-	FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->first_candidates, &ctx->d_counters->candidates, 8, cudaMemcpyDeviceToDevice, st));
-	FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->queued_rays, ml.rq.ctl + 2, 4, cudaMemcpyDeviceToDevice, st));
+	FM_TIME(ctx, ctx->ev[11], st);
 	if (ml.fast_normals)
 		k_march_long<true, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters);
 	else

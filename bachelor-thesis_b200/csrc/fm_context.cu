@@ -132,6 +132,7 @@ static Frame* get_frame(Context* c, int frame, bool must_be_valid)
 // upload / grid build times of the last frame build, once its events have completed
 static void read_build_timings(Context* c)
 {
+	if (!c->stage_timing) { c->build_timed = 0; return; }
 	float ms = 0.0f;
 	if (c->build_timed == 2) { if (cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]) == cudaSuccess) c->timings.upload_ms = ms; }
 	else if (c->build_timed == 1) c->timings.upload_ms = 0.0f;
@@ -148,9 +149,9 @@ static int finish_pending(Context* c)
 		c->render_pending = false;
 		read_build_timings(c);
 		float ms = 0.0f;
-		if (cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
-		if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) c->timings.march_ms = ms;
-		if (c->march_timed)
+		if (c->stage_timing && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
+		if (c->stage_timing && cudaEventElapsedTime(&ms, c->ev[5], c->ev[6]) == cudaSuccess) c->timings.march_ms = ms;
+		if (c->march_timed && c->stage_timing)
 		{
 			if (cudaEventElapsedTime(&ms, c->ev[5], c->ev[10]) == cudaSuccess) c->timings.classify_ms = ms;
 			if (cudaEventElapsedTime(&ms, c->ev[10], c->ev[11]) == cudaSuccess) c->timings.march_first_ms = ms;
@@ -326,9 +327,9 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 	if (rc) return rc;
 	if ((rc = finish_pending(ctx))) return rc;
 	if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
-	FM_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+	FM_TIME(ctx, ctx->ev[0], ctx->stream);
 	FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, xyz_host, n * 12, cudaMemcpyHostToDevice, ctx->stream));
-	FM_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+	FM_TIME(ctx, ctx->ev[1], ctx->stream);
 	rc = build_frame(ctx, f, ctx->d_xyz, n, h, h_ext_mult);
 	if (rc) return rc;
 	ctx->build_timed = 2;
@@ -489,17 +490,17 @@ int fr_render_async(fr_context* ctx, int passes)
 		memset(&wp, 0, sizeof wp);
 		FM_CUDA(cudaWaitExternalSemaphoresAsync(&ctx->ext_wait, &wp, 1, s));
 	}
-	FM_CUDA(cudaEventRecord(ctx->ev[4], s));
+	FM_TIME(ctx, ctx->ev[4], s);
 	if (passes & FR_PASS_DEPTH)
 	{
 		if ((rc = launch_depth_prepass(ctx, *f))) return rc;
 		ctx->have_depth = true;
 	}
-	FM_CUDA(cudaEventRecord(ctx->ev[5], s));
+	FM_TIME(ctx, ctx->ev[5], s);
 	ctx->march_timed = (passes & (FR_PASS_MARCH | FR_PASS_SHADE)) != 0;
 	if (ctx->march_timed)
 		if ((rc = launch_march(ctx, *f, (passes & FR_PASS_MARCH) != 0, (passes & FR_PASS_SHADE) != 0))) return rc;
-	FM_CUDA(cudaEventRecord(ctx->ev[6], s));
+	FM_TIME(ctx, ctx->ev[6], s);
 	if (ctx->ext_signal)
 	{
 		cudaExternalSemaphoreSignalParams sp;
@@ -536,15 +537,15 @@ int fr_download(fr_context* ctx, float* depth, float* positions, float* normals,
 	if (rc) return rc;
 	cudaStream_t const s = ctx->stream;
 	size_t const npix = (size_t)ctx->width * ctx->height;
-	FM_CUDA(cudaEventRecord(ctx->ev[7], s));
+	FM_TIME(ctx, ctx->ev[7], s);
 	if (depth) FM_CUDA(cudaMemcpyAsync(depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
 	if (positions) FM_CUDA(cudaMemcpyAsync(positions, ctx->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (normals) FM_CUDA(cudaMemcpyAsync(normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (rgba) FM_CUDA(cudaMemcpyAsync(rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
-	FM_CUDA(cudaEventRecord(ctx->ev[8], s));
+	FM_TIME(ctx, ctx->ev[8], s);
 	{ int const src = stream_sync(ctx); if (src) return src; }
 	float ms = 0.0f;
-	if (cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]) == cudaSuccess) ctx->timings.download_ms = ms;
+	if (ctx->stage_timing && cudaEventElapsedTime(&ms, ctx->ev[7], ctx->ev[8]) == cudaSuccess) ctx->timings.download_ms = ms;
 	return FR_OK;
 }
 
@@ -633,7 +634,7 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->neighbour_overflow = d.neighbour_overflow;
 	out->kernel_launches = ctx->kernel_launches;
 	out->first_candidates = d.first_candidates;
-	out->queued_rays = d.queued_rays;
+	out->queued_rays = d.ctl[2];          // slots of the ray queue that were filled
 	return FR_OK;
 }
 

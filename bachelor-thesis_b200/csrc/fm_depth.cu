@@ -82,9 +82,11 @@ struct Splat
 };
 
 __global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ depth_bits, uint32_t npix,
-													 uint32_t* __restrict__ tile_bound, uint32_t ntiles)
+													 uint32_t* __restrict__ tile_bound, uint32_t ntiles,
+													 uint32_t* __restrict__ n_survivors)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < 4u) n_survivors[i] = 0u;             // survivor count (+ padding) of k_depth_cull
 	if (i < npix) depth_bits[i] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
 	if (i < ntiles) tile_bound[i] = 0x3f800000u;
 }
@@ -429,10 +431,9 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles + ncoarse))) return rc;   // tiles + coarse blocks
 	if ((rc = ensure_capacity(&ctx->d_splat, &ctx->cap_splat, 8 * f.n))) return rc;            // 2 x 16 B per particle
 	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
-	FM_CUDA(cudaMemsetAsync(ctx->d_survivors, 0, 16, ctx->stream));
 
 	uint32_t const npix = (uint32_t)ctx->width * (uint32_t)ctx->height;
-	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles);
+	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles, ctx->d_survivors);
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{

@@ -188,7 +188,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 	return r;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* __restrict__ data, uint32_t m,
+// (src -> data: the per-cell counts stay in `src` for the scatter, their tile-local exclusive scan goes to `data`)
+__global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const uint32_t* __restrict__ src, uint32_t* __restrict__ data, uint32_t m,
 															 uint32_t* __restrict__ tile_sums)
 {
 	__shared__ uint32_t s_warp[33];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(uint32_t* __restric
 #pragma unroll
 	for (int k = 0; k < kScanItems; k++)
 	{
-		v[k] = (base + k < m) ? data[base + k] : 0u;
+		v[k] = (base + k < m) ? src[base + k] : 0u;
 		sum += v[k];
 	}
 	uint32_t total;
@@ -416,8 +417,7 @@ int build_frame_ext(Context* ctx, Frame* f)
 	b.inv_cw = 0.0f;
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	k_key_count4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, b, ctx->d_keys, d_cursor);
-	FM_CUDA(cudaMemcpyAsync(f->d_cell_start_ext, d_cursor, (size_t)cells32 * 4, cudaMemcpyDeviceToDevice, s));
-	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums);
+	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start_ext, cells32, d_tile_sums);
 	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums, tiles);
 	k_scatter4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, ctx->d_keys, f->d_cell_start_ext, d_cursor, ctx->d_sort_tmp);
@@ -440,7 +440,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	f->h = h;
 	f->h_ext = h_ext_mult * h;
 
-	FM_CUDA(cudaEventRecord(ctx->ev[2], s));
+	FM_TIME(ctx, ctx->ev[2], s);
 	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
 	k_init_params<<<1, 1, 0, s>>>(ctx->d_gp, f->d_occupied);
 	int const aabb_blocks = (int)min((size_t)ctx->sm_count * 8, (n + kThreads - 1) / kThreads);
@@ -493,8 +493,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, b, ctx->d_keys, d_cursor, f->d_grid_counts);
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter)
-	FM_CUDA(cudaMemcpyAsync(f->d_cell_start, d_cursor, (size_t)cells32 * 4, cudaMemcpyDeviceToDevice, s));
-	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums);
+	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start, cells32, d_tile_sums);
 	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums, tiles);
 	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_sort_tmp);
@@ -504,7 +503,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 																	  f->d_occ_bits, f->d_occupied);
 	ctx->kernel_launches += 10;   // init, aabb, params, key_count, 3 x scan, scatter, cell_order, flags
 	FM_CUDA(cudaGetLastError());
-	FM_CUDA(cudaEventRecord(ctx->ev[3], s));
+	FM_TIME(ctx, ctx->ev[3], s);
 	f->valid = true;
 	return FR_OK;
 }

@@ -51,8 +51,9 @@ struct DeviceCounters
 {
 	unsigned long long covered_rays, hit_rays, ray_steps, skip_iterations, candidates, neighbours,
 		early_exits, neighbour_overflow;
-	unsigned long long first_candidates;   // snapshot of `candidates` after k_march_first
-	unsigned long long queued_rays;
+	unsigned long long first_candidates;   // the share of `candidates` examined by k_march_first
+	unsigned long long queued_rays;        // (unused on the device: |q1| is read from the control words)
+	uint32_t ctl[8];                       // work-list control words of the march (RayQueues::ctl), zeroed with the counters
 };
 
 struct Context
@@ -76,6 +77,11 @@ struct Context
 	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
 	bool march_timed = false;
+	// per-stage CUDA events (fr_get_timings).  The lanes of a sequence switch them off: every record is one more
+	// command through PCIe per stage, and launch / completion traffic is what the bulk copies of a host -> host
+	// sequence slow down (tools/e2e_probe2.py: background copies alone take the device-resident sequence from 0.29
+	// to 0.42-0.55 ms per frame)
+	bool stage_timing = true;
 	int build_timed = 0;               // 1 / 2: grid (and upload) events of a frame build wait to be read
 
 	fr_settings settings{};
@@ -125,6 +131,9 @@ struct Context
 void set_error(const std::string& msg);
 int stream_sync(Context* c);          // waits for everything on c->stream (see Context::blocking_sync)
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define FM_TIME(ctx, event, stream)                                              \
+	do { if ((ctx)->stage_timing) FM_CUDA(cudaEventRecord((event), (stream))); } while (0)
 
 #define FM_CUDA(expr)                                                            \
 	do {                                                                         \

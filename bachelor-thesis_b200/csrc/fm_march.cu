@@ -43,16 +43,15 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	if ((rc = ensure_capacity(&ctx->d_tiles, &ctx->cap_tiles, (size_t)tiles_x * tiles_y + 8))) return rc;
 	if (do_march && (rc = ensure_capacity(&ctx->d_rayq, &ctx->cap_rayq, 2 * npix))) return rc;   // 32 B per pixel
 	RayQueues rq;
-	rq.ctl = ctx->d_tiles;
+	rq.ctl = ctx->d_counters->ctl;
 	rq.q1 = ctx->d_rayq;
-	uint32_t* const tiles = ctx->d_tiles + 8;
+	uint32_t* const tiles = ctx->d_tiles;
 	cudaStream_t const st = ctx->stream;
-	FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));
-	FM_CUDA(cudaMemsetAsync(ctx->d_tiles, 0, 32, st));
+	FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));      // counters + control words
 	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
 	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
 	ctx->kernel_launches += 1;
-	FM_CUDA(cudaEventRecord(ctx->ev[10], st));
+	FM_TIME(ctx, ctx->ev[10], st);
 	if (do_march)
 	{
 		// persistent: as many CTAs as stay resident (occupancy of this build), never more warps than tiles
@@ -81,9 +80,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 				k_march_first<true, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			else
 				k_march_first<false, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
-			FM_CUDA(cudaEventRecord(ctx->ev[11], st));
-			FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->first_candidates, &ctx->d_counters->candidates, 8, cudaMemcpyDeviceToDevice, st));
-			FM_CUDA(cudaMemcpyAsync(&ctx->d_counters->queued_rays, rq.ctl + 2, 4, cudaMemcpyDeviceToDevice, st));
+			FM_TIME(ctx, ctx->ev[11], st);
 			if (fast)
 				k_march_long<true, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 			else
@@ -91,7 +88,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 		}
 		ctx->kernel_launches += 2;
 	}
-	else FM_CUDA(cudaEventRecord(ctx->ev[11], st));
+	else FM_TIME(ctx, ctx->ev[11], st);
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }

@@ -650,13 +650,16 @@ __device__ __forceinline__ void write_pixel(const MarchParams& mp, uint32_t inde
 	if (mp.do_shade) rgba_out[index] = shade_pixel(mp, (int)(index % (uint32_t)mp.W), (int)(index / (uint32_t)mp.W), P, N);
 }
 
+template <bool FIRST = false>
 __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCounters* __restrict__ counters)
 {
-	// per-warp counter reduction, one atomic per counter per warp
-	uint32_t vals[8] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow };
+	// per-warp counter reduction, one atomic per counter per warp; k_march_first also books its candidates as
+	// DeviceCounters::first_candidates (slot 8)
+	constexpr int N = FIRST ? 9 : 8;
+	uint32_t vals[9] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow, lc.candidates };
 	unsigned long long* dst = reinterpret_cast<unsigned long long*>(counters);
 #pragma unroll
-	for (int k = 0; k < 8; k++)
+	for (int k = 0; k < N; k++)
 	{
 		uint32_t const s = __reduce_add_sync(0xffffffffu, vals[k]);
 		if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst + k, (unsigned long long)s);
@@ -740,7 +743,7 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : FM_MARCH_MINBLOCKS) k_march_f
 		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
 		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
 	}
-	flush_counters(lc, counters);
+	flush_counters<true>(lc, counters);
 }
 
 // phase B: the few rays that are left (about 0.3% at the default settings: rays that enter the fluid through a
