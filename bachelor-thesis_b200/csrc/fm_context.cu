@@ -276,6 +276,7 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_keys) cudaFree(ctx->d_keys);
 	if (ctx->d_sort_tmp) cudaFree(ctx->d_sort_tmp);
 	if (ctx->d_scan_tmp) cudaFree(ctx->d_scan_tmp);
+	if (ctx->d_aabb_partial) cudaFree(ctx->d_aabb_partial);
 	if (ctx->d_tile_bound) cudaFree(ctx->d_tile_bound);
 	if (ctx->d_splat) cudaFree(ctx->d_splat);
 	if (ctx->d_tiles) cudaFree(ctx->d_tiles);
@@ -491,6 +492,7 @@ int fr_render_async(fr_context* ctx, int passes)
 		FM_CUDA(cudaWaitExternalSemaphoresAsync(&ctx->ext_wait, &wp, 1, s));
 	}
 	FM_TIME(ctx, ctx->ev[4], s);
+	ctx->zero_counters_in_depth = (passes & FR_PASS_DEPTH) && (passes & (FR_PASS_MARCH | FR_PASS_SHADE));
 	if (passes & FR_PASS_DEPTH)
 	{
 		if ((rc = launch_depth_prepass(ctx, *f))) return rc;

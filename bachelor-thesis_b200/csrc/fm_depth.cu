@@ -83,10 +83,11 @@ struct Splat
 
 __global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ depth_bits, uint32_t npix,
 													 uint32_t* __restrict__ tile_bound, uint32_t ntiles,
-													 uint32_t* __restrict__ n_survivors)
+													 uint32_t* __restrict__ n_survivors, uint32_t* __restrict__ counters, uint32_t counter_words)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < 4u) n_survivors[i] = 0u;             // survivor count (+ padding) of k_depth_cull
+	if (i < counter_words) counters[i] = 0u;     // DeviceCounters + work-list control words of the march that follows
 	if (i < npix) depth_bits[i] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
 	if (i < ntiles) tile_bound[i] = 0x3f800000u;
 }
@@ -433,7 +434,8 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
 
 	uint32_t const npix = (uint32_t)ctx->width * (uint32_t)ctx->height;
-	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles, ctx->d_survivors);
+	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles, ctx->d_survivors,
+																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u);
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{

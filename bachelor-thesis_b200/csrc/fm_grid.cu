@@ -37,22 +37,19 @@ __device__ __forceinline__ float dec_ordered(uint32_t u)
 	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void k_init_params(GridParams* gp, unsigned long long* occupied)
+// Frame::ComputeAABB (Dataset.cpp:78-92): min/max are exact, so any reduction order gives the same bits.  Each block
+// leaves its extrema in `partial` (6 floats per block; no atomics, nothing to initialise); as a side job the grid
+// zeroes the two histogram buffers of the build up to their current capacity, which saves two memsets per frame.
+__global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz, uint32_t n, float* __restrict__ partial,
+												   uint32_t* __restrict__ zero_a, uint32_t words_a,
+												   uint32_t* __restrict__ zero_b, uint32_t words_b)
 {
-	for (int a = 0; a < 3; a++)
-	{
-		gp->raw_min[a] = 0xffffffffu;
-		gp->raw_max[a] = 0u;
-	}
-	*occupied = 0ull;
-}
-
-// Frame::ComputeAABB (Dataset.cpp:78-92): min/max are exact, so any reduction order gives the same bits
-__global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz, uint32_t n, GridParams* gp)
-{
+	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
+	for (uint32_t i = gtid; i < words_b; i += gsize) zero_b[i] = 0u;
 	float mn[3] = { INFINITY, INFINITY, INFINITY };
 	float mx[3] = { -INFINITY, -INFINITY, -INFINITY };
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	for (uint32_t i = gtid; i < n; i += gsize)
 	{
 #pragma unroll
 		for (int a = 0; a < 3; a++)
@@ -82,13 +79,42 @@ __global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz
 		int const a = threadIdx.x;
 		float lo = s_mn[a][0], hi = s_mx[a][0];
 		for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
-		atomicMin(&gp->raw_min[a], enc_ordered(lo));
-		atomicMax(&gp->raw_max[a], enc_ordered(hi));
+		partial[6 * blockIdx.x + a] = lo;
+		partial[6 * blockIdx.x + 3 + a] = hi;
 	}
 }
 
-__global__ void k_grid_params(GridParams* gp, float h)
+// one block: the extrema over the blocks of k_aabb, then m_Min / m_Max / dims / cell ranges with the reference's exact
+// FP32 expressions
+__global__ void __launch_bounds__(kThreads) k_grid_params(GridParams* gp, const float* __restrict__ partial, uint32_t blocks, float h,
+														  unsigned long long* occupied)
 {
+	float mn[3] = { INFINITY, INFINITY, INFINITY };
+	float mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+	for (uint32_t b = threadIdx.x; b < blocks; b += kThreads)
+#pragma unroll
+		for (int a = 0; a < 3; a++)
+		{
+			mn[a] = fminf(mn[a], partial[6 * b + a]);
+			mx[a] = fmaxf(mx[a], partial[6 * b + 3 + a]);
+		}
+#pragma unroll
+	for (int a = 0; a < 3; a++)
+	{
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+		{
+			mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+			mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+		}
+	}
+	__shared__ float s_mn[3][kThreads / 32], s_mx[3][kThreads / 32];
+	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (lane == 0)
+		for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+	__syncthreads();
+	if (threadIdx.x != 0) return;
+	*occupied = 0ull;
 	float const pad = mulr(1.0f, h);                 // padding = 1.0f * ParticleRadius (Dataset.cpp:89)
 	float const cw = mulr(1.0f, h);                  // cellWidth = 1.0f * ParticleRadius (Dataset.cpp:96)
 	float const search_inv = divr(1.0f, h);          // CompactNSearch: inverse cell size in Real
@@ -97,14 +123,16 @@ __global__ void k_grid_params(GridParams* gp, float h)
 	gp->search_inv = search_inv;
 	for (int a = 0; a < 3; a++)
 	{
-		float const lo = dec_ordered(gp->raw_min[a]);
-		float const hi = dec_ordered(gp->raw_max[a]);
-		float const mn = subr(lo, pad);
-		float const mx = addr(hi, pad);
-		gp->mn[a] = mn;
-		gp->mx[a] = mx;
-		gp->gdim[a] = (int32_t)ceilf(divr(subr(mx, mn), cw));   // int32_t(std::ceil(aabb / cellWidth)) (:102-104)
-		int const k0 = search_cell_of(search_inv, lo);           // cell index is monotone in x
+		float lo = s_mn[a][0], hi = s_mx[a][0];
+		for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
+		gp->raw_min[a] = enc_ordered(lo);            // kept for build_frame_ext (the r = h_ext search ranges)
+		gp->raw_max[a] = enc_ordered(hi);
+		float const mn_a = subr(lo, pad);
+		float const mx_a = addr(hi, pad);
+		gp->mn[a] = mn_a;
+		gp->mx[a] = mx_a;
+		gp->gdim[a] = (int32_t)ceilf(divr(subr(mx_a, mn_a), cw));   // int32_t(std::ceil(aabb / cellWidth)) (:102-104)
+		int const k0 = search_cell_of(search_inv, lo);              // cell index is monotone in x
 		int const k1 = search_cell_of(search_inv, hi);
 		gp->kmin[a] = k0;
 		gp->kdim[a] = k1 - k0 + 1;
@@ -213,32 +241,44 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const uint32_t* __r
 	if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// single block: exclusive scan of the tile sums (sequential over chunks of kScanThreads)
-__global__ void __launch_bounds__(kScanThreads) k_scan_sums(uint32_t* __restrict__ tile_sums, uint32_t tiles)
-{
-	__shared__ uint32_t s_warp[33];
-	uint32_t carry = 0;
-	for (uint32_t b = 0; b < tiles; b += kScanThreads)
-	{
-		uint32_t const i = b + threadIdx.x;
-		uint32_t const v = i < tiles ? tile_sums[i] : 0u;
-		uint32_t total;
-		uint32_t const r = block_exclusive_scan(v, s_warp, total);
-		if (i < tiles) tile_sums[i] = carry + r;
-		carry += total;
-	}
-	if (threadIdx.x == 0) tile_sums[tiles] = carry;
-}
-
+// adds to every tile the sum of the tiles in front of it (each block adds those few dozen sums up itself, which saves
+// the single-block scan of the tile sums and its launch) and writes the grand total behind the last element
 __global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* __restrict__ data, uint32_t m,
 														   const uint32_t* __restrict__ tile_sums, uint32_t tiles)
 {
-	uint32_t const off = tile_sums[blockIdx.x];
+	__shared__ uint32_t s_part[kScanThreads / 32];
+	__shared__ uint32_t s_off;
+	uint32_t const limit = blockIdx.x == gridDim.x - 1 ? tiles : blockIdx.x;       // the last block also needs the total
+	uint32_t acc_before = 0, acc_all = 0;
+	for (uint32_t i = threadIdx.x; i < limit; i += kScanThreads)
+	{
+		uint32_t const v = tile_sums[i];
+		acc_all += v;
+		if (i < blockIdx.x) acc_before += v;
+	}
+	// two block reductions (sum of the tiles in front, and -- last block -- of all tiles)
+	uint32_t total = 0;
+	for (int pass = 0; pass < 2; pass++)
+	{
+		uint32_t v = pass == 0 ? acc_before : acc_all;
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+		if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+		__syncthreads();
+		if (threadIdx.x == 0)
+		{
+			uint32_t t = 0;
+			for (int w = 0; w < kScanThreads / 32; w++) t += s_part[w];
+			if (pass == 0) s_off = t; else total = t;
+		}
+		__syncthreads();
+	}
+	uint32_t const off = s_off;
 	uint32_t const base = blockIdx.x * kScanTile + threadIdx.x * kScanItems;
 #pragma unroll
 	for (int k = 0; k < kScanItems; k++)
 		if (base + k < m) data[base + k] += off;
-	if (blockIdx.x == 0 && threadIdx.x == 0) data[m] = tile_sums[tiles];
+	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) data[m] = total;
 }
 
 // counting-sort scatter.  cursor[] holds the per-cell counts and is consumed (atomicSub), so no
@@ -418,11 +458,10 @@ int build_frame_ext(Context* ctx, Frame* f)
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	k_key_count4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, b, ctx->d_keys, d_cursor);
 	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start_ext, cells32, d_tile_sums);
-	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums, tiles);
 	k_scatter4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, ctx->d_keys, f->d_cell_start_ext, d_cursor, ctx->d_sort_tmp);
 	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start_ext, f->d_sorted_ext);
-	ctx->kernel_launches += 6;
+	ctx->kernel_launches += 5;
 	FM_CUDA(cudaGetLastError());
 	f->ext_valid = true;
 	return FR_OK;
@@ -442,10 +481,15 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 
 	FM_TIME(ctx, ctx->ev[2], s);
 	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
-	k_init_params<<<1, 1, 0, s>>>(ctx->d_gp, f->d_occupied);
 	int const aabb_blocks = (int)min((size_t)ctx->sm_count * 8, (n + kThreads - 1) / kThreads);
-	k_aabb<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_gp);
-	k_grid_params<<<1, 1, 0, s>>>(ctx->d_gp, h);
+	int rc;
+	if ((rc = ensure_capacity(&ctx->d_aabb_partial, &ctx->cap_aabb_partial, (size_t)6 * ctx->sm_count * 8))) return rc;
+	// the histogram buffers as they are now (they are re-checked against this frame's sizes below)
+	uint32_t* const zero_a = ctx->d_scan_tmp; size_t const cap_a = ctx->d_scan_tmp ? ctx->cap_scan_tmp : 0;
+	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->d_grid_counts ? f->cap_grid : 0;
+	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
+	k_aabb<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, zero_a, words_a, zero_b, words_b);
+	k_grid_params<<<1, kThreads, 0, s>>>(ctx->d_gp, ctx->d_aabb_partial, (uint32_t)aabb_blocks, h, f->d_occupied);
 	FM_CUDA(cudaMemcpyAsync(ctx->h_gp, ctx->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
 	{ int const src = stream_sync(ctx); if (src) return src; }   // table sizes depend on the AABB
 	f->gp = *ctx->h_gp;
@@ -467,7 +511,6 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	uint32_t const occ_words = (gcells32 + 31u) / 32u;
 	uint32_t const tiles = (cells32 + kScanTile - 1) / kScanTile;
 
-	int rc;
 	if ((rc = ensure_capacity(&f->d_sorted, &f->cap_sorted, n))) return rc;
 	if ((rc = ensure_capacity(&f->d_cell_start, &f->cap_cells, (size_t)cells32 + 1))) return rc;
 	if ((rc = ensure_capacity(&f->d_grid_counts, &f->cap_grid, gcells32))) return rc;
@@ -479,8 +522,9 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	uint32_t* const d_cursor = ctx->d_scan_tmp;
 	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
 
-	FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
-	FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, (size_t)gcells32 * 4, s));
+	// k_aabb has zeroed the buffers it was given; one that had to grow (or did not exist yet) is zeroed here
+	if (ctx->d_scan_tmp != zero_a || ctx->cap_scan_tmp != cap_a || words_a == 0u) FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
+	if (f->d_grid_counts != zero_b || f->cap_grid != cap_b || words_b == 0u) FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, (size_t)gcells32 * 4, s));
 
 	BuildView b;
 	b.kmin = make_int3(gp.kmin[0], gp.kmin[1], gp.kmin[2]);
@@ -494,14 +538,13 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, b, ctx->d_keys, d_cursor, f->d_grid_counts);
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter)
 	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start, cells32, d_tile_sums);
-	k_scan_sums<<<1, kScanThreads, 0, s>>>(d_tile_sums, tiles);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums, tiles);
 	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_sort_tmp);
 	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start, f->d_sorted);
 	FrameView const v = make_view(*f);
 	k_flags<<<(gcells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_grid_counts, gcells32, v.kernel.sig_d,
 																	  f->d_occ_bits, f->d_occupied);
-	ctx->kernel_launches += 10;   // init, aabb, params, key_count, 3 x scan, scatter, cell_order, flags
+	ctx->kernel_launches += 8;    // aabb, params, key_count, 2 x scan, scatter, cell_order, flags
 	FM_CUDA(cudaGetLastError());
 	FM_TIME(ctx, ctx->ev[3], s);
 	f->valid = true;

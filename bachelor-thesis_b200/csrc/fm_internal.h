@@ -77,6 +77,7 @@ struct Context
 	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
 	bool march_timed = false;
+	bool zero_counters_in_depth = false;   // this render call: k_depth_clear zeroes the march counters (one memset less)
 	// per-stage CUDA events (fr_get_timings).  The lanes of a sequence switch them off: every record is one more
 	// command through PCIe per stage, and launch / completion traffic is what the bulk copies of a host -> host
 	// sequence slow down (tools/e2e_probe2.py: background copies alone take the device-resident sequence from 0.29
@@ -109,6 +110,7 @@ struct Context
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
 	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // counting sort output before the in-cell ordering
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
+	float* d_aabb_partial = nullptr;  size_t cap_aabb_partial = 0;  // per-block extrema of k_aabb
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
 	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices

@@ -47,7 +47,9 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	rq.q1 = ctx->d_rayq;
 	uint32_t* const tiles = ctx->d_tiles;
 	cudaStream_t const st = ctx->stream;
-	FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));      // counters + control words
+	if (!ctx->zero_counters_in_depth)
+		FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));      // counters + control words
+	ctx->zero_counters_in_depth = false;
 	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
 	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
 	ctx->kernel_launches += 1;
