@@ -144,7 +144,8 @@ static int finish_pending(Context* c)
 {
 	if (c->render_pending)
 	{
-		if (c->blocking_sync) { int const rc = stream_sync(c); if (rc) return rc; }     // ev_done is the last thing on the stream
+		// (a lane records no completion event: it waits for its whole stream, copies behind the render included)
+		if (c->blocking_sync || !c->stage_timing) { int const rc = stream_sync(c); if (rc) return rc; }
 		else FM_CUDA(cudaEventSynchronize(c->ev_done));
 		c->render_pending = false;
 		read_build_timings(c);
@@ -509,7 +510,7 @@ int fr_render_async(fr_context* ctx, int passes)
 		memset(&sp, 0, sizeof sp);
 		FM_CUDA(cudaSignalExternalSemaphoresAsync(&ctx->ext_signal, &sp, 1, s));
 	}
-	FM_CUDA(cudaEventRecord(ctx->ev_done, s));
+	if (ctx->stage_timing) FM_CUDA(cudaEventRecord(ctx->ev_done, s));
 	ctx->render_pending = true;
 	return FR_OK;
 }
@@ -518,7 +519,7 @@ int fr_is_done(fr_context* ctx)
 {
 	FR_CHECK_CTX(ctx);
 	if (!ctx->render_pending) return 1;
-	cudaError_t const e = cudaEventQuery(ctx->ev_done);
+	cudaError_t const e = ctx->stage_timing ? cudaEventQuery(ctx->ev_done) : cudaStreamQuery(ctx->stream);
 	if (e == cudaSuccess) return 1;
 	if (e == cudaErrorNotReady) return 0;
 	return cuda_fail(e, "cudaEventQuery", __FILE__, __LINE__);

@@ -58,8 +58,7 @@ struct fr_sequence
 namespace
 {
 
-// device -> host copies of the requested images behind the render, then the lane's end-of-frame event (the timer
-// reads it), then wait
+// device -> host copies of the requested images behind the render, then one wait for the lane's whole stream
 int finish_job(Lane* ln, const fr_seq_job& job)
 {
 	Context* const c = ln->ctx;
@@ -69,11 +68,7 @@ int finish_job(Lane* ln, const fr_seq_job& job)
 	if (job.positions) FM_CUDA(cudaMemcpyAsync(job.positions, c->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, c->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, c->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
-	FM_CUDA(cudaEventRecord(ln->ev_end, s));
-	int const rc = fr_wait(ln->ctx);
-	if (rc) return rc;
-	if (!(job.depth || job.positions || job.normals || job.rgba)) return FR_OK;     // nothing behind the render
-	return stream_sync(ln->ctx);
+	return fr_wait(ln->ctx);       // the whole stream: render and copies (a lane context waits with stream_sync)
 }
 
 void lane_main(fr_sequence* seq, Lane* ln)
@@ -253,7 +248,9 @@ int fr_seq_wait(fr_sequence* seq, int64_t ticket)
 }
 
 // device time of everything submitted between the two calls: begin is recorded on lane 0's stream with every lane
-// idle; every lane records an event behind the last copy of each of its frames; the result is the latest of them
+// idle, end on every lane's stream as soon as the last frame has drained (the streams are idle by then, so the end
+// stamps are late by the drain's wake-up latency, a few 10 us per measurement: the time errs on the long side; a
+// per-frame end event would be exact but is one more stream operation per frame, see Context::stage_timing)
 int fr_seq_timer_begin(fr_sequence* seq)
 {
 	int rc = fr_seq_drain(seq);
@@ -270,10 +267,11 @@ int fr_seq_timer_end(fr_sequence* seq, float* ms)
 	if (rc) return rc;
 	if (!ms) { set_error("fr_seq_timer_end: null out"); return FR_ERR_INVALID; }
 	FM_CUDA(cudaSetDevice(seq->device));
+	for (Lane* ln : seq->lanes) FM_CUDA(cudaEventRecord(ln->ev_end, ln->ctx->stream));
 	float best = 0.0f;
 	for (Lane* ln : seq->lanes)
 	{
-		if (ln->done_ticket < 0) continue;        // lane never used: its event was never recorded
+		FM_CUDA(cudaEventSynchronize(ln->ev_end));
 		float t = 0.0f;
 		FM_CUDA(cudaEventElapsedTime(&t, seq->ev_begin, ln->ev_end));
 		if (t > best) best = t;
