@@ -341,6 +341,57 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 	return FR_OK;
 }
 
+}  // extern "C"
+
+// ---- a sequence lane's frame in two halves (fm_sequence.cu): everything up to the one host wait of the frame, and
+// ---- the rest, which is launches and copies only and can therefore be captured into a CUDA graph
+namespace fm
+{
+
+int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path)
+{
+	FM_CUDA(cudaSetDevice(ctx->device));
+	Frame* f;
+	int rc = frame_slot(ctx, 0, &f);
+	if (rc) return rc;
+	if ((rc = finish_pending(ctx))) return rc;
+	const float* d_xyz = nullptr;
+	size_t n = (size_t)job.n;
+	if (bgeo_path)
+	{
+		if ((rc = stage_bgeo(ctx, bgeo_path, &n))) return rc;
+		d_xyz = ctx->d_xyz;
+	}
+	else if (job.xyz_on_device) d_xyz = job.xyz;
+	else
+	{
+		if (!job.xyz || n == 0) { set_error("sequence job without particles"); return FR_ERR_INVALID; }
+		if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
+		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, job.xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+		d_xyz = ctx->d_xyz;
+	}
+	ctx->build_timed = 0;
+	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult);
+}
+
+int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
+{
+	int rc = build_frame_finish(ctx);
+	if (rc) return rc;
+	if ((rc = fr_render_async(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
+	cudaStream_t const s = ctx->stream;
+	size_t const npix = (size_t)ctx->width * ctx->height;
+	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
+	if (job.positions) FM_CUDA(cudaMemcpyAsync(job.positions, ctx->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
+	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
+	return FR_OK;
+}
+
+}  // namespace fm
+
+extern "C" {
+
 int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult)
 {
 	FR_CHECK_CTX(ctx);

@@ -469,6 +469,15 @@ int build_frame_ext(Context* ctx, Frame* f)
 
 int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
 {
+	int const rc = build_frame_begin(ctx, f, d_xyz, n, h, h_ext_mult);
+	return rc ? rc : build_frame_finish(ctx);
+}
+
+// first half: bounds, grid parameters (one host wait), table allocations.  Everything the second half launches is
+// fixed after this, so a sequence lane can capture the rest of the frame into a CUDA graph
+int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
+{
+	ctx->build.f = nullptr;
 	if (n == 0 || n > 0x7fffffffull) { set_error("fr_upload_frame: particle count must be in [1, 2^31)"); return FR_ERR_INVALID; }
 	if (!(h > 0.0f)) { set_error("fr_upload_frame: h must be positive"); return FR_ERR_INVALID; }
 	cudaStream_t const s = ctx->stream;
@@ -525,6 +534,23 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 	// k_aabb has zeroed the buffers it was given; one that had to grow (or did not exist yet) is zeroed here
 	if (ctx->d_scan_tmp != zero_a || ctx->cap_scan_tmp != cap_a || words_a == 0u) FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
 	if (f->d_grid_counts != zero_b || f->cap_grid != cap_b || words_b == 0u) FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, (size_t)gcells32 * 4, s));
+	ctx->build.f = f; ctx->build.d_xyz = d_xyz; ctx->build.n32 = n32; ctx->build.cells32 = cells32; ctx->build.gcells32 = gcells32;
+	ctx->build.tiles = tiles;
+	return FR_OK;
+}
+
+// second half: kernel launches only
+int build_frame_finish(Context* ctx)
+{
+	Frame* const f = ctx->build.f;
+	if (!f) { set_error("build_frame_finish without build_frame_begin"); return FR_ERR_STATE; }
+	ctx->build.f = nullptr;
+	cudaStream_t const s = ctx->stream;
+	const float* const d_xyz = ctx->build.d_xyz;
+	uint32_t const n32 = ctx->build.n32, cells32 = ctx->build.cells32, gcells32 = ctx->build.gcells32, tiles = ctx->build.tiles;
+	uint32_t* const d_cursor = ctx->d_scan_tmp;
+	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
+	const GridParams& gp = f->gp;
 
 	BuildView b;
 	b.kmin = make_int3(gp.kmin[0], gp.kmin[1], gp.kmin[2]);

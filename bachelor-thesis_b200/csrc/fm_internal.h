@@ -76,6 +76,7 @@ struct Context
 	uint32_t sync_seq = 0;
 	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
+	struct { Frame* f = nullptr; const float* d_xyz = nullptr; uint32_t n32 = 0, cells32 = 0, gcells32 = 0, tiles = 0; } build;   // between build_frame_begin / _finish
 	bool march_timed = false;
 	bool zero_counters_in_depth = false;   // this render call: k_depth_clear zeroes the march counters (one memset less)
 	// per-stage CUDA events (fr_get_timings).  The lanes of a sequence switch them off: every record is one more
@@ -156,6 +157,8 @@ int ensure_capacity(T** ptr, size_t* cap, size_t need)
 
 // fm_grid.cu
 int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
+int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
+int build_frame_finish(Context* ctx);
 int build_frame_ext(Context* ctx, Frame* f);      // no-op when already built
 FrameView make_view(const Frame& f);
 // fm_depth.cu
@@ -168,6 +171,9 @@ int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml);
 int march_occupancy_aniso(int* blocks_per_sm);
 int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float* points_host, size_t m, float* density,
 				float* grad, float* g9);
+// fm_context.cu: the two halves of a sequence lane's frame
+int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path);
+int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job);
 // fm_bgeo.cu
 int stage_bgeo(Context* ctx, const char* path, size_t* n_out);
 // fm_query.cu

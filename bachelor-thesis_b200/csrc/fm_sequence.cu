@@ -39,6 +39,11 @@ struct Lane
 	int done_status = FR_OK;
 	std::string done_error;
 	cudaEvent_t ev_end = nullptr;
+	// the part of a frame behind its one host wait (rest of the grid build, depth pre-pass, march, copies out) as a
+	// CUDA graph, re-captured every frame and patched into the instantiated graph: one launch instead of ~16 stream
+	// operations, which is what a host -> host sequence is short of while bulk copies keep PCIe busy
+	cudaGraphExec_t exec = nullptr;
+	bool graph_ok = true;
 };
 
 }  // namespace
@@ -53,22 +58,51 @@ struct fr_sequence
 	std::mutex err_m;
 	cudaEvent_t ev_begin = nullptr;
 	uint64_t frames_done = 0;
+	bool graphs = true;
 };
 
 namespace
 {
 
-// device -> host copies of the requested images behind the render, then one wait for the lane's whole stream
-int finish_job(Lane* ln, const fr_seq_job& job)
+// second half of the frame through a CUDA graph (see Lane::exec).  Any failure of the capture machinery switches the
+// lane back to plain launches; the frame itself is then enqueued directly.
+int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 {
-	Context* const c = ln->ctx;
-	cudaStream_t const s = c->stream;
-	size_t const npix = (size_t)c->width * c->height;
-	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, c->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
-	if (job.positions) FM_CUDA(cudaMemcpyAsync(job.positions, c->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
-	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, c->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
-	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, c->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
-	return fr_wait(ln->ctx);       // the whole stream: render and copies (a lane context waits with stream_sync)
+	fr_context* const c = ln->ctx;
+	auto const saved = c->build;                   // lane_frame_enqueue consumes it
+	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
+	{
+		cudaGetLastError();
+		ln->graph_ok = false;
+		return lane_frame_enqueue(c, job);
+	}
+	int const rc = lane_frame_enqueue(c, job);
+	cudaGraph_t g = nullptr;
+	cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+	if (rc != FR_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }      // a real error of the frame
+	if (e == cudaSuccess && ln->exec)
+	{
+		cudaGraphExecUpdateResultInfo info;
+		if (cudaGraphExecUpdate(ln->exec, g, &info) != cudaSuccess)       // topology changed (kernel variant, an extra memset)
+		{
+			cudaGetLastError();
+			cudaGraphExecDestroy(ln->exec);
+			ln->exec = nullptr;
+		}
+	}
+	if (e == cudaSuccess && !ln->exec) e = cudaGraphInstantiate(&ln->exec, g, 0);
+	if (e == cudaSuccess) e = cudaGraphLaunch(ln->exec, c->stream);
+	if (g) cudaGraphDestroy(g);
+	if (e != cudaSuccess)
+	{
+		cudaGetLastError();
+		ln->graph_ok = false;
+		if (ln->exec) { cudaGraphExecDestroy(ln->exec); ln->exec = nullptr; }
+		c->build = saved;
+		c->render_pending = false;
+		return lane_frame_enqueue(c, job);
+	}
+	return FR_OK;
 }
 
 void lane_main(fr_sequence* seq, Lane* ln)
@@ -90,12 +124,9 @@ void lane_main(fr_sequence* seq, Lane* ln)
 			ln->has_job = false;
 			ln->busy = true;
 		}
-		int rc;
-		if (job.bgeo_path) rc = fr_upload_frame_bgeo(ln->ctx, 0, path.c_str(), job.h, job.h_ext_mult);   // decode on this lane
-		else if (job.xyz_on_device) rc = fr_build_frame_device(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
-		else rc = fr_upload_frame(ln->ctx, 0, job.xyz, (size_t)job.n, job.h, job.h_ext_mult);
-		if (rc == FR_OK) rc = fr_render_async(ln->ctx, job.passes ? job.passes : FR_PASS_ALL);
-		if (rc == FR_OK) rc = finish_job(ln, job);
+		int rc = lane_frame_begin(ln->ctx, job, job.bgeo_path ? path.c_str() : nullptr);
+		if (rc == FR_OK) rc = seq->graphs && ln->graph_ok ? enqueue_as_graph(ln, job) : lane_frame_enqueue(ln->ctx, job);
+		if (rc == FR_OK) rc = fr_wait(ln->ctx);       // the whole stream: render and copies
 		if (rc == FR_OK && job.bmp_path) rc = fr_write_bmp(ln->ctx, bmp.c_str());      // recording (Renderer.cpp:400-409)
 		std::string err;
 		if (rc != FR_OK) err = fr_last_error();      // thread-local text of this worker
@@ -133,6 +164,7 @@ int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** ou
 	fr_sequence* seq = new (std::nothrow) fr_sequence();
 	if (!seq) { set_error("out of host memory"); return FR_ERR_INVALID; }
 	seq->device = device;
+	if (const char* e = getenv("FR_SEQ_GRAPH")) seq->graphs = e[0] != '0';
 	for (int k = 0; k < lanes; k++)
 	{
 		Lane* ln = new (std::nothrow) Lane();
@@ -162,6 +194,7 @@ void fr_seq_destroy(fr_sequence* seq)
 		}
 		cudaSetDevice(seq->device);
 		if (ln->ev_end) cudaEventDestroy(ln->ev_end);
+		if (ln->exec) cudaGraphExecDestroy(ln->exec);
 		if (ln->ctx) fr_destroy(ln->ctx);
 		delete ln;
 	}
