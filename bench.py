@@ -371,7 +371,9 @@ def run_b200(args):
     # ---- the sequence: `lanes` frames in flight (fr_seq_*), K steps timed as one region --------------------------
     def timed_sequence(seq, submit, steps, warmup, sampler=None):
         lane_ctx = [seq.context(l) for l in range(lanes)]
-        for k in range(warmup):
+        # every lane must have rendered before the clock starts (allocations, graph instantiation): at least two
+        # frames per lane, whatever W says
+        for k in range(max(warmup, 2 * lanes)):
             submit(k)
         seq.drain()
         before = sum(c.counters()["kernel_launches"] for c in lane_ctx)

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 for d in build_variants/*/; do
   n=$(basename $d)
-  FLUIDMARCH_AB=1 FLUIDMARCH_LIB=$PWD/$d/libfluidmarch.so timeout 300 python bench.py --steps ${STEPS:-60} --warmup 5 --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err || tail -3 gpurun_out/ab_$n.err
+  FLUIDMARCH_AB=1 FLUIDMARCH_LIB=$PWD/$d/libfluidmarch.so timeout 300 python bench.py --steps ${STEPS:-60} --warmup 12 --no-cpu-baseline ${BENCH_ARGS} > gpurun_out/ab_$n.json 2> gpurun_out/ab_$n.err || tail -3 gpurun_out/ab_$n.err
   python - <<PY
 import json
 d=json.load(open("gpurun_out/ab_$n.json"))
