@@ -162,6 +162,9 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 				uint32_t j = b;
 				if (resume && r == r0) j = j0;       // this range was counted when the walk first entered it
 				else lc.candidates += e - b;
+				// no branch in the loop: the store and the count are predicated; the first in-range candidate that no
+				// longer fits is remembered and the walk resumes there after the list has been evaluated
+				uint32_t over = 0xffffffffu;
 #pragma unroll (kWalkUnroll)
 				for (; j < e; j++)
 				{
@@ -169,13 +172,13 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 					// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to right); l2 < r2
 					float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
 					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
-					if (l2 < f.kernel.h_squared)
-					{
-						if (cnt == (uint32_t)kListCap) { full = true; resume = true; r0 = r; j0 = j; break; }
-						list[cnt * 32u] = j;
-						cnt++;
-					}
+					bool const in = l2 < f.kernel.h_squared;
+					bool const fits = cnt < (uint32_t)kListCap;
+					if (in && fits) list[cnt * 32u] = j;
+					over = (in && !fits) ? min(over, j) : over;
+					cnt += (in && fits) ? 1u : 0u;
 				}
+				if (over != 0xffffffffu) { full = true; resume = true; r0 = r; j0 = over; }
 			}
 		}
 		if (WARP) __syncwarp();
