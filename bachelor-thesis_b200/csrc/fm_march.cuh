@@ -91,6 +91,9 @@ struct LaneCounters
 #ifndef FM_MARCH_MINBLOCKS
 #define FM_MARCH_MINBLOCKS 4              // resident 256-thread CTAs per SM k_march_first is compiled for (64 registers)
 #endif
+#ifndef FM_ANISO_MINBLOCKS
+#define FM_ANISO_MINBLOCKS 4              // resident CTAs per SM the anisotropic march kernels are compiled for
+#endif
 #ifndef FM_WALK_UNROLL
 #define FM_WALK_UNROLL 1
 #endif
@@ -672,7 +675,7 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 // phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
 // together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? 2 : FM_MARCH_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_MARCH_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
@@ -755,7 +758,7 @@ __global__ void __launch_bounds__(256, ANISO ? 2 : FM_MARCH_MINBLOCKS) k_march_f
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? 2 : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
