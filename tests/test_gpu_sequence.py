@@ -52,18 +52,19 @@ def test_sequence_matches_single_context_bit_for_bit(fm, gpu_ctx_factory, lanes,
         seq.close()
 
 
-def test_sequence_frame_matches_oracle(fm, oracle):
+@pytest.mark.parametrize("aniso", [False, True])
+def test_sequence_frame_matches_oracle(fm, oracle, aniso):
     cam = golden_camera("camera_close_16x9")
     fs = frames(fm, 3)
     seq = fm.Sequence(W, H, lanes=2)
     try:
-        setup(seq, cam, fm)
+        setup(seq, cam, fm, EnableAnisotropy=aniso)
         jobs = [seq.submit(xyz, 0.1, 2.0, want=("depth", "positions", "normals")) for xyz in fs]
         seq.drain()
         xyz, (_, out) = fs[2], jobs[2]
         f = oracle.frame(xyz, 0.1, 2.0)
         depth = f.depth_prepass(W, H, cam["view"], cam["proj"])
-        pos, nrm, *_ = f.march(W, H, oracle_lib.Settings(), cam["inv_proj_view"], cam["position"], depth)
+        pos, nrm, *_ = f.march(W, H, oracle_lib.Settings(anisotropic=1 if aniso else 0), cam["inv_proj_view"], cam["position"], depth)
         assert np.array_equal(u(out["depth"]), u(depth))
         assert np.array_equal(u(out["positions"]), u(pos))
         assert np.array_equal(u(out["normals"]), u(nrm))
