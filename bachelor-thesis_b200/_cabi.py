@@ -103,6 +103,7 @@ SYMBOLS = [
     ("fr_query_neighbors_ext", C.c_int, [C.c_void_p, C.c_int, f32p, C.c_size_t, u32p, u32p, C.c_size_t]),
     ("fr_query_anisotropic", C.c_int, [C.c_void_p, C.c_int, f32p, C.c_size_t, f32p, f32p, f32p]),
     ("fr_download_frame_ext", C.c_int, [C.c_void_p, C.c_int, f32p, u32p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("fr_measure_l2_bandwidth", C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, f32p]),
     ("fr_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("fr_import_vk_memory_fd", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
     ("fr_import_vk_semaphores_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -778,6 +778,15 @@ int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_
 	return query_density(ctx, *f, points_host, m, density, grad);
 }
 
+int fr_measure_l2_bandwidth(fr_context* ctx, size_t bytes, uint32_t reps, float* gbs)
+{
+	FR_CHECK_CTX(ctx);
+	if (!gbs || reps == 0) { set_error("fr_measure_l2_bandwidth: bad arguments"); return FR_ERR_INVALID; }
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	return measure_l2_bandwidth(ctx, bytes, reps, gbs);
+}
+
 int fr_selftest_division(fr_context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches)
 {
 	FR_CHECK_CTX(ctx);

@@ -181,6 +181,7 @@ int query_neighbors(Context* ctx, const Frame& f, const float* points_host, size
 					uint32_t* ids, size_t cap, bool ext);
 int query_density(Context* ctx, const Frame& f, const float* points_host, size_t m, float* density, float* grad);
 int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
+int measure_l2_bandwidth(Context* ctx, size_t bytes, uint32_t reps, float* gbs);
 
 }  // namespace fm
 

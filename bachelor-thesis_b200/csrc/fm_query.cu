@@ -149,6 +149,48 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t per_thread, 
 
 }  // namespace
 
+// read-only streaming over a buffer that fits the L2 but not the L1s: the L2 -> SM bandwidth the march's gathers are
+// served at (SURVEY 8d asks for this number next to the HBM figure; MEASURED_PEAKS.json has no L2 entry)
+__global__ void __launch_bounds__(256) k_l2_stream(const uint4* __restrict__ buf, uint32_t n16, uint32_t reps, uint32_t* __restrict__ sink)
+{
+	uint32_t acc = 0;
+	uint32_t const gsize = gridDim.x * blockDim.x;
+	for (uint32_t r = 0; r < reps; r++)
+		for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gsize)
+		{
+			uint4 const v = __ldcg(buf + i);      // .cg: served by the L2, not an L1
+			acc += v.x ^ v.y ^ v.z ^ v.w;
+		}
+	if (acc == 0x9e3779b9u) *sink = acc;       // keeps the loads alive
+}
+
+int measure_l2_bandwidth(Context* ctx, size_t bytes, uint32_t reps, float* gbs)
+{
+	cudaStream_t const s = ctx->stream;
+	DevBuf db, ds;
+	size_t const n16 = bytes / 16;
+	if (n16 == 0 || n16 > 0x7fffffffull) { set_error("fr_measure_l2_bandwidth: bad size"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaMalloc(&db.p, n16 * 16));
+	FM_CUDA(cudaMalloc(&ds.p, 4));
+	FM_CUDA(cudaMemsetAsync(db.p, 0x5a, n16 * 16, s));
+	unsigned const blocks = (unsigned)ctx->sm_count * 8;
+	k_l2_stream<<<blocks, 256, 0, s>>>((const uint4*)db.p, (uint32_t)n16, 2, (uint32_t*)ds.p);      // warm the L2
+	cudaEvent_t e0, e1;
+	FM_CUDA(cudaEventCreate(&e0));
+	FM_CUDA(cudaEventCreate(&e1));
+	FM_CUDA(cudaEventRecord(e0, s));
+	k_l2_stream<<<blocks, 256, 0, s>>>((const uint4*)db.p, (uint32_t)n16, reps, (uint32_t*)ds.p);
+	FM_CUDA(cudaEventRecord(e1, s));
+	ctx->kernel_launches += 2;
+	FM_CUDA(cudaGetLastError());
+	FM_CUDA(cudaStreamSynchronize(s));
+	float ms = 0.0f;
+	FM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	*gbs = ms > 0.0f ? (float)((double)n16 * 16.0 * reps / (ms * 1e-3) / 1e9) : 0.0f;
+	return FR_OK;
+}
+
 int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches)
 {
 	cudaStream_t const s = ctx->stream;

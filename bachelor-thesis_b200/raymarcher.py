@@ -274,6 +274,12 @@ class Context:
         return rho, grad
 
 
+    def measure_l2_bandwidth(self, mbytes: int = 32, reps: int = 40) -> float:
+        """GB/s of read-only streaming over an L2-resident buffer (the roofline denominator of the march's gathers)"""
+        g = C.c_float()
+        check(self.lib.fr_measure_l2_bandwidth(self.h, mbytes << 20, reps, C.byref(g)), "fr_measure_l2_bandwidth")
+        return float(g.value)
+
     def selftest_division(self, n: int = 1 << 26, seed: int = 1) -> int:
         bad = C.c_uint64(0)
         check(self.lib.fr_selftest_division(self.h, n, seed, C.byref(bad)), "fr_selftest_division")

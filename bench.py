@@ -469,6 +469,20 @@ def run_b200(args):
                         "FP32-issue bound, not HBM bound (DESIGN.md 3.5): compulsory HBM traffic of the frame is ~0.1 GB; "
                         "`frac` is SURVEY 8(d)'s algorithmic-bytes figure against the HBM peak",
                 "ncu": ncu}
+        # the march is a gather served by L1/L2, so the same algorithmic bytes also go against the L2 -> SM
+        # bandwidth, measured live (fr_measure_l2_bandwidth: read-only streaming over an L2-resident 32 MB buffer)
+        try:
+            l2_peak = max(ctx.measure_l2_bandwidth(32, 40) for _ in range(3))
+        except Exception:
+            l2_peak = None
+        if l2_peak:
+            l2_actual = 32.0 * ncu["l2_sectors"] if ncu.get("l2_sectors") else None
+            roof["l2"] = {"peak": l2_peak, "unit": "GB/s", "peak_source": "measured in this run (fr_measure_l2_bandwidth, 32 MB, ld.cg)",
+                          "achieved_unshared": achieved, "frac_unshared": achieved / l2_peak,
+                          "traffic": l2_actual,
+                          "achieved_actual": (l2_actual / (dur_ms * 1e-3) / 1e9) if l2_actual else None,
+                          "note": "unshared = as if every ray fetched its own candidates (the CPU's access pattern); actual = ncu "
+                                  "lts__t_sectors x 32 B per launch: the rays of a warp share their candidates through L1"}
         if ncu.get("warp_instructions") and clocks and clocks.get("sm_mhz"):
             roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * clocks["sm_mhz"] * 1e6 * dur_ms * 1e-3)
         cpu = None

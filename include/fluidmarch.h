@@ -216,6 +216,9 @@ int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32
 /* device self-test of the shortcuts that claim bit-identity with IEEE division (shared-reciprocal quotients of
  * gradW, Kernel.cpp:43): n pseudo-random operand sets, *mismatches must come back 0 */
 int fr_selftest_division(fr_context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
+/* roofline denominator the driver does not measure: read-only streaming over `bytes` of device memory that stay
+ * resident in the L2 (pick 16-64 MB), `reps` passes, GB/s served by the L2 to the SMs */
+int fr_measure_l2_bandwidth(fr_context* ctx, size_t bytes, uint32_t reps, float* gbs);
 
 /* ---- CUDA-Vulkan hand-off: replaces BilateralBuffer::CopyToGPU/CopyFromGPU
  *      (src/app/AdvancedRenderer/BilateralBuffer.cpp:78-134) ------------------------------------------ */

@@ -20,6 +20,8 @@ KEYS = {
     "dram__bytes_read.sum": "dram_read_bytes",
     "dram__bytes_write.sum": "dram_write_bytes",
     "lts__t_bytes.sum": "l2_bytes",
+    "lts__t_sectors.sum": "l2_sectors",
+    "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum": "l1_global_load_sectors",
     "l1tex__t_bytes.sum": "l1_bytes",
     "sm__cycles_active.avg": "sm_active_cycles",
     "sm__cycles_elapsed.max": "sm_elapsed_cycles",
