@@ -483,6 +483,17 @@ def run_b200(args):
                           "achieved_actual": (l2_actual / (dur_ms * 1e-3) / 1e9) if l2_actual else None,
                           "note": "unshared = as if every ray fetched its own candidates (the CPU's access pattern); actual = ncu "
                                   "lts__t_sectors x 32 B per launch: the rays of a warp share their candidates through L1"}
+        if dom == "k_march_first":
+            # SURVEY 8(d) algorithmic flops: 9 per candidate (distance test) + 10 per in-range kernel evaluation + 25 per
+            # in-range gradient term (the first sample carries the normal's gradient sum)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            flops = 9.0 * cnt["first_candidates"] + 35.0 * cnt["neighbours"] * (cnt["first_candidates"] / max(cnt["candidates"], 1))
+            peak_tf = 148 * 128 * 2 * sm_mhz * 1e6 / 1e12
+            roof["fp32"] = {"achieved": flops / (dur_ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                            "frac": flops / (dur_ms * 1e-3) / 1e12 / peak_tf,
+                            "note": "algorithmic flops against the FMA peak at the sampled SM clock; the kernel cannot use FMA (one IEEE "
+                                    "rounding per operation, as the reference) and its divisions / square roots are correctly rounded "
+                                    "multi-instruction sequences, so issue slots (fp32_issue_frac) are the meaningful measure"}
         if ncu.get("warp_instructions") and clocks and clocks.get("sm_mhz"):
             roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * clocks["sm_mhz"] * 1e6 * dur_ms * 1e-3)
         cpu = None
