@@ -189,42 +189,53 @@ __device__ __forceinline__ bool splat_load(const float4* __restrict__ splat_a, c
 }
 
 // pass 2 (optional refinement): every tile the disc covers completely gets the particle's bound.  Only
-// particles that are still in front of the seed bound of their own centre tile take part.
+// particles that are still in front of the seed bound of their own centre tile take part -- a few lanes of a warp
+// (the particles of the fluid's front layers), so the warp handles them one after the other with lanes = tiles
+// instead of leaving most lanes idle while the few loop over their tiles.
 template <int T>
 __global__ void __launch_bounds__(256) k_depth_bounds(uint32_t n, DepthParams dp, const float4* __restrict__ splat_a,
 													  const uint4* __restrict__ splat_b, uint32_t* __restrict__ tile_bound)
 {
+	constexpr uint32_t FULL = 0xffffffffu;
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	int const lane = threadIdx.x & 31;
 	Splat s;
-	if (!splat_load(splat_a, splat_b, i, s)) return;
-	int tx0 = s.x0 / T, tx1 = s.x1 / T, ty0 = s.y0 / T, ty1 = s.y1 / T;
+	bool take = i < n && splat_load(splat_a, splat_b, i, s);
+	int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
+	if (take)
 	{
+		tx0 = s.x0 / T; tx1 = s.x1 / T; ty0 = s.y0 / T; ty1 = s.y1 / T;
 		int const cx = (tx0 + tx1) >> 1, cy = (ty0 + ty1) >> 1;
-		if (s.near_bits >= __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx)) return;
+		take = s.near_bits < __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx);
+		// the pixel box is the disc plus a margin of a pixel, so the tile that holds an unclipped box edge has pixel
+		// centres outside the disc and cannot be covered completely: leave the rim out (6 x 6 -> 4 x 4 tiles at C2)
+		if (s.x0 > 0) tx0++;
+		if (s.x1 < dp.W - 1) tx1--;
+		if (s.y0 > 0) ty0++;
+		if (s.y1 < dp.H - 1) ty1--;
+		take = take && tx1 >= tx0 && ty1 >= ty0;
 	}
-	// the pixel box is the disc plus a margin of a pixel, so the tile that holds an unclipped box edge has pixel
-	// centres outside the disc and cannot be covered completely: leave the rim out (6 x 6 -> 4 x 4 tiles at C2)
-	if (s.x0 > 0) tx0++;
-	if (s.x1 < dp.W - 1) tx1--;
-	if (s.y0 > 0) ty0++;
-	if (s.y1 < dp.H - 1) ty1--;
-	for (int ty = ty0; ty <= ty1; ty++)
+	uint32_t todo = __ballot_sync(FULL, take);
+	while (todo)
 	{
-		int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
-		float const v0 = frag_u((float)py0, dp.two_h_inv, s.ay, s.by);
-		float const v1 = frag_u((float)py1, dp.two_h_inv, s.ay, s.by);
-		float const vv = fmaxf(mulr(v0, v0), mulr(v1, v1));
-		if (vv > 1.0f) continue;
-		for (int tx = tx0; tx <= tx1; tx++)
+		int const src = __ffs(todo) - 1;
+		todo &= todo - 1u;
+		float const z_c = __shfl_sync(FULL, s.z_c, src), ax = __shfl_sync(FULL, s.ax, src), bx = __shfl_sync(FULL, s.bx, src);
+		float const ay = __shfl_sync(FULL, s.ay, src), by = __shfl_sync(FULL, s.by, src);
+		int const x0 = __shfl_sync(FULL, tx0, src), x1 = __shfl_sync(FULL, tx1, src);
+		int const y0 = __shfl_sync(FULL, ty0, src), y1 = __shfl_sync(FULL, ty1, src);
+		int const nx = x1 - x0 + 1, count = nx * (y1 - y0 + 1);
+		for (int t = lane; t < count; t += 32)
 		{
+			int const ty = y0 + t / nx, tx = x0 + t % nx;
 			int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
+			int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
 			if (!pixel_owned(dp, px0, py0)) continue;
-			float const u0 = frag_u((float)px0, dp.two_w_inv, s.ax, s.bx);
-			float const u1 = frag_u((float)px1, dp.two_w_inv, s.ax, s.bx);
-			float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), vv);
+			float const v0 = frag_u((float)py0, dp.two_h_inv, ay, by), v1 = frag_u((float)py1, dp.two_h_inv, ay, by);
+			float const u0 = frag_u((float)px0, dp.two_w_inv, ax, bx), u1 = frag_u((float)px1, dp.two_w_inv, ax, bx);
+			float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), fmaxf(mulr(v0, v0), mulr(v1, v1)));
 			if (l2 > 1.0f) continue;
-			float const d = frag_depth(dp, s.z_c, l2);
+			float const d = frag_depth(dp, z_c, l2);
 			uint32_t const bound = __float_as_uint(d) + 8u;
 			if (bound >= 0x3f800000u) continue;
 			uint32_t* const cell = tile_bound + (size_t)ty * dp.tiles_x + tx;
