@@ -91,7 +91,7 @@ class ClockSampler:
         self.index = index
         # NVML queries go through the driver and disturb concurrent kernel launches: at 1 kHz the pipelined arm
         # (6 lanes launching ~120 kernels per frame time) became erratic (0.30 .. 0.66 ms per frame, r01u)
-        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "10")) * 1e-3
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "5")) * 1e-3
         self.sm, self.mx, self.reasons = [], [], set()
         self.running = False
         self.thread = None
