@@ -1,6 +1,8 @@
 // fm_march.cu -- host side of the march: parameters, work lists, kernel launches (device code: fm_march.cuh).
 #include "fm_march.cuh"
 
+#include <stdlib.h>
+
 namespace fm
 {
 
@@ -64,6 +66,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			if (aniso) { if ((rc = march_occupancy_aniso(&nb))) return rc; }
 			else FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, 256, 0));
 			per_sm = nb > 0 ? nb : 1;
+			if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }   // tuning switch
 		}
 		uint32_t const max_ctas = (uint32_t)((tiles_x * tiles_y + 7) / 8);
 		uint32_t ctas = (uint32_t)(ctx->sm_count * per_sm);
