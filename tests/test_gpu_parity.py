@@ -132,6 +132,47 @@ def test_density_query_matches_oracle_kernels(fm, oracle, gpu_ctx_factory, small
         assert np.array_equal(bits(grad[i]), bits(g))
 
 
+def test_collisions_and_cell_boundaries(fm, oracle, gpu_ctx_factory):
+    """the domain's degenerate inputs: duplicated particles, query points that coincide with particles (r = 0: W = W0,
+    gradW = NaN through normalize(0), Kernel.cpp:43), particles and queries exactly on cell faces and at negative
+    coordinates (CompactNSearch's floor-like cell index, Dataset.cpp:28's multiply-by-reciprocal)"""
+    h = np.float32(0.1)
+    rng = np.random.default_rng(17)
+    base = rng.uniform(-0.35, 0.35, size=(3000, 3)).astype(np.float32)
+    lattice = (np.stack(np.meshgrid(*[np.arange(-3, 4)] * 3, indexing="ij"), -1).reshape(-1, 3) * h).astype(np.float32)   # on cell faces
+    xyz = np.concatenate([base, base[:200], base[:50], lattice, lattice[:40]]).astype(np.float32)      # duplicates and triplicates
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, xyz, float(h), 2.0)
+    f = oracle.frame(xyz, float(h), 2.0)
+    # grid structures first
+    got, info = ctx.download_frame(0), ctx.frame_info(0)
+    assert np.array_equal(info["grid_dims"], f.dims) and np.array_equal(bits(info["min"]), bits(f.min))
+    assert np.array_equal(got["grid_counts"], f.grid()[0]) and np.array_equal(got["grid_flags"], f.grid()[1])
+    # queries: on particles, on cell faces, just beside them
+    eps = np.float32(1e-7)
+    pts = np.concatenate([base[:40], lattice[100:140], lattice[100:140] + eps, lattice[100:140] - eps,
+                          np.array([[0, 0, 0], [-0.0, 0.1, -0.1], [0.35, -0.35, 0.0]], np.float32)]).astype(np.float32)
+    counts, ids = ctx.query_neighbors(0, pts, cap=512)
+    perm = f.particles()
+    rho, grad = ctx.query_density(0, pts)
+    for i, p in enumerate(pts):
+        want_ids = f.neighbors(p)
+        assert counts[i] == len(want_ids)
+        # same particles in the same order (the GPU reports original indices, the oracle its sorted ones)
+        assert np.array_equal(bits(xyz[ids[i, :counts[i]]]), bits(perm[want_ids]))
+        w = np.float32(0)
+        g = np.zeros(3, np.float32)
+        with np.errstate(all="ignore"):
+            for j in want_ids:
+                r = (perm[j] - p).astype(np.float32)
+                w = np.float32(w + oracle.W(float(h), r))
+                g = (g + oracle.gradW(float(h), r)).astype(np.float32)
+        assert bits(rho[i:i + 1])[0] == bits(np.array([w]))[0]
+        assert np.array_equal(np.isnan(grad[i]), np.isnan(g))
+        assert np.array_equal(bits(grad[i])[~np.isnan(g)], bits(g)[~np.isnan(g)])
+    assert np.isnan(grad[:40]).all()                  # a query on a particle: normalize(0) in gradW
+
+
 # ---- (a11) depth pre-pass ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("n,W,H,cam_name", [(8000, 160, 90, "camera_close_16x9"), (64000, 1280, 720, "camera_default_16x9"),
                                             (20000, 333, 187, "camera_orbit_a_16x9"), (20000, 320, 180, "camera_orbit_b_16x9")])
