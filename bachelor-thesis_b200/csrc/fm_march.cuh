@@ -94,6 +94,10 @@ struct LaneCounters
 #ifndef FM_ANISO_MINBLOCKS
 #define FM_ANISO_MINBLOCKS 4              // resident CTAs per SM the anisotropic march kernels are compiled for
 #endif
+#ifndef FM_ANISO_WALK_UNROLL
+#define FM_ANISO_WALK_UNROLL 2
+#endif
+constexpr int kAnisoWalkUnroll = FM_ANISO_WALK_UNROLL;
 #ifndef FM_WALK_UNROLL
 #define FM_WALK_UNROLL 1
 #endif
@@ -263,7 +267,7 @@ __device__ __forceinline__ uint32_t walk_ext(const FrameView& f, const CellBox& 
 			uint32_t const jb = __ldg(f.cell_start_ext + base + b.z0);
 			uint32_t const je = __ldg(f.cell_start_ext + base + b.z1 + 1);
 			visited += je - jb;
-#pragma unroll 2
+#pragma unroll (kAnisoWalkUnroll)
 			for (uint32_t j = jb; j < je; j++) visit(__ldg(f.sorted_ext + j));
 		}
 	}
