@@ -314,6 +314,7 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 	constexpr int TPR = 32 / LPT;                    // tiles per round
 	constexpr int RPT = PIX / LPT;                   // rounds per tile
 	uint32_t const lane = threadIdx.x & 31u;
+	__shared__ int s_open[8][32];
 	uint32_t const count = __ldcg(n_survivors);
 	// (survivors are dealt out statically: one atomic ticket per warp costs more than the imbalance it removes,
 	// 9 472 warps on one counter -- r01q)
@@ -336,17 +337,19 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 			if (tcol < 0) { trow--; tcol += pntx; } else if (tcol >= pntx) { trow++; tcol -= pntx; }
 			bool const alive = t < ntiles && pixel_owned(dp, (ptx0 + tcol) * T, (pty0 + trow) * T) &&
 				s.near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
-			uint32_t tiles = __ballot_sync(0xffffffffu, alive);
-			int const my_tile_xy = ((pty0 + trow) << 16) | (ptx0 + tcol);
-
-			while (tiles)
+			uint32_t const tiles = __ballot_sync(0xffffffffu, alive);
+			if (tiles == 0u) continue;
+			// the open tiles of this batch, compacted into the warp's shared-memory row: lane group g of round k takes
+			// entry k * TPR + g (a __fns per round cost 30% of the kernel's instructions, r01 final)
+			int const n_open = __popc(tiles);
+			__syncwarp();
+			if (alive) s_open[threadIdx.x >> 5][__popc(tiles & ((1u << lane) - 1u))] = ((pty0 + trow) << 16) | (ptx0 + tcol);
+			__syncwarp();
+			for (int ob = 0; ob < n_open; ob += TPR)
 			{
-				// lane group g takes the g-th open tile of this batch
-				uint32_t const sel = __fns(tiles, 0, (int)(lane / LPT) + 1);
-#pragma unroll
-				for (int k = 0; k < TPR; k++) tiles &= tiles - 1u;
-				int const txy = __shfl_sync(0xffffffffu, my_tile_xy, sel & 31u);
-				if (sel == 0xffffffffu) continue;
+				int const o = ob + (int)(lane / LPT);
+				if (o >= n_open) continue;
+				int const txy = s_open[threadIdx.x >> 5][o];
 				int const tpx = (txy & 0xffff) * T, tpy = (txy >> 16) * T;
 #pragma unroll
 				for (int r = 0; r < RPT; r++)
@@ -355,10 +358,11 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 					int const px = tpx + (k % T), py = tpy + (k / T);
 					if (px < s.x0 || px > s.x1 || py < s.y0 || py > s.y1) continue;
 					uint32_t* const cell = depth_bits + (size_t)py * (size_t)dp.W + (size_t)px;
-					if (s.near_bits >= __ldcg(cell)) continue;            // cannot win this pixel (L2 read: always fresh)
+					uint32_t const cur = __ldcg(cell);                  // L2 read: always fresh; in flight during the arithmetic below
 					float const u = frag_u((float)px, dp.two_w_inv, s.ax, s.bx);
 					float const v = frag_u((float)py, dp.two_h_inv, s.ay, s.by);
 					float const l2 = addr(mulr(u, u), mulr(v, v));
+					if (s.near_bits >= cur) continue;                   // cannot win this pixel
 					if (l2 > 1.0f) continue;                            // depth.frag:22 `if (l2 > 1) discard;`
 					float const d = frag_depth(dp, s.z_c, l2);
 					if (!(d < 1.0f)) continue;                          // compare Less against the clear value
