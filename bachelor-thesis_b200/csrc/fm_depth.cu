@@ -188,54 +188,69 @@ __device__ __forceinline__ bool splat_load(const float4* __restrict__ splat_a, c
 	return s.x1 >= s.x0;
 }
 
-// pass 2 (optional refinement): every tile the disc covers completely gets the particle's bound.  Only
-// particles that are still in front of the seed bound of their own centre tile take part -- a few lanes of a warp
-// (the particles of the fluid's front layers), so the warp handles them one after the other with lanes = tiles
-// instead of leaving most lanes idle while the few loop over their tiles.
+// pass 2 (optional refinement): every tile the disc covers completely gets the particle's bound.  Only particles
+// that are still in front of the seed bound of their own centre tile take part -- the fluid's front layers, which sit
+// next to each other in the cell-sorted array: handled by the thread that owns the particle they kept a few CTAs busy
+// while the rest of the GPU idled (ncu r01 final: SMs 58 % active, 28 % occupancy).  So k_depth_gate only lists them
+// (warp-aggregated append) and k_depth_bounds deals the list out evenly, one warp per particle, lanes = tiles.
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_bounds(uint32_t n, DepthParams dp, const float4* __restrict__ splat_a,
-													  const uint4* __restrict__ splat_b, uint32_t* __restrict__ tile_bound)
+__global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, DepthParams dp, const uint4* __restrict__ splat_b,
+													const uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ list,
+													uint32_t* __restrict__ n_list)
 {
-	constexpr uint32_t FULL = 0xffffffffu;
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	int const lane = threadIdx.x & 31;
-	Splat s;
-	bool take = i < n && splat_load(splat_a, splat_b, i, s);
-	int tx0 = 0, tx1 = -1, ty0 = 0, ty1 = -1;
-	if (take)
+	uint32_t const lane = threadIdx.x & 31u;
+	bool take = false;
+	if (i < n)
 	{
-		tx0 = s.x0 / T; tx1 = s.x1 / T; ty0 = s.y0 / T; ty1 = s.y1 / T;
-		int const cx = (tx0 + tx1) >> 1, cy = (ty0 + ty1) >> 1;
-		take = s.near_bits < __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx);
+		uint4 const b = __ldg(splat_b + i);
+		int const x0 = (int)(b.z & 0xffffu), x1 = (int)(b.z >> 16), y0 = (int)(b.w & 0xffffu), y1 = (int)(b.w >> 16);
+		if (x1 >= x0)
+		{
+			int const cx = (x0 / T + x1 / T) >> 1, cy = (y0 / T + y1 / T) >> 1;
+			take = b.y < __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx);
+		}
+	}
+	uint32_t const m = __ballot_sync(0xffffffffu, take);
+	if (m == 0u) return;
+	uint32_t base = 0;
+	if (lane == 0) base = atomicAdd(n_list, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (take) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+
+template <int T>
+__global__ void __launch_bounds__(256) k_depth_bounds(DepthParams dp, const float4* __restrict__ splat_a,
+													  const uint4* __restrict__ splat_b, const uint32_t* __restrict__ list,
+													  const uint32_t* __restrict__ n_list, uint32_t* __restrict__ tile_bound)
+{
+	int const lane = threadIdx.x & 31;
+	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t const count = __ldcg(n_list);
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < count; w += nwarps)
+	{
+		Splat s;
+		splat_load(splat_a, splat_b, __ldg(list + w), s);
+		int tx0 = s.x0 / T, tx1 = s.x1 / T, ty0 = s.y0 / T, ty1 = s.y1 / T;
 		// the pixel box is the disc plus a margin of a pixel, so the tile that holds an unclipped box edge has pixel
 		// centres outside the disc and cannot be covered completely: leave the rim out (6 x 6 -> 4 x 4 tiles at C2)
 		if (s.x0 > 0) tx0++;
 		if (s.x1 < dp.W - 1) tx1--;
 		if (s.y0 > 0) ty0++;
 		if (s.y1 < dp.H - 1) ty1--;
-		take = take && tx1 >= tx0 && ty1 >= ty0;
-	}
-	uint32_t todo = __ballot_sync(FULL, take);
-	while (todo)
-	{
-		int const src = __ffs(todo) - 1;
-		todo &= todo - 1u;
-		float const z_c = __shfl_sync(FULL, s.z_c, src), ax = __shfl_sync(FULL, s.ax, src), bx = __shfl_sync(FULL, s.bx, src);
-		float const ay = __shfl_sync(FULL, s.ay, src), by = __shfl_sync(FULL, s.by, src);
-		int const x0 = __shfl_sync(FULL, tx0, src), x1 = __shfl_sync(FULL, tx1, src);
-		int const y0 = __shfl_sync(FULL, ty0, src), y1 = __shfl_sync(FULL, ty1, src);
-		int const nx = x1 - x0 + 1, count = nx * (y1 - y0 + 1);
-		for (int t = lane; t < count; t += 32)
+		if (tx1 < tx0 || ty1 < ty0) continue;
+		int const nx = tx1 - tx0 + 1, ntile = nx * (ty1 - ty0 + 1);
+		for (int t = lane; t < ntile; t += 32)
 		{
-			int const ty = y0 + t / nx, tx = x0 + t % nx;
+			int const ty = ty0 + t / nx, tx = tx0 + t % nx;
 			int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
 			int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
 			if (!pixel_owned(dp, px0, py0)) continue;
-			float const v0 = frag_u((float)py0, dp.two_h_inv, ay, by), v1 = frag_u((float)py1, dp.two_h_inv, ay, by);
-			float const u0 = frag_u((float)px0, dp.two_w_inv, ax, bx), u1 = frag_u((float)px1, dp.two_w_inv, ax, bx);
+			float const v0 = frag_u((float)py0, dp.two_h_inv, s.ay, s.by), v1 = frag_u((float)py1, dp.two_h_inv, s.ay, s.by);
+			float const u0 = frag_u((float)px0, dp.two_w_inv, s.ax, s.bx), u1 = frag_u((float)px1, dp.two_w_inv, s.ax, s.bx);
 			float const l2 = addr(fmaxf(mulr(u0, u0), mulr(u1, u1)), fmaxf(mulr(v0, v0), mulr(v1, v1)));
 			if (l2 > 1.0f) continue;
-			float const d = frag_depth(dp, z_c, l2);
+			float const d = frag_depth(dp, s.z_c, l2);
 			uint32_t const bound = __float_as_uint(d) + 8u;
 			if (bound >= 0x3f800000u) continue;
 			uint32_t* const cell = tile_bound + (size_t)ty * dp.tiles_x + tx;
@@ -384,16 +399,21 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	uint32_t* const n_surv = ctx->d_survivors;
 	uint32_t* const surv = ctx->d_survivors + 4;
 	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, dp, splat_a, splat_b, ctx->d_tile_bound);
-	if (refine_bounds) k_depth_bounds<T><<<blocks, 256, 0, st>>>(n, dp, splat_a, splat_b, ctx->d_tile_bound);
+	uint32_t const want = (n + 7u) / 8u;
+	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
+	if (refine_bounds)
+	{
+		// the gate's list shares the survivor array (it is consumed before k_depth_cull writes there); its count is word 2
+		k_depth_gate<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2);
+		k_depth_bounds<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv + 2, ctx->d_tile_bound);
+	}
 	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
 	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
 	k_depth_coarse<<<(cx * cy + 255) / 256, 256, 0, st>>>(ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy);
 	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv);
-	uint32_t const want = (n + 7u) / 8u;
-	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	k_depth_splat<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
 															 (uint32_t*)ctx->d_depth);
-	ctx->kernel_launches += refine_bounds ? 5 : 4;
+	ctx->kernel_launches += refine_bounds ? 6 : 4;
 	return FR_OK;
 }
 

@@ -444,11 +444,11 @@ def run_b200(args):
         peak, peak_src = load_peaks()
         npart = n_actual[(args.warmup + args.steps - 1) % n_frames]
         # per-kernel device times of the stages (CUDA events on the context stream, one frame at a time, L2 flushed)
-        stages = {"grid build (10 kernels)": tim["grid_ms"], "depth pre-pass (6 kernels)": tim["depth_ms"],
+        stages = {"grid build (10 kernels)": tim["grid_ms"], "depth pre-pass (7 kernels)": tim["depth_ms"],
                   "k_classify": tim["classify_ms"], "k_march_first": tim["march_first_ms"], "k_march_long": tim["march_long_ms"]}
         # dominant KERNEL (not stage): the depth stage is five kernels, the largest of which (k_depth_splat) is ~43% of the
         # stage in every committed ncu launch list (profiles/*_launches_C2.csv)
-        dom = "k_march_first" if tim["march_first_ms"] >= 0.45 * tim["depth_ms"] else "depth pre-pass (6 kernels)"
+        dom = "k_march_first" if tim["march_first_ms"] >= 0.45 * tim["depth_ms"] else "depth pre-pass (7 kernels)"
         if dom == "k_march_first":
             # C_step x 16 B per density evaluation (the candidates of the 27-cell query, which any 27-cell
             # method incl. the CPU reference must examine) + per covered pixel 4 (depth) + 32 (pos, nrm) + 4 (rgba)
