@@ -432,12 +432,14 @@ __device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleSt
 __device__ __forceinline__ void sample_floor(f3 a, f3 r, float out[4])
 {
 	float const sN = subr(-1.0f, a.y);                         // FLOOR_HEIGHT - a.y
-	f3 const b = add3(a, divs3(scale3(r, sN), r.y));           // a + r * (..) / r.y, left to right
-	float const mx = subr(b.x, mulr(2.0f, floorf(divr(b.x, 2.0f))));   // mod(b.x, 2)
-	float const mz = subr(b.z, mulr(2.0f, floorf(divr(b.z, 2.0f))));
+	// (quotients by one divisor share its reciprocal, divs3_shared: the same correctly rounded results; a division by
+	// 2 or 4 is the multiplication by 0.5 or 0.25, exactly)
+	f3 const b = add3(a, divs3_shared(scale3(r, sN), r.y));    // a + r * (..) / r.y, left to right
+	float const mx = subr(b.x, mulr(2.0f, floorf(mulr(b.x, 0.5f))));   // mod(b.x, 2)
+	float const mz = subr(b.z, mulr(2.0f, floorf(mulr(b.z, 0.5f))));
 	float const fx = (1.0f < mx) ? 0.0f : 1.0f;                // step(m, 1)
 	float const fy = (1.0f < mz) ? 0.0f : 1.0f;
-	float const g = addr(0.25f, divr(addr(fx, fy), 4.0f));
+	float const g = addr(0.25f, mulr(addr(fx, fy), 0.25f));
 	out[0] = g; out[1] = g; out[2] = g; out[3] = 0.5f;
 }
 
@@ -465,7 +467,7 @@ __device__ __forceinline__ uchar4 shade_pixel(const MarchParams& mp, int px, int
 	// viewRay() (composition.frag:59-66): a far-plane POINT used as a direction
 	float wh[4];
 	mat4_mul_vec4(mp.ipv, subr(mulr(2.0f, u), 1.0f), subr(mulr(2.0f, v), 1.0f), 1.0f, 1.0f, wh);
-	f3 const view_ray = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
+	f3 const view_ray = divs3_shared(mk3(wh[0], wh[1], wh[2]), wh[3]);
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
 	float color[4];
 	if (P.w == 0.0f)
