@@ -718,7 +718,7 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_MARCH_MIN
 			float const cy = subr(mulr((float)py, mp.two_h_inv), 1.0f);
 			float wh[4];
 			mat4_mul_vec4(mp.ipv, cx, cy, z, 1.0f, wh);
-			position = divs3(mk3(wh[0], wh[1], wh[2]), wh[3]);
+			position = divs3_shared(mk3(wh[0], wh[1], wh[2]), wh[3]);
 			step = scale3(normalize3(sub3(position, cam)), mp.step_size);
 			prev = position;
 			if (mp.max_steps > 0)

@@ -141,6 +141,10 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t per_thread, 
 		bad += (__float_as_uint(q.x) != __float_as_uint(w.x) && !(isnan(q.x) && isnan(w.x))) ? 1 : 0;
 		bad += (__float_as_uint(q.y) != __float_as_uint(w.y) && !(isnan(q.y) && isnan(w.y))) ? 1 : 0;
 		bad += (__float_as_uint(q.z) != __float_as_uint(w.z) && !(isnan(q.z) && isnan(w.z))) ? 1 : 0;
+		float qa, qb;
+		div2_shared(a.x, a.y, d, qa, qb);
+		bad += (__float_as_uint(qa) != __float_as_uint(w.x) && !(isnan(qa) && isnan(w.x))) ? 1 : 0;
+		bad += (__float_as_uint(qb) != __float_as_uint(w.y) && !(isnan(qb) && isnan(w.y))) ? 1 : 0;
 		float const r1 = rcpr(d), r2 = divr(1.0f, d);
 		bad += (__float_as_uint(r1) != __float_as_uint(r2) && !(isnan(r1) && isnan(r2))) ? 1 : 0;
 	}
