@@ -29,6 +29,25 @@ def test_library_exports_every_declared_symbol(fm):
     assert fm.load().fr_abi_version() == 3
 
 
+def test_header_is_plain_c(tmp_path):
+    """the boundary is a C ABI: include/fluidmarch.h must compile as C99 on its own, and a C program must link it"""
+    import subprocess
+    src = tmp_path / "c_abi_check.c"
+    src.write_text('#include "fluidmarch.h"\n'
+                   'int main(void) { fr_seq_job j; fr_ipc_handle h; fr_bgeo_info b; (void)j; (void)h; (void)b;\n'
+                   '  return fr_abi_version() == FR_ABI_VERSION ? 0 : 1; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", inc, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lib_dir = os.path.join(ROOT, "bachelor-thesis_b200")
+    exe = tmp_path / "c_abi_check"
+    r = subprocess.run(["gcc", "-std=c99", "-I", inc, str(src), "-o", str(exe), "-L", lib_dir, "-lfluidmarch", f"-Wl,-rpath,{lib_dir}"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0          # fr_abi_version needs no device
+
+
 def test_struct_layouts(fm):
     abi = fm._cabi
     assert C.sizeof(abi.FrSettings) == 12 * 4
