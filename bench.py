@@ -360,6 +360,9 @@ def run_b200(args):
         return total_ms / steps, wall, clocks
 
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
+    if sampler and "BENCH_SAMPLER_MS" not in os.environ:
+        # a handful of samples inside the timed region (~0.3 ms per step), never faster than 1 kHz
+        sampler.period = min(5.0, max(1.0, args.steps * 0.3 / 8.0)) * 1e-3
     stage_log = []
     ctx.wait()
     serial_ms, serial_wall, serial_clocks = timed_serial(device_step, args.steps, args.warmup,
