@@ -694,11 +694,20 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_MARCH_MIN
 	uint32_t const count = __ldcg(rq.ctl + 0);
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
 
+	// the first tile of a warp is the one with its own number: thousands of warps drawing their first ticket from one
+	// counter at the same moment queue up at that address for longer than a tile takes to launch; afterwards the
+	// tickets are spread in time
+	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
+	bool first = true;
 	for (;;)
 	{
-		uint32_t t = 0;
-		if (lane == 0) t = atomicAdd(rq.ctl + 1, 1u);
-		t = __shfl_sync(FULL, t, 0);
+		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		if (!first)
+		{
+			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 1, 1u);
+			t = __shfl_sync(FULL, t, 0);
+		}
+		first = false;
 		if (t >= count) break;
 		uint32_t const txy = __ldg(tiles + t);
 		int const px = (int)(txy & 0xffffu) * 8 + (lane & 7), py = (int)(txy >> 16) * 4 + (lane >> 3);
@@ -774,11 +783,17 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_l
 	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 2);
+	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
+	bool first = true;
 	for (;;)
 	{
-		uint32_t t = 0;
-		if (lane == 0) t = atomicAdd(rq.ctl + 3, 1u);
-		t = __shfl_sync(FULL, t, 0);
+		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // first ray: the warp's own number (see k_march_first)
+		if (!first)
+		{
+			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 3, 1u);
+			t = __shfl_sync(FULL, t, 0);
+		}
+		first = false;
 		if (t >= count) break;
 		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
 		f3 cur = mk3(a.x, a.y, a.z);
