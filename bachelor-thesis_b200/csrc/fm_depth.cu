@@ -188,6 +188,30 @@ __device__ __forceinline__ bool splat_load(const float4* __restrict__ splat_a, c
 	return s.x1 >= s.x0;
 }
 
+// appends the `take` threads of a 256-thread CTA to a list with ONE atomic per CTA (one per warp is thousands of
+// atomics on a single address per kernel: they queue up at the L2); returns the thread's slot or 0xffffffff
+__device__ __forceinline__ uint32_t cta_append(bool take, uint32_t* __restrict__ counter)
+{
+	__shared__ uint32_t s_warp_cnt[8];
+	__shared__ uint32_t s_cta_base;
+	uint32_t const lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	uint32_t const m = __ballot_sync(0xffffffffu, take);
+	if (lane == 0) s_warp_cnt[warp] = (uint32_t)__popc(m);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t total = 0;
+#pragma unroll
+		for (int w = 0; w < 8; w++) total += s_warp_cnt[w];
+		s_cta_base = total ? atomicAdd(counter, total) : 0u;
+	}
+	__syncthreads();
+	if (!take) return 0xffffffffu;
+	uint32_t slot = s_cta_base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+	for (uint32_t w = 0; w < warp; w++) slot += s_warp_cnt[w];
+	return slot;
+}
+
 // pass 2 (optional refinement): every tile the disc covers completely gets the particle's bound.  Only particles
 // that are still in front of the seed bound of their own centre tile take part -- the fluid's front layers, which sit
 // next to each other in the cell-sorted array: handled by the thread that owns the particle they kept a few CTAs busy
@@ -211,12 +235,8 @@ __global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, DepthParams dp, 
 			take = b.y < __ldcg(tile_bound + (size_t)cy * dp.tiles_x + cx);
 		}
 	}
-	uint32_t const m = __ballot_sync(0xffffffffu, take);
-	if (m == 0u) return;
-	uint32_t base = 0;
-	if (lane == 0) base = atomicAdd(n_list, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (take) list[base + __popc(m & ((1u << lane) - 1u))] = i;
+	uint32_t const slot = cta_append(take, n_list);
+	if (take) list[slot] = i;
 }
 
 template <int T>
@@ -308,12 +328,8 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, 
 				}
 		}
 	}
-	uint32_t const m = __ballot_sync(0xffffffffu, wins);
-	if (m == 0u) return;
-	uint32_t base = 0;
-	if (lane == 0) base = atomicAdd(n_survivors, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, 0);
-	if (wins) survivors[base + __popc(m & ((1u << lane) - 1u))] = i;
+	uint32_t const slot = cta_append(wins, n_survivors);
+	if (wins) survivors[slot] = i;
 }
 
 // pass 4: one warp per surviving particle: lanes re-test the tiles in parallel, then evaluate the fragments of the
