@@ -14,20 +14,26 @@
 // is order-independent, so ANY superset of the winning fragments gives the same bits.  The kernels below
 // only decide which (particle, pixel) pairs are worth evaluating:
 //
-//   k_depth_clear    depth <- 1.0 (DepthRenderPass.cpp:54); tile bounds <- 1.0
-//   k_depth_bounds   hierarchical-Z seed.  Screen tiles of T x T pixels.  A particle whose disc contains all
-//                    pixel centres of a tile bounds the final depth of every pixel of that tile from above by
-//                    its own fragment depth at the tile's farthest corner (l2 is convex and, in FP32, monotone
-//                    along each axis, so the corner maximum bounds every pixel of the tile exactly; a few ulps of
-//                    slack cover the polynomial cosine).  atomicMin into tile_bound[].
-//   k_depth_splat    one thread per particle tests the particle's nearest possible depth (disc centre,
-//                    z_c - h) against the bounds of the tiles its pixel box overlaps; a particle that cannot win
-//                    any tile (every interior particle of the fluid) costs a handful of L1/L2-resident loads.
-//                    Survivors are handed to the whole warp: lanes re-test the tiles in parallel and then
-//                    evaluate the fragments of the surviving tiles, 32 pixels at a time, atomicMin on the
-//                    raw bits (depth in [0,1] orders like its uint bits).
+//   k_depth_clear    depth <- 1.0 (DepthRenderPass.cpp:54); tile bounds <- 1.0; survivor count and march counters <- 0
+//   k_depth_seed     per particle: projection, splat record (32 B), and the cheapest useful bound -- the tile under
+//                    the disc centre.  Screen tiles of T x T pixels.  A particle whose disc contains all pixel
+//                    centres of a tile bounds the final depth of every pixel of that tile from above by its own
+//                    fragment depth at the tile's farthest corner (l2 is convex and, in FP32, monotone along each
+//                    axis, so the corner maximum bounds every pixel of the tile exactly; a few ulps of slack cover
+//                    the polynomial cosine).  atomicMin into tile_bound[].
+//   k_depth_gate     lists the particles still in front of the bound of their own centre tile (front layers)
+//   k_depth_bounds   one warp per listed particle, lanes = tiles: the bound for every tile the disc covers completely
+//   k_depth_coarse   maximum of the bounds over every 4 x 4 block of tiles
+//   k_depth_cull     one thread per particle tests its nearest possible depth (disc centre, z_c - h) against the
+//                    coarse blocks, then the tiles, its pixel box overlaps; a particle that cannot win any tile
+//                    (every interior particle of the fluid) costs a handful of L1/L2-resident loads; the rest are
+//                    compacted into the survivor list (one atomic per CTA)
+//   k_depth_splat    one warp per survivor: lanes re-test the tiles in parallel, compact the open ones through shared
+//                    memory and evaluate their fragments 32 pixels at a time, atomicMin on the raw bits (depth in
+//                    [0,1] orders like its uint bits)
 //
-// Cost at C2 (1M particles, 1080p): ~1.05 G warp instructions for the brute-force splat -> see profiles/.
+// Cost at C2 (1M particles, 1080p): ~1.05 G warp instructions for a brute-force splat of every fragment (1.29 ms, r01a);
+// ~70 M for this pipeline (0.16 ms) -> see profiles/.
 #include "fm_internal.h"
 
 namespace fm
@@ -223,7 +229,6 @@ __global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, DepthParams dp, 
 													uint32_t* __restrict__ n_list)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t const lane = threadIdx.x & 31u;
 	bool take = false;
 	if (i < n)
 	{
@@ -303,7 +308,6 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, 
 													int coarse_x, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t const lane = threadIdx.x & 31u;
 	bool wins = false;
 	if (i < n)
 	{
