@@ -11,6 +11,8 @@ LIB_PATH = os.environ.get("FLUIDMARCH_LIB") or os.path.join(HERE, "libfluidmarch
 FR_OK = 0
 FR_PASS_DEPTH, FR_PASS_MARCH, FR_PASS_SHADE, FR_PASS_ALL = 1, 2, 4, 7
 FR_ERR_NO_DEVICE = -3
+FR_ERR_INVALID = -1
+FR_COUNT_CELL_EXACT, FR_COUNT_CENTRE_BOX = 0, 1
 
 f32p = C.POINTER(C.c_float)
 u32p = C.POINTER(C.c_uint32)
@@ -79,6 +81,7 @@ SYMBOLS = [
     ("fr_host_free", None, [C.c_void_p]),
     ("fr_upload_frame", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
     ("fr_build_frame_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
+    ("fr_set_count_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_get_frame_info", C.c_int, [C.c_void_p, C.c_int, C.POINTER(FrFrameInfo)]),
     ("fr_release_frame", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_download_frame", C.c_int, [C.c_void_p, C.c_int, f32p, u32p, u32p, u8p]),

@@ -153,3 +153,16 @@ class CameraController3D:
     def Direction(self):
         """System[2], what CompositionRenderPass uploads as CameraDirection (:319)."""
         return self.System[2].copy()
+
+
+def reference_default_camera(name: str = "camera_default_16x9") -> dict:
+    """The reference's default camera (orbit R = 10, fov 60 deg, 16:9, near 0.1, far 1000) as float32 arrays with the
+    exact bits the reference's own Camera3D / CameraController3D produce (dumped by tests/golden/make_golden.py from
+    the reference TUs; the numpy mirror above agrees to ~1e-7 relative, this table is what parity runs use so that the
+    CUDA path and the CPU reference see the same input bits).  Keys: view, proj, inv_proj, inv_proj_view, position,
+    system."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", name + ".json")) as f:
+        d = json.load(f)
+    return {k: np.array(v, dtype=np.float32) for k, v in d["float32"].items()}

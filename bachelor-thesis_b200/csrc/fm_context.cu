@@ -406,6 +406,14 @@ int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, s
 	return FR_OK;                  // xyz_device must stay valid until the host next waits for this context
 }
 
+int fr_set_count_mode(fr_context* ctx, int mode)
+{
+	FR_CHECK_CTX(ctx);
+	if (mode != FR_COUNT_CELL_EXACT && mode != FR_COUNT_CENTRE_BOX) { set_error("fr_set_count_mode: unknown mode"); return FR_ERR_INVALID; }
+	ctx->count_mode = mode;
+	return FR_OK;
+}
+
 int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out)
 {
 	FR_CHECK_CTX(ctx);

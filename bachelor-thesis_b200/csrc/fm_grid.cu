@@ -146,6 +146,8 @@ struct BuildView
 	float3 mn;
 	int3 gdim;
 	float inv_cw;
+	float cw, half;          // cell width, half the search radius (find_neighbors_box reading FR_COUNT_CENTRE_BOX)
+	int count_mode;
 };
 
 __device__ __forceinline__ uint32_t search_key(const BuildView& b, float x, float y, float z)
@@ -156,8 +158,29 @@ __device__ __forceinline__ uint32_t search_key(const BuildView& b, float x, floa
 	return ((uint32_t)kx * (uint32_t)b.kdim.y + (uint32_t)ky) * (uint32_t)b.kdim.z + (uint32_t)kz;
 }
 
-// cell key + histograms.  grid_counts follows the "cell-exact" reading of the fork-only
-// find_neighbors_box: a particle counts for the node QueryDensityGrid(particle) returns.
+// which of the density-grid cells c - 1, c, c + 1 of one axis hold coordinate p under the centre-box reading of
+// find_neighbors_box: query point = m_Min + (float(c) + 0.5) * cellWidth (Dataset.cpp:122-123), particle counted iff
+// centre - r/2 <= p < centre + r/2 with r = the search radius, all in FP32.  Rounding lets neighbouring boxes overlap
+// or leave a gap by an ulp, so a coordinate can fall into two cells or into none.  Bit k = cell c - 1 + k.
+__device__ __forceinline__ uint32_t centre_box_mask(float p, float mn, int c, int dim, float cw, float half)
+{
+	uint32_t m = 0;
+#pragma unroll
+	for (int k = 0; k < 3; k++)
+	{
+		int const cc = c - 1 + k;
+		if (cc < 0 || cc >= dim) continue;
+		float const centre = addr(mn, mulr(addr((float)cc, 0.5f), cw));
+		if (p >= subr(centre, half) && p < addr(centre, half)) m |= 1u << k;
+	}
+	return m;
+}
+
+// cell key + histograms.  grid_counts = OctreeNode::NumParticles = |find_neighbors_box(cell centre)| (Dataset.cpp:117-131);
+// that function exists only in the reference's un-vendored CompactNSearch fork, so its reading is a
+// switch (fr_set_count_mode): FR_COUNT_CENTRE_BOX (default) = the half-open box of half-width r/2 around the query
+// point, which is what the reference build under oracle/_ref does; FR_COUNT_CELL_EXACT = the node
+// QueryDensityGrid(particle) returns.  The two differ only for particles within an ulp of a cell face.
 __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, BuildView b,
 														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
 														uint32_t* __restrict__ grid_counts)
@@ -172,11 +195,31 @@ __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict_
 	float const fx = floorf(mulr(subr(x, b.mn.x), b.inv_cw));
 	float const fy = floorf(mulr(subr(y, b.mn.y), b.inv_cw));
 	float const fz = floorf(mulr(subr(z, b.mn.z), b.inv_cw));
-	if (fx >= 0.0f && fx < (float)b.gdim.x && fy >= 0.0f && fy < (float)b.gdim.y && fz >= 0.0f && fz < (float)b.gdim.z)
+	if (b.count_mode == FR_COUNT_CELL_EXACT)
 	{
-		uint32_t const c = (uint32_t)fx + (uint32_t)b.gdim.x * ((uint32_t)fy + (uint32_t)b.gdim.y * (uint32_t)fz);
-		atomicAdd(grid_counts + c, 1u);
+		if (fx >= 0.0f && fx < (float)b.gdim.x && fy >= 0.0f && fy < (float)b.gdim.y && fz >= 0.0f && fz < (float)b.gdim.z)
+		{
+			uint32_t const c = (uint32_t)fx + (uint32_t)b.gdim.x * ((uint32_t)fy + (uint32_t)b.gdim.y * (uint32_t)fz);
+			atomicAdd(grid_counts + c, 1u);
+		}
+		return;
 	}
+	// floor() of a coordinate relative to m_Min lies in [-1, dim] for every particle (m_Min = min - h); clamp for safety
+	int const cx = (int)fminf(fmaxf(fx, -2.0f), (float)b.gdim.x + 1.0f), cy = (int)fminf(fmaxf(fy, -2.0f), (float)b.gdim.y + 1.0f),
+		cz = (int)fminf(fmaxf(fz, -2.0f), (float)b.gdim.z + 1.0f);
+	uint32_t const mx = centre_box_mask(x, b.mn.x, cx, b.gdim.x, b.cw, b.half);
+	uint32_t const my = centre_box_mask(y, b.mn.y, cy, b.gdim.y, b.cw, b.half);
+	uint32_t const mz = centre_box_mask(z, b.mn.z, cz, b.gdim.z, b.cw, b.half);
+	if (mx == 2u && my == 2u && mz == 2u)      // the usual case: exactly the particle's own cell
+	{
+		atomicAdd(grid_counts + ((uint32_t)cx + (uint32_t)b.gdim.x * ((uint32_t)cy + (uint32_t)b.gdim.y * (uint32_t)cz)), 1u);
+		return;
+	}
+	for (int kz = 0; kz < 3; kz++)
+		for (int ky = 0; ky < 3; ky++)
+			for (int kx = 0; kx < 3; kx++)
+				if ((mx >> kx & 1u) && (my >> ky & 1u) && (mz >> kz & 1u))
+					atomicAdd(grid_counts + ((uint32_t)(cx - 1 + kx) + (uint32_t)b.gdim.x * ((uint32_t)(cy - 1 + ky) + (uint32_t)b.gdim.y * (uint32_t)(cz - 1 + kz))), 1u);
 }
 
 // ---- exclusive scan over m counts, in place: data[i] <- sum(data[0..i)), data[m] <- total ------------
@@ -455,6 +498,7 @@ int build_frame_ext(Context* ctx, Frame* f)
 	b.mn = make_float3(0.0f, 0.0f, 0.0f);
 	b.gdim = make_int3(0, 0, 0);
 	b.inv_cw = 0.0f;
+	b.cw = 0.0f; b.half = 0.0f; b.count_mode = FR_COUNT_CELL_EXACT;
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	k_key_count4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, b, ctx->d_keys, d_cursor);
 	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start_ext, cells32, d_tile_sums);
@@ -559,6 +603,9 @@ int build_frame_finish(Context* ctx)
 	b.mn = make_float3(gp.mn[0], gp.mn[1], gp.mn[2]);
 	b.gdim = make_int3(gp.gdim[0], gp.gdim[1], gp.gdim[2]);
 	b.inv_cw = gp.inv_cell_width;
+	b.cw = gp.cell_width;
+	b.half = 0.5f * f->h;                 // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
+	b.count_mode = ctx->count_mode;
 
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, b, ctx->d_keys, d_cursor, f->d_grid_counts);

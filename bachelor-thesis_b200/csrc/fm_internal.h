@@ -92,6 +92,7 @@ struct Context
 	bool have_camera = false;
 	bool have_depth = false;
 	int part_rank = 0, part_world = 1, part_tw = 64, part_th = 64;
+	int count_mode = FR_COUNT_CENTRE_BOX;   // reading of find_neighbors_box (fr_set_count_mode)
 
 	std::vector<Frame> frames;
 

@@ -96,6 +96,11 @@ class Context:
         check(self.lib.fr_build_frame_device(self.h, frame, C.c_void_p(dev_ptr), n, h, h_ext_mult),
               "fr_build_frame_device")
 
+    def set_count_mode(self, mode: int):
+        """reading of the fork-only find_neighbors_box for frames built afterwards: FR_COUNT_CENTRE_BOX (default, what the
+        reference build under oracle/_ref computes) or FR_COUNT_CELL_EXACT"""
+        check(self.lib.fr_set_count_mode(self.h, mode), "fr_set_count_mode")
+
     def frame_info(self, frame: int) -> dict:
         fi = abi.FrFrameInfo()
         check(self.lib.fr_get_frame_info(self.h, frame, C.byref(fi)), "fr_get_frame_info")

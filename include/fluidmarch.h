@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define FR_ABI_VERSION 3
+#define FR_ABI_VERSION 4
 
 enum
 {
@@ -144,6 +144,15 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 /* same, particles already resident in device memory (n packed float3); the build is left on the context's stream:
  * xyz_device must stay valid and unchanged until the host next waits for the context (fr_wait, fr_download, ...) */
 int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult);
+/* OctreeNode::NumParticles = |m_Search.find_neighbors_box(cell centre)| (Dataset.cpp:117-131).  find_neighbors_box exists
+ * only in the reference's un-vendored CompactNSearch fork, so its reading is a switch; applies to frames built afterwards:
+ *   FR_COUNT_CENTRE_BOX (default): particles p with centre - r/2 <= p < centre + r/2 on every axis (FP32), centre = the
+ *                                  query point m_Min + (vec3(x,y,z) + 0.5) * cellWidth -- what the reference's own
+ *                                  translation units compute under oracle/_ref (oracle/ref/shim/CompactNSearch.h)
+ *   FR_COUNT_CELL_EXACT:           particles p with QueryDensityGrid(p) == the node
+ * The two differ only for particles within an ulp of a cell face (41 of 1M at BASELINE C2). */
+enum { FR_COUNT_CELL_EXACT = 0, FR_COUNT_CENTRE_BOX = 1 };
+int fr_set_count_mode(fr_context* ctx, int mode);
 int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out);
 int fr_release_frame(fr_context* ctx, int frame);
 /* parity access to the built structures (any pointer may be NULL):

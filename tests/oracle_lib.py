@@ -168,8 +168,9 @@ class Oracle:
     def cos_half_pi(self, s):
         return np.float32(self.lib.fo_cos_half_pi(float(s)))
 
-    def frame(self, xyz, h=0.1, mult=2.0, count_mode=0):
-        """count_mode 0 = cell-exact (CUDA convention), 1 = centre box (== the oracle/_ref build)"""
+    def frame(self, xyz, h=0.1, mult=2.0, count_mode=1):
+        """count_mode 1 = centre box (== the oracle/_ref build, the CUDA default FR_COUNT_CENTRE_BOX), 0 = cell-exact
+        (FR_COUNT_CELL_EXACT)"""
         self.lib.fo_set_count_mode(count_mode)
         try:
             return OracleFrame(self, xyz, h, mult)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(fm):
     lib = C.CDLL(fm.LIB_PATH)
     for name in header_functions():
         assert hasattr(lib, name), name
-    assert fm.load().fr_abi_version() == 3
+    assert fm.load().fr_abi_version() == 4
 
 
 def test_header_is_plain_c(tmp_path):

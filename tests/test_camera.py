@@ -31,3 +31,13 @@ def test_default_camera_contract():
     assert np.allclose(np.array(g["system"]).reshape(3, 3), np.eye(3))
     proj = np.array(g["proj"], np.float32)
     assert proj[5] < 0 and proj[11] == 1.0 and abs(proj[10] - 1.0001) < 1e-6
+
+
+def test_package_camera_table_is_the_golden_dump(fm):
+    """bachelor-thesis_b200/data holds a copy of the matrices dumped from the reference's camera TUs (bench.py and
+    smoke() read it, so that neither depends on tests/)"""
+    from conftest import golden_camera
+    a, b = fm.camera.reference_default_camera(), golden_camera("camera_default_16x9")
+    assert set(a) == set(b)
+    for k in a:
+        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k

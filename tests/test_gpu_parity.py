@@ -80,9 +80,36 @@ def test_grid_matches_golden_reference_frame(fm, gpu_ctx_factory, small):
     assert np.array_equal(bits(g["info"]["min"]), bits(small["frame_min"]))
     assert np.array_equal(bits(g["info"]["max"]), bits(small["frame_max"]))
     assert np.array_equal(g["info"]["grid_dims"], small["grid_dims"])
-    # cell-exact vs box reading of find_neighbors_box: only particles within an ulp of a face may move
+    # FR_COUNT_CENTRE_BOX (the default) is the reading of find_neighbors_box the reference build used: identical
+    assert np.array_equal(g["grid_counts"], small["grid_counts"])
+    assert np.array_equal(g["grid_flags"], small["grid_flags"])
+    # cell-exact reading: only particles within an ulp of a face may move
+    ctx.set_count_mode(fm.FR_COUNT_CELL_EXACT)
+    ctx.upload_frame(0, small["xyz"], float(small["h"]), float(small["mult"]))
+    g = ctx.download_frame(0)
+    ctx.set_count_mode(fm.FR_COUNT_CENTRE_BOX)
     assert (g["grid_counts"] != small["grid_counts"]).sum() <= 8
     assert (g["grid_flags"] != small["grid_flags"]).sum() <= 4
+    assert int(g["grid_counts"].sum()) == len(small["xyz"])
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_count_modes_match_oracle(fm, oracle, gpu_ctx_factory, mode):
+    """both readings of find_neighbors_box, on particles that sit on and next to cell faces"""
+    rng = np.random.default_rng(5)
+    h = np.float32(0.1)
+    lattice = (np.stack(np.meshgrid(*[np.arange(-4, 5)] * 3, indexing="ij"), -1).reshape(-1, 3) * h).astype(np.float32)
+    near = np.nextafter(lattice[:300], np.float32(10.0)).astype(np.float32)
+    xyz = np.concatenate([scenes.dam_break(20000), lattice, near, rng.uniform(-0.4, 0.4, (2000, 3)).astype(np.float32)])
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.set_count_mode(mode)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    g = ctx.download_frame(0)
+    ctx.set_count_mode(fm.FR_COUNT_CENTRE_BOX)
+    counts, flags = oracle.frame(xyz, 0.1, 2.0, count_mode=mode).grid()
+    assert np.array_equal(g["grid_counts"], counts)
+    assert np.array_equal(g["grid_flags"], flags)
+    assert g["info"]["occupied_cells"] == int(flags.sum())
 
 
 # ---- (a5) neighbour sets ---------------------------------------------------------------------------------
@@ -482,9 +509,14 @@ def test_full_size_properties(fm, gpu_ctx_factory):
     cam = golden_camera("camera_default_16x9")
     W, H = 1920, 1080
     ctx = gpu_ctx_factory(W, H)
+    ctx.set_count_mode(fm.FR_COUNT_CELL_EXACT)
     ctx.upload_frame(0, xyz, 0.1, 2.0)
     g = ctx.download_frame(0)
-    assert int(g["grid_counts"].sum()) == len(xyz)                       # every particle counted once
+    assert int(g["grid_counts"].sum()) == len(xyz)                       # cell-exact reading: every particle counted once
+    ctx.set_count_mode(fm.FR_COUNT_CENTRE_BOX)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    g = ctx.download_frame(0)
+    assert abs(int(g["grid_counts"].sum()) - len(xyz)) < 100             # centre boxes overlap / leave gaps by an ulp
     assert int(g["cell_start"][-1]) == len(xyz)
     idx = g["sorted_index"].astype(np.int64)
     assert np.array_equal(np.sort(idx), np.arange(len(xyz)))             # a permutation

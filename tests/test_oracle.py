@@ -69,7 +69,7 @@ def test_frame_geometry_golden(oracle, small):
 
 
 def test_count_modes_differ_only_at_cell_faces(oracle, small):
-    """cell-exact (CUDA convention) vs centre-box (the _ref stand-in): same total, few cells differ"""
+    """cell-exact (FR_COUNT_CELL_EXACT) vs centre-box (the _ref stand-in, the CUDA default): same total, few cells differ"""
     a = oracle.frame(small["xyz"], 0.1, 2.0, count_mode=0).grid()[0]
     b = oracle.frame(small["xyz"], 0.1, 2.0, count_mode=1).grid()[0]
     assert int(a.sum()) == len(small["xyz"])
