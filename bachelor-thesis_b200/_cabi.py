@@ -43,7 +43,8 @@ class FrFrameInfo(C.Structure):
 class FrCounters(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("pixels", "covered_rays", "hit_rays", "ray_steps", "skip_iterations",
                                           "candidates", "neighbours", "early_exits", "neighbour_overflow",
-                                          "kernel_launches", "first_candidates", "queued_rays")]
+                                          "kernel_launches", "first_candidates", "queued_rays",
+                                          "first_examined", "first_fallbacks")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -697,6 +697,8 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->kernel_launches = ctx->kernel_launches;
 	out->first_candidates = d.first_candidates;
 	out->queued_rays = d.ctl[2];          // slots of the ray queue that were filled
+	out->first_examined = d.first_examined;
+	out->first_fallbacks = d.first_fallbacks;
 	return FR_OK;
 }
 

@@ -52,7 +52,8 @@ struct DeviceCounters
 	unsigned long long covered_rays, hit_rays, ray_steps, skip_iterations, candidates, neighbours,
 		early_exits, neighbour_overflow;
 	unsigned long long first_candidates;   // the share of `candidates` examined by k_march_first
-	unsigned long long queued_rays;        // (unused on the device: |q1| is read from the control words)
+	unsigned long long first_examined;     // candidates k_march_first ran the distance test on (its staged walk culls cells)
+	unsigned long long first_fallbacks;    // first samples walked out of global memory (tile did not fit the stage)
 	uint32_t ctl[8];                       // work-list control words of the march (RayQueues::ctl), zeroed with the counters
 };
 
@@ -118,7 +119,7 @@ struct Context
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
 	bool depth_refine_bounds = true;
 	uint32_t* d_tiles = nullptr;      size_t cap_tiles = 0;        // march: [0] count, [1] cursor, [2..] covered 8x4 tiles
-	int march_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
+	int march_ctas_per_sm = 0, march_long_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
 	float4* d_rayq = nullptr;         size_t cap_rayq = 0;         // march: ray queues between the phases
 	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;

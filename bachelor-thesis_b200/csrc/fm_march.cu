@@ -3,6 +3,8 @@
 
 #include <stdlib.h>
 
+#include <algorithm>
+
 namespace fm
 {
 
@@ -59,37 +61,50 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	if (do_march)
 	{
 		// persistent: as many CTAs as stay resident (occupancy of this build), never more warps than tiles
-		int& per_sm = aniso ? ctx->march_ctas_per_sm_aniso : ctx->march_ctas_per_sm;
-		if (per_sm == 0)
-		{
-			int nb = 0;
-			if (aniso) { if ((rc = march_occupancy_aniso(&nb))) return rc; }
-			else FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, 256, 0));
-			per_sm = nb > 0 ? nb : 1;
-			if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }   // tuning switch
-		}
-		uint32_t const max_ctas = (uint32_t)((tiles_x * tiles_y + 7) / 8);
-		uint32_t ctas = (uint32_t)(ctx->sm_count * per_sm);
-		if (ctas > max_ctas) ctas = max_ctas;
 		FrameView const fv = make_view(f);
 		bool const fast = ctx->settings.fast_normals != 0;
 		if (aniso)
 		{
+			int& per_sm = ctx->march_ctas_per_sm_aniso;
+			if (per_sm == 0)
+			{
+				int nb = 0;
+				if ((rc = march_occupancy_aniso(&nb))) return rc;
+				per_sm = nb > 0 ? nb : 1;
+				if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < per_sm) per_sm = v; }   // tuning switch
+			}
+			uint32_t const max_ctas = (uint32_t)((tiles_x * tiles_y + 7) / 8);
+			uint32_t ctas = (uint32_t)(ctx->sm_count * per_sm);
+			if (ctas > max_ctas) ctas = max_ctas;
 			MarchLaunch ml;
 			ml.fv = fv; ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
 			if ((rc = launch_march_kernels_aniso(ctx, ml))) return rc;
 		}
 		else
 		{
-			if (fast)
-				k_march_first<true, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
-			else
-				k_march_first<false, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+			// k_march_first: FM_FIRST_WARPS warps per CTA, one shared-memory stage per warp (dynamic, above the 48 KB default)
+			size_t const smem_first = (size_t)FM_FIRST_WARPS * sizeof(WarpStage);
+			auto const first = fast ? k_march_first<true, false> : k_march_first<false, false>;
+			auto const longk = fast ? k_march_long<true, false> : k_march_long<false, false>;
+			if (ctx->march_ctas_per_sm == 0)
+			{
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
+				int nb = 0, nl = 0;
+				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, kFirstThreads, smem_first));
+				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false>, 256, 0));
+				if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < nb) nb = v; }   // tuning switch
+				ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
+				ctx->march_long_ctas_per_sm = nl > 0 ? nl : 1;
+			}
+			uint32_t const ntiles = (uint32_t)(tiles_x * tiles_y);
+			uint32_t ctas_first = (uint32_t)(ctx->sm_count * ctx->march_ctas_per_sm);
+			ctas_first = std::min(ctas_first, (ntiles + FM_FIRST_WARPS - 1) / FM_FIRST_WARPS);
+			uint32_t ctas_long = (uint32_t)(ctx->sm_count * ctx->march_long_ctas_per_sm);
+			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
+			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			FM_TIME(ctx, ctx->ev[11], st);
-			if (fast)
-				k_march_long<true, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
-			else
-				k_march_long<false, false><<<ctas, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			longk<<<ctas_long, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		}
 		ctx->kernel_launches += 2;
 	}

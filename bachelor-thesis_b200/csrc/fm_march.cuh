@@ -86,6 +86,8 @@ constexpr int kMaxNeighbors = 2 * 4096;   // MAX_NEIGHBORS (RayMarcher.cpp:14)
 struct LaneCounters
 {
 	uint32_t covered, hits, steps, skips, candidates, neighbours, early_exits, overflow;
+	uint32_t examined;       // candidates the distance test actually ran on (<= candidates: the staged walk culls cells)
+	uint32_t fallbacks;      // samples whose tile did not fit the shared-memory stage (walked out of global memory)
 };
 
 #ifndef FM_MARCH_MINBLOCKS
@@ -208,6 +210,245 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
 	grad = g;
 	return density;
+}
+
+// ---- the first sample of a tile out of shared memory ------------------------------------------------------------------
+// The 32 rays of an 8x4 pixel tile start within about one search cell of each other, so their 27-cell queries overlap
+// almost completely: the union of the cells they touch is a box of 3..4 x 3..4 columns (x, y) times 3..5 cells in z, and
+// -- z running fastest in the cell key -- every column of that box is ONE contiguous range of the sorted particle
+// array.  The warp copies those ranges into shared memory with coalesced 128-bit loads (one load instruction per 32
+// candidates instead of one per candidate and lane), then every lane walks its own 9 sub-ranges out of shared memory:
+// LDS.128 broadcasts, no global-memory latency in the inner loop, a loop body of a dozen instructions.  In-range
+// candidates are collected as 16-bit stage indices (list of 64 per lane), and the W / gradW sums run over that list
+// in the reference's order, reading the particles from the stage as well.  A lane also skips the cells of its 27 that
+// its search sphere cannot reach (corner and edge columns: ~24 % of the candidates), with a margin that covers every
+// rounding of the cell assignment -- a skipped particle could not have passed `l2 < h^2` (see cull_margins).
+// Tiles whose union does not fit (depth discontinuities inside the tile) use the global-memory walk (eval_density).
+#ifndef FM_STAGE_CAP
+#define FM_STAGE_CAP 512                  // particles a warp can stage (16 B each)
+#endif
+#ifndef FM_FIRST_WARPS
+#define FM_FIRST_WARPS 4                  // warps per CTA of the isotropic k_march_first
+#endif
+#ifndef FM_FIRST_MINBLOCKS
+#define FM_FIRST_MINBLOCKS 4
+#endif
+#ifndef FM_STAGE_CULL
+#define FM_STAGE_CULL 1
+#endif
+#ifndef FM_STAGE_UNROLL
+#define FM_STAGE_UNROLL 4
+#endif
+constexpr int kStageCap = FM_STAGE_CAP;
+constexpr int kStageUnroll = FM_STAGE_UNROLL;
+constexpr int kStageCols = 16;            // columns (x, y) of the union box
+constexpr int kStageZ = 8;                // cells per column
+constexpr int kStageZP = kStageZ + 1;
+constexpr int kList16Cap = 64;            // in-range candidates a lane collects before it evaluates them
+
+struct alignas(16) WarpStage
+{
+	float4 cand[kStageCap];                       // the staged particle ranges, column after column
+	uint32_t cs[kStageCols * kStageZP];           // stage offset at which cell k of column c starts (k = nz: its end)
+	uint16_t list[kList16Cap * 32];               // list[k * 32 + lane]: stage index of the lane's k-th in-range candidate
+};
+
+// Squared lower bounds of |p - x| per axis for particles in the cell below / the own cell / the cell above the sample's
+// cell, shrunk by a margin.  A particle stored in search cell c has fl(inv * x) in [c, c + 1] (cell_index truncates the
+// rounded product), hence x in [c h, (c + 1) h] up to a relative 2^-22; the face coordinate computed here and the
+// subtraction add 2^-23 each.  The margin (|p| + h) * 4e-6 is more than five times their sum, and the threshold the
+// bounds are compared with is h^2 (1 + 1e-5), which covers the three roundings of the distance sum itself.
+__device__ __forceinline__ void cull_margins(float p, int cell_abs, float h, float& below2, float& above2)
+{
+	float const face = (float)cell_abs * h;
+	float const m = (fabsf(p) + h) * 4e-6f;
+	float const lo = fmaxf(p - face - m, 0.0f), hi = fmaxf(face + h - p - m, 0.0f);
+	below2 = lo * lo; above2 = hi * hi;
+}
+
+// 32-bit shared-window addressing for the per-lane list (a generic uint16_t* is carried as a 64-bit pair with carries)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+	unsigned short v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+	return v;
+}
+
+// density and (GRAD) gradient sum at p for every lane of the warp; returns false -- for the whole warp, nothing done --
+// when the union of the lanes' cells does not fit the stage.  Lanes with on == false take part in the copies only.
+template <bool GRAD, bool FAST>
+__device__ __forceinline__ bool eval_density_staged(const FrameView& f, f3 p, bool on, WarpStage& ws, float& density_out, f3& grad_out,
+													LaneCounters& lc)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	// own cell relative to the table, clamped to [-2, kdim + 1] so that +-1 cannot overflow (a lane whose true cell is
+	// farther out has an empty range either way)
+	int const cx = min(max(search_cell_of(f.search_inv, p.x), f.kmin.x - 2), f.kmin.x + f.kdim.x + 1) - f.kmin.x;
+	int const cy = min(max(search_cell_of(f.search_inv, p.y), f.kmin.y - 2), f.kmin.y + f.kdim.y + 1) - f.kmin.y;
+	int const cz = min(max(search_cell_of(f.search_inv, p.z), f.kmin.z - 2), f.kmin.z + f.kdim.z + 1) - f.kmin.z;
+	int const x0 = max(cx - 1, 0), x1 = min(cx + 1, f.kdim.x - 1);
+	int const y0 = max(cy - 1, 0), y1 = min(cy + 1, f.kdim.y - 1);
+	int const z0 = max(cz - 1, 0), z1 = min(cz + 1, f.kdim.z - 1);
+	bool const valid = on && x0 <= x1 && y0 <= y1 && z0 <= z1;
+	int const big = 0x7fffffff;
+	int const ux0 = __reduce_min_sync(FULL, valid ? x0 : big), ux1 = __reduce_max_sync(FULL, valid ? x1 : -1);
+	density_out = 0.0f;
+	grad_out = mk3(0.0f, 0.0f, 0.0f);
+	if (ux1 < 0) return true;                               // no lane has anything to walk
+	int const uy0 = __reduce_min_sync(FULL, valid ? y0 : big), uy1 = __reduce_max_sync(FULL, valid ? y1 : -1);
+	int const uz0 = __reduce_min_sync(FULL, valid ? z0 : big), uz1 = __reduce_max_sync(FULL, valid ? z1 : -1);
+	int const ncy = uy1 - uy0 + 1, nz = uz1 - uz0 + 1, ncols = (ux1 - ux0 + 1) * ncy;
+	if (ncols > kStageCols || nz > kStageZ) return false;
+	int const nzp = nz + 1;
+	__syncwarp();                                           // the previous sample's reads of the stage are over
+	// cell starts of the union box (global offsets first)
+	for (int i = lane; i < ncols * nzp; i += 32)
+	{
+		int const c = i / nzp, k = i - c * nzp;
+		uint32_t const base = ((uint32_t)(ux0 + c / ncy) * (uint32_t)f.kdim.y + (uint32_t)(uy0 + c % ncy)) * (uint32_t)f.kdim.z;
+		ws.cs[c * kStageZP + k] = __ldg(f.cell_start + base + (uint32_t)(uz0 + k));
+	}
+	__syncwarp();
+	uint32_t col_b = 0, col_n = 0;                          // lane c < ncols: global start and length of column c
+	if (lane < ncols) { col_b = ws.cs[lane * kStageZP]; col_n = ws.cs[lane * kStageZP + nz] - col_b; }
+	uint32_t inc = col_n;
+#pragma unroll
+	for (int o = 1; o < 16; o <<= 1)
+	{
+		uint32_t const t = __shfl_up_sync(FULL, inc, o);
+		if (lane >= o) inc += t;
+	}
+	uint32_t const col_off = inc - col_n;
+	uint32_t const total = __shfl_sync(FULL, inc, 15);
+	if (total > (uint32_t)kStageCap) return false;
+	if (lane < ncols)
+		for (int k = 0; k <= nz; k++) ws.cs[lane * kStageZP + k] += col_off - col_b;      // -> stage offsets
+	// the columns, one after the other, 32 particles per load instruction
+	for (int c = 0; c < ncols; c++)
+	{
+		uint32_t const b = __shfl_sync(FULL, col_b, c), n = __shfl_sync(FULL, col_n, c), o = __shfl_sync(FULL, col_off, c);
+		for (uint32_t i = lane; i < n; i += 32) ws.cand[o + i] = __ldg(f.sorted + b + i);
+	}
+	__syncwarp();
+
+	float ax_lo = 0.0f, ax_hi = 0.0f, ay_lo = 0.0f, ay_hi = 0.0f, az_lo = 0.0f, az_hi = 0.0f;
+	float const hh_m = f.kernel.h_squared * (1.0f + 1e-5f);
+	if (FM_STAGE_CULL)
+	{
+		cull_margins(p.x, cx + f.kmin.x, f.kernel.h, ax_lo, ax_hi);
+		cull_margins(p.y, cy + f.kmin.y, f.kernel.h, ay_lo, ay_hi);
+		cull_margins(p.z, cz + f.kmin.z, f.kernel.h, az_lo, az_hi);
+	}
+	float density = 0.0f;
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t nn = 0;
+	int r = 0;                       // next of the lane's 9 columns
+	int resume_a = -1;               // byte offset into the stage at which a column is resumed after a full list
+	uint32_t const my_list = smem_addr(ws.list + lane);                 // shared-window byte addresses
+	uint32_t const list_end = my_list + kList16Cap * 64u;
+	uint32_t const cb = smem_addr(ws.cand);
+	float const hh = f.kernel.h_squared;
+	// one candidate at byte offset `off` of the stage.  CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to
+	// right); l2 < r2.  The list keeps the byte offset (16 bits: the stage holds at most 4096 particles).
+#define FM_STAGE_TEST(q, off)                                                                        \
+	{                                                                                                \
+		float const d0 = subr(p.x, (q).x), d1 = subr(p.y, (q).y), d2 = subr(p.z, (q).z);             \
+		float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));                       \
+		if (l2 < hh) { sts_u16(lp, (off)); lp += 64u; }                                              \
+	}
+	for (;;)
+	{
+		uint32_t lp = my_list;           // next free slot of the lane's list
+		bool full = false;
+		if (valid)
+		{
+#pragma unroll 1
+			while (r < 9 && !full)
+			{
+				int const dx = r / 3 - 1, dy = r % 3 - 1;
+				int const x = cx + dx, y = cy + dy;
+				if ((unsigned)x >= (unsigned)f.kdim.x || (unsigned)y >= (unsigned)f.kdim.y) { r++; continue; }
+				const uint32_t* const ccs = ws.cs + ((x - ux0) * ncy + (y - uy0)) * kStageZP - uz0;
+				int zl = z0, zh = z1;
+				if (resume_a < 0) lc.candidates += ccs[z1 + 1] - ccs[z0];
+				if (FM_STAGE_CULL)
+				{
+					float const m2 = (dx == 0 ? 0.0f : (dx < 0 ? ax_lo : ax_hi)) + (dy == 0 ? 0.0f : (dy < 0 ? ay_lo : ay_hi));
+					if (m2 >= hh_m) { r++; continue; }
+					float const rz2 = hh_m - m2;
+					zl = max(az_lo >= rz2 ? cz : cz - 1, 0);
+					zh = min(az_hi >= rz2 ? cz : cz + 1, f.kdim.z - 1);
+					if (zl > zh) { r++; continue; }
+				}
+				uint32_t a = ccs[zl] * 16u;
+				uint32_t const ae = ccs[zh + 1] * 16u;
+				if (resume_a >= 0) { a = (uint32_t)resume_a; resume_a = -1; }
+				else lc.examined += (ae - a) >> 4;
+				if ((ae - a) >> 4 <= (list_end - lp) >> 6)
+				{
+					// the list cannot overflow in this column: nothing but the test in the loop, four loads in flight
+#pragma unroll 1
+					for (; a + 64u <= ae; a += 64u)
+					{
+						float4 const q0 = lds_f4(cb + a), q1 = lds_f4(cb + a + 16u), q2 = lds_f4(cb + a + 32u), q3 = lds_f4(cb + a + 48u);
+						FM_STAGE_TEST(q0, a) FM_STAGE_TEST(q1, a + 16u) FM_STAGE_TEST(q2, a + 32u) FM_STAGE_TEST(q3, a + 48u)
+					}
+#pragma unroll 1
+					for (; a < ae; a += 16u)
+					{
+						float4 const q0 = lds_f4(cb + a);
+						FM_STAGE_TEST(q0, a)
+					}
+					r++;
+				}
+				else
+				{
+#pragma unroll 1
+					for (; a < ae; a += 16u)
+					{
+						float4 const q = lds_f4(cb + a);
+						float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
+						float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+						if (l2 < hh)
+						{
+							if (lp == list_end) { full = true; resume_a = (int)a; break; }
+							sts_u16(lp, a);
+							lp += 64u;
+						}
+					}
+					if (!full) r++;
+				}
+			}
+		}
+		__syncwarp();
+#pragma unroll 1
+		for (uint32_t it = my_list; it != lp; it += 64u)
+		{
+			float4 const q = lds_f4(cb + lds_u16(it));
+			float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
+			float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+			add_neighbour<true, GRAD, FAST>(f, d0, d1, d2, l2, density, g, nn);
+		}
+		if (!__any_sync(FULL, full)) break;                 // the warp stays together while any lane has more to walk
+	}
+#undef FM_STAGE_TEST
+	lc.neighbours += nn;
+	if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
+	density_out = density;
+	grad_out = g;
+	return true;
 }
 
 #ifdef FM_NO_FMAD
@@ -666,9 +907,10 @@ template <bool FIRST = false>
 __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCounters* __restrict__ counters)
 {
 	// per-warp counter reduction, one atomic per counter per warp; k_march_first also books its candidates as
-	// DeviceCounters::first_candidates (slot 8)
-	constexpr int N = FIRST ? 9 : 8;
-	uint32_t vals[9] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow, lc.candidates };
+	// DeviceCounters::first_candidates (slot 8), the candidates its staged walk examined (9) and its fallbacks (10)
+	constexpr int N = FIRST ? 11 : 8;
+	uint32_t vals[11] = { lc.covered, lc.hits, lc.steps, lc.skips, lc.candidates, lc.neighbours, lc.early_exits, lc.overflow, lc.candidates,
+						  lc.examined, lc.fallbacks };
 	unsigned long long* dst = reinterpret_cast<unsigned long long*>(counters);
 #pragma unroll
 	for (int k = 0; k < N; k++)
@@ -680,16 +922,23 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 
 // phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
 // together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
+// (isotropic: FM_FIRST_WARPS warps per CTA, one WarpStage of dynamic shared memory per warp; anisotropic: 8 warps, none)
+constexpr int kFirstThreads = FM_FIRST_WARPS * 32;
+static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
+static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
+
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_MARCH_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : FM_FIRST_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
-	__shared__ uint32_t s_list[ANISO ? 1 : 8 * kListWords];      // in-range candidate lists, one column per lane
-	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	WarpStage& ws = reinterpret_cast<WarpStage*>(s_dyn)[ANISO ? 0 : (threadIdx.x >> 5)];      // (never touched when ANISO)
+	// the global-memory walk (tiles that do not fit the stage, bisection samples) keeps its list in the stage's particle area
+	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (sizeof(WarpStage) / 4) + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 0);
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
@@ -743,9 +992,22 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_MARCH_MIN
 		__syncwarp();
 		// isotropic: the gradient sum rides along with the density on this sample (unless bisection moves the hit)
 		SampleState<ANISO> st;
-		float const density = (!ANISO && mp.bisection_steps == 0)
-			? sample_density<ANISO, true, FAST, true>(f, mp, position, st, lc, list, sample)
-			: sample_density<ANISO, false, false, true>(f, mp, position, st, lc, list, sample);
+		float density = 0.0f;
+		bool staged = false;
+		if constexpr (!ANISO)
+		{
+			if (mp.bisection_steps == 0)
+			{
+				staged = eval_density_staged<true, FAST>(f, position, sample, ws, density, st.grad, lc);
+				st.have_grad = true;
+				if (!staged && sample) lc.fallbacks++;
+				__syncwarp();
+			}
+		}
+		if (!staged)
+			density = (!ANISO && mp.bisection_steps == 0)
+				? sample_density<ANISO, true, FAST, true>(f, mp, position, st, lc, list, sample)
+				: sample_density<ANISO, false, false, true>(f, mp, position, st, lc, list, sample);
 		__syncwarp();
 		if (sample)
 		{

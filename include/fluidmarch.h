@@ -107,6 +107,9 @@ typedef struct fr_counters
 	uint64_t kernel_launches;    /* kernels this context has launched since fr_create (cumulative) */
 	uint64_t first_candidates;   /* share of `candidates` examined by k_march_first (first sample of every ray) */
 	uint64_t queued_rays;        /* rays that needed more than the first sample (handled by k_march_long) */
+	uint64_t first_examined;     /* candidates k_march_first ran the distance test on: its staged walk skips the cells of
+	                                the 27 that the search sphere cannot reach (first_candidates counts all 27) */
+	uint64_t first_fallbacks;    /* first samples whose tile did not fit the shared-memory stage (walked from global memory) */
 } fr_counters;
 
 /* device time of the last call of each stage, milliseconds (CUDA events on the context stream) */
