@@ -52,7 +52,7 @@ def test_struct_layouts(fm):
     abi = fm._cabi
     assert C.sizeof(abi.FrSettings) == 12 * 4
     assert C.sizeof(abi.FrCamera) == (16 * 3 + 6) * 4
-    assert C.sizeof(abi.FrCounters) == 12 * 8
+    assert C.sizeof(abi.FrCounters) == 14 * 8
     assert C.sizeof(abi.FrTimings) == 8 * 4
 
 
