@@ -19,6 +19,7 @@
 #include "fm_internal.h"
 
 #include <errno.h>
+#include <stdlib.h>
 #include <fcntl.h>
 #include <string.h>
 #include <sys/stat.h>
@@ -115,19 +116,43 @@ int read_whole_file(const char* path, std::vector<unsigned char>& out)
 	return FR_OK;
 }
 
-// gzip member -> bytes (partio inflates .bgeo files that start with 1f 8b, ZIP.cpp:100-110, 260-300)
-int gunzip(const unsigned char* src, size_t n, std::vector<unsigned char>& out)
+// gzip member -> bytes (partio inflates .bgeo files that start with 1f 8b, ZIP.cpp:100-110, 260-300).  `want` > 0:
+// stop after that many bytes (header probe).  The output is bounded: deflate cannot expand beyond ~1032 : 1, and
+// FR_BGEO_MAX_INFLATED (default 16 GiB) caps what a crafted stream may make the host allocate.
+int gunzip(const unsigned char* src, size_t n, std::vector<unsigned char>& out, size_t want = 0)
 {
+	static size_t const hard_cap = [] {
+		const char* e = getenv("FR_BGEO_MAX_INFLATED");
+		unsigned long long const v = e ? strtoull(e, nullptr, 10) : 0ull;
+		return (size_t)(v ? v : (16ull << 30));
+	}();
 	z_stream zs;
 	memset(&zs, 0, sizeof zs);
 	if (inflateInit2(&zs, 16 + MAX_WBITS) != Z_OK) { set_error("bgeo: inflateInit2 failed"); return FR_ERR_INVALID; }
-	out.resize(n * 4 + 65536);
-	zs.next_in = const_cast<unsigned char*>(src);
-	zs.avail_in = (uInt)n;
-	size_t produced = 0;
+	size_t const first = want ? want : n * 4 + 65536;
+	out.resize(first < hard_cap ? first : hard_cap);
+	size_t consumed = 0, produced = 0;
 	for (;;)
 	{
-		if (produced == out.size()) out.resize(out.size() * 2);
+		if (want && produced >= want) break;
+		if (produced == out.size())
+		{
+			if (out.size() >= hard_cap)
+			{
+				inflateEnd(&zs);
+				set_error("bgeo: gzip stream inflates beyond FR_BGEO_MAX_INFLATED");
+				return FR_ERR_INVALID;
+			}
+			size_t const grown = out.size() * 2;
+			out.resize(grown < hard_cap ? grown : hard_cap);
+		}
+		if (zs.avail_in == 0 && consumed < n)
+		{
+			size_t const chunk = n - consumed > 0x40000000u ? 0x40000000u : n - consumed;      // avail_in is 32 bits
+			zs.next_in = const_cast<unsigned char*>(src) + consumed;
+			zs.avail_in = (uInt)chunk;
+			consumed += chunk;
+		}
 		zs.next_out = out.data() + produced;
 		size_t const room = out.size() - produced;
 		zs.avail_out = (uInt)(room > 0x40000000u ? 0x40000000u : room);
@@ -135,7 +160,7 @@ int gunzip(const unsigned char* src, size_t n, std::vector<unsigned char>& out)
 		int const rc = inflate(&zs, Z_NO_FLUSH);
 		produced += before - zs.avail_out;
 		if (rc == Z_STREAM_END) break;
-		if (rc != Z_OK || (zs.avail_in == 0 && before == zs.avail_out))
+		if (rc != Z_OK || (zs.avail_in == 0 && consumed == n && before == zs.avail_out))
 		{
 			inflateEnd(&zs);
 			set_error("bgeo: corrupt gzip stream");
@@ -156,7 +181,9 @@ struct LoadedFile
 	fr_bgeo_info info{};
 };
 
-int load_file(const char* path, LoadedFile& lf)
+// header_only: a gzip'd file is inflated only as far as its header and attribute table reach (fr_bgeo_probe); the
+// length of the point block is then checked against the member's ISIZE trailer instead of the inflated bytes
+int load_file(const char* path, LoadedFile& lf, bool header_only = false)
 {
 	if (!path) { set_error("bgeo: null path"); return FR_ERR_INVALID; }
 	int rc = read_whole_file(path, lf.raw);
@@ -164,7 +191,32 @@ int load_file(const char* path, LoadedFile& lf)
 	lf.bytes = lf.raw.data();
 	lf.size = lf.raw.size();
 	memset(&lf.info, 0, sizeof lf.info);
-	if (lf.size >= 2 && lf.raw[0] == 0x1f && lf.raw[1] == 0x8b)
+	bool const gz = lf.size >= 2 && lf.raw[0] == 0x1f && lf.raw[1] == 0x8b;
+	if (gz && header_only)
+	{
+		fr_bgeo_info info;
+		for (size_t want = 65536;; want *= 4)
+		{
+			if ((rc = gunzip(lf.raw.data(), lf.raw.size(), lf.inflated, want))) return rc;
+			memset(&info, 0, sizeof info);
+			rc = parse_header(lf.inflated.data(), lf.inflated.size(), &info);
+			if (rc != FR_ERR_STATE || lf.inflated.size() < want) break;      // parsed, malformed, or the whole stream is in
+		}
+		if (rc == FR_ERR_STATE) { set_error("bgeo: file ends inside the header"); return FR_ERR_INVALID; }
+		if (rc) return rc;
+		info.compressed = 1;
+		info.file_bytes = lf.raw.size();
+		uint64_t const need = info.data_offset + info.num_particles * info.record_words * 4ull;
+		uint32_t isize = 0;
+		if (lf.raw.size() >= 18) memcpy(&isize, lf.raw.data() + lf.raw.size() - 4, 4);      // uncompressed size mod 2^32 (little-endian hosts)
+		if (need < 0xffffffffull && lf.inflated.size() < need && (uint64_t)isize < need)
+		{ set_error("bgeo: file ends inside the point block"); return FR_ERR_INVALID; }
+		lf.info = info;
+		lf.bytes = lf.inflated.data();
+		lf.size = lf.inflated.size();
+		return FR_OK;
+	}
+	if (gz)
 	{
 		if ((rc = gunzip(lf.raw.data(), lf.raw.size(), lf.inflated))) return rc;
 		lf.bytes = lf.inflated.data();
@@ -238,7 +290,7 @@ int stage_bgeo(Context* ctx, const char* path, size_t* n_out)
 	int rc = ensure_pinned(ctx, fsize + 16);
 	if (rc) { close(fd); return rc; }
 	// the previous upload from this staging buffer must have left it
-	{ int const src = stream_sync(ctx); if (src) return src; }
+	{ int const src = stream_sync(ctx); if (src) { close(fd); return src; } }
 	size_t got = 0;
 	while (got < fsize)
 	{
@@ -292,7 +344,7 @@ int fr_bgeo_probe(const char* path, fr_bgeo_info* out)
 {
 	if (!out) { set_error("fr_bgeo_probe: null out"); return FR_ERR_INVALID; }
 	LoadedFile lf;
-	int const rc = load_file(path, lf);
+	int const rc = load_file(path, lf, true);
 	if (rc) return rc;
 	*out = lf.info;
 	return FR_OK;
@@ -380,15 +432,14 @@ int fr_upload_frame_bgeo(fr_context* ctx, int frame, const char* path, float h, 
 {
 	if (!ctx) { set_error("null context"); return FR_ERR_INVALID; }
 	FM_CUDA(cudaSetDevice(ctx->device));
+	int rc = fr_wait(ctx);             // a pending render's events are read before they are recorded again
+	if (rc) return rc;
 	FM_TIME(ctx, ctx->ev[0], ctx->stream);
 	size_t n = 0;
-	int rc = stage_bgeo(ctx, path, &n);
-	if (rc) return rc;
+	if ((rc = stage_bgeo(ctx, path, &n))) return rc;
 	FM_TIME(ctx, ctx->ev[1], ctx->stream);
 	rc = fr_build_frame_device(ctx, frame, ctx->d_xyz, n, h, h_ext_mult);
 	if (rc == FR_OK && ctx->build_timed) ctx->build_timed = 2;      // upload_ms = file block copy + decode
-	float ms = 0.0f;
-	(void)ms;                      // upload_ms (file block copy + decode) is read with the other build timings
 	return rc;
 }
 

@@ -84,6 +84,7 @@ int stream_sync(Context* c)
 
 static void free_frame(Frame& f)
 {
+	free_frame_small(f);
 	if (f.d_sorted) cudaFree(f.d_sorted);
 	if (f.d_cell_start) cudaFree(f.d_cell_start);
 	if (f.d_grid_counts) cudaFree(f.d_grid_counts);
@@ -140,14 +141,41 @@ static void read_build_timings(Context* c)
 	c->build_timed = 0;
 }
 
-static int finish_pending(Context* c)
+static int render_passes(fr_context* ctx, int passes);
+
+// every host wait of a context ends here: the stream is drained, the grid parameters of the frames built since the
+// last wait come back (resolve_frame), and a frame whose build found the tables of its slot too small has been rebuilt
+// -- the render queued behind the first attempt is then repeated.  Returns FR_RETRIED in that case (copies the caller
+// queued behind the render carry the first attempt's pixels), FR_OK or an error otherwise.
+static int finish_pending_ex(Context* c)
 {
+	bool const rendered = c->render_pending;
 	if (c->render_pending)
 	{
 		// (a lane records no completion event: it waits for its whole stream, copies behind the render included)
 		if (c->blocking_sync || !c->stage_timing) { int const rc = stream_sync(c); if (rc) return rc; }
 		else FM_CUDA(cudaEventSynchronize(c->ev_done));
 		c->render_pending = false;
+	}
+	int retried = FR_OK;
+	for (size_t k = 0; k < c->pending_frames.size(); k++)
+	{
+		int const idx = c->pending_frames[k];
+		if (idx < 0 || (size_t)idx >= c->frames.size()) continue;
+		int const rc = resolve_frame(c, &c->frames[idx], rendered);
+		if (rc < 0) { c->pending_frames.clear(); c->build_timed = 0; return rc; }
+		if (rc == FR_RETRIED) retried = FR_RETRIED;
+	}
+	c->pending_frames.clear();
+	if (retried == FR_RETRIED && rendered)
+	{
+		int rc = render_passes(static_cast<fr_context*>(c), c->last_passes);
+		if (rc) return rc;
+		if ((rc = stream_sync(c))) return rc;
+		c->render_pending = false;
+	}
+	if (rendered)
+	{
 		read_build_timings(c);
 		float ms = 0.0f;
 		if (c->stage_timing && cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]) == cudaSuccess) c->timings.depth_ms = ms;
@@ -159,13 +187,24 @@ static int finish_pending(Context* c)
 			if (cudaEventElapsedTime(&ms, c->ev[11], c->ev[6]) == cudaSuccess) c->timings.march_long_ms = ms;
 		}
 	}
-	else if (c->build_timed)       // a frame build without a render behind it
+	else if (c->build_timed)       // a frame build without a render behind it: its times are read at the next real wait
 	{
-		int const rc = stream_sync(c);
-		if (rc) return rc;
-		read_build_timings(c);
+		if (cudaEventQuery(c->ev[3]) == cudaSuccess) read_build_timings(c);
 	}
-	return FR_OK;
+	return retried;
+}
+
+static int finish_pending(Context* c)
+{
+	int const rc = finish_pending_ex(c);
+	return rc == FR_RETRIED ? FR_OK : rc;
+}
+
+// host copy of a frame's grid parameters for the entry points that need them
+static int resolved(Context* c, Frame* f)
+{
+	int const rc = resolve_frame(c, f);
+	return rc == FR_RETRIED ? FR_OK : rc;
 }
 
 }  // namespace fm
@@ -216,16 +255,17 @@ int fr_create(int device, int width, int height, fr_context** out)
 	{
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaHostAlloc((void**)&c->h_sync_flag, 64, cudaHostAllocMapped) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		*c->h_sync_flag = 0u;
 		if (cudaHostGetDevicePointer((void**)&c->d_sync_flag, (void*)c->h_sync_flag, 0) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		for (auto& ev : c->ev)
 			if (cudaEventCreate(&ev) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (rc) break;
-		if (cudaMalloc((void**)&c->d_gp, sizeof(GridParams)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		c->cslot = cslot_acquire();
+		if (c->cslot < 0) { set_error("fr_create: more than 64 contexts alive in this process"); rc = FR_ERR_STATE; break; }
 		if (cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
-		if (cudaMallocHost((void**)&c->h_gp, sizeof(GridParams)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaMallocHost((void**)&c->h_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		rc = alloc_images(c, width, height);
 	} while (0);
@@ -283,15 +323,16 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_tiles) cudaFree(ctx->d_tiles);
 	if (ctx->d_rayq) cudaFree(ctx->d_rayq);
 	if (ctx->d_survivors) cudaFree(ctx->d_survivors);
-	if (ctx->d_gp) cudaFree(ctx->d_gp);
+	if (ctx->d_tmp_idx) cudaFree(ctx->d_tmp_idx);
+	cslot_release(ctx->cslot);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
-	if (ctx->h_gp) cudaFreeHost(ctx->h_gp);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	if (ctx->ext_wait) cudaDestroyExternalSemaphore(ctx->ext_wait);
 	if (ctx->ext_signal) cudaDestroyExternalSemaphore(ctx->ext_signal);
 	if (ctx->ext_mem) cudaDestroyExternalMemory(ctx->ext_mem);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
+	if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
 	if (ctx->h_sync_flag) cudaFreeHost((void*)ctx->h_sync_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -332,12 +373,21 @@ int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n,
 	FM_TIME(ctx, ctx->ev[0], ctx->stream);
 	FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, xyz_host, n * 12, cudaMemcpyHostToDevice, ctx->stream));
 	FM_TIME(ctx, ctx->ev[1], ctx->stream);
+	FM_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
 	rc = build_frame(ctx, f, ctx->d_xyz, n, h, h_ext_mult);
 	if (rc) return rc;
+	ctx->pending_frames.push_back(frame);
 	ctx->build_timed = 2;
-	// The copy out of xyz_host is complete (build_frame waits for the grid parameters behind it); the rest of the
-	// build is left on the stream, so a render can be queued right behind it.  Its times are read when the host
-	// next waits for the stream (fr_wait / fr_download / fr_get_timings).
+	// The build stays queued on the stream (a build into the tables of an earlier frame never waited for the device at
+	// all), so a render can be queued right behind it; xyz_host, however, is the caller's again when this returns
+	FM_CUDA(cudaEventSynchronize(ctx->ev_copy));
+	return FR_OK;
+}
+
+int fr_set_async_build(fr_context* ctx, int on)
+{
+	FR_CHECK_CTX(ctx);
+	ctx->async_build = on != 0;
 	return FR_OK;
 }
 
@@ -357,6 +407,7 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 	if ((rc = finish_pending(ctx))) return rc;
 	const float* d_xyz = nullptr;
 	size_t n = (size_t)job.n;
+	ctx->lane_h2d_src = nullptr;
 	if (bgeo_path)
 	{
 		if ((rc = stage_bgeo(ctx, bgeo_path, &n))) return rc;
@@ -367,18 +418,25 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 	{
 		if (!job.xyz || n == 0) { set_error("sequence job without particles"); return FR_ERR_INVALID; }
 		if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
-		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, job.xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
+		// the copy is queued by lane_frame_enqueue, in front of the build: one graph holds the whole frame
+		ctx->lane_h2d_src = job.xyz;
+		ctx->lane_h2d_bytes = n * 12;
 		d_xyz = ctx->d_xyz;
 	}
 	ctx->build_timed = 0;
-	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult);
+	// the anisotropic march needs the host copy of the grid parameters for its second search (build_frame_ext)
+	bool const allow_async = !ctx->settings.enable_anisotropy;
+	if (ctx->lane_h2d_src && !(allow_async && ctx->async_build && f->cap_cells > 1))
+	{
+		// this build will wait for the device inside build_frame_begin: the particles have to be on their way first
+		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, ctx->lane_h2d_src, ctx->lane_h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->lane_h2d_src = nullptr;
+	}
+	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult, allow_async);
 }
 
-int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
+int lane_frame_copies(fr_context* ctx, const fr_seq_job& job)
 {
-	int rc = build_frame_finish(ctx);
-	if (rc) return rc;
-	if ((rc = fr_render_async(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
 	cudaStream_t const s = ctx->stream;
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
@@ -386,6 +444,30 @@ int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
 	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
 	return FR_OK;
+}
+
+int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
+{
+	int rc;
+	if (ctx->lane_h2d_src)
+	{
+		if (!ctx->build.async)       // (the prediction of lane_frame_begin and the decision of build_frame_begin differ only here)
+		{ set_error("lane: a synchronous build without its particles"); return FR_ERR_STATE; }
+		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, ctx->lane_h2d_src, ctx->lane_h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
+		ctx->lane_h2d_src = nullptr;
+	}
+	if ((rc = build_frame_finish(ctx))) return rc;
+	ctx->pending_frames.push_back(0);
+	if ((rc = fr_render_async(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
+	return lane_frame_copies(ctx, job);
+}
+
+// the lane's wait for its frame; FR_RETRIED: the frame was rebuilt and rendered again (its tables had to grow), the
+// copies queued behind the first attempt have to be repeated
+int lane_frame_wait(fr_context* ctx)
+{
+	FM_CUDA(cudaSetDevice(ctx->device));
+	return finish_pending_ex(ctx);
 }
 
 }  // namespace fm
@@ -402,6 +484,7 @@ int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, s
 	if ((rc = finish_pending(ctx))) return rc;
 	rc = build_frame(ctx, f, xyz_device, n, h, h_ext_mult);
 	if (rc) return rc;
+	ctx->pending_frames.push_back(frame);
 	ctx->build_timed = 1;
 	return FR_OK;                  // xyz_device must stay valid until the host next waits for this context
 }
@@ -420,6 +503,7 @@ int fr_get_frame_info(fr_context* ctx, int frame, fr_frame_info* out)
 	if (!out) { set_error("fr_get_frame_info: null out"); return FR_ERR_INVALID; }
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
+	{ int const rrc = resolved(ctx, f); if (rrc) return rrc; }
 	unsigned long long occ = 0;
 	FM_CUDA(cudaMemcpyAsync(&occ, f->d_occupied, sizeof occ, cudaMemcpyDeviceToHost, ctx->stream));
 	{ int const src = stream_sync(ctx); if (src) return src; }
@@ -454,6 +538,7 @@ int fr_download_frame(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* 
 	FR_CHECK_CTX(ctx);
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
+	{ int const rrc = resolved(ctx, f); if (rrc) return rrc; }
 	cudaStream_t const s = ctx->stream;
 	size_t const cells = (size_t)f->gp.kdim[0] * f->gp.kdim[1] * f->gp.kdim[2];
 	size_t const gcells = (size_t)f->gp.gdim[0] * f->gp.gdim[1] * f->gp.gdim[2];
@@ -540,11 +625,31 @@ int fr_render_async(fr_context* ctx, int passes)
 		set_error("fr_render_async: march without a depth image (call fr_set_depth or include FR_PASS_DEPTH)");
 		return FR_ERR_STATE;
 	}
-	int rc = finish_pending(ctx);
-	if (rc) return rc;
+	// a render still in flight is finished first (its timings are read); a frame build that is merely queued is not
+	// waited for: the render goes right behind it on the stream
+	if (ctx->render_pending) { int const rc = finish_pending(ctx); if (rc) return rc; }
+	return render_passes(ctx, passes);
+}
+
+}  // extern "C"
+
+namespace fm
+{
+
+static int render_passes(fr_context* ctx, int passes)
+{
+	Frame* f = get_frame(ctx, ctx->settings.frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc;
 	cudaStream_t const s = ctx->stream;
-	// Frame::m_SearchExt (the reference builds it in Frame::Frame; here on the frame's first anisotropic render)
-	if ((passes & FR_PASS_MARCH) && ctx->settings.enable_anisotropy && (rc = build_frame_ext(ctx, f))) return rc;
+	// Frame::m_SearchExt (the reference builds it in Frame::Frame; here on the frame's first anisotropic render).  Its
+	// cell ranges are computed on the host from the frame's extrema
+	if ((passes & FR_PASS_MARCH) && ctx->settings.enable_anisotropy && !f->ext_valid)
+	{
+		if (!f->gp_host_valid && (rc = resolved(ctx, f))) return rc;
+		if ((rc = build_frame_ext(ctx, f))) return rc;
+		if ((rc = upload_view_ext(ctx, f))) return rc;
+	}
 	if (ctx->ext_wait)
 	{
 		cudaExternalSemaphoreWaitParams wp;
@@ -571,8 +676,13 @@ int fr_render_async(fr_context* ctx, int passes)
 	}
 	if (ctx->stage_timing) FM_CUDA(cudaEventRecord(ctx->ev_done, s));
 	ctx->render_pending = true;
+	ctx->last_passes = passes;
 	return FR_OK;
 }
+
+}  // namespace fm
+
+extern "C" {
 
 int fr_is_done(fr_context* ctx)
 {
@@ -729,6 +839,8 @@ int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, siz
 	if ((m && (!points_host || !counts))) { set_error("fr_query_neighbors: null array"); return FR_ERR_INVALID; }
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
+	{ int const rrc = finish_pending(ctx); if (rrc) return rrc; }
+	{ int const rrc = resolved(ctx, f); if (rrc) return rrc; }
 	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap, false);
 }
 
@@ -741,6 +853,7 @@ int fr_query_neighbors_ext(fr_context* ctx, int frame, const float* points_host,
 	if (!f) return FR_ERR_STATE;
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
+	if ((rc = resolved(ctx, f))) return rc;
 	if ((rc = build_frame_ext(ctx, f))) return rc;
 	return query_neighbors(ctx, *f, points_host, m, counts, ids, cap, true);
 }
@@ -753,6 +866,7 @@ int fr_query_anisotropic(fr_context* ctx, int frame, const float* points_host, s
 	if (!f) return FR_ERR_STATE;
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
+	if ((rc = resolved(ctx, f))) return rc;
 	if ((rc = build_frame_ext(ctx, f))) return rc;
 	return query_aniso(ctx, *f, ctx->settings, points_host, m, density, grad, g9);
 }
@@ -765,6 +879,7 @@ int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32
 	if (!f) return FR_ERR_STATE;
 	int rc = finish_pending(ctx);
 	if (rc) return rc;
+	if ((rc = resolved(ctx, f))) return rc;
 	if ((rc = build_frame_ext(ctx, f))) return rc;
 	cudaStream_t const s = ctx->stream;
 	size_t const cells = (size_t)f->kdim_ext[0] * f->kdim_ext[1] * f->kdim_ext[2];
@@ -785,6 +900,8 @@ int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_
 	if ((m && (!points_host || !density))) { set_error("fr_query_density: null array"); return FR_ERR_INVALID; }
 	Frame* f = get_frame(ctx, frame, true);
 	if (!f) return FR_ERR_STATE;
+	{ int const rrc = finish_pending(ctx); if (rrc) return rrc; }
+	{ int const rrc = resolved(ctx, f); if (rrc) return rrc; }
 	return query_density(ctx, *f, points_host, m, density, grad);
 }
 

@@ -3,19 +3,27 @@
 // Replaces Frame::Frame (src/app/Dataset.cpp:9-24): BuildSearch (CompactNSearch hash + z-sort,
 // :49-76), ComputeAABB (:78-92) and BuildDensityGrid (:94-165) with a uniform-grid counting sort:
 //
-//   k_aabb          particle min/max                      reads 12 B/particle
-//   k_grid_params   m_Min/m_Max/dims/cell ranges          (1 thread; exact FP32 ops of the reference)
-//   k_key_count     cell key + histogram (+ occupancy histogram)   reads 12 B, writes 4 B/particle
-//   k_scan_*        exclusive prefix sum over the cell histogram   8 B/cell
-//   k_scatter       counting-sort scatter into float4 SoA           reads 16 B, writes 16 B/particle
-//   k_cell_order    particles of a cell into ascending original index (deterministic sums)   reads 16+ B, writes 16 B/particle
-//   k_flags         OctreeNode::Flag bitmask                        4 B/cell
+//   k_aabb_params   particle min/max (12 B/particle), non-finite check; the last block to finish derives m_Min/m_Max/
+//                   dims/cell ranges with the reference's exact FP32 expressions, checks them against the table
+//                   capacities and leaves GridParams + the march's FrameView in device memory
+//   k_key_count     cell key + histogram + occupancy histogram            reads 12 B, writes 4 B/particle
+//   k_scan_flags    exclusive prefix sum over the cell histogram in ONE pass (decoupled look-back, 8 B/cell)
+//                   + OctreeNode::Flag bitmask (4 B/cell)
+//   k_scatter       counting-sort scatter of the particle indices         reads 4 B, writes 4 B/particle
+//   k_cell_order    particles of a cell into ascending original index (deterministic sums), gathers the positions
+//                   into the float4 SoA                                    reads 16+ B, writes 16 B/particle
 //
-// All of it is HBM/L2-bound integer and copy work; nothing here is a contraction.
+// Every kernel behind k_aabb_params reads the grid parameters from device memory, so a build into tables that already
+// exist (every frame of a sequence but the first) needs no host round trip: the host sizes its launches by the table
+// capacities, the device compares the real sizes with them and raises FM_GRID_OVERFLOW (checked when the host next
+// waits; the frame is then rebuilt with the round trip).  All of it is HBM/L2-bound integer and copy work.
 #include "fm_internal.h"
 
 #include <math.h>
 #include <string.h>
+
+#include <algorithm>
+#include <mutex>
 
 namespace fm
 {
@@ -24,37 +32,40 @@ namespace
 {
 
 constexpr int kThreads = 256;
+constexpr int kPartialStride = 8;         // floats per block in the AABB scratch: 3 min, 3 max, non-finite flag, pad
 
-// order-preserving float <-> uint encoding for atomicMin/atomicMax
+// order-preserving float <-> uint encoding
 __device__ __forceinline__ uint32_t enc_ordered(float f)
 {
 	uint32_t const u = __float_as_uint(f);
 	return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
-__device__ __forceinline__ float dec_ordered(uint32_t u)
-{
-	return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
-}
-
-// Frame::ComputeAABB (Dataset.cpp:78-92): min/max are exact, so any reduction order gives the same bits.  Each block
-// leaves its extrema in `partial` (6 floats per block; no atomics, nothing to initialise); as a side job the grid
-// zeroes the two histogram buffers of the build up to their current capacity, which saves two memsets per frame.
-__global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz, uint32_t n, float* __restrict__ partial,
-												   uint32_t* __restrict__ zero_a, uint32_t words_a,
-												   uint32_t* __restrict__ zero_b, uint32_t words_b)
+// Frame::ComputeAABB (Dataset.cpp:78-92) + the grid parameters.  min/max are exact, so any reduction order gives the
+// reference's bits.  Each block leaves its extrema in `partial`; the block that finishes last (ticket) reduces them
+// and one thread evaluates the reference's FP32 expressions for m_Min / m_Max / dims (Dataset.cpp:78-104) and the
+// CompactNSearch cell ranges.  As a side job the grid zeroes the histogram / scan-state buffers of the build up to
+// their current capacity, which saves the memsets.
+__global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restrict__ xyz, uint32_t n, float* __restrict__ partial,
+														  uint32_t* __restrict__ ticket,
+														  uint32_t* __restrict__ zero_a, uint32_t words_a,
+														  uint32_t* __restrict__ zero_b, uint32_t words_b,
+														  float h, BuildCaps caps, FrameView view, GridParams* __restrict__ gp,
+														  FrameView* __restrict__ view_out, unsigned long long* __restrict__ occupied)
 {
 	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
 	for (uint32_t i = gtid; i < words_b; i += gsize) zero_b[i] = 0u;
 	float mn[3] = { INFINITY, INFINITY, INFINITY };
 	float mx[3] = { -INFINITY, -INFINITY, -INFINITY };
+	bool bad = false;
 	for (uint32_t i = gtid; i < n; i += gsize)
 	{
 #pragma unroll
 		for (int a = 0; a < 3; a++)
 		{
 			float const v = __ldg(xyz + 3ull * i + a);
+			bad |= !isfinite(v);                // fminf / fmaxf would silently drop a NaN
 			mn[a] = fminf(mn[a], v);
 			mx[a] = fmaxf(mx[a], v);
 		}
@@ -69,35 +80,49 @@ __global__ void __launch_bounds__(kThreads) k_aabb(const float* __restrict__ xyz
 			mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
 		}
 	}
+	bad = __any_sync(0xffffffffu, bad);
 	__shared__ float s_mn[3][kThreads / 32], s_mx[3][kThreads / 32];
+	__shared__ uint32_t s_bad[kThreads / 32];
+	__shared__ bool s_last;
 	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (lane == 0)
-		for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
-	__syncthreads();
-	if (threadIdx.x < 3)
 	{
-		int const a = threadIdx.x;
-		float lo = s_mn[a][0], hi = s_mx[a][0];
-		for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
-		partial[6 * blockIdx.x + a] = lo;
-		partial[6 * blockIdx.x + 3 + a] = hi;
+		for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+		s_bad[warp] = bad ? 1u : 0u;
 	}
-}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t any_bad = 0;
+		for (int w = 0; w < kThreads / 32; w++) any_bad |= s_bad[w];
+		for (int a = 0; a < 3; a++)
+		{
+			float lo = s_mn[a][0], hi = s_mx[a][0];
+			for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
+			partial[kPartialStride * blockIdx.x + a] = lo;
+			partial[kPartialStride * blockIdx.x + 3 + a] = hi;
+		}
+		partial[kPartialStride * blockIdx.x + 6] = any_bad ? 1.0f : 0.0f;
+		__threadfence();
+		s_last = atomicAdd(ticket, 1u) == gridDim.x - 1u;
+	}
+	__syncthreads();
+	if (!s_last) return;
 
-// one block: the extrema over the blocks of k_aabb, then m_Min / m_Max / dims / cell ranges with the reference's exact
-// FP32 expressions
-__global__ void __launch_bounds__(kThreads) k_grid_params(GridParams* gp, const float* __restrict__ partial, uint32_t blocks, float h,
-														  unsigned long long* occupied)
-{
-	float mn[3] = { INFINITY, INFINITY, INFINITY };
-	float mx[3] = { -INFINITY, -INFINITY, -INFINITY };
-	for (uint32_t b = threadIdx.x; b < blocks; b += kThreads)
+	// ---- the last block: extrema over all blocks, then the parameters ------------------------------------------------
+	__threadfence();
+	for (int a = 0; a < 3; a++) { mn[a] = INFINITY; mx[a] = -INFINITY; }
+	float fbad = 0.0f;
+	for (uint32_t b = threadIdx.x; b < gridDim.x; b += kThreads)
+	{
 #pragma unroll
 		for (int a = 0; a < 3; a++)
 		{
-			mn[a] = fminf(mn[a], partial[6 * b + a]);
-			mx[a] = fmaxf(mx[a], partial[6 * b + 3 + a]);
+			mn[a] = fminf(mn[a], __ldcg(partial + kPartialStride * b + a));
+			mx[a] = fmaxf(mx[a], __ldcg(partial + kPartialStride * b + 3 + a));
 		}
+		fbad = fmaxf(fbad, __ldcg(partial + kPartialStride * b + 6));
+	}
 #pragma unroll
 	for (int a = 0; a < 3; a++)
 	{
@@ -108,37 +133,79 @@ __global__ void __launch_bounds__(kThreads) k_grid_params(GridParams* gp, const 
 			mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
 		}
 	}
-	__shared__ float s_mn[3][kThreads / 32], s_mx[3][kThreads / 32];
-	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	bad = __any_sync(0xffffffffu, fbad != 0.0f);
+	__syncthreads();
 	if (lane == 0)
+	{
 		for (int a = 0; a < 3; a++) { s_mn[a][warp] = mn[a]; s_mx[a][warp] = mx[a]; }
+		s_bad[warp] = bad ? 1u : 0u;
+	}
 	__syncthreads();
 	if (threadIdx.x != 0) return;
+	*ticket = 0u;                                    // ready for the next build
 	*occupied = 0ull;
+	uint32_t status = 0;
+	for (int w = 0; w < kThreads / 32; w++) status |= s_bad[w] ? (uint32_t)FM_GRID_NONFINITE : 0u;
 	float const pad = mulr(1.0f, h);                 // padding = 1.0f * ParticleRadius (Dataset.cpp:89)
 	float const cw = mulr(1.0f, h);                  // cellWidth = 1.0f * ParticleRadius (Dataset.cpp:96)
 	float const search_inv = divr(1.0f, h);          // CompactNSearch: inverse cell size in Real
-	gp->cell_width = cw;
-	gp->inv_cell_width = divr(1.0f, cw);             // m_InvCellWidthVec = 1.0f / vec3(cellWidth) (:98)
-	gp->search_inv = search_inv;
+	GridParams g;
+	g.cell_width = cw;
+	g.inv_cell_width = divr(1.0f, cw);               // m_InvCellWidthVec = 1.0f / vec3(cellWidth) (:98)
+	g.search_inv = search_inv;
+	double cells = 1.0, gcells = 1.0;
 	for (int a = 0; a < 3; a++)
 	{
 		float lo = s_mn[a][0], hi = s_mx[a][0];
 		for (int w = 1; w < kThreads / 32; w++) { lo = fminf(lo, s_mn[a][w]); hi = fmaxf(hi, s_mx[a][w]); }
-		gp->raw_min[a] = enc_ordered(lo);            // kept for build_frame_ext (the r = h_ext search ranges)
-		gp->raw_max[a] = enc_ordered(hi);
+		g.raw_min[a] = enc_ordered(lo);              // kept for build_frame_ext (the r = h_ext search ranges)
+		g.raw_max[a] = enc_ordered(hi);
 		float const mn_a = subr(lo, pad);
 		float const mx_a = addr(hi, pad);
-		gp->mn[a] = mn_a;
-		gp->mx[a] = mx_a;
-		gp->gdim[a] = (int32_t)ceilf(divr(subr(mx_a, mn_a), cw));   // int32_t(std::ceil(aabb / cellWidth)) (:102-104)
+		g.mn[a] = mn_a;
+		g.mx[a] = mx_a;
+		float const fdim = ceilf(divr(subr(mx_a, mn_a), cw));       // int32_t(std::ceil(aabb / cellWidth)) (:102-104)
+		float const k0f = floorf(mulr(search_inv, lo)), k1f = floorf(mulr(search_inv, hi));
+		if (!isfinite(mn_a) || !isfinite(mx_a) || !(fdim >= 1.0f) || !(fdim < 2147483000.0f) || !(fabsf(k0f) < 2147483000.0f) ||
+			!(fabsf(k1f) < 2147483000.0f))
+		{
+			status |= (uint32_t)FM_GRID_DEGENERATE;
+			g.gdim[a] = 0; g.kmin[a] = 0; g.kdim[a] = 0;
+			continue;
+		}
+		g.gdim[a] = (int32_t)fdim;
 		int const k0 = search_cell_of(search_inv, lo);              // cell index is monotone in x
 		int const k1 = search_cell_of(search_inv, hi);
-		gp->kmin[a] = k0;
-		gp->kdim[a] = k1 - k0 + 1;
+		g.kmin[a] = k0;
+		g.kdim[a] = k1 - k0 + 1;
+		cells *= (double)g.kdim[a];
+		gcells *= (double)g.gdim[a];
 	}
+	if (!status && (cells >= 2147483000.0 || gcells >= 2147483000.0)) status |= (uint32_t)FM_GRID_DEGENERATE;
+	if (!status)
+	{
+		uint32_t const c32 = (uint32_t)cells, g32 = (uint32_t)gcells;
+		if (c32 > caps.cells || g32 > caps.gcells || (g32 + 31u) / 32u > caps.occ_words) status |= (uint32_t)FM_GRID_OVERFLOW;
+	}
+	g.cells = status ? 0u : (uint32_t)cells;
+	g.gcells = status ? 0u : (uint32_t)gcells;
+	g.status = status;
+	g.max_cell = 0u;
+	*gp = g;
+	// the frame as the march kernels see it; an unusable frame is an empty one (no cell is ever looked up)
+	view.kmin = make_int3(g.kmin[0], g.kmin[1], g.kmin[2]);
+	view.kdim = status ? make_int3(0, 0, 0) : make_int3(g.kdim[0], g.kdim[1], g.kdim[2]);
+	view.search_inv = g.search_inv;
+	view.mn = make_float3(g.mn[0], g.mn[1], g.mn[2]);
+	view.mx = make_float3(g.mx[0], g.mx[1], g.mx[2]);
+	view.gdim = status ? make_int3(0, 0, 0) : make_int3(g.gdim[0], g.gdim[1], g.gdim[2]);
+	view.cell_width = g.cell_width;
+	view.inv_cell_width = make_float3(g.inv_cell_width, g.inv_cell_width, g.inv_cell_width);
+	if (status) view.n = 0u;
+	*view_out = view;
 }
 
+// what the particle kernels need of GridParams, loaded once per thread (every lane reads the same words: L1 broadcasts)
 struct BuildView
 {
 	int3 kmin, kdim;
@@ -149,6 +216,21 @@ struct BuildView
 	float cw, half;          // cell width, half the search radius (find_neighbors_box reading FR_COUNT_CENTRE_BOX)
 	int count_mode;
 };
+
+__device__ __forceinline__ BuildView load_build_view(const GridParams* __restrict__ gp, float half, int count_mode)
+{
+	BuildView b;
+	b.kmin = make_int3(gp->kmin[0], gp->kmin[1], gp->kmin[2]);
+	b.kdim = make_int3(gp->kdim[0], gp->kdim[1], gp->kdim[2]);
+	b.search_inv = gp->search_inv;
+	b.mn = make_float3(gp->mn[0], gp->mn[1], gp->mn[2]);
+	b.gdim = make_int3(gp->gdim[0], gp->gdim[1], gp->gdim[2]);
+	b.inv_cw = gp->inv_cell_width;
+	b.cw = gp->cell_width;
+	b.half = half;
+	b.count_mode = count_mode;
+	return b;
+}
 
 __device__ __forceinline__ uint32_t search_key(const BuildView& b, float x, float y, float z)
 {
@@ -181,12 +263,14 @@ __device__ __forceinline__ uint32_t centre_box_mask(float p, float mn, int c, in
 // switch (fr_set_count_mode): FR_COUNT_CENTRE_BOX (default) = the half-open box of half-width r/2 around the query
 // point, which is what the reference build under oracle/_ref does; FR_COUNT_CELL_EXACT = the node
 // QueryDensityGrid(particle) returns.  The two differ only for particles within an ulp of a cell face.
-__global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, BuildView b,
+__global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, const GridParams* __restrict__ gp,
+														float half, int count_mode,
 														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
 														uint32_t* __restrict__ grid_counts)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	if (i >= n || gp->status) return;
+	BuildView const b = load_build_view(gp, half, count_mode);
 	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
 	uint32_t const key = search_key(b, x, y, z);
 	keys[i] = key;
@@ -222,10 +306,15 @@ __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict_
 					atomicAdd(grid_counts + ((uint32_t)(cx - 1 + kx) + (uint32_t)b.gdim.x * ((uint32_t)(cy - 1 + ky) + (uint32_t)b.gdim.y * (uint32_t)(cz - 1 + kz))), 1u);
 }
 
-// ---- exclusive scan over m counts, in place: data[i] <- sum(data[0..i)), data[m] <- total ------------
+// ---- exclusive scan over the per-cell counts in one pass + the occupancy flags ---------------------------------------
+// cell_start[i] <- sum(counts[0..i)), cell_start[cells] <- total.  Tiles of 4096 counts are handed out through a ticket
+// (a block that holds ticket t knows every smaller ticket is held by a block that is running or done, so waiting for
+// them cannot deadlock); a tile publishes its sum as soon as it has it, then looks back over its predecessors a warp
+// at a time until it meets one that already knows its prefix (decoupled look-back).
 constexpr int kScanThreads = 512;
 constexpr int kScanItems = 8;
 constexpr int kScanTile = kScanThreads * kScanItems;
+constexpr unsigned long long kTileSum = 1ull << 32, kTilePrefix = 2ull << 32;
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t& total)
 {
@@ -259,7 +348,146 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* s
 	return r;
 }
 
-// (src -> data: the per-cell counts stay in `src` for the scatter, their tile-local exclusive scan goes to `data`)
+// OctreeNode::Flag (Dataset.cpp:136-164).  The reference sums exp(-1000 * r) * NumParticles over the 27
+// cells; expf(-1000 r) is exactly 0 for r >= 1 and 1 for r = 0, and adding exact zeros changes nothing,
+// so N_c == float(NumParticles of the cell itself).  Flag = N_c * W0 > isoDensity with isoDensity = 1
+// (BuildDensityGrid(1), Dataset.cpp:23).
+__global__ void __launch_bounds__(kScanThreads) k_scan_flags(GridParams* __restrict__ gp, const uint32_t* __restrict__ counts,
+															 uint32_t* __restrict__ cell_start, unsigned long long* __restrict__ tile_state,
+															 uint32_t* __restrict__ ticket, const uint32_t* __restrict__ grid_counts, float W0,
+															 uint32_t* __restrict__ occ_bits, unsigned long long* __restrict__ occupied)
+{
+	if (gp->status) return;
+	uint32_t const m = gp->cells, gcells = gp->gcells;
+	uint32_t const ntiles = (m + kScanTile - 1) / kScanTile;
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	__shared__ uint32_t s_warp[33];
+	__shared__ uint32_t s_tile, s_prefix;
+	if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+	__syncthreads();
+	uint32_t const tile = s_tile;
+	if (tile < ntiles)
+	{
+		uint32_t const base = tile * kScanTile + threadIdx.x * kScanItems;
+		uint32_t v[kScanItems];
+		uint32_t sum = 0, biggest = 0;
+#pragma unroll
+		for (int k = 0; k < kScanItems; k++)
+		{
+			v[k] = (base + k < m) ? counts[base + k] : 0u;
+			sum += v[k];
+			biggest = max(biggest, v[k]);
+		}
+		biggest = __reduce_max_sync(0xffffffffu, biggest);
+		if (lane == 0 && biggest > kMaxCellParticles) atomicMax(&gp->max_cell, biggest);
+		uint32_t total;
+		uint32_t run = block_exclusive_scan(sum, s_warp, total);
+		if (warp == 0)
+		{
+			// publish, look back
+			if (lane == 0) atomicExch(tile_state + tile, (tile == 0 ? kTilePrefix : kTileSum) | total);
+			uint32_t prefix = 0;
+			int p = (int)tile - 1;
+			while (p >= 0)
+			{
+				int const mine = p - lane;
+				unsigned long long st = kTilePrefix;                          // lanes in front of tile 0: a zero prefix
+				if (mine >= 0)
+					do st = *reinterpret_cast<volatile unsigned long long*>(tile_state + mine); while ((st >> 32) == 0ull);
+				uint32_t const has_prefix = __ballot_sync(0xffffffffu, (st >> 32) == 2ull);
+				int const stop = has_prefix ? __ffs(has_prefix) - 1 : 32;    // nearest predecessor that knows its prefix
+				uint32_t const add = lane <= stop ? (uint32_t)st : 0u;
+				prefix += __reduce_add_sync(0xffffffffu, add);
+				if (has_prefix) break;
+				p -= 32;
+			}
+			if (lane == 0)
+			{
+				if (tile != 0) atomicExch(tile_state + tile, kTilePrefix | (unsigned long long)(prefix + total));
+				s_prefix = prefix;
+				if (tile == ntiles - 1) cell_start[m] = prefix + total;
+			}
+		}
+		__syncthreads();
+		run += s_prefix;
+#pragma unroll
+		for (int k = 0; k < kScanItems; k++)
+		{
+			if (base + k < m) cell_start[base + k] = run;
+			run += v[k];
+		}
+	}
+	// occupancy flags, a warp per 32 cells
+	uint32_t const warps = gridDim.x * (kScanThreads / 32);
+	uint32_t found = 0;
+	for (uint32_t w = blockIdx.x * (kScanThreads / 32) + warp; w * 32u < gcells; w += warps)
+	{
+		uint32_t const c = w * 32u + lane;
+		bool flag = false;
+		if (c < gcells) flag = mulr((float)grid_counts[c], W0) > 1.0f;
+		uint32_t const word = __ballot_sync(0xffffffffu, flag);
+		if (lane == 0) { occ_bits[w] = word; found += __popc(word); }
+	}
+	if (lane == 0 && found) atomicAdd(occupied, (unsigned long long)found);
+}
+
+// counting-sort scatter of the particle INDICES.  cursor[] holds the per-cell counts and is consumed (atomicSub), so
+// no second table is needed; the slot order inside a cell is arbitrary here and fixed by k_cell_order.
+__global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const GridParams* __restrict__ gp,
+													  const uint32_t* __restrict__ keys,
+													  const uint32_t* __restrict__ cell_start,
+													  uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_index)
+{
+	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n || gp->status) return;
+	uint32_t const key = keys[i];
+	uint32_t const left = atomicSub(cursor + key, 1u);       // count .. 1
+	slot_index[cell_start[key] + (left - 1u)] = i;
+}
+
+// one thread per particle slot: the final place of a particle inside its cell is its rank by original index
+// (number of cell mates with a smaller index), so that every FP32 sum over a cell runs in the reference's order
+// (ascending point id) and results are reproducible from run to run and from GPU to GPU.  `slot_index` holds the
+// cell's particles in arrival order of the scatter atomics; the positions are gathered from the input array.
+// The ranking is quadratic in the cell population: a cell with more than kMaxCellParticles particles (a collapsed
+// simulation) marks the frame FM_GRID_CROWDED instead of occupying the GPU for seconds.
+__global__ void __launch_bounds__(kThreads) k_cell_order(const float* __restrict__ xyz, uint32_t n, GridParams* __restrict__ gp,
+														 const uint32_t* __restrict__ slot_index,
+														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
+{
+	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n || gp->status) return;
+	if (gp->max_cell > kMaxCellParticles)
+	{
+		if (s == 0) atomicOr(&gp->status, (uint32_t)FM_GRID_CROWDED);     // (read by the host only: the march of this frame sees stale slots)
+		return;
+	}
+	uint32_t const id = __ldg(slot_index + s);
+	float const x = __ldg(xyz + 3ull * id), y = __ldg(xyz + 3ull * id + 1), z = __ldg(xyz + 3ull * id + 2);
+	BuildView const b = load_build_view(gp, 0.0f, 0);
+	uint32_t const key = search_key(b, x, y, z);
+	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
+	uint32_t rank = 0;
+	for (uint32_t t = cb; t < ce; t++) rank += __ldg(slot_index + t) < id ? 1u : 0u;
+	sorted[cb + rank] = make_float4(x, y, z, __uint_as_float(id));
+}
+
+// the r = h_ext search orders float4 records (k_scatter4): same ranking
+__global__ void __launch_bounds__(kThreads) k_cell_order4(const float4* __restrict__ unordered, uint32_t n, BuildView b,
+														  const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
+{
+	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= n) return;
+	float4 const v = __ldg(unordered + s);
+	uint32_t const id = __float_as_uint(v.w);
+	uint32_t const key = search_key(b, v.x, v.y, v.z);
+	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
+	uint32_t rank = 0;
+	for (uint32_t t = cb; t < ce; t++) rank += __float_as_uint(__ldg(&unordered[t].w)) < id ? 1u : 0u;
+	sorted[cb + rank] = v;
+}
+
+// two-kernel scan of the r = h_ext build (host-sized, not on the per-frame path)
 __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const uint32_t* __restrict__ src, uint32_t* __restrict__ data, uint32_t m,
 															 uint32_t* __restrict__ tile_sums)
 {
@@ -284,8 +512,6 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_tiles(const uint32_t* __r
 	if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
 }
 
-// adds to every tile the sum of the tiles in front of it (each block adds those few dozen sums up itself, which saves
-// the single-block scan of the tile sums and its launch) and writes the grand total behind the last element
 __global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* __restrict__ data, uint32_t m,
 														   const uint32_t* __restrict__ tile_sums, uint32_t tiles)
 {
@@ -299,7 +525,6 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* __restrict_
 		acc_all += v;
 		if (i < blockIdx.x) acc_before += v;
 	}
-	// two block reductions (sum of the tiles in front, and -- last block -- of all tiles)
 	uint32_t total = 0;
 	for (int pass = 0; pass < 2; pass++)
 	{
@@ -324,40 +549,6 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_add(uint32_t* __restrict_
 	if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) data[m] = total;
 }
 
-// counting-sort scatter.  cursor[] holds the per-cell counts and is consumed (atomicSub), so no
-// second table is needed; the slot order inside a cell is arbitrary here and fixed by k_cell_order.
-__global__ void __launch_bounds__(kThreads) k_scatter(const float* __restrict__ xyz, uint32_t n,
-													  const uint32_t* __restrict__ keys,
-													  const uint32_t* __restrict__ cell_start,
-													  uint32_t* __restrict__ cursor, float4* __restrict__ sorted)
-{
-	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	uint32_t const key = keys[i];
-	uint32_t const left = atomicSub(cursor + key, 1u);       // count .. 1
-	uint32_t const pos = cell_start[key] + (left - 1u);
-	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
-	sorted[pos] = make_float4(x, y, z, __uint_as_float(i));
-}
-
-// one thread per particle slot: the final place of a particle inside its cell is its rank by original index
-// (number of cell mates with a smaller index), so that every FP32 sum over a cell runs in the reference's order
-// (ascending point id) and results are reproducible from run to run and from GPU to GPU.  `unordered` holds the
-// cell's particles in arrival order of the scatter atomics.
-__global__ void __launch_bounds__(kThreads) k_cell_order(const float4* __restrict__ unordered, uint32_t n, BuildView b,
-														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
-{
-	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n) return;
-	float4 const v = __ldg(unordered + s);
-	uint32_t const id = __float_as_uint(v.w);
-	uint32_t const key = search_key(b, v.x, v.y, v.z);
-	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
-	uint32_t rank = 0;
-	for (uint32_t t = cb; t < ce; t++) rank += __float_as_uint(__ldg(&unordered[t].w)) < id ? 1u : 0u;
-	sorted[cb + rank] = v;
-}
-
 // ---- second search structure (r = h_ext) from the already sorted particles ----------------------------------------
 __global__ void __launch_bounds__(kThreads) k_key_count4(const float4* __restrict__ src, uint32_t n, BuildView b,
 														 uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count)
@@ -380,28 +571,6 @@ __global__ void __launch_bounds__(kThreads) k_scatter4(const float4* __restrict_
 	uint32_t const key = keys[i];
 	uint32_t const left = atomicSub(cursor + key, 1u);
 	out[cell_start[key] + (left - 1u)] = __ldg(src + i);
-}
-
-// OctreeNode::Flag (Dataset.cpp:136-164).  The reference sums exp(-1000 * r) * NumParticles over the 27
-// cells; expf(-1000 r) is exactly 0 for r >= 1 and 1 for r = 0, and adding exact zeros changes nothing,
-// so N_c == float(NumParticles of the cell itself).  Flag = N_c * W0 > isoDensity with isoDensity = 1
-// (BuildDensityGrid(1), Dataset.cpp:23).
-__global__ void __launch_bounds__(kThreads) k_flags(const uint32_t* __restrict__ grid_counts, uint32_t cells, float W0,
-													uint32_t* __restrict__ occ_bits, unsigned long long* occupied)
-{
-	uint32_t const c = blockIdx.x * blockDim.x + threadIdx.x;
-	bool flag = false;
-	if (c < cells)
-	{
-		float const rho = mulr((float)grid_counts[c], W0);
-		flag = rho > 1.0f;
-	}
-	uint32_t const word = __ballot_sync(0xffffffffu, flag);
-	if ((threadIdx.x & 31) == 0 && (c >> 5) < ((cells + 31u) >> 5))
-	{
-		occ_bits[c >> 5] = word;
-		if (word) atomicAdd(occupied, (unsigned long long)__popc(word));
-	}
 }
 
 }  // namespace
@@ -504,82 +673,175 @@ int build_frame_ext(Context* ctx, Frame* f)
 	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start_ext, cells32, d_tile_sums);
 	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start_ext, cells32, d_tile_sums, tiles);
 	k_scatter4<<<pblocks, kThreads, 0, s>>>(f->d_sorted, n32, ctx->d_keys, f->d_cell_start_ext, d_cursor, ctx->d_sort_tmp);
-	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start_ext, f->d_sorted_ext);
+	k_cell_order4<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start_ext, f->d_sorted_ext);
 	ctx->kernel_launches += 5;
 	FM_CUDA(cudaGetLastError());
 	f->ext_valid = true;
 	return FR_OK;
 }
 
-int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
+// ---- __constant__ slots of the march kernels (one per context, process-wide numbering) ---------------------------------
+static std::mutex g_slot_mutex;
+static unsigned long long g_slot_mask = 0ull;
+
+int cslot_acquire()
 {
-	int const rc = build_frame_begin(ctx, f, d_xyz, n, h, h_ext_mult);
+	std::lock_guard<std::mutex> lk(g_slot_mutex);
+	for (int k = 0; k < kConstSlots; k++)
+		if (!(g_slot_mask >> k & 1ull)) { g_slot_mask |= 1ull << k; return k; }
+	return -1;
+}
+
+void cslot_release(int slot)
+{
+	if (slot < 0) return;
+	std::lock_guard<std::mutex> lk(g_slot_mutex);
+	g_slot_mask &= ~(1ull << slot);
+}
+
+void free_frame_small(Frame& f)
+{
+	if (f.d_gp) cudaFree(f.d_gp);
+	if (f.d_fv) cudaFree(f.d_fv);
+	if (f.h_gp) cudaFreeHost(f.h_gp);
+	f.d_gp = nullptr; f.d_fv = nullptr; f.h_gp = nullptr;
+}
+
+// the part of the march's view the host knows without the grid parameters
+static FrameView static_view(const Frame& f)
+{
+	FrameView v;
+	memset(&v, 0, sizeof v);
+	v.sorted = f.d_sorted;
+	v.cell_start = f.d_cell_start;
+	v.occ_bits = f.d_occ_bits;
+	v.n = (uint32_t)f.n;
+	// CubicSplineKernel::CubicSplineKernel (Kernel.cpp:8-14), evaluated in FP32 like the reference
+	float const h = f.h;
+	v.kernel.h = h;
+	v.kernel.h_squared = h * h;
+	v.kernel.h_inv = 1.0f / h;
+	volatile float t = 3.14159265358979323846264338327950288f * h;
+	t = t * h;
+	t = t * h;
+	v.kernel.sig_d = 8.0f / t;
+	v.h_ext = f.h_ext;
+	v.h_ext_squared = f.h_ext * f.h_ext;
+	v.aniso_sig = 8.0f / 3.14159265358979323846264338327950288f;
+	return v;
+}
+
+// layout of ctx->d_scan_tmp for `cells` histogram entries: [cursor: cells, padded to even][tile states: 2 words per
+// tile][scan ticket][AABB ticket]
+static size_t scan_tmp_words(size_t cells) { return ((cells + 1) & ~(size_t)1) + 2 * ((cells + kScanTile - 1) / kScanTile + 1) + 2; }
+
+int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async)
+{
+	int const rc = build_frame_begin(ctx, f, d_xyz, n, h, h_ext_mult, allow_async);
 	return rc ? rc : build_frame_finish(ctx);
 }
 
-// first half: bounds, grid parameters (one host wait), table allocations.  Everything the second half launches is
-// fixed after this, so a sequence lane can capture the rest of the frame into a CUDA graph
-int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult)
+static int launch_aabb_params(Context* ctx, Frame* f, const float* d_xyz, uint32_t n32, float h, BuildCaps caps)
+{
+	cudaStream_t const s = ctx->stream;
+	int const aabb_blocks = (int)std::min((size_t)ctx->sm_count * 8, ((size_t)n32 + kThreads - 1) / kThreads);
+	// the histogram / scan-state buffers as they are now: zeroed by the same grid
+	uint32_t* const zero_a = ctx->d_scan_tmp; size_t const cap_a = ctx->d_scan_tmp ? ctx->cap_scan_tmp : 0;
+	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->d_grid_counts ? f->cap_grid : 0;
+	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
+	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
+	k_aabb_params<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
+												  static_view(*f), f->d_gp, f->d_fv, f->d_occupied);
+	ctx->kernel_launches += 1;
+	FM_CUDA(cudaGetLastError());
+	return FR_OK;
+}
+
+static const char* grid_status_text(uint32_t status)
+{
+	if (status & FM_GRID_NONFINITE) return "frame build: a particle coordinate is NaN or infinite";
+	if (status & FM_GRID_DEGENERATE) return "frame build: degenerate particle bounds (extent / h exceeds 2^31 cells)";
+	if (status & FM_GRID_CROWDED) return "frame build: more than 2048 particles in one search cell (collapsed simulation or h far too large)";
+	return "frame build failed";
+}
+
+int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async)
 {
 	ctx->build.f = nullptr;
 	if (n == 0 || n > 0x7fffffffull) { set_error("fr_upload_frame: particle count must be in [1, 2^31)"); return FR_ERR_INVALID; }
-	if (!(h > 0.0f)) { set_error("fr_upload_frame: h must be positive"); return FR_ERR_INVALID; }
+	if (!(h > 0.0f) || !isfinite(h)) { set_error("fr_upload_frame: h must be positive"); return FR_ERR_INVALID; }
 	cudaStream_t const s = ctx->stream;
 	uint32_t const n32 = (uint32_t)n;
 	f->valid = false;
 	f->ext_valid = false;
+	f->gp_pending = false;
+	f->gp_host_valid = false;
 	f->n = n;
 	f->h = h;
 	f->h_ext = h_ext_mult * h;
+	f->build_serial++;
 
-	FM_TIME(ctx, ctx->ev[2], s);
-	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
-	int const aabb_blocks = (int)min((size_t)ctx->sm_count * 8, (n + kThreads - 1) / kThreads);
 	int rc;
-	if ((rc = ensure_capacity(&ctx->d_aabb_partial, &ctx->cap_aabb_partial, (size_t)6 * ctx->sm_count * 8))) return rc;
-	// the histogram buffers as they are now (they are re-checked against this frame's sizes below)
-	uint32_t* const zero_a = ctx->d_scan_tmp; size_t const cap_a = ctx->d_scan_tmp ? ctx->cap_scan_tmp : 0;
-	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->d_grid_counts ? f->cap_grid : 0;
-	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
-	k_aabb<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, zero_a, words_a, zero_b, words_b);
-	k_grid_params<<<1, kThreads, 0, s>>>(ctx->d_gp, ctx->d_aabb_partial, (uint32_t)aabb_blocks, h, f->d_occupied);
-	FM_CUDA(cudaMemcpyAsync(ctx->h_gp, ctx->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
-	{ int const src = stream_sync(ctx); if (src) return src; }   // table sizes depend on the AABB
-	f->gp = *ctx->h_gp;
-	const GridParams& gp = f->gp;
-	for (int a = 0; a < 3; a++)
-		if (gp.gdim[a] <= 0 || gp.kdim[a] <= 0 || !isfinite(gp.mn[a]) || !isfinite(gp.mx[a]))
-		{
-			set_error("fr_upload_frame: degenerate particle bounds (NaN/inf positions?)");
-			return FR_ERR_INVALID;
-		}
-	uint64_t const cells = (uint64_t)gp.kdim[0] * (uint64_t)gp.kdim[1] * (uint64_t)gp.kdim[2];
-	uint64_t const gcells = (uint64_t)gp.gdim[0] * (uint64_t)gp.gdim[1] * (uint64_t)gp.gdim[2];
-	if (cells >= 0x7fffff00ull || gcells >= 0x7fffff00ull)
+	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
+	if (!f->d_gp) FM_CUDA(cudaMalloc((void**)&f->d_gp, sizeof(GridParams)));
+	if (!f->d_fv) FM_CUDA(cudaMalloc((void**)&f->d_fv, sizeof(FrameView)));
+	if (!f->h_gp) FM_CUDA(cudaMallocHost((void**)&f->h_gp, sizeof(GridParams)));
+	if (!ctx->d_aabb_partial)
 	{
-		set_error("fr_upload_frame: grid too large (extent / h exceeds 2^31 cells)");
+		if ((rc = ensure_capacity(&ctx->d_aabb_partial, &ctx->cap_aabb_partial, (size_t)kPartialStride * ctx->sm_count * 8 + 4))) return rc;
+		FM_CUDA(cudaMemsetAsync(ctx->d_aabb_partial, 0, ctx->cap_aabb_partial * sizeof(float), s));      // the block ticket starts at 0
+	}
+	// everything sized by the particle count
+	if ((rc = ensure_capacity(&f->d_sorted, &f->cap_sorted, n))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, n))) return rc;
+	if ((rc = ensure_capacity(&ctx->d_tmp_idx, &ctx->cap_tmp_idx, n))) return rc;
+
+	// tables of an earlier build of this slot that the scan scratch also covers: no host round trip
+	bool const async = allow_async && ctx->async_build && f->cap_cells > 1 && f->cap_grid > 0 && f->cap_occ_words > 0 &&
+		ctx->d_scan_tmp && ctx->cap_scan_tmp >= scan_tmp_words(f->cap_cells - 1);
+	ctx->build.f = f; ctx->build.d_xyz = d_xyz; ctx->build.n = n; ctx->build.h = h; ctx->build.h_ext_mult = h_ext_mult;
+	ctx->build.async = async;
+	f->src_xyz = d_xyz; f->src_mult = h_ext_mult;                  // for the rebuild after FM_GRID_OVERFLOW
+	FM_TIME(ctx, ctx->ev[2], s);
+	if (async)
+	{
+		ctx->build.scan_blocks = (uint32_t)((f->cap_cells - 1 + kScanTile - 1) / kScanTile);
+		ctx->build.flag_cells = (uint32_t)f->cap_grid;
+		return FR_OK;                   // k_aabb_params is launched by build_frame_finish with the capacities to check
+	}
+
+	BuildCaps const nocaps = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
+	if ((rc = launch_aabb_params(ctx, f, d_xyz, n32, h, nocaps))) return rc;
+	FM_CUDA(cudaMemcpyAsync(f->h_gp, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
+	{ int const src = stream_sync(ctx); if (src) return src; }   // table sizes depend on the AABB
+	f->gp = *f->h_gp;
+	f->gp_host_valid = true;
+	const GridParams& gp = f->gp;
+	if (gp.status)
+	{
+		ctx->build.f = nullptr;
+		set_error(grid_status_text(gp.status));
 		return FR_ERR_INVALID;
 	}
-	uint32_t const cells32 = (uint32_t)cells, gcells32 = (uint32_t)gcells;
+	uint32_t const cells32 = gp.cells, gcells32 = gp.gcells;
 	uint32_t const occ_words = (gcells32 + 31u) / 32u;
-	uint32_t const tiles = (cells32 + kScanTile - 1) / kScanTile;
-
-	if ((rc = ensure_capacity(&f->d_sorted, &f->cap_sorted, n))) return rc;
+	uint32_t* const zero_a = ctx->d_scan_tmp; size_t const cap_a = ctx->cap_scan_tmp;
+	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->cap_grid;
 	if ((rc = ensure_capacity(&f->d_cell_start, &f->cap_cells, (size_t)cells32 + 1))) return rc;
 	if ((rc = ensure_capacity(&f->d_grid_counts, &f->cap_grid, gcells32))) return rc;
 	if ((rc = ensure_capacity(&f->d_occ_bits, &f->cap_occ_words, occ_words))) return rc;
-	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, n))) return rc;
-	if ((rc = ensure_capacity(&ctx->d_sort_tmp, &ctx->cap_sort_tmp, n))) return rc;
-	// scan scratch: per-cell cursor copy + tile sums
-	if ((rc = ensure_capacity(&ctx->d_scan_tmp, &ctx->cap_scan_tmp, (size_t)cells32 + tiles + 2))) return rc;
-	uint32_t* const d_cursor = ctx->d_scan_tmp;
-	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
-
-	// k_aabb has zeroed the buffers it was given; one that had to grow (or did not exist yet) is zeroed here
-	if (ctx->d_scan_tmp != zero_a || ctx->cap_scan_tmp != cap_a || words_a == 0u) FM_CUDA(cudaMemsetAsync(d_cursor, 0, (size_t)cells32 * 4, s));
-	if (f->d_grid_counts != zero_b || f->cap_grid != cap_b || words_b == 0u) FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, (size_t)gcells32 * 4, s));
-	ctx->build.f = f; ctx->build.d_xyz = d_xyz; ctx->build.n32 = n32; ctx->build.cells32 = cells32; ctx->build.gcells32 = gcells32;
-	ctx->build.tiles = tiles;
+	// scan scratch for the whole capacity of the cell table, so that later frames of this slot can build without the host
+	if ((rc = ensure_capacity(&ctx->d_scan_tmp, &ctx->cap_scan_tmp, scan_tmp_words(f->cap_cells - 1)))) return rc;
+	// k_aabb_params has zeroed the buffers it was given; one that had to grow (or did not exist yet) is zeroed here
+	if (ctx->d_scan_tmp != zero_a || ctx->cap_scan_tmp != cap_a || !zero_a) FM_CUDA(cudaMemsetAsync(ctx->d_scan_tmp, 0, ctx->cap_scan_tmp * 4, s));
+	if (f->d_grid_counts != zero_b || f->cap_grid != cap_b || !zero_b) FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, f->cap_grid * 4, s));
+	// the view was written with the old table pointers if a table moved: write it again (cheap, rare)
+	ctx->build.scan_blocks = (cells32 + kScanTile - 1) / kScanTile;
+	ctx->build.flag_cells = gcells32;
+	{
+		FrameView v = make_view(*f);
+		FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, s));      // pageable source: staged at call time
+	}
 	return FR_OK;
 }
 
@@ -591,36 +853,76 @@ int build_frame_finish(Context* ctx)
 	ctx->build.f = nullptr;
 	cudaStream_t const s = ctx->stream;
 	const float* const d_xyz = ctx->build.d_xyz;
-	uint32_t const n32 = ctx->build.n32, cells32 = ctx->build.cells32, gcells32 = ctx->build.gcells32, tiles = ctx->build.tiles;
+	uint32_t const n32 = (uint32_t)ctx->build.n;
+	int rc;
+	size_t const cursor_cells = f->cap_cells - 1;                  // histogram capacity in cells
+	if (ctx->build.async)
+	{
+		BuildCaps caps;
+		caps.cells = (uint32_t)std::min<size_t>(cursor_cells, 0x7fffffffu);
+		caps.gcells = (uint32_t)std::min<size_t>(f->cap_grid, 0x7fffffffu);
+		caps.occ_words = (uint32_t)std::min<size_t>(f->cap_occ_words, 0x7fffffffu);
+		caps.scan_tiles = ctx->build.scan_blocks;
+		if ((rc = launch_aabb_params(ctx, f, d_xyz, n32, ctx->build.h, caps))) return rc;
+	}
 	uint32_t* const d_cursor = ctx->d_scan_tmp;
-	uint32_t* const d_tile_sums = ctx->d_scan_tmp + cells32;
-	const GridParams& gp = f->gp;
-
-	BuildView b;
-	b.kmin = make_int3(gp.kmin[0], gp.kmin[1], gp.kmin[2]);
-	b.kdim = make_int3(gp.kdim[0], gp.kdim[1], gp.kdim[2]);
-	b.search_inv = gp.search_inv;
-	b.mn = make_float3(gp.mn[0], gp.mn[1], gp.mn[2]);
-	b.gdim = make_int3(gp.gdim[0], gp.gdim[1], gp.gdim[2]);
-	b.inv_cw = gp.inv_cell_width;
-	b.cw = gp.cell_width;
-	b.half = 0.5f * f->h;                 // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
-	b.count_mode = ctx->count_mode;
+	size_t const state_off = (cursor_cells + 1) & ~(size_t)1;
+	unsigned long long* const tile_state = (unsigned long long*)(ctx->d_scan_tmp + state_off);
+	uint32_t* const scan_ticket = ctx->d_scan_tmp + state_off + 2 * ((cursor_cells + kScanTile - 1) / kScanTile + 1);
 
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
-	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, b, ctx->d_keys, d_cursor, f->d_grid_counts);
-	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter)
-	k_scan_tiles<<<tiles, kScanThreads, 0, s>>>(d_cursor, f->d_cell_start, cells32, d_tile_sums);
-	k_scan_add<<<tiles, kScanThreads, 0, s>>>(f->d_cell_start, cells32, d_tile_sums, tiles);
-	k_scatter<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_sort_tmp);
-	k_cell_order<<<pblocks, kThreads, 0, s>>>(ctx->d_sort_tmp, n32, b, f->d_cell_start, f->d_sorted);
-	FrameView const v = make_view(*f);
-	k_flags<<<(gcells32 + kThreads - 1) / kThreads, kThreads, 0, s>>>(f->d_grid_counts, gcells32, v.kernel.sig_d,
-																	  f->d_occ_bits, f->d_occupied);
-	ctx->kernel_launches += 8;    // aabb, params, key_count, 2 x scan, scatter, cell_order, flags
+	float const half = 0.5f * f->h;                   // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
+	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, ctx->d_keys, d_cursor, f->d_grid_counts);
+	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter); occupancy flags
+	FrameView const sv = static_view(*f);
+	uint32_t const flag_blocks = (ctx->build.flag_cells + kScanThreads - 1) / kScanThreads;
+	uint32_t const scan_grid = std::max(ctx->build.scan_blocks, std::min(flag_blocks, (uint32_t)ctx->sm_count * 4u));
+	k_scan_flags<<<scan_grid, kScanThreads, 0, s>>>(f->d_gp, d_cursor, f->d_cell_start, tile_state, scan_ticket, f->d_grid_counts,
+													   sv.kernel.sig_d, f->d_occ_bits, f->d_occupied);
+	k_scatter<<<pblocks, kThreads, 0, s>>>(n32, f->d_gp, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx);
+	k_cell_order<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted);
+	ctx->kernel_launches += 4;
 	FM_CUDA(cudaGetLastError());
+	// the parameters (with the status bits of the later kernels) come back with the frame's results
+	FM_CUDA(cudaMemcpyAsync(f->h_gp, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
+	f->gp_pending = true;
 	FM_TIME(ctx, ctx->ev[3], s);
 	f->valid = true;
+	return FR_OK;
+}
+
+// host copy of the grid parameters of a frame whose build is (or may still be) queued
+int resolve_frame(Context* ctx, Frame* f, bool synced)
+{
+	if (!f->gp_pending) return FR_OK;
+	if (!synced) { int const src = stream_sync(ctx); if (src) return src; }
+	f->gp_pending = false;
+	GridParams const gp = *f->h_gp;
+	if (gp.status & FM_GRID_OVERFLOW)
+	{
+		// the tables of the earlier frame are too small for this one: once more, with the host sizing them
+		int const rc = build_frame(ctx, f, f->src_xyz, f->n, f->h, f->src_mult, false);
+		if (rc) return rc;
+		int const rc2 = resolve_frame(ctx, f, false);
+		return rc2 < 0 ? rc2 : FR_RETRIED;
+	}
+	if (gp.status)
+	{
+		f->valid = false;
+		set_error(grid_status_text(gp.status));
+		return (gp.status & FM_GRID_CROWDED) ? FR_ERR_UNSUPPORTED : FR_ERR_INVALID;
+	}
+	f->gp = gp;
+	f->gp_host_valid = true;
+	return FR_OK;
+}
+
+// the r = h_ext fields of the device copy of the view (build_frame_ext ran after the frame build)
+int upload_view_ext(Context* ctx, Frame* f)
+{
+	FrameView v = make_view(*f);
+	FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
+	f->build_serial++;                 // the march's __constant__ copy is stale
 	return FR_OK;
 }
 

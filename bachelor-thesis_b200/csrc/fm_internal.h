@@ -14,7 +14,8 @@
 namespace fm
 {
 
-// written by the device (k_grid_params), read back once per frame upload to size the tables
+// written by the device (k_aabb_params) and read by every later kernel of the frame build from device memory, so that
+// the build needs no host round trip; a copy comes back to the host with the frame's results (Frame::h_gp)
 struct GridParams
 {
 	float mn[3], mx[3];          // m_Min, m_Max (Dataset.cpp:78-92)
@@ -23,7 +24,26 @@ struct GridParams
 	float inv_cell_width;
 	int32_t kmin[3], kdim[3];    // neighbour-search cell range
 	float search_inv;
-	uint32_t raw_min[3], raw_max[3];   // order-preserving encodings used by the AABB atomics
+	uint32_t raw_min[3], raw_max[3];   // order-preserving encodings of the particle extrema (kept for build_frame_ext)
+	uint32_t cells, gcells;      // kdim / gdim products; 0 when status != 0
+	uint32_t status;             // FM_GRID_* bits; != 0: the frame is unusable and every kernel of the build returns at once
+	uint32_t max_cell;           // largest number of particles in one search cell (k_scan_flags)
+};
+
+enum
+{
+	FM_GRID_NONFINITE = 1,       // a particle coordinate is NaN or infinite
+	FM_GRID_DEGENERATE = 2,      // empty / non-finite bounds, or extent / h beyond 2^31 cells
+	FM_GRID_OVERFLOW = 4,        // the tables sized for an earlier frame are too small: rebuild with a host round trip
+	FM_GRID_CROWDED = 8          // more than kMaxCellParticles particles in one search cell
+};
+constexpr uint32_t kMaxCellParticles = 2048;     // in-cell ordering is quadratic in the cell population (k_cell_order)
+
+// table capacities the device checks the grid parameters against (all 0xffffffff: no check, the host sizes the tables
+// after reading the parameters back)
+struct BuildCaps
+{
+	uint32_t cells, gcells, occ_words, scan_tiles;
 };
 
 struct Frame
@@ -31,7 +51,15 @@ struct Frame
 	bool valid = false;
 	size_t n = 0;
 	float h = 0.0f, h_ext = 0.0f;
-	GridParams gp{};
+	GridParams gp{};                  // host copy: valid once gp_pending is false (resolve_frame)
+	GridParams* d_gp = nullptr;       // device: written by k_aabb_params, read by the build kernels
+	FrameView* d_fv = nullptr;        // device: the frame as the march kernels see it (copied into their __constant__ slot)
+	GridParams* h_gp = nullptr;       // pinned: the copy that comes back at the end of the build
+	bool gp_pending = false;          // the build is queued and its parameters have not been read back yet
+	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (always after resolve_frame; at once after a build with a host wait)
+	uint64_t build_serial = 0;        // bumped by every build (the march's __constant__ slot remembers what it holds)
+	const float* src_xyz = nullptr;   // device particles of the queued build (must stay valid until the host next waits)
+	float src_mult = 0.0f;
 	uint64_t occupied = 0;
 	// device buffers (capacities in elements)
 	float4* d_sorted = nullptr;       size_t cap_sorted = 0;
@@ -64,6 +92,7 @@ struct Context
 	int sm_count = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
+	cudaEvent_t ev_copy = nullptr;     // behind the host -> device copy of fr_upload_frame
 	// Host waits.  By default a thread waits inside the driver (cudaStreamSynchronize spins: lowest latency, best
 	// throughput while every waiting thread has a core of its own -- 0.296 ms per C2 frame at 6 lanes).  When the host
 	// is oversubscribed (8 ranks x 6 lanes on a 32-core box: 0.47 ms) the lanes of a sequence can instead append a
@@ -77,7 +106,14 @@ struct Context
 	uint32_t sync_seq = 0;
 	cudaEvent_t ev[16] = {};
 	bool render_pending = false;
-	struct { Frame* f = nullptr; const float* d_xyz = nullptr; uint32_t n32 = 0, cells32 = 0, gcells32 = 0, tiles = 0; } build;   // between build_frame_begin / _finish
+	// between build_frame_begin / _finish
+	struct { Frame* f = nullptr; const float* d_xyz = nullptr; size_t n = 0; float h = 0.0f, h_ext_mult = 0.0f;
+			 bool async = false; uint32_t scan_blocks = 0, flag_cells = 0; } build;
+	bool async_build = true;           // builds into tables that already exist skip the host round trip (fr_set_async_build)
+	int last_passes = 0;               // passes of the pending render (repeated after a rebuild)
+	int cslot = -1;                    // this context's slot in the march kernels' __constant__ frame tables
+	const Frame* cslot_frame[2] = { nullptr, nullptr };   // what the slot holds (isotropic TU, anisotropic TU) ...
+	uint64_t cslot_serial[2] = { 0, 0 };                   // ... and from which build
 	bool march_timed = false;
 	bool zero_counters_in_depth = false;   // this render call: k_depth_clear zeroes the march counters (one memset less)
 	// per-stage CUDA events (fr_get_timings).  The lanes of a sequence switch them off: every record is one more
@@ -96,6 +132,8 @@ struct Context
 	int count_mode = FR_COUNT_CENTRE_BOX;   // reading of find_neighbors_box (fr_set_count_mode)
 
 	std::vector<Frame> frames;
+	std::vector<int> pending_frames;   // frames built since the last host wait (resolve_frame at the next one)
+	const float* lane_h2d_src = nullptr; size_t lane_h2d_bytes = 0;   // a lane's particle upload, queued with the rest of its frame
 
 	// images
 	float* d_depth = nullptr;
@@ -111,9 +149,10 @@ struct Context
 	uchar4* d_bmp = nullptr;          size_t cap_bmp = 0;       // recording: B G R A rows bottom-up (fm_record.cu)
 	uint8_t* h_bmp = nullptr;         size_t cap_bmp_host = 0;  // pinned: header + pixels of one .bmp
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
-	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // counting sort output before the in-cell ordering
+	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // r = h_ext search: counting sort output before the in-cell ordering
+	uint32_t* d_tmp_idx = nullptr;    size_t cap_tmp_idx = 0;      // counting sort output (particle indices) before the in-cell ordering
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
-	float* d_aabb_partial = nullptr;  size_t cap_aabb_partial = 0;  // per-block extrema of k_aabb
+	float* d_aabb_partial = nullptr;  size_t cap_aabb_partial = 0;  // per-block extrema of k_aabb_params (+ its block ticket)
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
 	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
@@ -121,9 +160,7 @@ struct Context
 	uint32_t* d_tiles = nullptr;      size_t cap_tiles = 0;        // march: [0] count, [1] cursor, [2..] covered 8x4 tiles
 	int march_ctas_per_sm = 0, march_long_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
 	float4* d_rayq = nullptr;         size_t cap_rayq = 0;         // march: ray queues between the phases
-	GridParams* d_gp = nullptr;
 	DeviceCounters* d_counters = nullptr;
-	GridParams* h_gp = nullptr;        // pinned
 	DeviceCounters* h_counters = nullptr;
 
 	fr_timings timings{};
@@ -158,11 +195,23 @@ int ensure_capacity(T** ptr, size_t* cap, size_t need)
 }
 
 // fm_grid.cu
-int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
-int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult);
+int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async = true);
+// first half: everything that may need the host (allocations; without usable tables: bounds + one host wait); second
+// half: launches only, so a sequence lane can capture it into a CUDA graph
+int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async = true);
 int build_frame_finish(Context* ctx);
+// the host copy of the frame's grid parameters (waits for the build if it is still queued); FR_RETRIED: the tables
+// were too small, the frame has been rebuilt -- work queued behind the first build ran on an unusable frame
+constexpr int FR_RETRIED = 1;
+int resolve_frame(Context* ctx, Frame* f, bool synced = false);     // synced: the caller has just drained the stream
 int build_frame_ext(Context* ctx, Frame* f);      // no-op when already built
-FrameView make_view(const Frame& f);
+FrameView make_view(const Frame& f);              // needs resolve_frame
+int upload_view_ext(Context* ctx, Frame* f);      // the r = h_ext fields into the device copy of the view
+void free_frame_small(Frame& f);
+// __constant__ slots of the march kernels
+int cslot_acquire();
+void cslot_release(int slot);
+constexpr int kConstSlots = 64;
 // fm_depth.cu
 int launch_depth_prepass(Context* ctx, const Frame& f);
 // fm_march.cu
@@ -176,6 +225,8 @@ int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float*
 // fm_context.cu: the two halves of a sequence lane's frame
 int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path);
 int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job);
+int lane_frame_copies(fr_context* ctx, const fr_seq_job& job);
+int lane_frame_wait(fr_context* ctx);
 // fm_bgeo.cu
 int stage_bgeo(Context* ctx, const char* path, size_t* n_out);
 // fm_query.cu

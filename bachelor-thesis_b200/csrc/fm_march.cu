@@ -61,7 +61,6 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	if (do_march)
 	{
 		// persistent: as many CTAs as stay resident (occupancy of this build), never more warps than tiles
-		FrameView const fv = make_view(f);
 		bool const fast = ctx->settings.fast_normals != 0;
 		if (aniso)
 		{
@@ -77,13 +76,14 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			uint32_t ctas = (uint32_t)(ctx->sm_count * per_sm);
 			if (ctas > max_ctas) ctas = max_ctas;
 			MarchLaunch ml;
-			ml.fv = fv; ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
+			ml.frame = &f; ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
 			if ((rc = launch_march_kernels_aniso(ctx, ml))) return rc;
 		}
 		else
 		{
-			// k_march_first: FM_FIRST_WARPS warps per CTA, one shared-memory stage per warp (dynamic, above the 48 KB default)
-			size_t const smem_first = (size_t)FM_FIRST_WARPS * sizeof(WarpStage);
+			// k_march_first: dynamic shared memory (lists of the walk, or one stage per warp: above the 48 KB default)
+			size_t const smem_first = kFirstSmem;
+			int const first_warps = kFirstThreads / 32;
 			auto const first = fast ? k_march_first<true, false> : k_march_first<false, false>;
 			auto const longk = fast ? k_march_long<true, false> : k_march_long<false, false>;
 			if (ctx->march_ctas_per_sm == 0)
@@ -99,12 +99,14 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			}
 			uint32_t const ntiles = (uint32_t)(tiles_x * tiles_y);
 			uint32_t ctas_first = (uint32_t)(ctx->sm_count * ctx->march_ctas_per_sm);
-			ctas_first = std::min(ctas_first, (ntiles + FM_FIRST_WARPS - 1) / FM_FIRST_WARPS);
+			ctas_first = std::min(ctas_first, (ntiles + first_warps - 1) / first_warps);
 			uint32_t ctas_long = (uint32_t)(ctx->sm_count * ctx->march_long_ctas_per_sm);
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
-			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+			if ((rc = bind_view(ctx, f, 0))) return rc;
+			int const slot = ctx->cslot;
+			first<<<ctas_first, kFirstThreads, smem_first, st>>>(slot, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			FM_TIME(ctx, ctx->ev[11], st);
-			longk<<<ctas_long, 256, 0, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			longk<<<ctas_long, 256, 0, st>>>(slot, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		}
 		ctx->kernel_launches += 2;
 	}

@@ -70,7 +70,7 @@ struct RayQueues
 
 struct MarchLaunch
 {
-	FrameView fv;
+	const Frame* frame;
 	MarchParams mp;
 	RayQueues rq;
 	const uint32_t* tiles;
@@ -83,6 +83,23 @@ namespace
 
 constexpr int kMaxNeighbors = 2 * 4096;   // MAX_NEIGHBORS (RayMarcher.cpp:14)
 
+// The frame as the march kernels see it lives in __constant__ memory, one slot per context, so that its fields reach
+// the instructions the way kernel parameters do (uniform loads from a constant bank).  The slot is filled ON THE STREAM
+// from the device copy k_aabb_params leaves behind (Frame::d_fv): the host does not have to know the grid parameters
+// of a frame to march it, which is what lets a frame build run without a host round trip (fm_grid.cu).
+__constant__ FrameView c_frames[kConstSlots];
+
+// (this translation unit's table; `which` = 0 isotropic TU, 1 anisotropic TU)
+static int bind_view(Context* ctx, const Frame& f, int which)
+{
+	if (ctx->cslot_frame[which] == &f && ctx->cslot_serial[which] == f.build_serial) return FR_OK;
+	FM_CUDA(cudaMemcpyToSymbolAsync(c_frames, f.d_fv, sizeof(FrameView), (size_t)ctx->cslot * sizeof(FrameView),
+									cudaMemcpyDeviceToDevice, ctx->stream));
+	ctx->cslot_frame[which] = &f;
+	ctx->cslot_serial[which] = f.build_serial;
+	return FR_OK;
+}
+
 struct LaneCounters
 {
 	uint32_t covered, hits, steps, skips, candidates, neighbours, early_exits, overflow;
@@ -91,7 +108,8 @@ struct LaneCounters
 };
 
 #ifndef FM_MARCH_MINBLOCKS
-#define FM_MARCH_MINBLOCKS 4              // resident 256-thread CTAs per SM k_march_first is compiled for (64 registers)
+#define FM_MARCH_MINBLOCKS 3              // resident 256-thread CTAs per SM k_march_first is compiled for (<= 85 registers; r02b: 4 CTAs
+                                          // at 64 registers and a 32-entry list: C2 0.139 ms, C3 0.450; 3 CTAs with 48 entries: 0.138 / 0.419)
 #endif
 #ifndef FM_ANISO_MINBLOCKS
 #define FM_ANISO_MINBLOCKS 4              // resident CTAs per SM the anisotropic march kernels are compiled for
@@ -104,11 +122,37 @@ constexpr int kAnisoWalkUnroll = FM_ANISO_WALK_UNROLL;
 #define FM_WALK_UNROLL 1
 #endif
 constexpr int kWalkUnroll = FM_WALK_UNROLL;   // candidates per iteration of the walk loop
+#ifndef FM_WALK_FAST
+#define FM_WALK_FAST 1                    // ranges that cannot overflow the list are walked by a loop with nothing but the test in it
+#endif
 #ifndef FM_LIST_CAP
-#define FM_LIST_CAP 32                    // in-range candidates a lane collects before it evaluates them
+#define FM_LIST_CAP 48                    // in-range candidates a lane collects before it evaluates them
 #endif
 constexpr int kListCap = FM_LIST_CAP;
 constexpr int kListWords = kListCap * 32;  // shared-memory words per warp: list[k * 32 + lane]
+
+// 32-bit shared-window addressing for the per-lane list (a generic uint16_t* is carried as a 64-bit pair with carries)
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
+{
+	asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
+{
+	unsigned short v;
+	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a)
+{
+	float4 v;
+	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+	return v;
+}
 
 // one neighbour (d = p - x_j, l2 = |d|^2 < h^2) into the running sums, in the reference's list order
 template <bool DENS, bool GRAD, bool FAST>
@@ -171,6 +215,34 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 				uint32_t j = b;
 				if (resume && r == r0) j = j0;       // this range was counted when the walk first entered it
 				else lc.candidates += e - b;
+#if FM_WALK_FAST
+				if (cnt + (e - j) <= (uint32_t)kListCap)
+				{
+					// the list cannot overflow in this range: nothing but the test in the loop, four loads in flight
+					uint32_t lp = smem_addr(list) + cnt * 128u;
+#define FM_WALK_TEST(q, jj)                                                                          \
+	{                                                                                                \
+		float const d0 = subr(p.x, (q).x), d1 = subr(p.y, (q).y), d2 = subr(p.z, (q).z);             \
+		float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));                       \
+		if (l2 < f.kernel.h_squared) { sts_u32(lp, (jj)); lp += 128u; }                              \
+	}
+#pragma unroll 1
+					for (; j + 4u <= e; j += 4u)
+					{
+						float4 const q0 = __ldg(f.sorted + j), q1 = __ldg(f.sorted + j + 1), q2 = __ldg(f.sorted + j + 2), q3 = __ldg(f.sorted + j + 3);
+						FM_WALK_TEST(q0, j) FM_WALK_TEST(q1, j + 1u) FM_WALK_TEST(q2, j + 2u) FM_WALK_TEST(q3, j + 3u)
+					}
+#pragma unroll 1
+					for (; j < e; j++)
+					{
+						float4 const q0 = __ldg(f.sorted + j);
+						FM_WALK_TEST(q0, j)
+					}
+#undef FM_WALK_TEST
+					cnt = (lp - smem_addr(list)) >> 7;
+					continue;
+				}
+#endif
 				// no branch in the loop: the store and the count are predicated; the first in-range candidate that no
 				// longer fits is remembered and the walk resumes there after the list has been evaluated
 				uint32_t over = 0xffffffffu;
@@ -264,25 +336,6 @@ __device__ __forceinline__ void cull_margins(float p, int cell_abs, float h, flo
 	float const m = (fabsf(p) + h) * 4e-6f;
 	float const lo = fmaxf(p - face - m, 0.0f), hi = fmaxf(face + h - p - m, 0.0f);
 	below2 = lo * lo; above2 = hi * hi;
-}
-
-// 32-bit shared-window addressing for the per-lane list (a generic uint16_t* is carried as a 64-bit pair with carries)
-__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
-{
-	asm volatile("st.shared.u16 [%0], %1;" :: "r"(a), "h"((unsigned short)v) : "memory");
-}
-__device__ __forceinline__ uint32_t lds_u16(uint32_t a)
-{
-	unsigned short v;
-	asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a) : "memory");
-	return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t a)
-{
-	float4 v;
-	asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
-	return v;
 }
 
 // density and (GRAD) gradient sum at p for every lane of the warp; returns false -- for the whole warp, nothing done --
@@ -922,23 +975,30 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 
 // phase A: warp = one covered 8x4 tile, lanes = rays, the FIRST sample of every ray with density and gradient sums
 // together (the depth pre-pass seeds the ray right in front of the surface, so ~95% of the rays end here)
-// (isotropic: FM_FIRST_WARPS warps per CTA, one WarpStage of dynamic shared memory per warp; anisotropic: 8 warps, none)
-constexpr int kFirstThreads = FM_FIRST_WARPS * 32;
+// isotropic k_march_first: FM_FIRST_STAGED = 1: FM_FIRST_WARPS warps per CTA, one WarpStage of dynamic shared memory per warp;
+// 0: 8 warps per CTA, dynamic shared memory = the in-range lists of the global-memory walk.  Anisotropic: 8 warps, none.
+#ifndef FM_FIRST_STAGED
+#define FM_FIRST_STAGED 0
+#endif
+constexpr int kFirstThreads = FM_FIRST_STAGED ? FM_FIRST_WARPS * 32 : 256;
+constexpr size_t kFirstWarpBytes = FM_FIRST_STAGED ? sizeof(WarpStage) : (size_t)kListWords * 4;      // dynamic shared memory per warp
+constexpr size_t kFirstSmem = (size_t)(kFirstThreads / 32) * kFirstWarpBytes;
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : FM_FIRST_MINBLOCKS) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
+__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(int slot, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
+	const FrameView& f = c_frames[slot];
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];
-	WarpStage& ws = reinterpret_cast<WarpStage*>(s_dyn)[ANISO ? 0 : (threadIdx.x >> 5)];      // (never touched when ANISO)
-	// the global-memory walk (tiles that do not fit the stage, bisection samples) keeps its list in the stage's particle area
-	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (sizeof(WarpStage) / 4) + lane);
+	// the global-memory walk (every tile when FM_FIRST_STAGED = 0, else tiles that do not fit the stage and bisection
+	// samples) keeps its list at the start of the warp's share
+	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (kFirstWarpBytes / 4) + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 0);
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
@@ -994,10 +1054,11 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 		SampleState<ANISO> st;
 		float density = 0.0f;
 		bool staged = false;
-		if constexpr (!ANISO)
+		if constexpr (!ANISO && FM_FIRST_STAGED)
 		{
 			if (mp.bisection_steps == 0)
 			{
+				WarpStage& ws = *reinterpret_cast<WarpStage*>(s_dyn + (threadIdx.x >> 5) * kFirstWarpBytes);
 				staged = eval_density_staged<true, FAST>(f, position, sample, ws, density, st.grad, lc);
 				st.have_grad = true;
 				if (!staged && sample) lc.fallbacks++;
@@ -1035,11 +1096,12 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(int slot, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
+	const FrameView& f = c_frames[slot];
 	int const lane = threadIdx.x & 31;
 	__shared__ uint32_t s_list[ANISO ? 1 : 8 * kListWords];
 	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;

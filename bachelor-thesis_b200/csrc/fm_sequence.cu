@@ -18,6 +18,7 @@
 #include <mutex>
 #include <new>
 #include <thread>
+#include <utility>
 #include <vector>
 
 using namespace fm;
@@ -38,6 +39,9 @@ struct Lane
 	int64_t done_ticket = -1;      // last ticket finished on this lane
 	int done_status = FR_OK;
 	std::string done_error;
+	// status of the frames that FAILED on this lane and have not been waited for yet: a caller that submits ahead may
+	// ask for ticket t after ticket t + lanes has already finished here (fr_seq_wait; cleared by wait and drain)
+	std::vector<std::pair<int64_t, std::pair<int, std::string>>> failed;
 	cudaEvent_t ev_end = nullptr;
 	// the part of a frame behind its one host wait (rest of the grid build, depth pre-pass, march, copies out) as a
 	// CUDA graph, re-captured every frame and patched into the instantiated graph: one launch instead of ~16 stream
@@ -70,6 +74,7 @@ int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 {
 	fr_context* const c = ln->ctx;
 	auto const saved = c->build;                   // lane_frame_enqueue consumes it
+	const float* const saved_src = c->lane_h2d_src;
 	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
 	{
 		cudaGetLastError();
@@ -99,6 +104,7 @@ int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 		ln->graph_ok = false;
 		if (ln->exec) { cudaGraphExecDestroy(ln->exec); ln->exec = nullptr; }
 		c->build = saved;
+		c->lane_h2d_src = saved_src;
 		c->render_pending = false;
 		return lane_frame_enqueue(c, job);
 	}
@@ -126,7 +132,15 @@ void lane_main(fr_sequence* seq, Lane* ln)
 		}
 		int rc = lane_frame_begin(ln->ctx, job, job.bgeo_path ? path.c_str() : nullptr);
 		if (rc == FR_OK) rc = seq->graphs && ln->graph_ok ? enqueue_as_graph(ln, job) : lane_frame_enqueue(ln->ctx, job);
-		if (rc == FR_OK) rc = fr_wait(ln->ctx);       // the whole stream: render and copies
+		if (rc == FR_OK)
+		{
+			rc = lane_frame_wait(ln->ctx);            // the whole stream: build, render and copies
+			if (rc == FR_RETRIED)                     // the tables of the lane's slot had to grow: the frame was rebuilt and
+			{                                         // rendered again, the copies carry the first attempt's pixels
+				rc = lane_frame_copies(ln->ctx, job);
+				if (rc == FR_OK) rc = lane_frame_wait(ln->ctx);
+			}
+		}
 		if (rc == FR_OK && job.bmp_path) rc = fr_write_bmp(ln->ctx, bmp.c_str());      // recording (Renderer.cpp:400-409)
 		std::string err;
 		if (rc != FR_OK) err = fr_last_error();      // thread-local text of this worker
@@ -136,6 +150,11 @@ void lane_main(fr_sequence* seq, Lane* ln)
 			ln->done_ticket = ticket;
 			ln->done_status = rc;
 			ln->done_error = err;
+			if (rc != FR_OK)
+			{
+				if (ln->failed.size() >= 64) ln->failed.erase(ln->failed.begin());
+				ln->failed.push_back({ ticket, { rc, err } });
+			}
 		}
 		if (rc != FR_OK)
 		{
@@ -222,7 +241,12 @@ int fr_seq_context(fr_sequence* seq, int lane, fr_context** out)
 int fr_seq_drain(fr_sequence* seq)
 {
 	if (!seq) { set_error("null sequence"); return FR_ERR_INVALID; }
-	for (Lane* ln : seq->lanes) wait_lane_idle(ln);
+	for (Lane* ln : seq->lanes)
+	{
+		wait_lane_idle(ln);
+		std::lock_guard<std::mutex> lk(ln->m);
+		ln->failed.clear();
+	}
 	std::lock_guard<std::mutex> lk(seq->err_m);
 	int const rc = seq->first_error;
 	if (rc != FR_OK) set_error(seq->first_error_text);
@@ -276,7 +300,14 @@ int fr_seq_wait(fr_sequence* seq, int64_t ticket)
 	Lane* ln = seq->lanes[(size_t)(ticket % (int64_t)seq->lanes.size())];
 	std::unique_lock<std::mutex> lk(ln->m);
 	ln->cv.wait(lk, [&] { return ln->done_ticket >= ticket; });
-	if (ln->done_ticket == ticket && ln->done_status != FR_OK) { set_error(ln->done_error); return ln->done_status; }
+	for (size_t k = 0; k < ln->failed.size(); k++)
+		if (ln->failed[k].first == ticket)
+		{
+			int const rc = ln->failed[k].second.first;
+			set_error(ln->failed[k].second.second);
+			ln->failed.erase(ln->failed.begin() + (long)k);
+			return rc;
+		}
 	return FR_OK;
 }
 

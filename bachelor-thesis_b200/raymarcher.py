@@ -101,6 +101,11 @@ class Context:
         reference build under oracle/_ref computes) or FR_COUNT_CELL_EXACT"""
         check(self.lib.fr_set_count_mode(self.h, mode), "fr_set_count_mode")
 
+    def set_async_build(self, on: bool):
+        """frame builds into a slot that already has tables skip the host round trip (default on); errors of such a
+        build surface at the next wait"""
+        check(self.lib.fr_set_async_build(self.h, 1 if on else 0), "fr_set_async_build")
+
     def frame_info(self, frame: int) -> dict:
         fi = abi.FrFrameInfo()
         check(self.lib.fr_get_frame_info(self.h, frame, C.byref(fi)), "fr_get_frame_info")

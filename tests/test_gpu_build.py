@@ -1,0 +1,188 @@
+"""Frame builds without a host round trip (builds into the tables of an earlier frame of the same slot read the grid
+parameters from device memory), and what the host used to check in that round trip: non-finite particle coordinates,
+tables too small for the new bounds (rebuild + the render behind it repeated), collapsed cells.  Also fr_seq_wait's
+per-ticket status.  Everything through the C ABI."""
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_camera
+
+pytestmark = pytest.mark.gpu
+scenes = importlib.import_module("bachelor-thesis_b200.scenes")
+W, H = 320, 180
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint8)
+
+
+def set_cam(ctx, cam):
+    ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+
+
+def render_fresh(fm, xyz, cam):
+    c = fm.Context(W, H)
+    try:
+        set_cam(c, cam)
+        c.upload_frame(0, xyz, 0.1, 2.0)                 # first build of the slot: host-sized tables
+        c.render(fm.FR_PASS_ALL)
+        return c.download(), c.download_frame(0), c.counters()
+    finally:
+        c.close()
+
+
+def test_build_into_existing_tables_is_bit_identical(fm, gpu_ctx_factory):
+    cam = golden_camera("camera_close_16x9")
+    a, b = scenes.dam_break(20000, t=0.5), scenes.dam_break(20000, t=0.55)
+    want_img, want_grid, want_cnt = render_fresh(fm, b, cam)
+    ctx = gpu_ctx_factory(W, H)
+    set_cam(ctx, cam)
+    ctx.upload_frame(0, a, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    ctx.upload_frame(0, b, 0.1, 2.0)                     # same slot: no host wait inside this build
+    ctx.render(fm.FR_PASS_ALL)
+    got_img, got_grid, got_cnt = ctx.download(), ctx.download_frame(0), ctx.counters()
+    for x, y in zip(got_img, want_img):
+        assert np.array_equal(bits(x), bits(y))
+    for k in ("sorted_xyz", "sorted_index", "cell_start", "grid_counts", "grid_flags"):
+        assert np.array_equal(bits(got_grid[k]), bits(want_grid[k])), k
+    for k in ("min", "max", "grid_dims", "search_min", "search_dims"):
+        assert np.array_equal(bits(got_grid["info"][k]), bits(want_grid["info"][k])), k
+    assert got_grid["info"]["occupied_cells"] == want_grid["info"]["occupied_cells"]
+    for k in ("covered_rays", "hit_rays", "ray_steps", "skip_iterations", "candidates", "neighbours"):
+        assert got_cnt[k] == want_cnt[k], k
+    # the round-1 behaviour (every build waits once) is still there, same bits
+    ctx.set_async_build(False)
+    ctx.upload_frame(0, b, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    for x, y in zip(ctx.download(), want_img):
+        assert np.array_equal(bits(x), bits(y))
+    ctx.set_async_build(True)
+
+
+def test_tables_too_small_are_rebuilt_and_the_render_repeated(fm, gpu_ctx_factory):
+    cam = golden_camera("camera_default_16x9")
+    small = scenes.random_block(2000, 0.3)               # 8 x 8 x 8 cells
+    big = scenes.dam_break(64000)                        # a few thousand cells: the slot's tables cannot hold it
+    want_img, want_grid, _ = render_fresh(fm, big, cam)
+    ctx = gpu_ctx_factory(W, H)
+    set_cam(ctx, cam)
+    ctx.upload_frame(0, small, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    ctx.upload_frame(0, big, 0.1, 2.0)                   # queued against the small tables: FM_GRID_OVERFLOW on the device
+    ctx.render_async(fm.FR_PASS_ALL)
+    got_img = ctx.download()                             # the wait rebuilds the frame and renders it again
+    for x, y in zip(got_img, want_img):
+        assert np.array_equal(bits(x), bits(y))
+    got_grid = ctx.download_frame(0)
+    assert np.array_equal(got_grid["cell_start"], want_grid["cell_start"])
+    assert np.array_equal(bits(got_grid["sorted_xyz"]), bits(want_grid["sorted_xyz"]))
+    # and back to a small frame in the now large tables
+    want_small, _, _ = render_fresh(fm, small, cam)
+    ctx.upload_frame(0, small, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    for x, y in zip(ctx.download(), want_small):
+        assert np.array_equal(bits(x), bits(y))
+
+
+@pytest.mark.parametrize("poison", [np.nan, np.inf, -np.inf])
+def test_non_finite_particles_are_rejected(fm, gpu_ctx_factory, poison, tmp_path):
+    """one NaN coordinate used to index the cell histogram out of bounds"""
+    cam = golden_camera("camera_close_16x9")
+    good = scenes.dam_break(8000)
+    bad = good.copy()
+    bad[1234, 1] = poison
+    ctx = gpu_ctx_factory(W, H)
+    set_cam(ctx, cam)
+    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):       # first build of the slot: reported at once
+        ctx.upload_frame(0, bad, 0.1, 2.0)
+    ctx.upload_frame(0, good, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    want = ctx.download()
+    ctx.upload_frame(0, bad, 0.1, 2.0)                    # tables exist: the build is only queued ...
+    ctx.render_async(fm.FR_PASS_ALL)
+    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):       # ... and the next wait reports it
+        ctx.wait()
+    path = str(tmp_path / "bad.bgeo")
+    fm.bgeo_write(path, bad)
+    ctx.upload_frame_bgeo(0, path, 0.1, 2.0)
+    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):
+        ctx.frame_info(0)
+    # the context is still usable and nothing was corrupted
+    ctx.upload_frame(0, good, 0.1, 2.0)
+    ctx.render(fm.FR_PASS_ALL)
+    for x, y in zip(ctx.download(), want):
+        assert np.array_equal(bits(x), bits(y))
+    other = gpu_ctx_factory(W, H)
+    set_cam(other, cam)
+    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):
+        other.upload_frame_bgeo(0, path, 0.1, 2.0)
+
+
+def test_collapsed_cell_is_refused_not_ranked(fm, gpu_ctx_factory):
+    """the in-cell ordering is quadratic; a collapsed simulation must not occupy the GPU for seconds"""
+    xyz = np.concatenate([scenes.dam_break(8000), np.full((5000, 3), 0.01234, np.float32)])
+    ctx = gpu_ctx_factory(64, 64)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    with pytest.raises(fm.FluidMarchError, match="2048 particles in one search cell"):
+        ctx.frame_info(0)
+    ok = np.concatenate([scenes.dam_break(8000), np.full((1500, 3), 0.01234, np.float32)])
+    ctx.upload_frame(0, ok, 0.1, 2.0)
+    g = ctx.download_frame(0)
+    idx = g["sorted_index"].astype(np.int64)
+    assert np.array_equal(np.sort(idx), np.arange(len(ok)))
+
+
+def test_many_search_cells_scan_in_one_pass(fm, oracle, gpu_ctx_factory):
+    """sparse particles over a large extent: ~1.3 M search cells = 300+ scan tiles through the decoupled look-back"""
+    rng = np.random.default_rng(3)
+    xyz = rng.uniform(-5.5, 5.5, (30000, 3)).astype(np.float32)
+    ctx = gpu_ctx_factory(64, 64)
+    for _ in range(2):                                    # host-sized, then device-checked
+        ctx.upload_frame(0, xyz, 0.1, 2.0)
+        g = ctx.download_frame(0)
+        info = g["info"]
+        inv = np.float32(1.0) / np.float32(0.1)
+        t = (inv * xyz).astype(np.int32)
+        k = np.where(xyz >= 0, t, t - 1) - info["search_min"][None, :]
+        kd = info["search_dims"].astype(np.int64)
+        key = (k[:, 0].astype(np.int64) * kd[1] + k[:, 1]) * kd[2] + k[:, 2]
+        cells = int(np.prod(kd))
+        assert cells > 1_000_000
+        want = np.concatenate([[0], np.cumsum(np.bincount(key, minlength=cells))])
+        assert np.array_equal(g["cell_start"].astype(np.int64), want)
+        counts, flags = oracle.frame(xyz, 0.1, 2.0).grid()
+        assert np.array_equal(g["grid_counts"], counts) and np.array_equal(g["grid_flags"], flags)
+
+
+def test_seq_wait_reports_the_status_of_that_ticket(fm):
+    """a failed frame must not read as FR_OK once a later frame of its lane has finished"""
+    cam = golden_camera("camera_close_16x9")
+    seq = fm.Sequence(W, H, lanes=2)
+    try:
+        seq.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
+        seq.set_settings(fm.VisualizationSettings())
+        good = scenes.dam_break(8000)
+        bad = good.copy()
+        bad[5, 0] = np.nan
+        tickets = []
+        for k in range(8):                                # tickets 2 and 5 fail; later frames of their lanes succeed
+            t, out = seq.submit(bad if k in (2, 5) else good)
+            tickets.append((t, out))
+        seq.wait(tickets[-1][0])
+        seq.wait(tickets[-2][0])                          # both lanes are past the failed tickets now
+        for k, (t, out) in enumerate(tickets):
+            if k in (2, 5):
+                with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):
+                    seq.wait(t)
+            else:
+                seq.wait(t)
+                assert out["rgba"].any()
+        with pytest.raises(fm.FluidMarchError):
+            seq.drain()
+        seq.drain()
+    finally:
+        seq.close()

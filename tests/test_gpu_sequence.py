@@ -99,9 +99,9 @@ def test_sequence_reports_job_errors(fm):
     seq = fm.Sequence(W, H, lanes=2)
     try:
         setup(seq, cam, fm)
-        bad = np.full((10, 3), np.nan, np.float32)          # degenerate bounds -> FR_ERR_INVALID from the frame build
+        bad = np.full((10, 3), np.nan, np.float32)          # non-finite coordinates -> FR_ERR_INVALID from the frame build
         t, _ = seq.submit(bad)
-        with pytest.raises(fm.FluidMarchError, match="degenerate|bounds"):
+        with pytest.raises(fm.FluidMarchError, match="NaN or infinite|degenerate|bounds"):
             seq.wait(t)
         with pytest.raises(fm.FluidMarchError):
             seq.drain()

@@ -7,5 +7,7 @@ for name in sorted(os.listdir(os.path.join(ROOT, "build_variants"))):
     if not os.path.exists(lib):
         continue
     env = dict(os.environ, FLUIDMARCH_LIB=lib, FLUIDMARCH_AB="1")
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_step.py"), cfg, "6"], env=env, capture_output=True, text=True)
-    print(name, out.stdout.strip().split("{'pixels'")[0][:400], out.stderr[-400:], flush=True)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "prof_step.py"), cfg, "12"], env=env, capture_output=True, text=True)
+    txt = out.stdout.strip()
+    tail = txt.split("'first_candidates'")[-1][:120] if "'first_candidates'" in txt else ""
+    print(name, txt.split("{'pixels'")[0][:400], tail, out.stderr[-400:], flush=True)
