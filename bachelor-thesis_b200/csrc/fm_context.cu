@@ -407,7 +407,6 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 	if ((rc = finish_pending(ctx))) return rc;
 	const float* d_xyz = nullptr;
 	size_t n = (size_t)job.n;
-	ctx->lane_h2d_src = nullptr;
 	if (bgeo_path)
 	{
 		if ((rc = stage_bgeo(ctx, bgeo_path, &n))) return rc;
@@ -418,21 +417,12 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 	{
 		if (!job.xyz || n == 0) { set_error("sequence job without particles"); return FR_ERR_INVALID; }
 		if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
-		// the copy is queued by lane_frame_enqueue, in front of the build: one graph holds the whole frame
-		ctx->lane_h2d_src = job.xyz;
-		ctx->lane_h2d_bytes = n * 12;
+		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, job.xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
 		d_xyz = ctx->d_xyz;
 	}
 	ctx->build_timed = 0;
 	// the anisotropic march needs the host copy of the grid parameters for its second search (build_frame_ext)
-	bool const allow_async = !ctx->settings.enable_anisotropy;
-	if (ctx->lane_h2d_src && !(allow_async && ctx->async_build && f->cap_cells > 1))
-	{
-		// this build will wait for the device inside build_frame_begin: the particles have to be on their way first
-		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, ctx->lane_h2d_src, ctx->lane_h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		ctx->lane_h2d_src = nullptr;
-	}
-	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult, allow_async);
+	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult, !ctx->settings.enable_anisotropy);
 }
 
 int lane_frame_copies(fr_context* ctx, const fr_seq_job& job)
@@ -449,13 +439,6 @@ int lane_frame_copies(fr_context* ctx, const fr_seq_job& job)
 int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
 {
 	int rc;
-	if (ctx->lane_h2d_src)
-	{
-		if (!ctx->build.async)       // (the prediction of lane_frame_begin and the decision of build_frame_begin differ only here)
-		{ set_error("lane: a synchronous build without its particles"); return FR_ERR_STATE; }
-		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, ctx->lane_h2d_src, ctx->lane_h2d_bytes, cudaMemcpyHostToDevice, ctx->stream));
-		ctx->lane_h2d_src = nullptr;
-	}
 	if ((rc = build_frame_finish(ctx))) return rc;
 	ctx->pending_frames.push_back(0);
 	if ((rc = fr_render_async(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;

@@ -23,6 +23,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 namespace fm
@@ -779,7 +780,8 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	f->n = n;
 	f->h = h;
 	f->h_ext = h_ext_mult * h;
-	f->build_serial++;
+	static std::atomic<uint64_t> g_build_serial{ 0 };
+	f->build_serial = ++g_build_serial;        // process-wide: a Frame object may move (std::vector) and its address be reused
 
 	int rc;
 	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
@@ -922,7 +924,7 @@ int upload_view_ext(Context* ctx, Frame* f)
 {
 	FrameView v = make_view(*f);
 	FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
-	f->build_serial++;                 // the march's __constant__ copy is stale
+	f->build_serial += 1ull << 40;     // the march's __constant__ copy is stale (keeps the serial unique)
 	return FR_OK;
 }
 

@@ -133,7 +133,6 @@ struct Context
 
 	std::vector<Frame> frames;
 	std::vector<int> pending_frames;   // frames built since the last host wait (resolve_frame at the next one)
-	const float* lane_h2d_src = nullptr; size_t lane_h2d_bytes = 0;   // a lane's particle upload, queued with the rest of its frame
 
 	// images
 	float* d_depth = nullptr;

@@ -74,7 +74,6 @@ int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 {
 	fr_context* const c = ln->ctx;
 	auto const saved = c->build;                   // lane_frame_enqueue consumes it
-	const float* const saved_src = c->lane_h2d_src;
 	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
 	{
 		cudaGetLastError();
@@ -104,7 +103,6 @@ int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 		ln->graph_ok = false;
 		if (ln->exec) { cudaGraphExecDestroy(ln->exec); ln->exec = nullptr; }
 		c->build = saved;
-		c->lane_h2d_src = saved_src;
 		c->render_pending = false;
 		return lane_frame_enqueue(c, job);
 	}

@@ -38,7 +38,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "rays_per_sec_1080p_1M_particles"
 UNIT = "rays/s"
@@ -77,8 +76,20 @@ def workload_string(cfg_name, n_actual, W, H):
 
 
 def camera():
-    from conftest import golden_camera
-    return golden_camera("camera_default_16x9")     # reference default: orbit R = 10, fov 60 deg
+    """reference default: orbit R = 10, fov 60 deg -- the exact bits the reference's camera TUs produce"""
+    return importlib.import_module("bachelor-thesis_b200.camera").reference_default_camera()
+
+
+def checker():
+    """the CPU checkers (oracle/ + tests/oracle_lib.py): cpu_baseline leg and --impl reference only"""
+    tests = os.path.join(ROOT, "tests")
+    if tests not in sys.path:
+        sys.path.insert(0, tests)
+    import oracle_lib
+    return oracle_lib
+
+
+FRAME_T = 0.6      # the ONE synthetic frame every arm renders (scenes.dam_break default; tests/test_gpu_fullsize.py pins it)
 
 
 class ClockSampler:
@@ -169,11 +180,13 @@ class ClockSampler:
 def reference_step_fn(cfg_name, threads=0):
     """the reference's CPU path for one frame: Frame::Frame (search + AABB + density grid) + the per-pixel march
     over all pixels on `threads` host threads.  The depth image is an INPUT of the reference marcher (its
-    GPU raster pass makes it); it is produced once, outside the timed step, by the oracle's restatement."""
-    import oracle_lib
+    GPU raster pass makes it); it is produced once, outside the timed step, by the oracle's restatement.
+    step(pool=False) -> (seconds, build seconds, march seconds, positions, normals); pool=True runs the march on the
+    reference's own ThreadPool (hardware_concurrency() - 1 workers, one atomic per pixel, ThreadPool.cpp:38-55)."""
+    oracle_lib = checker()
     n, W, H, h, dx = CONFIGS[cfg_name]
     fm_scenes = importlib.import_module("bachelor-thesis_b200.scenes")
-    xyz = fm_scenes.dam_break(n, h=h, dx=dx)
+    xyz = fm_scenes.dam_break(n, h=h, dx=dx, t=FRAME_T)
     cam = camera()
     orc = oracle_lib.Oracle()
     depth = orc.frame(xyz, h, 2.0).depth_prepass(W, H, cam["view"], cam["proj"])
@@ -183,54 +196,76 @@ def reference_step_fn(cfg_name, threads=0):
         kind = "reference"
         nthreads = threads or ref.lib.ref_hardware_threads()
 
-        def step():
+        def step(pool=False):
             t0 = time.perf_counter()
             ds = ref.dataset(xyz, h, 2.0)
             t1 = time.perf_counter()
-            _, _, march_s = ds.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads)
+            pos, nrm, march_s = ds.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads,
+                                         use_ref_pool=1 if pool else 0)
             ds.close()
-            return time.perf_counter() - t0, t1 - t0, march_s
+            return time.perf_counter() - t0, t1 - t0, march_s, pos, nrm
     else:
         kind = "port"
         nthreads = threads or orc.lib.fo_get_threads()
 
-        def step():
+        def step(pool=False):
             t0 = time.perf_counter()
             f = orc.frame(xyz, h, 2.0)
             t1 = time.perf_counter()
-            f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads, want_band=False)
+            pos, nrm, *_ = f.march(W, H, s, cam["inv_proj_view"], cam["position"], depth, threads=nthreads, want_band=False)
             t2 = time.perf_counter()
-            return t2 - t0, t1 - t0, t2 - t1
-    return step, kind, nthreads, (n, W, H, len(xyz))
+            return t2 - t0, t1 - t0, t2 - t1, pos, nrm
+    return step, kind, nthreads, (n, W, H, len(xyz)), depth
+
+
+def image_digest(pos, nrm):
+    """sha256 over the bits of the hit positions and normals: equal in both arms <=> bit-identical images"""
+    import hashlib
+    m = hashlib.sha256()
+    m.update(np.ascontiguousarray(pos, np.float32).tobytes())
+    m.update(np.ascontiguousarray(nrm, np.float32).tobytes())
+    return m.hexdigest()[:16]
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    step, kind, nthreads, (n, W, H, n_actual) = reference_step_fn(args.config)
-    for _ in range(max(0, min(args.warmup, 1))):
+    step, kind, nthreads, (n, W, H, n_actual), _ = reference_step_fn(args.config)
+    budget = time.perf_counter() + 240.0     # full C2 frames take ~0.45 s each on the host cores
+    warm = 0
+    for _ in range(args.warmup):
         step()
+        warm += 1
+        if time.perf_counter() > budget - 120.0:
+            break
     times, builds, marches = [], [], []
-    budget = time.perf_counter() + 150.0     # full C2 frames take ~0.45 s each on the host cores
+    pos = nrm = None
     for _ in range(args.steps):
-        t, b, m = step()
+        t, b, m, pos, nrm = step()
         times.append(t); builds.append(b); marches.append(m)
         if time.perf_counter() > budget:
             break
     ms = 1e3 * sum(times) / len(times)
     value = W * H / (ms * 1e-3)
+    pool = None
+    if kind == "reference":
+        tp = step(pool=True)
+        pool = {"ms_per_step": 1e3 * tp[0], "march_ms": 1e3 * tp[2], "value": W * H / tp[0],
+                "note": "the march on the reference's own ThreadPool (hardware_concurrency() - 1 workers, one atomic per pixel, "
+                        "ThreadPool.cpp:38-55; pixel W*H-1 is skipped there) instead of the harness's chunked parallel-for"}
     sample = (f"{len(times)} full frames of {args.config} ({n_actual} particles, {W}x{H}): Frame::Frame build "
               f"{1e3 * sum(builds) / len(builds):.0f} ms + march {1e3 * sum(marches) / len(marches):.0f} ms per frame; "
               "depth image precomputed (the reference rasterises it on its GPU); neighbour search = API-compatible "
               "stand-in for the un-vendored CompactNSearch fork")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
-        "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_string(args.config, n_actual, W, H),
-                   "step": "Frame::Frame (search + AABB + density grid) + PerPixel_Isotropic over all pixels, host cores"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample},
+                   "step": "Frame::Frame (search + AABB + density grid) + PerPixel_Isotropic over all pixels, host cores",
+                   "image_sha256_16": image_digest(pos, nrm)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nthreads, "kind": kind, "sample": sample, "reference_thread_pool": pool},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -262,13 +297,13 @@ def run_b200(args):
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     cores = os.cpu_count() or 8
     lanes = 1 if tiles_mode else max(1, args.lanes)
-    # frame-parallel: rank r renders frames r, r + world, ... of the animation (distinct t per frame).  Enough
-    # distinct frames that the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush)
+    # Every step renders THE SAME synthetic frame (FRAME_T) -- the one the reference arm, the cpu_baseline leg and
+    # tests/test_gpu_fullsize.py march -- out of n_frames separate device / pinned-host buffers, enough of them that
+    # the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush).  Frame-parallel: rank r
+    # renders steps r, r + world, ... of that sequence
     n_frames = 1 if tiles_mode else max(4, min(24, -(-150_000_000 // (12 * n))))
-    frames = []
-    for k in range(n_frames):
-        t = 0.6 if tiles_mode else 0.45 + 0.3 * (((k * world + rank) % 240) / 239.0)
-        frames.append(fm.scenes.dam_break(n, h=h, dx=dx, t=t))
+    frame0 = fm.scenes.dam_break(n, h=h, dx=dx, t=FRAME_T)
+    frames = [frame0.copy() for _ in range(n_frames)]
     n_actual = [len(f) for f in frames]
     settings = fm.VisualizationSettings(FastNormals=args.fast_normals)
 
@@ -447,7 +482,7 @@ def run_b200(args):
         peak, peak_src = load_peaks()
         npart = n_actual[(args.warmup + args.steps - 1) % n_frames]
         # per-kernel device times of the stages (CUDA events on the context stream, one frame at a time, L2 flushed)
-        stages = {"grid build (10 kernels)": tim["grid_ms"], "depth pre-pass (7 kernels)": tim["depth_ms"],
+        stages = {"grid build (5 kernels)": tim["grid_ms"], "depth pre-pass (7 kernels)": tim["depth_ms"],
                   "k_classify": tim["classify_ms"], "k_march_first": tim["march_first_ms"], "k_march_long": tim["march_long_ms"]}
         # dominant KERNEL (not stage): the depth stage is five kernels, the largest of which (k_depth_splat) is ~43% of the
         # stage in every committed ncu launch list (profiles/*_launches_C2.csv)
@@ -464,14 +499,29 @@ def run_b200(args):
             note = "16 B x particles + 32 B x particles (splat records) + 4 B x pixels (clear) + 4 B x covered pixels"
         achieved = alg / (dur_ms * 1e-3) / 1e9
         ncu = load_ncu_stats(args.config, dom)
-        roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu.get("dram_bytes"), "peak_source": peak_src, "algorithmic_bytes": alg,
-                "algorithmic_bytes_def": note, "kernel_ms": dur_ms, "kernel_share_of_step": dur_ms / serial_ms,
-                "stage_ms": stages,
-                "note": "kernel_ms is the kernel's CUDA-event time with one frame in flight and L2 flushed; the path is "
-                        "FP32-issue bound, not HBM bound (DESIGN.md 3.5): compulsory HBM traffic of the frame is ~0.1 GB; "
-                        "`frac` is SURVEY 8(d)'s algorithmic-bytes figure against the HBM peak",
-                "ncu": ncu}
+        sm_mhz_now = (clocks or {}).get("sm_mhz") or 1965.0
+        hbm_alg = {"achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                   "algorithmic_bytes": alg, "algorithmic_bytes_def": note,
+                   "note": "SURVEY 8(d)'s figure: the bytes a 27-cell method examines, as if every ray fetched its own candidates from "
+                           "HBM.  Not a physical HBM fraction: the kernel's DRAM traffic is `traffic` (candidates are L1 / L2 hits)"}
+        if ncu.get("warp_instructions"):
+            # the binding resource (ncu: DRAM < 1 %, L2 < 5 % of peak, issue slots ~60-70 % busy in active cycles): warp
+            # instructions issued per second against 4 schedulers x 148 SMs x SM clock
+            ipeak = 148 * 4 * sm_mhz_now * 1e6 / 1e9
+            iach = ncu["warp_instructions"] / (dur_ms * 1e-3) / 1e9
+            roof = {"bound": "issue", "kernel": dom, "achieved": iach, "peak": ipeak, "unit": "Ginst/s", "frac": iach / ipeak,
+                    "traffic": ncu.get("dram_bytes"),
+                    "peak_source": f"4 warp schedulers x 148 SMs x {sm_mhz_now:.0f} MHz (SM clock sampled in this run)",
+                    "warp_instructions_per_launch": ncu["warp_instructions"],
+                    "warp_instructions_source": f"profiles/{ncu.get('source', 'ncu_stats.json')} (ncu smsp__inst_executed.sum of the committed capture of this kernel)"}
+        else:
+            roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": ncu.get("dram_bytes"), "peak_source": peak_src}
+        roof.update({"hbm_algorithmic": hbm_alg, "kernel_ms": dur_ms, "kernel_share_of_step": dur_ms / serial_ms, "stage_ms": stages,
+                     "note": "kernel_ms is the kernel's CUDA-event time with one frame in flight and L2 flushed.  The path is bound by "
+                             "instruction issue (FP32 without FMA contraction, correctly rounded division / sqrt sequences), not by HBM: "
+                             "compulsory HBM traffic of a frame is ~0.1 GB (DESIGN.md 3.8)",
+                     "ncu": ncu})
         # the march is a gather served by L1/L2, so the same algorithmic bytes also go against the L2 -> SM
         # bandwidth, measured live (fr_measure_l2_bandwidth: read-only streaming over an L2-resident 32 MB buffer)
         try:
@@ -497,17 +547,35 @@ def run_b200(args):
                             "note": "algorithmic flops against the FMA peak at the sampled SM clock; the kernel cannot use FMA (one IEEE "
                                     "rounding per operation, as the reference) and its divisions / square roots are correctly rounded "
                                     "multi-instruction sequences, so issue slots (fp32_issue_frac) are the meaningful measure"}
-        if ncu.get("warp_instructions") and clocks and clocks.get("sm_mhz"):
-            roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * clocks["sm_mhz"] * 1e6 * dur_ms * 1e-3)
+        if ncu.get("warp_instructions"):
+            roof["fp32_issue_frac"] = ncu["warp_instructions"] / (148 * 4 * sm_mhz_now * 1e6 * dur_ms * 1e-3)
         cpu = None
+        parity = {"parity_checked": False, "pixels_differing": None}
         if world == 1 and not args.no_cpu_baseline:
-            step, kind, nthreads, _ = reference_step_fn(args.config)
+            step, kind, nthreads, _, ref_depth = reference_step_fn(args.config)
             ts = [step() for _ in range(3)]
             best = min(t[0] for t in ts)
             cpu = {"value": W * H / best, "unit": UNIT, "cores": nthreads, "kind": kind,
                    "sample": f"best of 3 full frames of {args.config} on the host cores: Frame::Frame build "
                              f"{1e3 * min(t[1] for t in ts):.0f} ms + march {1e3 * min(t[2] for t in ts):.0f} ms "
                              "(depth image precomputed; neighbour search = stand-in for the un-vendored CompactNSearch fork)"}
+            if kind == "reference":
+                tp = step(pool=True)
+                cpu["reference_thread_pool"] = {"ms_per_step": 1e3 * tp[0], "march_ms": 1e3 * tp[2], "value": W * H / tp[0],
+                                                "note": "the march on the reference's own ThreadPool (hardware_concurrency() - 1 workers, "
+                                                        "one atomic per pixel, ThreadPool.cpp:38-55)"}
+            # parity of the frame just timed: this context's images against the CPU arm's, bit for bit
+            ctx.build_frame_device(0, d_frames[0].data_ptr(), n_actual[0], h, 2.0)
+            ctx.render(fm.FR_PASS_ALL)
+            g_depth, g_pos, g_nrm, _ = ctx.download()
+            u = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+            ref_pos, ref_nrm = ts[0][3], ts[0][4]
+            diff = (u(g_pos) != u(ref_pos)).any(-1) | (u(g_nrm) != u(ref_nrm)).any(-1)
+            parity = {"parity_checked": True, "pixels_differing": int(diff.sum()),
+                      "depth_pixels_differing": int((u(g_depth) != u(ref_depth)).sum()),
+                      "parity_against": f"{kind}: hit mask, positions and normals bit for bit ({'oracle/_ref = the reference TUs' if kind == 'reference' else 'oracle C port'}); "
+                                        "depth image against the oracle's restatement of depth.vert/frag",
+                      "image_sha256_16": image_digest(g_pos, g_nrm)}
         if tiles_mode:
             par = (f"tile-parallel {args.tile}x{args.tile} interleaved, every rank's shading epilogue stores its tiles into the presenting GPU's image "
                    "over NVLink peer memory (CUDA IPC), barrier" if peer_mode else f"tile-parallel {args.tile}x{args.tile} interleaved + NCCL gather")
@@ -515,8 +583,8 @@ def run_b200(args):
         else:
             par = (f"frame-parallel x{world}, {lanes} frames in flight per GPU (fr_seq_*), lane workers "
                    f"{'poll pinned memory and yield' if yielding else 'wait in the driver'} ({cores} host cores)")
-            l2 = (f"inputs larger than L2: {n_frames} distinct frames of {12 * npart / 1e6:.1f} MB cycled "
-                  f"({n_frames * 12 * npart / 1e6:.0f} MB of particles, + {lanes} x {W * H * 40 / 1e6:.0f} MB of images); "
+            l2 = (f"inputs larger than L2: {n_frames} separate buffers of {12 * npart / 1e6:.1f} MB cycled "
+                  f"({n_frames * 12 * npart / 1e6:.0f} MB of particles, + {lanes} x {W * H * 40 / 1e6:.0f} MB of images; every buffer holds the same frame); "
                   "latency_ms_per_frame / stage_ms: L2 flushed between steps (512 MiB memset outside the timed events)")
         e2e = {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
                "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * 4),
@@ -542,6 +610,7 @@ def run_b200(args):
                        "frames_per_s": (1 if tiles_mode else world) / (ms_step * 1e-3),
                        "wall_s_timed_region": wall},
             "clocks": clocks,
+            "parity_checked": parity["parity_checked"], "pixels_differing": parity["pixels_differing"], "parity": parity,
             "e2e": e2e,
             "gpu_launches": int(kernel_launches_timed),
             "roofline": roof,

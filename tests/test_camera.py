@@ -37,7 +37,8 @@ def test_package_camera_table_is_the_golden_dump(fm):
     """bachelor-thesis_b200/data holds a copy of the matrices dumped from the reference's camera TUs (bench.py and
     smoke() read it, so that neither depends on tests/)"""
     from conftest import golden_camera
-    a, b = fm.camera.reference_default_camera(), golden_camera("camera_default_16x9")
-    assert set(a) == set(b)
-    for k in a:
-        assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+    for name in ("camera_default_16x9", "camera_close_16x9"):
+        a, b = fm.camera.reference_default_camera(name), golden_camera(name)
+        assert set(a) == set(b)
+        for k in a:
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), (name, k)
