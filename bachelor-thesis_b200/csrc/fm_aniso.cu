@@ -49,8 +49,7 @@ int march_occupancy_aniso(int* blocks_per_sm)
 int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml)
 {
 	cudaStream_t const st = ctx->stream;
-	{ int const rc = bind_view(ctx, *ml.frame, 1); if (rc) return rc; }
-	int const slot = ctx->cslot;
+	const FrameView* const slot = ml.frame->d_fv;
 	if (ml.fast_normals)
 		k_march_first<true, true><<<ml.ctas, 256, 0, st>>>(slot, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
 	else

@@ -262,8 +262,6 @@ int fr_create(int device, int width, int height, fr_context** out)
 		for (auto& ev : c->ev)
 			if (cudaEventCreate(&ev) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (rc) break;
-		c->cslot = cslot_acquire();
-		if (c->cslot < 0) { set_error("fr_create: more than 64 contexts alive in this process"); rc = FR_ERR_STATE; break; }
 		if (cudaMalloc((void**)&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaMallocHost((void**)&c->h_counters, sizeof(DeviceCounters)) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
@@ -324,7 +322,6 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_rayq) cudaFree(ctx->d_rayq);
 	if (ctx->d_survivors) cudaFree(ctx->d_survivors);
 	if (ctx->d_tmp_idx) cudaFree(ctx->d_tmp_idx);
-	cslot_release(ctx->cslot);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	if (ctx->ext_wait) cudaDestroyExternalSemaphore(ctx->ext_wait);

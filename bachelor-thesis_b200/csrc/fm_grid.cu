@@ -681,25 +681,6 @@ int build_frame_ext(Context* ctx, Frame* f)
 	return FR_OK;
 }
 
-// ---- __constant__ slots of the march kernels (one per context, process-wide numbering) ---------------------------------
-static std::mutex g_slot_mutex;
-static unsigned long long g_slot_mask = 0ull;
-
-int cslot_acquire()
-{
-	std::lock_guard<std::mutex> lk(g_slot_mutex);
-	for (int k = 0; k < kConstSlots; k++)
-		if (!(g_slot_mask >> k & 1ull)) { g_slot_mask |= 1ull << k; return k; }
-	return -1;
-}
-
-void cslot_release(int slot)
-{
-	if (slot < 0) return;
-	std::lock_guard<std::mutex> lk(g_slot_mutex);
-	g_slot_mask &= ~(1ull << slot);
-}
-
 void free_frame_small(Frame& f)
 {
 	if (f.d_gp) cudaFree(f.d_gp);
@@ -924,7 +905,6 @@ int upload_view_ext(Context* ctx, Frame* f)
 {
 	FrameView v = make_view(*f);
 	FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
-	f->build_serial += 1ull << 40;     // the march's __constant__ copy is stale (keeps the serial unique)
 	return FR_OK;
 }
 

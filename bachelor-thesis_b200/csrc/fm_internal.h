@@ -53,11 +53,11 @@ struct Frame
 	float h = 0.0f, h_ext = 0.0f;
 	GridParams gp{};                  // host copy: valid once gp_pending is false (resolve_frame)
 	GridParams* d_gp = nullptr;       // device: written by k_aabb_params, read by the build kernels
-	FrameView* d_fv = nullptr;        // device: the frame as the march kernels see it (copied into their __constant__ slot)
+	FrameView* d_fv = nullptr;        // device: the frame as the march kernels see it
 	GridParams* h_gp = nullptr;       // pinned: the copy that comes back at the end of the build
 	bool gp_pending = false;          // the build is queued and its parameters have not been read back yet
 	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (always after resolve_frame; at once after a build with a host wait)
-	uint64_t build_serial = 0;        // bumped by every build (the march's __constant__ slot remembers what it holds)
+	uint64_t build_serial = 0;        // process-wide number of this build
 	const float* src_xyz = nullptr;   // device particles of the queued build (must stay valid until the host next waits)
 	float src_mult = 0.0f;
 	uint64_t occupied = 0;
@@ -111,9 +111,6 @@ struct Context
 			 bool async = false; uint32_t scan_blocks = 0, flag_cells = 0; } build;
 	bool async_build = true;           // builds into tables that already exist skip the host round trip (fr_set_async_build)
 	int last_passes = 0;               // passes of the pending render (repeated after a rebuild)
-	int cslot = -1;                    // this context's slot in the march kernels' __constant__ frame tables
-	const Frame* cslot_frame[2] = { nullptr, nullptr };   // what the slot holds (isotropic TU, anisotropic TU) ...
-	uint64_t cslot_serial[2] = { 0, 0 };                   // ... and from which build
 	bool march_timed = false;
 	bool zero_counters_in_depth = false;   // this render call: k_depth_clear zeroes the march counters (one memset less)
 	// per-stage CUDA events (fr_get_timings).  The lanes of a sequence switch them off: every record is one more
@@ -207,10 +204,7 @@ int build_frame_ext(Context* ctx, Frame* f);      // no-op when already built
 FrameView make_view(const Frame& f);              // needs resolve_frame
 int upload_view_ext(Context* ctx, Frame* f);      // the r = h_ext fields into the device copy of the view
 void free_frame_small(Frame& f);
-// __constant__ slots of the march kernels
-int cslot_acquire();
-void cslot_release(int slot);
-constexpr int kConstSlots = 64;
+
 // fm_depth.cu
 int launch_depth_prepass(Context* ctx, const Frame& f);
 // fm_march.cu

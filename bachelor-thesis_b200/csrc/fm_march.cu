@@ -92,7 +92,9 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
 				int nb = 0, nl = 0;
 				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, kFirstThreads, smem_first));
-				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false>, 256, 0));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
+				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false>, 256, kLongSmem));
 				if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < nb) nb = v; }   // tuning switch
 				ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
 				ctx->march_long_ctas_per_sm = nl > 0 ? nl : 1;
@@ -102,11 +104,9 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			ctas_first = std::min(ctas_first, (ntiles + first_warps - 1) / first_warps);
 			uint32_t ctas_long = (uint32_t)(ctx->sm_count * ctx->march_long_ctas_per_sm);
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
-			if ((rc = bind_view(ctx, f, 0))) return rc;
-			int const slot = ctx->cslot;
-			first<<<ctas_first, kFirstThreads, smem_first, st>>>(slot, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+			first<<<ctas_first, kFirstThreads, smem_first, st>>>(f.d_fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			FM_TIME(ctx, ctx->ev[11], st);
-			longk<<<ctas_long, 256, 0, st>>>(slot, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			longk<<<ctas_long, 256, kLongSmem, st>>>(f.d_fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		}
 		ctx->kernel_launches += 2;
 	}

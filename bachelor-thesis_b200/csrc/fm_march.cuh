@@ -83,22 +83,19 @@ namespace
 
 constexpr int kMaxNeighbors = 2 * 4096;   // MAX_NEIGHBORS (RayMarcher.cpp:14)
 
-// The frame as the march kernels see it lives in __constant__ memory, one slot per context, so that its fields reach
-// the instructions the way kernel parameters do (uniform loads from a constant bank).  The slot is filled ON THE STREAM
-// from the device copy k_aabb_params leaves behind (Frame::d_fv): the host does not have to know the grid parameters
-// of a frame to march it, which is what lets a frame build run without a host round trip (fm_grid.cu).
-__constant__ FrameView c_frames[kConstSlots];
-
-// (this translation unit's table; `which` = 0 isotropic TU, 1 anisotropic TU)
-static int bind_view(Context* ctx, const Frame& f, int which)
+// The frame as the march kernels see it is read from DEVICE memory (Frame::d_fv, written by k_aabb_params): the host
+// does not have to know the grid parameters of a frame to march it, which is what lets a frame build run without a
+// host round trip (fm_grid.cu).  Every CTA copies the ~50 words into shared memory once (the kernels are persistent);
+// loops keep what they need in registers.  (A __constant__ table indexed by a per-context slot was measured first, r02c:
+// the index is a vector register to the compiler, every field access became an indexed LDC, k_march_first +20 %.)
+__device__ __forceinline__ void load_view(FrameView& dst, const FrameView* __restrict__ src)
 {
-	if (ctx->cslot_frame[which] == &f && ctx->cslot_serial[which] == f.build_serial) return FR_OK;
-	FM_CUDA(cudaMemcpyToSymbolAsync(c_frames, f.d_fv, sizeof(FrameView), (size_t)ctx->cslot * sizeof(FrameView),
-									cudaMemcpyDeviceToDevice, ctx->stream));
-	ctx->cslot_frame[which] = &f;
-	ctx->cslot_serial[which] = f.build_serial;
-	return FR_OK;
+	const uint32_t* const s = reinterpret_cast<const uint32_t*>(src);
+	uint32_t* const d = reinterpret_cast<uint32_t*>(&dst);
+	for (uint32_t i = threadIdx.x; i < sizeof(FrameView) / 4; i += blockDim.x) d[i] = __ldg(s + i);
+	__syncthreads();
 }
+static_assert(sizeof(FrameView) % 4 == 0, "FrameView is copied word by word");
 
 struct LaneCounters
 {
@@ -194,6 +191,9 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	float density = 0.0f;
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t nn = 0;
+	// (the view lives in shared memory: what the loops need is kept in registers, out of reach of the memory clobbers)
+	const float4* const sorted = f.sorted;
+	float const hh = f.kernel.h_squared;
 	bool const walk = z0 <= z1 && on;
 	int r0 = 0;              // where the walk resumes after a full list: range r0, particle j0
 	uint32_t j0 = 0;
@@ -224,18 +224,18 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	{                                                                                                \
 		float const d0 = subr(p.x, (q).x), d1 = subr(p.y, (q).y), d2 = subr(p.z, (q).z);             \
 		float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));                       \
-		if (l2 < f.kernel.h_squared) { sts_u32(lp, (jj)); lp += 128u; }                              \
+		if (l2 < hh) { sts_u32(lp, (jj)); lp += 128u; }                                              \
 	}
 #pragma unroll 1
 					for (; j + 4u <= e; j += 4u)
 					{
-						float4 const q0 = __ldg(f.sorted + j), q1 = __ldg(f.sorted + j + 1), q2 = __ldg(f.sorted + j + 2), q3 = __ldg(f.sorted + j + 3);
+						float4 const q0 = __ldg(sorted + j), q1 = __ldg(sorted + j + 1), q2 = __ldg(sorted + j + 2), q3 = __ldg(sorted + j + 3);
 						FM_WALK_TEST(q0, j) FM_WALK_TEST(q1, j + 1u) FM_WALK_TEST(q2, j + 2u) FM_WALK_TEST(q3, j + 3u)
 					}
 #pragma unroll 1
 					for (; j < e; j++)
 					{
-						float4 const q0 = __ldg(f.sorted + j);
+						float4 const q0 = __ldg(sorted + j);
 						FM_WALK_TEST(q0, j)
 					}
 #undef FM_WALK_TEST
@@ -249,11 +249,11 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 #pragma unroll (kWalkUnroll)
 				for (; j < e; j++)
 				{
-					float4 const q = __ldg(f.sorted + j);
+					float4 const q = __ldg(sorted + j);
 					// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to right); l2 < r2
 					float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
 					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
-					bool const in = l2 < f.kernel.h_squared;
+					bool const in = l2 < hh;
 					bool const fits = cnt < (uint32_t)kListCap;
 					if (in && fits) list[cnt * 32u] = j;
 					over = (in && !fits) ? min(over, j) : over;
@@ -266,7 +266,7 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 #pragma unroll 1
 		for (uint32_t k = 0; k < cnt; k++)
 		{
-			float4 const q = __ldg(f.sorted + list[k * 32u]);
+			float4 const q = __ldg(sorted + list[k * 32u]);
 			float const d0 = subr(p.x, q.x), d1 = subr(p.y, q.y), d2 = subr(p.z, q.z);
 			float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
 			add_neighbour<DENS, GRAD, FAST>(f, d0, d1, d2, l2, density, g, nn);
@@ -983,17 +983,20 @@ __device__ __forceinline__ void flush_counters(const LaneCounters& lc, DeviceCou
 constexpr int kFirstThreads = FM_FIRST_STAGED ? FM_FIRST_WARPS * 32 : 256;
 constexpr size_t kFirstWarpBytes = FM_FIRST_STAGED ? sizeof(WarpStage) : (size_t)kListWords * 4;      // dynamic shared memory per warp
 constexpr size_t kFirstSmem = (size_t)(kFirstThreads / 32) * kFirstWarpBytes;
+constexpr size_t kLongSmem = (size_t)8 * kListWords * 4;           // k_march_long, isotropic: the lists of its 8 warps
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(int slot, MarchParams mp, const float* __restrict__ depth,
+__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(const FrameView* __restrict__ fvp, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	const FrameView& f = c_frames[slot];
+	__shared__ FrameView s_view;
+	load_view(s_view, fvp);
+	const FrameView& f = s_view;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	// the global-memory walk (every tile when FM_FIRST_STAGED = 0, else tiles that do not fit the stage and bisection
@@ -1096,15 +1099,17 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(int slot, MarchParams mp, float4* __restrict__ pos_out,
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(const FrameView* __restrict__ fvp, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	const FrameView& f = c_frames[slot];
+	__shared__ FrameView s_view;
+	load_view(s_view, fvp);
+	const FrameView& f = s_view;
 	int const lane = threadIdx.x & 31;
-	__shared__ uint32_t s_list[ANISO ? 1 : 8 * kListWords];
-	uint32_t* const list = ANISO ? s_list : s_list + (threadIdx.x >> 5) * kListWords + lane;
+	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
+	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 2);
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
