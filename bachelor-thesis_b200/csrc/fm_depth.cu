@@ -370,8 +370,30 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 			int trow = (int)(((float)t + 0.5f) * inv_ntx);
 			int tcol = t - trow * pntx;
 			if (tcol < 0) { trow--; tcol += pntx; } else if (tcol >= pntx) { trow++; tcol -= pntx; }
-			bool const alive = t < ntiles && pixel_owned(dp, (ptx0 + tcol) * T, (pty0 + trow) * T) &&
-				s.near_bits < __ldg(tile_bound + (size_t)(pty0 + trow) * dp.tiles_x + (ptx0 + tcol));
+			// a tile stays open only if the NEAREST fragment the particle can produce on it -- the pixel centre closest
+			// to the disc centre: u and v are monotone in the pixel index, so per axis that is 0 when the tile straddles
+			// the centre line and the smaller end otherwise; FP32 mul / add are monotone, the polynomial cosine is up
+			// to a few ulps (16 of slack) -- is in front of the tile's bound.  The disc-centre depth (near_bits) only
+			// tells front layers from interior ones: with discs of ~12 px radius at ~5 px spacing a front-layer particle
+			// overlaps ~50 tiles but can win only the handful next to its centre.
+			bool alive = t < ntiles && pixel_owned(dp, (ptx0 + tcol) * T, (pty0 + trow) * T);
+			if (alive)
+			{
+				int const tx = ptx0 + tcol, ty = pty0 + trow;
+				int const qx0 = max(tx * T, s.x0), qx1 = min(tx * T + T - 1, s.x1);
+				int const qy0 = max(ty * T, s.y0), qy1 = min(ty * T + T - 1, s.y1);
+				float const u0 = frag_u((float)qx0, dp.two_w_inv, s.ax, s.bx), u1 = frag_u((float)qx1, dp.two_w_inv, s.ax, s.bx);
+				float const v0 = frag_u((float)qy0, dp.two_h_inv, s.ay, s.by), v1 = frag_u((float)qy1, dp.two_h_inv, s.ay, s.by);
+				float const un = (u0 <= 0.0f) != (u1 <= 0.0f) ? 0.0f : fminf(fabsf(u0), fabsf(u1));
+				float const vn = (v0 <= 0.0f) != (v1 <= 0.0f) ? 0.0f : fminf(fabsf(v0), fabsf(v1));
+				float const l2n = addr(mulr(un, un), mulr(vn, vn));
+				alive = l2n <= 1.0f;                                   // else every pixel of the tile is discarded (depth.frag:22)
+				if (alive)
+				{
+					uint32_t const dn = __float_as_uint(frag_depth(dp, s.z_c, l2n));
+					alive = (dn > 16u ? dn - 16u : 0u) < __ldg(tile_bound + (size_t)ty * dp.tiles_x + tx);
+				}
+			}
 			uint32_t const tiles = __ballot_sync(0xffffffffu, alive);
 			if (tiles == 0u) continue;
 			// the open tiles of this batch, compacted into the warp's shared-memory row: lane group g of round k takes

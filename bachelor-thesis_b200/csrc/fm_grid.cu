@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	*view_out = view;
 }
 
+// the device copy of a view the host has complete (after a build with a host wait, after build_frame_ext): a kernel
+// parameter, not a host-memory copy, so that it can be captured into a lane's CUDA graph
+__global__ void k_store_view(FrameView v, FrameView* __restrict__ dst) { if (threadIdx.x == 0) *dst = v; }
+
 // what the particle kernels need of GridParams, loaded once per thread (every lane reads the same words: L1 broadcasts)
 struct BuildView
 {
@@ -821,10 +825,9 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	// the view was written with the old table pointers if a table moved: write it again (cheap, rare)
 	ctx->build.scan_blocks = (cells32 + kScanTile - 1) / kScanTile;
 	ctx->build.flag_cells = gcells32;
-	{
-		FrameView v = make_view(*f);
-		FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, s));      // pageable source: staged at call time
-	}
+	k_store_view<<<1, 32, 0, s>>>(make_view(*f), f->d_fv);
+	ctx->kernel_launches += 1;
+	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }
 
@@ -903,8 +906,9 @@ int resolve_frame(Context* ctx, Frame* f, bool synced)
 // the r = h_ext fields of the device copy of the view (build_frame_ext ran after the frame build)
 int upload_view_ext(Context* ctx, Frame* f)
 {
-	FrameView v = make_view(*f);
-	FM_CUDA(cudaMemcpyAsync(f->d_fv, &v, sizeof v, cudaMemcpyHostToDevice, ctx->stream));
+	k_store_view<<<1, 32, 0, ctx->stream>>>(make_view(*f), f->d_fv);
+	ctx->kernel_launches += 1;
+	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }
 

@@ -71,6 +71,8 @@ struct RayQueues
 struct MarchLaunch
 {
 	const Frame* frame;
+	bool by_value;           // the host knows the frame's grid parameters: the view goes in as a kernel parameter
+	FrameView fv;            // (valid when by_value)
 	MarchParams mp;
 	RayQueues rq;
 	const uint32_t* tiles;
@@ -987,16 +989,18 @@ constexpr size_t kLongSmem = (size_t)8 * kListWords * 4;           // k_march_lo
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
-template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(const FrameView* __restrict__ fvp, MarchParams mp, const float* __restrict__ depth,
+// BYVAL: the view is a kernel parameter (the host knows the frame's grid parameters: every render of a frame after the
+// first host wait behind its build); else it is read from device memory (Frame::d_fv) into shared memory
+template <bool FAST, bool ANISO, bool BYVAL>
+__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(FrameView fval, const FrameView* __restrict__ fvp, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
 	__shared__ FrameView s_view;
-	load_view(s_view, fvp);
-	const FrameView& f = s_view;
+	if (!BYVAL) load_view(s_view, fvp);
+	const FrameView& f = BYVAL ? fval : s_view;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	// the global-memory walk (every tile when FM_FIRST_STAGED = 0, else tiles that do not fit the stage and bisection
@@ -1098,15 +1102,15 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 // 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
-template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(const FrameView* __restrict__ fvp, MarchParams mp, float4* __restrict__ pos_out,
+template <bool FAST, bool ANISO, bool BYVAL>
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView fval, const FrameView* __restrict__ fvp, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
 	__shared__ FrameView s_view;
-	load_view(s_view, fvp);
-	const FrameView& f = s_view;
+	if (!BYVAL) load_view(s_view, fvp);
+	const FrameView& f = BYVAL ? fval : s_view;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);

@@ -26,6 +26,8 @@ def main():
     ctx = fm.Context(W, H)
     ctx.set_camera(cam["view"], cam["proj"], cam["inv_proj_view"], cam["position"], cam["system"].reshape(3, 3)[2])
     ctx.set_settings(fm.VisualizationSettings())
+    if os.environ.get("FR_ASYNC") == "0":
+        ctx.set_async_build(False)          # every build waits once for the device; the march takes the view by value
     log = []
     for _ in range(steps):
         ctx.upload_frame(0, xyz, h, 2.0)
