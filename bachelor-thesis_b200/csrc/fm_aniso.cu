@@ -42,31 +42,24 @@ struct DevBuf
 
 int march_occupancy_aniso(int* blocks_per_sm)
 {
-	FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_march_first<false, true, false>, 256, 0));
-	return FR_OK;
-}
-
-template <bool BYVAL>
-static int launch_aniso(Context* ctx, const MarchLaunch& ml)
-{
-	cudaStream_t const st = ctx->stream;
-	const FrameView* const fp = ml.frame->d_fv;
-	if (ml.fast_normals)
-		k_march_first<true, true, BYVAL><<<ml.ctas, 256, 0, st>>>(ml.fv, fp, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
-	else
-		k_march_first<false, true, BYVAL><<<ml.ctas, 256, 0, st>>>(ml.fv, fp, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
-	FM_TIME(ctx, ctx->ev[11], st);
-	if (ml.fast_normals)
-		k_march_long<true, true, BYVAL><<<ml.ctas, 256, 0, st>>>(ml.fv, fp, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters);
-	else
-		k_march_long<false, true, BYVAL><<<ml.ctas, 256, 0, st>>>(ml.fv, fp, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters);
-	FM_CUDA(cudaGetLastError());
+	FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_march_first<false, true>, 256, 0));
 	return FR_OK;
 }
 
 int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml)
 {
-	return ml.by_value ? launch_aniso<true>(ctx, ml) : launch_aniso<false>(ctx, ml);
+	cudaStream_t const st = ctx->stream;
+	if (ml.fast_normals)
+		k_march_first<true, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
+	else
+		k_march_first<false, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
+	FM_TIME(ctx, ctx->ev[11], st);
+	if (ml.fast_normals)
+		k_march_long<true, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters);
+	else
+		k_march_long<false, true><<<ml.ctas, 256, 0, st>>>(ml.fv, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters);
+	FM_CUDA(cudaGetLastError());
+	return FR_OK;
 }
 
 int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float* points_host, size_t m, float* density,

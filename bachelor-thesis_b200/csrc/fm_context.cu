@@ -143,10 +143,9 @@ static void read_build_timings(Context* c)
 
 static int render_passes(fr_context* ctx, int passes);
 
-// every host wait of a context ends here: the stream is drained, the grid parameters of the frames built since the
-// last wait come back (resolve_frame), and a frame whose build found the tables of its slot too small has been rebuilt
-// -- the render queued behind the first attempt is then repeated.  Returns FR_RETRIED in that case (copies the caller
-// queued behind the render carry the first attempt's pixels), FR_OK or an error otherwise.
+// every host wait of a context ends here: the stream is drained and the end-of-build status of the frames built since
+// the last wait is read (resolve_frame).  FR_RETRIED: a frame that had only been built, not rendered, found the tables
+// of its slot too small and has been rebuilt.
 static int finish_pending_ex(Context* c)
 {
 	bool const rendered = c->render_pending;
@@ -167,13 +166,6 @@ static int finish_pending_ex(Context* c)
 		if (rc == FR_RETRIED) retried = FR_RETRIED;
 	}
 	c->pending_frames.clear();
-	if (retried == FR_RETRIED && rendered)
-	{
-		int rc = render_passes(static_cast<fr_context*>(c), c->last_passes);
-		if (rc) return rc;
-		if ((rc = stream_sync(c))) return rc;
-		c->render_pending = false;
-	}
 	if (rendered)
 	{
 		read_build_timings(c);
@@ -187,7 +179,7 @@ static int finish_pending_ex(Context* c)
 			if (cudaEventElapsedTime(&ms, c->ev[11], c->ev[6]) == cudaSuccess) c->timings.march_long_ms = ms;
 		}
 	}
-	else if (c->build_timed)       // a frame build without a render behind it: its times are read at the next real wait
+	else if (c->build_timed)       // a frame build without a render behind it: its times are read once they exist
 	{
 		if (cudaEventQuery(c->ev[3]) == cudaSuccess) read_build_timings(c);
 	}
@@ -256,6 +248,8 @@ int fr_create(int device, int width, int height, fr_context** out)
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaHostAlloc((void**)&c->h_sync_flag, 64, cudaHostAllocMapped) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		*c->h_sync_flag = 0u;
 		if (cudaHostGetDevicePointer((void**)&c->d_sync_flag, (void*)c->h_sync_flag, 0) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
@@ -330,6 +324,8 @@ void fr_destroy(fr_context* ctx)
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
 	if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+	if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
+	if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
 	if (ctx->h_sync_flag) cudaFreeHost((void*)ctx->h_sync_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -418,12 +414,27 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 		d_xyz = ctx->d_xyz;
 	}
 	ctx->build_timed = 0;
-	// the anisotropic march needs the host copy of the grid parameters for its second search (build_frame_ext)
-	return build_frame_begin(ctx, f, d_xyz, n, job.h, job.h_ext_mult, !ctx->settings.enable_anisotropy);
+	if (!ctx->have_camera) { set_error("sequence: fr_seq_set_camera has not been called"); return FR_ERR_STATE; }
+	// Everything that does not need the frame's grid parameters on the host is queued here, without a wait: the build
+	// and the depth pre-pass.  Then the parameters are picked up from the side stream (they left right behind the
+	// first build kernel; a first frame of the lane waits inside build_frame instead)
+	if ((rc = build_frame(ctx, f, d_xyz, n, job.h, job.h_ext_mult, true))) return rc;
+	ctx->pending_frames.push_back(0);
+	int const passes = job.passes ? job.passes : FR_PASS_ALL;
+	if ((passes & FR_PASS_MARCH) && !(passes & FR_PASS_DEPTH) && !ctx->have_depth)
+	{
+		set_error("sequence: march without a depth image");
+		return FR_ERR_STATE;
+	}
+	if ((rc = render_depth(ctx, passes, false))) return rc;
+	return render_resolve(ctx, passes);
 }
 
-int lane_frame_copies(fr_context* ctx, const fr_seq_job& job)
+// the rest of the frame -- march, copies out -- is launches only: a lane captures it into its CUDA graph
+int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
 {
+	int rc;
+	if ((rc = render_march(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
 	cudaStream_t const s = ctx->stream;
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
@@ -433,21 +444,10 @@ int lane_frame_copies(fr_context* ctx, const fr_seq_job& job)
 	return FR_OK;
 }
 
-int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
-{
-	int rc;
-	if ((rc = build_frame_finish(ctx))) return rc;
-	ctx->pending_frames.push_back(0);
-	if ((rc = fr_render_async(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
-	return lane_frame_copies(ctx, job);
-}
-
-// the lane's wait for its frame; FR_RETRIED: the frame was rebuilt and rendered again (its tables had to grow), the
-// copies queued behind the first attempt have to be repeated
 int lane_frame_wait(fr_context* ctx)
 {
 	FM_CUDA(cudaSetDevice(ctx->device));
-	return finish_pending_ex(ctx);
+	return finish_pending(ctx);
 }
 
 }  // namespace fm
@@ -616,21 +616,14 @@ int fr_render_async(fr_context* ctx, int passes)
 namespace fm
 {
 
-static int render_passes(fr_context* ctx, int passes)
+// the part of a render that does not need the frame's grid parameters on the host: the depth pre-pass
+int render_depth(fr_context* ctx, int passes, bool again)
 {
 	Frame* f = get_frame(ctx, ctx->settings.frame, true);
 	if (!f) return FR_ERR_STATE;
 	int rc;
 	cudaStream_t const s = ctx->stream;
-	// Frame::m_SearchExt (the reference builds it in Frame::Frame; here on the frame's first anisotropic render).  Its
-	// cell ranges are computed on the host from the frame's extrema
-	if ((passes & FR_PASS_MARCH) && ctx->settings.enable_anisotropy && !f->ext_valid)
-	{
-		if (!f->gp_host_valid && (rc = resolved(ctx, f))) return rc;
-		if ((rc = build_frame_ext(ctx, f))) return rc;
-		if ((rc = upload_view_ext(ctx, f))) return rc;
-	}
-	if (ctx->ext_wait)
+	if (ctx->ext_wait && !again)
 	{
 		cudaExternalSemaphoreWaitParams wp;
 		memset(&wp, 0, sizeof wp);
@@ -644,6 +637,18 @@ static int render_passes(fr_context* ctx, int passes)
 		ctx->have_depth = true;
 	}
 	FM_TIME(ctx, ctx->ev[5], s);
+	return FR_OK;
+}
+
+// the part that does (the march kernels take the frame's geometry as kernel parameters): resolve_early comes first
+int render_march(fr_context* ctx, int passes)
+{
+	Frame* f = get_frame(ctx, ctx->settings.frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc;
+	cudaStream_t const s = ctx->stream;
+	// Frame::m_SearchExt (the reference builds it in Frame::Frame; here on the frame's first anisotropic render)
+	if ((passes & FR_PASS_MARCH) && ctx->settings.enable_anisotropy && (rc = build_frame_ext(ctx, f))) return rc;
 	ctx->march_timed = (passes & (FR_PASS_MARCH | FR_PASS_SHADE)) != 0;
 	if (ctx->march_timed)
 		if ((rc = launch_march(ctx, *f, (passes & FR_PASS_MARCH) != 0, (passes & FR_PASS_SHADE) != 0))) return rc;
@@ -658,6 +663,30 @@ static int render_passes(fr_context* ctx, int passes)
 	ctx->render_pending = true;
 	ctx->last_passes = passes;
 	return FR_OK;
+}
+
+// depth pre-pass (queued behind the build without waiting), then the frame's grid parameters from the side stream --
+// long there by now: the rest of the build and the pre-pass are still running --, then the march
+int render_resolve(fr_context* ctx, int passes)
+{
+	Frame* f = get_frame(ctx, ctx->settings.frame, true);
+	if (!f) return FR_ERR_STATE;
+	int rc = resolve_early(ctx, f);
+	if (rc < 0) return rc;
+	if (rc == FR_RETRIED)
+	{
+		ctx->pending_frames.push_back(ctx->settings.frame);
+		if ((rc = render_depth(ctx, passes, true))) return rc;      // the pre-pass ran on the unusable first attempt
+	}
+	return FR_OK;
+}
+
+static int render_passes(fr_context* ctx, int passes)
+{
+	int rc = render_depth(ctx, passes, false);
+	if (rc) return rc;
+	if ((rc = render_resolve(ctx, passes))) return rc;
+	return render_march(ctx, passes);
 }
 
 }  // namespace fm

@@ -14,12 +14,16 @@
 //                   into the float4 SoA                                    reads 16+ B, writes 16 B/particle
 //
 // Every kernel behind k_aabb_params reads the grid parameters from device memory, so a build into tables that already
-// exist (every frame of a sequence but the first) needs no host round trip: the host sizes its launches by the table
-// capacities, the device compares the real sizes with them and raises FM_GRID_OVERFLOW (checked when the host next
-// waits; the frame is then rebuilt with the round trip).  All of it is HBM/L2-bound integer and copy work.
+// exist (every frame of a sequence but the first) does not wait for the host: the host sizes its launches by the table
+// capacities, the device compares the real sizes with them and raises FM_GRID_OVERFLOW.  A copy of the parameters
+// leaves for the host on a side stream as soon as k_aabb_params is done, while the rest of the build and the depth
+// pre-pass keep the GPU busy; the host picks it up when it launches the march (resolve_early: the march kernels take
+// the frame's geometry as kernel parameters) and rebuilds the frame with a host wait in the overflow case.
+// All of it is HBM/L2-bound integer and copy work.
 #include "fm_internal.h"
 
 #include <math.h>
+#include <sched.h>
 #include <string.h>
 
 #include <algorithm>
@@ -51,8 +55,7 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 														  uint32_t* __restrict__ ticket,
 														  uint32_t* __restrict__ zero_a, uint32_t words_a,
 														  uint32_t* __restrict__ zero_b, uint32_t words_b,
-														  float h, BuildCaps caps, FrameView view, GridParams* __restrict__ gp,
-														  FrameView* __restrict__ view_out, unsigned long long* __restrict__ occupied)
+														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied)
 {
 	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
@@ -193,22 +196,7 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	g.status = status;
 	g.max_cell = 0u;
 	*gp = g;
-	// the frame as the march kernels see it; an unusable frame is an empty one (no cell is ever looked up)
-	view.kmin = make_int3(g.kmin[0], g.kmin[1], g.kmin[2]);
-	view.kdim = status ? make_int3(0, 0, 0) : make_int3(g.kdim[0], g.kdim[1], g.kdim[2]);
-	view.search_inv = g.search_inv;
-	view.mn = make_float3(g.mn[0], g.mn[1], g.mn[2]);
-	view.mx = make_float3(g.mx[0], g.mx[1], g.mx[2]);
-	view.gdim = status ? make_int3(0, 0, 0) : make_int3(g.gdim[0], g.gdim[1], g.gdim[2]);
-	view.cell_width = g.cell_width;
-	view.inv_cell_width = make_float3(g.inv_cell_width, g.inv_cell_width, g.inv_cell_width);
-	if (status) view.n = 0u;
-	*view_out = view;
 }
-
-// the device copy of a view the host has complete (after a build with a host wait, after build_frame_ext): a kernel
-// parameter, not a host-memory copy, so that it can be captured into a lane's CUDA graph
-__global__ void k_store_view(FrameView v, FrameView* __restrict__ dst) { if (threadIdx.x == 0) *dst = v; }
 
 // what the particle kernels need of GridParams, loaded once per thread (every lane reads the same words: L1 broadcasts)
 struct BuildView
@@ -688,33 +676,18 @@ int build_frame_ext(Context* ctx, Frame* f)
 void free_frame_small(Frame& f)
 {
 	if (f.d_gp) cudaFree(f.d_gp);
-	if (f.d_fv) cudaFree(f.d_fv);
 	if (f.h_gp) cudaFreeHost(f.h_gp);
-	f.d_gp = nullptr; f.d_fv = nullptr; f.h_gp = nullptr;
+	if (f.ev_gp) cudaEventDestroy(f.ev_gp);
+	f.d_gp = nullptr; f.h_gp = nullptr; f.ev_gp = nullptr;
 }
 
-// the part of the march's view the host knows without the grid parameters
-static FrameView static_view(const Frame& f)
+// CubicSplineKernel::sig_d = 8 / (pi h^3) (Kernel.cpp:8-14), evaluated in FP32 like the reference
+static float spline_sig_d(float h)
 {
-	FrameView v;
-	memset(&v, 0, sizeof v);
-	v.sorted = f.d_sorted;
-	v.cell_start = f.d_cell_start;
-	v.occ_bits = f.d_occ_bits;
-	v.n = (uint32_t)f.n;
-	// CubicSplineKernel::CubicSplineKernel (Kernel.cpp:8-14), evaluated in FP32 like the reference
-	float const h = f.h;
-	v.kernel.h = h;
-	v.kernel.h_squared = h * h;
-	v.kernel.h_inv = 1.0f / h;
 	volatile float t = 3.14159265358979323846264338327950288f * h;
 	t = t * h;
 	t = t * h;
-	v.kernel.sig_d = 8.0f / t;
-	v.h_ext = f.h_ext;
-	v.h_ext_squared = f.h_ext * f.h_ext;
-	v.aniso_sig = 8.0f / 3.14159265358979323846264338327950288f;
-	return v;
+	return 8.0f / t;
 }
 
 // layout of ctx->d_scan_tmp for `cells` histogram entries: [cursor: cells, padded to even][tile states: 2 words per
@@ -737,7 +710,7 @@ static int launch_aabb_params(Context* ctx, Frame* f, const float* d_xyz, uint32
 	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
 	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
 	k_aabb_params<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
-												  static_view(*f), f->d_gp, f->d_fv, f->d_occupied);
+												  f->d_gp, f->d_occupied);
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
@@ -761,6 +734,7 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	f->valid = false;
 	f->ext_valid = false;
 	f->gp_pending = false;
+	f->gp_early_pending = false;
 	f->gp_host_valid = false;
 	f->n = n;
 	f->h = h;
@@ -771,8 +745,8 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	int rc;
 	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
 	if (!f->d_gp) FM_CUDA(cudaMalloc((void**)&f->d_gp, sizeof(GridParams)));
-	if (!f->d_fv) FM_CUDA(cudaMalloc((void**)&f->d_fv, sizeof(FrameView)));
-	if (!f->h_gp) FM_CUDA(cudaMallocHost((void**)&f->h_gp, sizeof(GridParams)));
+	if (!f->h_gp) FM_CUDA(cudaMallocHost((void**)&f->h_gp, 2 * sizeof(GridParams)));      // [0] early copy, [1] end of the build
+	if (!f->ev_gp) FM_CUDA(cudaEventCreateWithFlags(&f->ev_gp, cudaEventDisableTiming));
 	if (!ctx->d_aabb_partial)
 	{
 		if ((rc = ensure_capacity(&ctx->d_aabb_partial, &ctx->cap_aabb_partial, (size_t)kPartialStride * ctx->sm_count * 8 + 4))) return rc;
@@ -822,12 +796,8 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	// k_aabb_params has zeroed the buffers it was given; one that had to grow (or did not exist yet) is zeroed here
 	if (ctx->d_scan_tmp != zero_a || ctx->cap_scan_tmp != cap_a || !zero_a) FM_CUDA(cudaMemsetAsync(ctx->d_scan_tmp, 0, ctx->cap_scan_tmp * 4, s));
 	if (f->d_grid_counts != zero_b || f->cap_grid != cap_b || !zero_b) FM_CUDA(cudaMemsetAsync(f->d_grid_counts, 0, f->cap_grid * 4, s));
-	// the view was written with the old table pointers if a table moved: write it again (cheap, rare)
 	ctx->build.scan_blocks = (cells32 + kScanTile - 1) / kScanTile;
 	ctx->build.flag_cells = gcells32;
-	k_store_view<<<1, 32, 0, s>>>(make_view(*f), f->d_fv);
-	ctx->kernel_launches += 1;
-	FM_CUDA(cudaGetLastError());
 	return FR_OK;
 }
 
@@ -850,6 +820,12 @@ int build_frame_finish(Context* ctx)
 		caps.occ_words = (uint32_t)std::min<size_t>(f->cap_occ_words, 0x7fffffffu);
 		caps.scan_tiles = ctx->build.scan_blocks;
 		if ((rc = launch_aabb_params(ctx, f, d_xyz, n32, ctx->build.h, caps))) return rc;
+		// the parameters leave for the host right away, beside the rest of the build (resolve_early)
+		FM_CUDA(cudaEventRecord(ctx->ev_k1, s));
+		FM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_k1, 0));
+		FM_CUDA(cudaMemcpyAsync(f->h_gp, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, ctx->side_stream));
+		FM_CUDA(cudaEventRecord(f->ev_gp, ctx->side_stream));
+		f->gp_early_pending = true;
 	}
 	uint32_t* const d_cursor = ctx->d_scan_tmp;
 	size_t const state_off = (cursor_cells + 1) & ~(size_t)1;
@@ -860,56 +836,77 @@ int build_frame_finish(Context* ctx)
 	float const half = 0.5f * f->h;                   // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
 	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, ctx->d_keys, d_cursor, f->d_grid_counts);
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter); occupancy flags
-	FrameView const sv = static_view(*f);
 	uint32_t const flag_blocks = (ctx->build.flag_cells + kScanThreads - 1) / kScanThreads;
 	uint32_t const scan_grid = std::max(ctx->build.scan_blocks, std::min(flag_blocks, (uint32_t)ctx->sm_count * 4u));
 	k_scan_flags<<<scan_grid, kScanThreads, 0, s>>>(f->d_gp, d_cursor, f->d_cell_start, tile_state, scan_ticket, f->d_grid_counts,
-													   sv.kernel.sig_d, f->d_occ_bits, f->d_occupied);
+													   spline_sig_d(f->h), f->d_occ_bits, f->d_occupied);
 	k_scatter<<<pblocks, kThreads, 0, s>>>(n32, f->d_gp, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx);
 	k_cell_order<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted);
 	ctx->kernel_launches += 4;
 	FM_CUDA(cudaGetLastError());
-	// the parameters (with the status bits of the later kernels) come back with the frame's results
-	FM_CUDA(cudaMemcpyAsync(f->h_gp, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
+	// the status bits of the later kernels (FM_GRID_CROWDED) come back with the frame's results
+	FM_CUDA(cudaMemcpyAsync(f->h_gp + 1, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
 	f->gp_pending = true;
 	FM_TIME(ctx, ctx->ev[3], s);
 	f->valid = true;
 	return FR_OK;
 }
 
-// host copy of the grid parameters of a frame whose build is (or may still be) queued
-int resolve_frame(Context* ctx, Frame* f, bool synced)
+static int wait_event(Context* ctx, cudaEvent_t ev)
 {
-	if (!f->gp_pending) return FR_OK;
-	if (!synced) { int const src = stream_sync(ctx); if (src) return src; }
-	f->gp_pending = false;
-	GridParams const gp = *f->h_gp;
+	if (!ctx->blocking_sync) { FM_CUDA(cudaEventSynchronize(ev)); return FR_OK; }
+	for (uint32_t spins = 0;; spins++)                 // oversubscribed hosts: give the core away between polls
+	{
+		cudaError_t const e = cudaEventQuery(ev);
+		if (e == cudaSuccess) return FR_OK;
+		if (e != cudaErrorNotReady) return cuda_fail(e, "cudaEventQuery", __FILE__, __LINE__);
+		if ((spins & 15u) == 15u) sched_yield(); else __builtin_ia32_pause();
+	}
+}
+
+// The host copy of the grid parameters of a frame whose build was queued without a host wait: waits for the early
+// side-stream copy only (k_aabb_params), not for the stream.  FR_RETRIED: the tables of the slot were too small, the
+// frame has been rebuilt (with a host wait) -- whatever was queued on it in between ran on an unusable frame.
+int resolve_early(Context* ctx, Frame* f)
+{
+	if (f->gp_host_valid || !f->gp_early_pending) return FR_OK;
+	{ int const rc = wait_event(ctx, f->ev_gp); if (rc) return rc; }
+	f->gp_early_pending = false;
+	GridParams const gp = f->h_gp[0];
 	if (gp.status & FM_GRID_OVERFLOW)
 	{
 		// the tables of the earlier frame are too small for this one: once more, with the host sizing them
 		int const rc = build_frame(ctx, f, f->src_xyz, f->n, f->h, f->src_mult, false);
-		if (rc) return rc;
-		int const rc2 = resolve_frame(ctx, f, false);
-		return rc2 < 0 ? rc2 : FR_RETRIED;
+		return rc ? rc : FR_RETRIED;
 	}
 	if (gp.status)
 	{
 		f->valid = false;
+		f->gp_pending = false;
 		set_error(grid_status_text(gp.status));
-		return (gp.status & FM_GRID_CROWDED) ? FR_ERR_UNSUPPORTED : FR_ERR_INVALID;
+		return FR_ERR_INVALID;
 	}
 	f->gp = gp;
 	f->gp_host_valid = true;
 	return FR_OK;
 }
 
-// the r = h_ext fields of the device copy of the view (build_frame_ext ran after the frame build)
-int upload_view_ext(Context* ctx, Frame* f)
+// end of the build (the caller has drained the stream, or `synced` is false and this does): late status bits
+int resolve_frame(Context* ctx, Frame* f, bool synced)
 {
-	k_store_view<<<1, 32, 0, ctx->stream>>>(make_view(*f), f->d_fv);
-	ctx->kernel_launches += 1;
-	FM_CUDA(cudaGetLastError());
-	return FR_OK;
+	if (!f->gp_pending) return FR_OK;
+	int const erc = resolve_early(ctx, f);
+	if (erc < 0) return erc;
+	if (!synced || erc == FR_RETRIED) { int const src = stream_sync(ctx); if (src) return src; }
+	f->gp_pending = false;
+	GridParams const gp = f->h_gp[1];
+	if (gp.status)
+	{
+		f->valid = false;
+		set_error(grid_status_text(gp.status));
+		return (gp.status & FM_GRID_CROWDED) ? FR_ERR_UNSUPPORTED : FR_ERR_INVALID;
+	}
+	return erc;
 }
 
 }  // namespace fm

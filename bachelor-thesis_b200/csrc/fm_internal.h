@@ -53,10 +53,11 @@ struct Frame
 	float h = 0.0f, h_ext = 0.0f;
 	GridParams gp{};                  // host copy: valid once gp_pending is false (resolve_frame)
 	GridParams* d_gp = nullptr;       // device: written by k_aabb_params, read by the build kernels
-	FrameView* d_fv = nullptr;        // device: the frame as the march kernels see it
-	GridParams* h_gp = nullptr;       // pinned: the copy that comes back at the end of the build
-	bool gp_pending = false;          // the build is queued and its parameters have not been read back yet
-	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (always after resolve_frame; at once after a build with a host wait)
+	GridParams* h_gp = nullptr;       // pinned, 2 entries: [0] leaves right behind k_aabb_params on the side stream, [1] at the end of the build
+	cudaEvent_t ev_gp = nullptr;      // behind the early copy
+	bool gp_early_pending = false;    // the early copy is on its way (resolve_early)
+	bool gp_pending = false;          // the build is queued: its end-of-build status has not been read yet (resolve_frame)
+	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (after resolve_early; at once after a build with a host wait)
 	uint64_t build_serial = 0;        // process-wide number of this build
 	const float* src_xyz = nullptr;   // device particles of the queued build (must stay valid until the host next waits)
 	float src_mult = 0.0f;
@@ -93,6 +94,8 @@ struct Context
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
 	cudaEvent_t ev_copy = nullptr;     // behind the host -> device copy of fr_upload_frame
+	cudaStream_t side_stream = nullptr; // carries the early copy of a queued build's grid parameters to the host
+	cudaEvent_t ev_k1 = nullptr;       // behind k_aabb_params (the side stream waits for it)
 	// Host waits.  By default a thread waits inside the driver (cudaStreamSynchronize spins: lowest latency, best
 	// throughput while every waiting thread has a core of its own -- 0.296 ms per C2 frame at 6 lanes).  When the host
 	// is oversubscribed (8 ranks x 6 lanes on a 32-core box: 0.47 ms) the lanes of a sequence can instead append a
@@ -199,10 +202,10 @@ int build_frame_finish(Context* ctx);
 // the host copy of the frame's grid parameters (waits for the build if it is still queued); FR_RETRIED: the tables
 // were too small, the frame has been rebuilt -- work queued behind the first build ran on an unusable frame
 constexpr int FR_RETRIED = 1;
+int resolve_early(Context* ctx, Frame* f);
 int resolve_frame(Context* ctx, Frame* f, bool synced = false);     // synced: the caller has just drained the stream
 int build_frame_ext(Context* ctx, Frame* f);      // no-op when already built
 FrameView make_view(const Frame& f);              // needs resolve_frame
-int upload_view_ext(Context* ctx, Frame* f);      // the r = h_ext fields into the device copy of the view
 void free_frame_small(Frame& f);
 
 // fm_depth.cu
@@ -218,8 +221,10 @@ int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float*
 // fm_context.cu: the two halves of a sequence lane's frame
 int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path);
 int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job);
-int lane_frame_copies(fr_context* ctx, const fr_seq_job& job);
 int lane_frame_wait(fr_context* ctx);
+int render_depth(fr_context* ctx, int passes, bool again);
+int render_resolve(fr_context* ctx, int passes);
+int render_march(fr_context* ctx, int passes);
 // fm_bgeo.cu
 int stage_bgeo(Context* ctx, const char* path, size_t* n_out);
 // fm_query.cu

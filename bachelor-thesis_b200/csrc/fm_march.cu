@@ -77,7 +77,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			uint32_t ctas = (uint32_t)(ctx->sm_count * per_sm);
 			if (ctas > max_ctas) ctas = max_ctas;
 			MarchLaunch ml;
-			ml.frame = &f; ml.by_value = f.gp_host_valid; if (ml.by_value) ml.fv = make_view(f); ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
+			ml.fv = make_view(f); ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
 			if ((rc = launch_march_kernels_aniso(ctx, ml))) return rc;
 		}
 		else
@@ -85,27 +85,18 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			// k_march_first: dynamic shared memory (lists of the walk, or one stage per warp: above the 48 KB default)
 			size_t const smem_first = kFirstSmem;
 			int const first_warps = kFirstThreads / 32;
-			bool const byval = f.gp_host_valid;
-			FrameView fv;
-			memset(&fv, 0, sizeof fv);
-			if (byval) fv = make_view(f);
-			auto const first = byval ? (fast ? k_march_first<true, false, true> : k_march_first<false, false, true>)
-									 : (fast ? k_march_first<true, false, false> : k_march_first<false, false, false>);
-			auto const longk = byval ? (fast ? k_march_long<true, false, true> : k_march_long<false, false, true>)
-									 : (fast ? k_march_long<true, false, false> : k_march_long<false, false, false>);
+			FrameView const fv = make_view(f);
+			auto const first = fast ? k_march_first<true, false> : k_march_first<false, false>;
+			auto const longk = fast ? k_march_long<true, false> : k_march_long<false, false>;
 			if (ctx->march_ctas_per_sm == 0)
 			{
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
 				int nb = 0, nl = 0;
-				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false, false>, kFirstThreads, smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
-				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false, false>, 256, kLongSmem));
+				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, kFirstThreads, smem_first));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
+				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false>, 256, kLongSmem));
 				if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < nb) nb = v; }   // tuning switch
 				ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
 				ctx->march_long_ctas_per_sm = nl > 0 ? nl : 1;
@@ -115,9 +106,9 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			ctas_first = std::min(ctas_first, (ntiles + first_warps - 1) / first_warps);
 			uint32_t ctas_long = (uint32_t)(ctx->sm_count * ctx->march_long_ctas_per_sm);
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
-			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, f.d_fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			FM_TIME(ctx, ctx->ev[11], st);
-			longk<<<ctas_long, 256, kLongSmem, st>>>(fv, f.d_fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			longk<<<ctas_long, 256, kLongSmem, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		}
 		ctx->kernel_launches += 2;
 	}

@@ -70,9 +70,7 @@ struct RayQueues
 
 struct MarchLaunch
 {
-	const Frame* frame;
-	bool by_value;           // the host knows the frame's grid parameters: the view goes in as a kernel parameter
-	FrameView fv;            // (valid when by_value)
+	FrameView fv;
 	MarchParams mp;
 	RayQueues rq;
 	const uint32_t* tiles;
@@ -85,19 +83,6 @@ namespace
 
 constexpr int kMaxNeighbors = 2 * 4096;   // MAX_NEIGHBORS (RayMarcher.cpp:14)
 
-// The frame as the march kernels see it is read from DEVICE memory (Frame::d_fv, written by k_aabb_params): the host
-// does not have to know the grid parameters of a frame to march it, which is what lets a frame build run without a
-// host round trip (fm_grid.cu).  Every CTA copies the ~50 words into shared memory once (the kernels are persistent);
-// loops keep what they need in registers.  (A __constant__ table indexed by a per-context slot was measured first, r02c:
-// the index is a vector register to the compiler, every field access became an indexed LDC, k_march_first +20 %.)
-__device__ __forceinline__ void load_view(FrameView& dst, const FrameView* __restrict__ src)
-{
-	const uint32_t* const s = reinterpret_cast<const uint32_t*>(src);
-	uint32_t* const d = reinterpret_cast<uint32_t*>(&dst);
-	for (uint32_t i = threadIdx.x; i < sizeof(FrameView) / 4; i += blockDim.x) d[i] = __ldg(s + i);
-	__syncthreads();
-}
-static_assert(sizeof(FrameView) % 4 == 0, "FrameView is copied word by word");
 
 struct LaneCounters
 {
@@ -193,7 +178,6 @@ __device__ __forceinline__ float eval_density(const FrameView& f, f3 p, f3& grad
 	float density = 0.0f;
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
 	uint32_t nn = 0;
-	// (the view lives in shared memory: what the loops need is kept in registers, out of reach of the memory clobbers)
 	const float4* const sorted = f.sorted;
 	float const hh = f.kernel.h_squared;
 	bool const walk = z0 <= z1 && on;
@@ -989,18 +973,17 @@ constexpr size_t kLongSmem = (size_t)8 * kListWords * 4;           // k_march_lo
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
-// BYVAL: the view is a kernel parameter (the host knows the frame's grid parameters: every render of a frame after the
-// first host wait behind its build); else it is read from device memory (Frame::d_fv) into shared memory
-template <bool FAST, bool ANISO, bool BYVAL>
-__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(FrameView fval, const FrameView* __restrict__ fvp, MarchParams mp, const float* __restrict__ depth,
+// (The view is a kernel parameter: its fields reach the instructions as uniform constant-bank operands.  Reading it
+// from device memory instead -- which would let the march be queued before the host knows the frame's grid parameters
+// -- was measured, r02c-e: through a __constant__ table indexed per context k_march_first +20 %, through a shared-memory
+// copy +12 %, k_march_long +9 %.  The host gets the parameters early on a side stream instead, fm_grid.cu.)
+template <bool FAST, bool ANISO>
+__global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	__shared__ FrameView s_view;
-	if (!BYVAL) load_view(s_view, fvp);
-	const FrameView& f = BYVAL ? fval : s_view;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];
 	// the global-memory walk (every tile when FM_FIRST_STAGED = 0, else tiles that do not fit the stage and bisection
@@ -1102,15 +1085,12 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 // 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
-template <bool FAST, bool ANISO, bool BYVAL>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView fval, const FrameView* __restrict__ fvp, MarchParams mp, float4* __restrict__ pos_out,
+template <bool FAST, bool ANISO>
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
 														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	__shared__ FrameView s_view;
-	if (!BYVAL) load_view(s_view, fvp);
-	const FrameView& f = BYVAL ? fval : s_view;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);

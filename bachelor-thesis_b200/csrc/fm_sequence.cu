@@ -73,7 +73,6 @@ namespace
 int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 {
 	fr_context* const c = ln->ctx;
-	auto const saved = c->build;                   // lane_frame_enqueue consumes it
 	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
 	{
 		cudaGetLastError();
@@ -102,7 +101,6 @@ int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
 		cudaGetLastError();
 		ln->graph_ok = false;
 		if (ln->exec) { cudaGraphExecDestroy(ln->exec); ln->exec = nullptr; }
-		c->build = saved;
 		c->render_pending = false;
 		return lane_frame_enqueue(c, job);
 	}
@@ -130,15 +128,7 @@ void lane_main(fr_sequence* seq, Lane* ln)
 		}
 		int rc = lane_frame_begin(ln->ctx, job, job.bgeo_path ? path.c_str() : nullptr);
 		if (rc == FR_OK) rc = seq->graphs && ln->graph_ok ? enqueue_as_graph(ln, job) : lane_frame_enqueue(ln->ctx, job);
-		if (rc == FR_OK)
-		{
-			rc = lane_frame_wait(ln->ctx);            // the whole stream: build, render and copies
-			if (rc == FR_RETRIED)                     // the tables of the lane's slot had to grow: the frame was rebuilt and
-			{                                         // rendered again, the copies carry the first attempt's pixels
-				rc = lane_frame_copies(ln->ctx, job);
-				if (rc == FR_OK) rc = lane_frame_wait(ln->ctx);
-			}
-		}
+		if (rc == FR_OK) rc = lane_frame_wait(ln->ctx);       // the whole stream: build, render and copies
 		if (rc == FR_OK && job.bmp_path) rc = fr_write_bmp(ln->ctx, bmp.c_str());      // recording (Renderer.cpp:400-409)
 		std::string err;
 		if (rc != FR_OK) err = fr_last_error();      // thread-local text of this worker

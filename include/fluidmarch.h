@@ -144,11 +144,12 @@ void fr_host_free(void* p);
  * (BuildDensityGrid).  h = particleRadius, h_ext_mult = particleRadiusMultiplier (assets/config.yml:19-20).
  * Returns once xyz_host has been consumed; the build stays queued on the context's stream.
  * The first build of a frame slot waits once for the device (the table sizes depend on the particle bounds) and
- * reports an unusable frame at once.  Later builds into the same slot reuse its tables and never wait: the grid
- * parameters stay on the device, and what the host would have checked -- non-finite coordinates (FR_ERR_INVALID), more
- * than 2048 particles in one h-cell (FR_ERR_UNSUPPORTED), tables too small for the new bounds (the frame is rebuilt and
- * the render behind it repeated, transparently) -- is checked when the host next waits for the context (fr_wait,
- * fr_download, fr_get_frame_info, ...), which then returns the error. */
+ * reports an unusable frame at once.  Later builds into the same slot reuse its tables and do not wait: the build
+ * kernels read the grid parameters from device memory, a copy travels to the host on a side stream and is picked up by
+ * the next fr_render_async of the frame (its depth pre-pass is queued first, so the GPU never idles), which then
+ * reports non-finite coordinates (FR_ERR_INVALID) or, if the tables are too small for the new bounds, rebuilds the
+ * frame transparently.  More than 2048 particles in one h-cell (FR_ERR_UNSUPPORTED) is reported by the next call that
+ * waits for the context (fr_wait, fr_download, fr_get_frame_info, ...). */
 int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult);
 /* 0: every frame build waits for the device once and reports its errors immediately (round-1 behaviour); default 1 */
 int fr_set_async_build(fr_context* ctx, int on);

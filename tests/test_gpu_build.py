@@ -1,6 +1,7 @@
-"""Frame builds without a host round trip (builds into the tables of an earlier frame of the same slot read the grid
-parameters from device memory), and what the host used to check in that round trip: non-finite particle coordinates,
-tables too small for the new bounds (rebuild + the render behind it repeated), collapsed cells.  Also fr_seq_wait's
+"""Frame builds that do not wait for the host (builds into the tables of an earlier frame of the same slot read the grid
+parameters from device memory; the host picks them up from a side stream when it launches the march), and what the host
+used to check in its round trip: non-finite particle coordinates, tables too small for the new bounds (rebuild),
+collapsed cells.  Also fr_seq_wait's
 per-ticket status.  Everything through the C ABI."""
 import importlib
 import os
@@ -73,8 +74,8 @@ def test_tables_too_small_are_rebuilt_and_the_render_repeated(fm, gpu_ctx_factor
     ctx.upload_frame(0, small, 0.1, 2.0)
     ctx.render(fm.FR_PASS_ALL)
     ctx.upload_frame(0, big, 0.1, 2.0)                   # queued against the small tables: FM_GRID_OVERFLOW on the device
-    ctx.render_async(fm.FR_PASS_ALL)
-    got_img = ctx.download()                             # the wait rebuilds the frame and renders it again
+    ctx.render_async(fm.FR_PASS_ALL)                     # picks the parameters up, rebuilds the frame, repeats the pre-pass
+    got_img = ctx.download()
     for x, y in zip(got_img, want_img):
         assert np.array_equal(bits(x), bits(y))
     got_grid = ctx.download_frame(0)
@@ -103,9 +104,9 @@ def test_non_finite_particles_are_rejected(fm, gpu_ctx_factory, poison, tmp_path
     ctx.render(fm.FR_PASS_ALL)
     want = ctx.download()
     ctx.upload_frame(0, bad, 0.1, 2.0)                    # tables exist: the build is only queued ...
-    ctx.render_async(fm.FR_PASS_ALL)
-    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):       # ... and the next wait reports it
-        ctx.wait()
+    with pytest.raises(fm.FluidMarchError, match="NaN or infinite"):       # ... and the render that needs the frame reports it
+        ctx.render_async(fm.FR_PASS_ALL)
+    ctx.wait()
     path = str(tmp_path / "bad.bgeo")
     fm.bgeo_write(path, bad)
     ctx.upload_frame_bgeo(0, path, 0.1, 2.0)
