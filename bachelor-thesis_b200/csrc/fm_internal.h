@@ -157,7 +157,7 @@ struct Context
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices
 	bool depth_refine_bounds = true;
 	uint32_t* d_tiles = nullptr;      size_t cap_tiles = 0;        // march: [0] count, [1] cursor, [2..] covered 8x4 tiles
-	int march_ctas_per_sm = 0, march_long_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
+	int march_ctas_per_sm = 0, march_long_ctas_per_sm = 0, march_coop_ctas_per_sm = 0, march_ctas_per_sm_aniso = 0;
 	float4* d_rayq = nullptr;         size_t cap_rayq = 0;         // march: ray queues between the phases
 	DeviceCounters* d_counters = nullptr;
 	DeviceCounters* h_counters = nullptr;

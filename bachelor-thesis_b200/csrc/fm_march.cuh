@@ -970,6 +970,9 @@ constexpr int kFirstThreads = FM_FIRST_STAGED ? FM_FIRST_WARPS * 32 : 256;
 constexpr size_t kFirstWarpBytes = FM_FIRST_STAGED ? sizeof(WarpStage) : (size_t)kListWords * 4;      // dynamic shared memory per warp
 constexpr size_t kFirstSmem = (size_t)(kFirstThreads / 32) * kFirstWarpBytes;
 constexpr size_t kLongSmem = (size_t)8 * kListWords * 4;           // k_march_long, isotropic: the lists of its 8 warps
+#ifndef FM_LONG_COOP
+#define FM_LONG_COOP 1                    // isotropic long rays: one ray per CTA, lanes = candidates (k_march_long_coop)
+#endif
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
@@ -1153,6 +1156,264 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_l
 		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
 	}
 	flush_counters(lc, counters);
+}
+
+// phase B, isotropic, one ray per CTA.  k_march_long above gives a queued ray one warp and each of 32 samples one lane;
+// a lane then walks its ~100 candidates and sums its ~20 kernels alone, and with only ~2 000 such rays the kernel is a
+// latency chain on a mostly idle GPU (r01: 15 % occupancy, 14.5 % of the issue roofline).  Here the 8 warps of a CTA
+// share a ray: warp 0 walks the next window of 32 sample positions (a serial chain: empty-space skips), then every
+// warp evaluates samples of the window with LANES = CANDIDATES -- the 9 ranges of the query are one flat index space,
+// 32 candidates per load instruction; the in-range ones are compacted in order (ballot), their W / gradW are computed
+// one per lane, and only the sums themselves run as the reference's ordered chain.  Same operations in the same order
+// as eval_density, hence the same bits; the latency of a sample drops from ~17 000 cycles to ~1 000.
+#ifndef FM_COOP_CAP
+#define FM_COOP_CAP 128                   // in-range candidates a warp collects before it sums them
+#endif
+constexpr int kCoopCap = FM_COOP_CAP;
+
+struct CoopWarp
+{
+	float4 ent[kCoopCap];                 // (d0, d1, d2, l2) of the in-range candidates, in the reference's list order
+	float4 con[kCoopCap];                 // their contributions: (W, gradW) or, fast normals, (W, coefficient)
+};
+
+struct CoopShared
+{
+	CoopWarp warp[8];
+	float4 pos[32];                       // the window: sample positions (w: skip iterations up to and including the sample)
+	float4 prev[32];
+	float4 result[32];                    // (density, gradient sum)
+	uint32_t cand[32], nn[32];
+	float4 hitP, hitN;
+	int n_valid, gone, done;
+	uint32_t ray;
+};
+
+template <bool FAST>
+__device__ __forceinline__ void coop_flush(const FrameView& f, CoopWarp& cw, uint32_t cnt, uint32_t& nn, float& density, f3& g)
+{
+	int const lane = threadIdx.x & 31;
+	__syncwarp();
+	for (uint32_t k = lane; k < cnt; k += 32)
+	{
+		float4 const e = cw.ent[k];
+		float const W = spline_W_inrange(f.kernel, e.w);
+		if (!FAST)
+		{
+			f3 const gw = spline_gradW_inrange(f.kernel, mk3(-e.x, -e.y, -e.z), e.w);
+			cw.con[k] = make_float4(W, gw.x, gw.y, gw.z);
+		}
+		else cw.con[k] = make_float4(W, spline_gradW_coeff_fast(f.kernel, e.w, mulr(sqrtr(e.w), f.kernel.h_inv)), 0.0f, 0.0f);
+	}
+	__syncwarp();
+	// the sums, in list order (every lane runs the chain: the result is warp-uniform without a broadcast)
+#pragma unroll 1
+	for (uint32_t k = 0; k < cnt; k++)
+	{
+		if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
+		{
+			float4 const c = cw.con[k];
+			if (!FAST) g = add3(g, mk3(c.y, c.z, c.w));
+			else
+			{
+				float4 const e = cw.ent[k];
+				g.x = fmaf(c.y, -e.x, g.x); g.y = fmaf(c.y, -e.y, g.y); g.z = fmaf(c.y, -e.z, g.z);
+			}
+			density = addr(density, c.x);
+		}
+		nn++;
+	}
+	__syncwarp();
+}
+
+// density and gradient sum at p, the whole warp on one sample; warp-uniform results
+template <bool FAST>
+__device__ __forceinline__ void coop_eval(const FrameView& f, f3 p, CoopWarp& cw, float& density_out, f3& grad_out, uint32_t& cand_out,
+										  uint32_t& nn_out)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	int const kx = search_cell_of(f.search_inv, p.x) - f.kmin.x;
+	int const ky = search_cell_of(f.search_inv, p.y) - f.kmin.y;
+	int const kz = search_cell_of(f.search_inv, p.z) - f.kmin.z;
+	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
+	// lane r < 9: range r of the query (x, then y; three z cells = one contiguous particle range)
+	uint32_t rb = 0, rn = 0;
+	if (lane < 9 && z0 <= z1)
+	{
+		int const x = kx + lane / 3 - 1, y = ky + lane % 3 - 1;
+		if ((unsigned)x < (unsigned)f.kdim.x && (unsigned)y < (unsigned)f.kdim.y)
+		{
+			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim.y + (uint32_t)y) * (uint32_t)f.kdim.z;
+			rb = __ldg(f.cell_start + base + z0);
+			rn = __ldg(f.cell_start + base + z1 + 1) - rb;
+		}
+	}
+	uint32_t inc = rn;
+#pragma unroll
+	for (int o = 1; o < 16; o <<= 1)
+	{
+		uint32_t const t = __shfl_up_sync(FULL, inc, o);
+		if (lane >= o) inc += t;
+	}
+	uint32_t const total = __shfl_sync(FULL, inc, 8);
+	uint32_t ro[9], rnn[9], rbb[9];
+#pragma unroll
+	for (int r = 0; r < 9; r++)
+	{
+		rnn[r] = __shfl_sync(FULL, rn, r);
+		ro[r] = __shfl_sync(FULL, inc, r) - rnn[r];
+		rbb[r] = __shfl_sync(FULL, rb, r);
+	}
+	float density = 0.0f;
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t nn = 0, cnt = 0;
+	float const hh = f.kernel.h_squared;
+	for (uint32_t i0 = 0; i0 < total; i0 += 32u)
+	{
+		uint32_t const i = i0 + (uint32_t)lane;
+		bool const act = i < total;
+		uint32_t j = 0;
+#pragma unroll
+		for (int r = 0; r < 9; r++)
+			if (i - ro[r] < rnn[r]) j = rbb[r] + (i - ro[r]);          // (unsigned: also false for i < ro[r])
+		bool in = false;
+		float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, l2 = 0.0f;
+		if (act)
+		{
+			float4 const q = __ldg(f.sorted + j);
+			// CompactNSearch: d = x - xb; l2 = d0*d0 + d1*d1 + d2*d2 (left to right); l2 < r2
+			d0 = subr(p.x, q.x); d1 = subr(p.y, q.y); d2 = subr(p.z, q.z);
+			l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
+			in = l2 < hh;
+		}
+		uint32_t const m = __ballot_sync(FULL, in);
+		uint32_t const add = (uint32_t)__popc(m);
+		if (cnt + add > (uint32_t)kCoopCap) { coop_flush<FAST>(f, cw, cnt, nn, density, g); cnt = 0; }
+		if (in) cw.ent[cnt + (uint32_t)__popc(m & ((1u << lane) - 1u))] = make_float4(d0, d1, d2, l2);
+		cnt += add;
+	}
+	coop_flush<FAST>(f, cw, cnt, nn, density, g);
+	density_out = density;
+	grad_out = g;
+	cand_out = total;
+	nn_out = nn;
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(256, 3) k_march_long_coop(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+															float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
+															RayQueues rq, DeviceCounters* __restrict__ counters)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	extern __shared__ __align__(16) unsigned char s_dyn[];
+	CoopShared& sh = *reinterpret_cast<CoopShared*>(s_dyn);
+	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	LaneCounters lc = {};
+	uint32_t const count = __ldcg(rq.ctl + 2);
+	bool first = true;
+	for (;;)
+	{
+		// the first ray of a CTA is the one with its own number (see k_march_first), then tickets
+		if (threadIdx.x == 0) sh.ray = first ? blockIdx.x : gridDim.x + atomicAdd(rq.ctl + 3, 1u);
+		first = false;
+		__syncthreads();
+		uint32_t const t = sh.ray;
+		if (t >= count) break;
+		// warp 0 owns the ray's state
+		f3 cur = mk3(0.0f, 0.0f, 0.0f), rstep = cur, prv = cur;
+		uint32_t index = 0;
+		int ri = 0;
+		if (warp == 0)
+		{
+			float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
+			cur = mk3(a.x, a.y, a.z);
+			rstep = mk3(b.x, b.y, b.z);
+			index = __float_as_uint(a.w);
+			ri = __float_as_int(b.w);
+			prv = cur;
+			if (lane == 0) sh.done = 0;
+		}
+		for (;;)
+		{
+			if (warp == 0)
+			{
+				// every lane walks the same 32 positions and keeps its own (uniform control flow)
+				f3 my_pos = cur, my_prev = cur;
+				uint32_t skips = 0, my_skips = 0;
+				int n_valid = 32, gone = 0;
+				for (int k = 0; k < 32; k++)
+				{
+					if (ri + k >= mp.max_steps) { n_valid = k; break; }
+					if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = 1; break; }
+					if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
+				}
+				sh.pos[lane] = make_float4(my_pos.x, my_pos.y, my_pos.z, __uint_as_float(my_skips));
+				sh.prev[lane] = make_float4(my_prev.x, my_prev.y, my_prev.z, __uint_as_float(skips));
+				if (lane == 0) { sh.n_valid = n_valid; sh.gone = gone; }
+			}
+			__syncthreads();
+			int const n_valid = sh.n_valid;
+			for (int k = warp; k < n_valid; k += 8)
+			{
+				float4 const sp = sh.pos[k];
+				float density;
+				f3 g;
+				uint32_t cand, nn;
+				coop_eval<FAST>(f, mk3(sp.x, sp.y, sp.z), sh.warp[warp], density, g, cand, nn);
+				if (lane == 0) { sh.result[k] = make_float4(density, g.x, g.y, g.z); sh.cand[k] = cand; sh.nn[k] = nn; }
+			}
+			__syncthreads();
+			if (warp == 0)
+			{
+				float4 const res = lane < n_valid ? sh.result[lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				uint32_t const hits = __ballot_sync(FULL, lane < n_valid && res.x >= mp.iso);      // RayMarcher.cpp:327
+				int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
+				if (lane <= kstar)
+				{
+					lc.candidates += sh.cand[lane]; lc.neighbours += sh.nn[lane];
+					if (sh.nn[lane] > (uint32_t)kMaxNeighbors) lc.overflow++;
+					lc.steps++;
+				}
+				int done = 0;
+				if (hits)
+				{
+					if (lane == kstar)
+					{
+						float4 const sp = sh.pos[lane];
+						lc.skips += __float_as_uint(sp.w);
+						f3 const n = normalize3(mk3(res.y, res.z, res.w));      // glm::normalize(normal) (RayMarcher.cpp:338)
+						sh.hitP = make_float4(sp.x, sp.y, sp.z, 1.0f);
+						sh.hitN = make_float4(n.x, n.y, n.z, 1.0f);
+						lc.hits++;
+					}
+					done = 1;
+				}
+				else
+				{
+					if (lane == 0)
+					{
+						lc.skips += __float_as_uint(sh.prev[0].w);            // every skip iteration of the window
+						if (sh.gone) lc.early_exits++;
+						sh.hitP = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+						sh.hitN = sh.hitP;
+					}
+					ri += n_valid;
+					if (sh.gone || ri >= mp.max_steps) done = 1;
+				}
+				__syncwarp();
+				if (done && lane == 0)
+				{
+					write_pixel(mp, index, sh.hitP, sh.hitN, pos_out, nrm_out, rgba_out);
+					sh.done = 1;
+				}
+				else if (lane == 0) sh.done = 0;
+			}
+			__syncthreads();
+			if (sh.done) break;
+		}
+	}
+	if (warp == 0) flush_counters(lc, counters);
 }
 
 
