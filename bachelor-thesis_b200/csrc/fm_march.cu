@@ -108,23 +108,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
 			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
 			FM_TIME(ctx, ctx->ev[11], st);
-			if (FM_LONG_COOP && mp.bisection_steps == 0)
-			{
-				// one ray per CTA (bisection keeps the one-ray-per-warp kernel: its extra samples need the per-lane walk)
-				auto const coop = fast ? k_march_long_coop<true> : k_march_long_coop<false>;
-				if (ctx->march_coop_ctas_per_sm == 0)
-				{
-					FM_CUDA(cudaFuncSetAttribute(k_march_long_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopShared)));
-					FM_CUDA(cudaFuncSetAttribute(k_march_long_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CoopShared)));
-					int nc = 0;
-					FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nc, k_march_long_coop<false>, 256, sizeof(CoopShared)));
-					ctx->march_coop_ctas_per_sm = nc > 0 ? nc : 1;
-				}
-				uint32_t const ctas_coop = (uint32_t)(ctx->sm_count * ctx->march_coop_ctas_per_sm);
-				coop<<<ctas_coop, 256, sizeof(CoopShared), st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
-			}
-			else
-				longk<<<ctas_long, 256, kLongSmem, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			longk<<<ctas_long, 256, kLongSmem, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
 		}
 		ctx->kernel_launches += 2;
 	}

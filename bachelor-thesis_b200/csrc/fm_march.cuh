@@ -970,9 +970,6 @@ constexpr int kFirstThreads = FM_FIRST_STAGED ? FM_FIRST_WARPS * 32 : 256;
 constexpr size_t kFirstWarpBytes = FM_FIRST_STAGED ? sizeof(WarpStage) : (size_t)kListWords * 4;      // dynamic shared memory per warp
 constexpr size_t kFirstSmem = (size_t)(kFirstThreads / 32) * kFirstWarpBytes;
 constexpr size_t kLongSmem = (size_t)8 * kListWords * 4;           // k_march_long, isotropic: the lists of its 8 warps
-#ifndef FM_LONG_COOP
-#define FM_LONG_COOP 1                    // isotropic long rays: one ray per CTA, lanes = candidates (k_march_long_coop)
-#endif
 static_assert(kStageCap * 16 <= 65536, "stage byte offsets are kept in 16 bits");
 static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's list lives in the stage");
 
@@ -1083,89 +1080,16 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	flush_counters<true>(lc, counters);
 }
 
-// phase B: the few rays that are left (about 0.3% at the default settings: rays that enter the fluid through a
-// sparse region, and silhouette rays that graze it for up to MaxSteps samples).  One ray per warp, lanes = samples:
-// 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
-// densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
-// and not counted.
-template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
-														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
-														RayQueues rq, DeviceCounters* __restrict__ counters)
-{
-	constexpr uint32_t FULL = 0xffffffffu;
-	int const lane = threadIdx.x & 31;
-	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
-	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
-	LaneCounters lc = {};
-	uint32_t const count = __ldcg(rq.ctl + 2);
-	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
-	bool first = true;
-	for (;;)
-	{
-		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // first ray: the warp's own number (see k_march_first)
-		if (!first)
-		{
-			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 3, 1u);
-			t = __shfl_sync(FULL, t, 0);
-		}
-		first = false;
-		if (t >= count) break;
-		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
-		f3 cur = mk3(a.x, a.y, a.z);
-		f3 const rstep = mk3(b.x, b.y, b.z);
-		uint32_t const index = __float_as_uint(a.w);
-		int ri = __float_as_int(b.w);
-		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
-		for (;;)
-		{
-			// every lane walks the same 32 positions and keeps its own (uniform control flow)
-			f3 my_pos = cur, my_prev = cur, prv = cur;
-			uint32_t skips = 0, my_skips = 0;
-			int n_valid = 32;
-			bool gone = false;
-			for (int k = 0; k < 32; k++)
-			{
-				if (ri + k >= mp.max_steps) { n_valid = k; break; }
-				if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = true; break; }
-				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
-			}
-			LaneCounters tc = {};
-			SampleState<ANISO> st;
-			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
-			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
-			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
-			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
-			if (hits)
-			{
-				if (lane == kstar)
-				{
-					lc.skips += my_skips;
-					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, list, P, N);
-				}
-				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
-				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
-				N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
-				N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
-				break;
-			}
-			if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
-			ri += n_valid;
-			if (gone || ri >= mp.max_steps) break;
-		}
-		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
-	}
-	flush_counters(lc, counters);
-}
-
-// phase B, isotropic, one ray per CTA.  k_march_long above gives a queued ray one warp and each of 32 samples one lane;
-// a lane then walks its ~100 candidates and sums its ~20 kernels alone, and with only ~2 000 such rays the kernel is a
-// latency chain on a mostly idle GPU (r01: 15 % occupancy, 14.5 % of the issue roofline).  Here the 8 warps of a CTA
-// share a ray: warp 0 walks the next window of 32 sample positions (a serial chain: empty-space skips), then every
-// warp evaluates samples of the window with LANES = CANDIDATES -- the 9 ranges of the query are one flat index space,
-// 32 candidates per load instruction; the in-range ones are compacted in order (ballot), their W / gradW are computed
-// one per lane, and only the sums themselves run as the reference's ordered chain.  Same operations in the same order
-// as eval_density, hence the same bits; the latency of a sample drops from ~17 000 cycles to ~1 000.
+// ---- one sample evaluated by the whole warp: LANES = CANDIDATES ----------------------------------------------------------
+// The 9 ranges of the query are one flat index space, 32 candidates per load instruction; the in-range ones are
+// compacted in order (ballot), their W / gradW are computed one per lane, and only the sums themselves run as the
+// reference's ordered chain: the same operations in the same order as eval_density, hence the same bits, at ~1/10 of
+// the latency of one lane doing it alone.  k_march_long uses it for the gradient sum of a hit (one lane of the warp
+// used to re-walk the 27 cells alone while 31 waited: 6 % of the kernel's stall samples, at the end of every hitting
+// ray's critical path).  (A whole kernel built on it -- one queued ray per CTA, 8 warps x 4 samples of a window each --
+// was measured, r02f: per-ray latency fell by more than half, but with ~1 700 rays and one CTA per ray the rays no
+// longer run all at once: C2 0.062 -> 0.105 ms, C3 0.080 -> 0.222 ms.  More than half of k_march_long is the serial
+// walk through empty cells (ncu: 56 % of its instructions), which no amount of evaluation parallelism shortens.)
 #ifndef FM_COOP_CAP
 #define FM_COOP_CAP 128                   // in-range candidates a warp collects before it sums them
 #endif
@@ -1177,17 +1101,7 @@ struct CoopWarp
 	float4 con[kCoopCap];                 // their contributions: (W, gradW) or, fast normals, (W, coefficient)
 };
 
-struct CoopShared
-{
-	CoopWarp warp[8];
-	float4 pos[32];                       // the window: sample positions (w: skip iterations up to and including the sample)
-	float4 prev[32];
-	float4 result[32];                    // (density, gradient sum)
-	uint32_t cand[32], nn[32];
-	float4 hitP, hitN;
-	int n_valid, gone, done;
-	uint32_t ray;
-};
+static_assert(sizeof(CoopWarp) <= (size_t)kListWords * 4, "k_march_long evaluates the hit gradient in its warp's list area");
 
 template <bool FAST>
 __device__ __forceinline__ void coop_flush(const FrameView& f, CoopWarp& cw, uint32_t cnt, uint32_t& nn, float& density, f3& g)
@@ -1300,120 +1214,106 @@ __device__ __forceinline__ void coop_eval(const FrameView& f, f3 p, CoopWarp& cw
 	nn_out = nn;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(256, 3) k_march_long_coop(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
-															float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
-															RayQueues rq, DeviceCounters* __restrict__ counters)
+
+// phase B: the few rays that are left (about 0.3% at the default settings: rays that enter the fluid through a
+// sparse region, and silhouette rays that graze it for up to MaxSteps samples).  One ray per warp, lanes = samples:
+// 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
+// densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
+// and not counted.
+template <bool FAST, bool ANISO>
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
+														RayQueues rq, DeviceCounters* __restrict__ counters)
 {
 	constexpr uint32_t FULL = 0xffffffffu;
-	extern __shared__ __align__(16) unsigned char s_dyn[];
-	CoopShared& sh = *reinterpret_cast<CoopShared*>(s_dyn);
-	int const lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	int const lane = threadIdx.x & 31;
+	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
+	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 2);
+	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
 	bool first = true;
 	for (;;)
 	{
-		// the first ray of a CTA is the one with its own number (see k_march_first), then tickets
-		if (threadIdx.x == 0) sh.ray = first ? blockIdx.x : gridDim.x + atomicAdd(rq.ctl + 3, 1u);
-		first = false;
-		__syncthreads();
-		uint32_t const t = sh.ray;
-		if (t >= count) break;
-		// warp 0 owns the ray's state
-		f3 cur = mk3(0.0f, 0.0f, 0.0f), rstep = cur, prv = cur;
-		uint32_t index = 0;
-		int ri = 0;
-		if (warp == 0)
+		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // first ray: the warp's own number (see k_march_first)
+		if (!first)
 		{
-			float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
-			cur = mk3(a.x, a.y, a.z);
-			rstep = mk3(b.x, b.y, b.z);
-			index = __float_as_uint(a.w);
-			ri = __float_as_int(b.w);
-			prv = cur;
-			if (lane == 0) sh.done = 0;
+			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 3, 1u);
+			t = __shfl_sync(FULL, t, 0);
 		}
+		first = false;
+		if (t >= count) break;
+		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
+		f3 cur = mk3(a.x, a.y, a.z);
+		f3 const rstep = mk3(b.x, b.y, b.z);
+		uint32_t const index = __float_as_uint(a.w);
+		int ri = __float_as_int(b.w);
+		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
 		for (;;)
 		{
-			if (warp == 0)
+			// every lane walks the same 32 positions and keeps its own (uniform control flow)
+			f3 my_pos = cur, my_prev = cur, prv = cur;
+			uint32_t skips = 0, my_skips = 0;
+			int n_valid = 32;
+			bool gone = false;
+			for (int k = 0; k < 32; k++)
 			{
-				// every lane walks the same 32 positions and keeps its own (uniform control flow)
-				f3 my_pos = cur, my_prev = cur;
-				uint32_t skips = 0, my_skips = 0;
-				int n_valid = 32, gone = 0;
-				for (int k = 0; k < 32; k++)
-				{
-					if (ri + k >= mp.max_steps) { n_valid = k; break; }
-					if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = 1; break; }
-					if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
-				}
-				sh.pos[lane] = make_float4(my_pos.x, my_pos.y, my_pos.z, __uint_as_float(my_skips));
-				sh.prev[lane] = make_float4(my_prev.x, my_prev.y, my_prev.z, __uint_as_float(skips));
-				if (lane == 0) { sh.n_valid = n_valid; sh.gone = gone; }
+				if (ri + k >= mp.max_steps) { n_valid = k; break; }
+				if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = true; break; }
+				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
 			}
-			__syncthreads();
-			int const n_valid = sh.n_valid;
-			for (int k = warp; k < n_valid; k += 8)
+			LaneCounters tc = {};
+			SampleState<ANISO> st;
+			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
+			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
+			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
+			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
+			if (hits)
 			{
-				float4 const sp = sh.pos[k];
-				float density;
-				f3 g;
-				uint32_t cand, nn;
-				coop_eval<FAST>(f, mk3(sp.x, sp.y, sp.z), sh.warp[warp], density, g, cand, nn);
-				if (lane == 0) { sh.result[k] = make_float4(density, g.x, g.y, g.z); sh.cand[k] = cand; sh.nn[k] = nn; }
-			}
-			__syncthreads();
-			if (warp == 0)
-			{
-				float4 const res = lane < n_valid ? sh.result[lane] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-				uint32_t const hits = __ballot_sync(FULL, lane < n_valid && res.x >= mp.iso);      // RayMarcher.cpp:327
-				int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
-				if (lane <= kstar)
+				bool coop = false;
+				if constexpr (!ANISO)
 				{
-					lc.candidates += sh.cand[lane]; lc.neighbours += sh.nn[lane];
-					if (sh.nn[lane] > (uint32_t)kMaxNeighbors) lc.overflow++;
-					lc.steps++;
-				}
-				int done = 0;
-				if (hits)
-				{
-					if (lane == kstar)
+					if (mp.bisection_steps == 0)
 					{
-						float4 const sp = sh.pos[lane];
-						lc.skips += __float_as_uint(sp.w);
-						f3 const n = normalize3(mk3(res.y, res.z, res.w));      // glm::normalize(normal) (RayMarcher.cpp:338)
-						sh.hitP = make_float4(sp.x, sp.y, sp.z, 1.0f);
-						sh.hitN = make_float4(n.x, n.y, n.z, 1.0f);
-						lc.hits++;
+						// the normal of the hit: gradient sum at the hit sample, the whole warp on it (the warp's list area is free)
+						coop = true;
+						f3 const hp = mk3(__shfl_sync(FULL, my_pos.x, kstar), __shfl_sync(FULL, my_pos.y, kstar), __shfl_sync(FULL, my_pos.z, kstar));
+						CoopWarp& cw = *reinterpret_cast<CoopWarp*>(s_dyn + (threadIdx.x >> 5) * (size_t)kListWords * 4);
+						float rho;
+						f3 g;
+						uint32_t cand, nn;
+						__syncwarp();
+						coop_eval<FAST>(f, hp, cw, rho, g, cand, nn);
+						if (lane == kstar)
+						{
+							lc.skips += my_skips;
+							lc.candidates += cand; lc.neighbours += nn;
+							if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
+							f3 const n = normalize3(g);                                   // glm::normalize(normal) (RayMarcher.cpp:338)
+							P = make_float4(hp.x, hp.y, hp.z, 1.0f);
+							N = make_float4(n.x, n.y, n.z, 1.0f);
+							lc.hits++;
+						}
 					}
-					done = 1;
 				}
-				else
+				if (!coop && lane == kstar)
 				{
-					if (lane == 0)
-					{
-						lc.skips += __float_as_uint(sh.prev[0].w);            // every skip iteration of the window
-						if (sh.gone) lc.early_exits++;
-						sh.hitP = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-						sh.hitN = sh.hitP;
-					}
-					ri += n_valid;
-					if (sh.gone || ri >= mp.max_steps) done = 1;
+					lc.skips += my_skips;
+					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, list, P, N);
 				}
-				__syncwarp();
-				if (done && lane == 0)
-				{
-					write_pixel(mp, index, sh.hitP, sh.hitN, pos_out, nrm_out, rgba_out);
-					sh.done = 1;
-				}
-				else if (lane == 0) sh.done = 0;
+				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
+				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
+				N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
+				N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
+				break;
 			}
-			__syncthreads();
-			if (sh.done) break;
+			if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
+			ri += n_valid;
+			if (gone || ri >= mp.max_steps) break;
 		}
+		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
 	}
-	if (warp == 0) flush_counters(lc, counters);
+	flush_counters(lc, counters);
 }
 
 

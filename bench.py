@@ -272,6 +272,134 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
+
+class _DevPtr:
+    """a raw device pointer as a CUDA array (for torch.as_tensor): lets the bench poison a library-owned image"""
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def host_ceiling(torch, dist, dev, world, h2d_bytes, d2h_bytes, reps=40):
+    """what the host side of this box sustains with all ranks copying at once: pinned host -> device of one frame's
+    particles and device -> pinned host of one image, on two streams, nothing else running.  GB/s per rank."""
+    h_in = torch.empty(h2d_bytes, dtype=torch.uint8).pin_memory()
+    h_out = torch.empty(d2h_bytes, dtype=torch.uint8).pin_memory()
+    d_in = torch.empty(h2d_bytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(d2h_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def pair():
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+    for _ in range(3):
+        pair()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        pair()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"ms_per_frame_pair": ms, "gbs_per_rank": (h2d_bytes + d2h_bytes) / ms / 1e6,
+            "gbs_all_ranks": world * (h2d_bytes + d2h_bytes) / ms / 1e6,
+            "note": "all ranks at once: one frame's particles host -> device and one RGBA image device -> host per pair, pinned "
+                    "memory, two streams, max over ranks; the e2e arm cannot be faster than this per frame"}
+
+
+def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, tile, steps=12):
+    """BASELINE config C3 (4M particles, 3840x2160): ONE frame split into interleaved screen tiles over the ranks, every
+    rank's shading epilogue storing its tiles straight into the presenting GPU's image over NVLink peer memory
+    (fr_ipc_*); strong scaling against the same frame rendered by one GPU alone, and bit-identity of the assembled image"""
+    n, W, H, h, dx = CONFIGS["C3"]
+    xyz = fm.scenes.dam_break(n, h=h, dx=dx, t=FRAME_T)
+    npart = len(xyz)
+    d_xyz = torch.from_numpy(xyz).to(dev)
+    ctx = fm.Context(W, H, device=local)
+    ctx.set_camera(*cam_args)
+    ctx.set_settings(fm.VisualizationSettings())
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(step_fn, k):
+        for _ in range(3):
+            step_fn()
+        ctx.wait()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        total, wall = 0.0, 0.0
+        for _ in range(k):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+            step_fn()
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            ctx.wait()
+            if world > 1:
+                dist.barrier()                  # every rank's tiles have landed in the presenter's image
+            wall += time.perf_counter() - t0
+            total += e0.elapsed_time(e1)
+        ms = total / k
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, 1e3 * wall / k
+
+    def step():
+        ctx.build_frame_device(0, d_xyz.data_ptr(), npart, h, 2.0)
+        ctx.render_async(fm.FR_PASS_ALL)
+
+    one_ms, _ = timed(step, steps)                     # this GPU alone, the whole frame
+    rec = {"workload": workload_string("C3", npart, W, H), "n_gpus": world, "ms_per_frame_one_gpu": one_ms}
+    if world == 1:
+        ctx.close()
+        return rec
+    want = ctx.download(False, False, False, True)[3].copy() if rank == 0 else None
+    handle = [ctx.ipc_export_color() if rank == 0 else None]
+    dist.broadcast_object_list(handle, src=0)
+    if rank != 0:
+        ctx.ipc_open_color_target(handle[0])
+    else:
+        torch.as_tensor(_DevPtr(ctx.device_images()["rgba"], W * H * 4), device=dev).fill_(0x5a)      # stale pixels must not pass
+        torch.cuda.synchronize()
+    ctx.set_tile_partition(rank, world, tile, tile)
+    dist.barrier()
+    n_ms, n_wall = timed(step, steps)
+    same, differing = None, None
+    if rank == 0:
+        got = ctx.download(False, False, False, True)[3]
+        differing = int((got != want).any(-1).sum())
+        same = differing == 0
+    dist.barrier()
+    if rank != 0:
+        ctx.ipc_close_color_target()
+    ctx.close()
+    rec.update({"ms_per_frame": n_ms, "ms_per_frame_wall_with_barrier": n_wall, "scaling": "strong",
+                "efficiency_vs_one_gpu": one_ms / (world * n_ms), "speedup_vs_one_gpu": one_ms / n_ms,
+                "bit_identical": same, "pixels_differing": differing, "tile": tile,
+                "parallelism": f"tile-parallel {tile}x{tile} interleaved; each rank's march epilogue stores its pixels into the presenting "
+                               "GPU's image over NVLink peer memory (fr_ipc_export_color / fr_ipc_open_color_target), no gather",
+                "timing": "CUDA events on each rank's context stream around build + pre-pass + march of its share, max over ranks; "
+                          "L2 flushed between frames; ms_per_frame_wall_with_barrier adds the NCCL barrier that tells the presenter "
+                          "the image is complete"})
+    return rec
+
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -473,6 +601,11 @@ def run_b200(args):
         e2e_ms, _, _ = timed_sequence(seq, submit_e2e, args.steps, max(3, min(args.warmup, 6)))
         e2e_ref_ms, _, _ = timed_sequence(seq, submit_e2e_refproto, max(4, args.steps // 2), 3)
         seq.close()
+    ceiling, tiles_rec = None, None
+    if not tiles_mode:
+        ceiling = host_ceiling(torch, dist, dev, world, 12 * n_actual[0], W * H * 4)
+        if not args.no_tiles:
+            tiles_rec = tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, args.tile)
 
     units = W * H * (1 if tiles_mode else world)          # rays per step over all ranks
     value = units / (ms_step * 1e-3)
@@ -590,6 +723,10 @@ def run_b200(args):
                "h2d_bytes_per_step": int(12 * npart), "d2h_bytes_per_step": int(W * H * 4),
                "path": ("fr_upload_frame(host xyz) -> fr_render_async(ALL) -> fr_download(rgba), pinned host buffers" if tiles_mode else
                         f"fr_seq_submit(host xyz -> host rgba), pinned host buffers, {lanes} frames in flight")}
+        if ceiling:
+            e2e["host_ceiling"] = ceiling
+            e2e["host_ceiling_gbs"] = ceiling["gbs_all_ranks"]
+            e2e["fraction_of_host_ceiling"] = ceiling["ms_per_frame_pair"] / e2e_ms
         if e2e_ref_ms is not None:
             e2e["reference_protocol"] = {"value": units / (e2e_ref_ms * 1e-3), "ms_per_step": e2e_ref_ms,
                                          "d2h_bytes_per_step": int(W * H * (16 + 16 + 4)),
@@ -615,6 +752,7 @@ def run_b200(args):
             "gpu_launches": int(kernel_launches_timed),
             "roofline": roof,
             "cpu_baseline": cpu,
+            "tiles": tiles_rec,
         }
         print(json.dumps(out), flush=True)
     ctx.close()
@@ -636,6 +774,7 @@ def main():
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
                     help="--mode tiles: peer = ranks render into the presenter's image over NVLink peer memory; nccl = gather collective")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tiles", action="store_true", help="skip the C3 tile-parallel sub-record")
     ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
