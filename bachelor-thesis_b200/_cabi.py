@@ -91,6 +91,7 @@ SYMBOLS = [
     ("fr_set_camera", C.c_int, [C.c_void_p, C.POINTER(FrCamera)]),
     ("fr_set_depth", C.c_int, [C.c_void_p, C.c_void_p]),
     ("fr_set_tile_partition", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
+    ("fr_set_region_partition", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("fr_render_async", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_is_done", C.c_int, [C.c_void_p]),
     ("fr_wait", C.c_int, [C.c_void_p]),

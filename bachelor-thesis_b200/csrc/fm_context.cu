@@ -591,6 +591,21 @@ int fr_set_tile_partition(fr_context* ctx, int rank, int world, int tile_w, int 
 	return FR_OK;
 }
 
+int fr_set_region_partition(fr_context* ctx, int x0, int y0, int x1, int y1)
+{
+	FR_CHECK_CTX(ctx);
+	if (x1 == 0 && y1 == 0 && x0 == 0 && y0 == 0) { ctx->region[0] = ctx->region[1] = ctx->region[2] = ctx->region[3] = 0; return FR_OK; }
+	bool const ok = x0 >= 0 && y0 >= 0 && x1 > x0 && y1 > y0 && x1 <= ctx->width && y1 <= ctx->height && x0 % 64 == 0 && y0 % 64 == 0 &&
+		(x1 % 64 == 0 || x1 == ctx->width) && (y1 % 64 == 0 || y1 == ctx->height);
+	if (!ok)
+	{
+		set_error("fr_set_region_partition: need 0 <= x0 < x1 <= W, 0 <= y0 < y1 <= H, bounds multiples of 64 (or the image edge)");
+		return FR_ERR_INVALID;
+	}
+	ctx->region[0] = x0; ctx->region[1] = y0; ctx->region[2] = x1; ctx->region[3] = y1;
+	return FR_OK;
+}
+
 // ---- render ----------------------------------------------------------------------------------------
 
 int fr_render_async(fr_context* ctx, int passes)

@@ -55,6 +55,9 @@ struct DepthParams
 	// partition tile size is a multiple of 64 and every hi-Z tile / coarse block size divides 64, so a hi-Z tile or
 	// coarse block has exactly one owner
 	int part_rank, part_world, part_sw, part_sh, part_tiles_x;     // tile width / height = 1 << part_sw / part_sh
+	// region partition (fr_set_region_partition): only the pixel rectangle [rx0, rx1) x [ry0, ry1) is needed; its bounds are
+	// multiples of 64 (or the image edge), so a hi-Z tile or coarse block lies inside or outside as a whole.  rx1 == 0: none
+	int rx0, ry0, rx1, ry1;
 };
 
 __device__ __forceinline__ bool tile_owned(const DepthParams& dp, int tx, int ty)
@@ -62,16 +65,18 @@ __device__ __forceinline__ bool tile_owned(const DepthParams& dp, int tx, int ty
 	return (uint32_t)(ty * dp.part_tiles_x + tx) % (uint32_t)dp.part_world == (uint32_t)dp.part_rank;
 }
 
-// does this rank own the partition tile that holds pixel (px, py)?
+// does this rank own the partition tile / region that holds pixel (px, py)?
 __device__ __forceinline__ bool pixel_owned(const DepthParams& dp, int px, int py)
 {
+	if (dp.rx1 > 0) return px >= dp.rx0 && px < dp.rx1 && py >= dp.ry0 && py < dp.ry1;
 	if (dp.part_world <= 1) return true;
 	return tile_owned(dp, px >> dp.part_sw, py >> dp.part_sh);
 }
 
-// does the pixel box touch any partition tile of this rank?
+// does the pixel box touch any partition tile of this rank / its region?
 __device__ __forceinline__ bool box_owned(const DepthParams& dp, int x0, int y0, int x1, int y1)
 {
+	if (dp.rx1 > 0) return x1 >= dp.rx0 && x0 < dp.rx1 && y1 >= dp.ry0 && y0 < dp.ry1;
 	if (dp.part_world <= 1) return true;
 	for (int ty = y0 >> dp.part_sh; ty <= (y1 >> dp.part_sh); ty++)
 		for (int tx = x0 >> dp.part_sw; tx <= (x1 >> dp.part_sw); tx++)
@@ -87,15 +92,22 @@ struct Splat
 	int x0, y0, x1, y1;          // conservative pixel box, clipped to the screen (x1 < x0: nothing to draw)
 };
 
-__global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ depth_bits, uint32_t npix,
+// (npix pixels of a rectangle rw wide at (rx0, ry0) of an image W wide: the whole image, or the context's region)
+__global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ depth_bits, uint32_t npix, uint32_t rw, uint32_t rx0, uint32_t ry0, uint32_t W,
 													 uint32_t* __restrict__ tile_bound, uint32_t ntiles,
 													 uint32_t* __restrict__ n_survivors, uint32_t* __restrict__ counters, uint32_t counter_words)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < 4u) n_survivors[i] = 0u;             // survivor count (+ padding) of k_depth_cull
 	if (i < counter_words) counters[i] = 0u;     // DeviceCounters + work-list control words of the march that follows
-	if (i < npix) depth_bits[i] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
+	if (i < npix) depth_bits[(size_t)(ry0 + i / rw) * W + rx0 + i % rw] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
 	if (i < ntiles) tile_bound[i] = 0x3f800000u;
+}
+
+// particles in the sorted array: the frame's, or fewer under a region partition (k_scan_flags); none of an unusable frame
+__device__ __forceinline__ uint32_t sorted_count(const GridParams* __restrict__ gp, uint32_t n)
+{
+	return gp->status ? 0u : min(n, gp->n_sorted);
 }
 
 __device__ __forceinline__ float frag_depth(const DepthParams& dp, float z_c, float l2)
@@ -150,12 +162,12 @@ __device__ __forceinline__ bool splat_setup(const DepthParams& dp, float4 p, Spl
 // pass 1: per-particle splat parameters -> scratch, and the cheapest useful bound: the tile that contains the
 // disc centre (fully covered whenever the disc radius exceeds the tile diagonal, which is how T is chosen)
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, uint32_t n, DepthParams dp,
+__global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, uint32_t n, const GridParams* __restrict__ gp, DepthParams dp,
 													float4* __restrict__ splat_a, uint4* __restrict__ splat_b,
 													uint32_t* __restrict__ tile_bound)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	if (i >= sorted_count(gp, n)) return;
 	Splat s;
 	bool live = splat_setup(dp, __ldg(sorted + i), s);
 	if (live && !box_owned(dp, s.x0, s.y0, s.x1, s.y1)) live = false;      // cannot touch a pixel this rank renders
@@ -224,13 +236,13 @@ __device__ __forceinline__ uint32_t cta_append(bool take, uint32_t* __restrict__
 // while the rest of the GPU idled (ncu r01 final: SMs 58 % active, 28 % occupancy).  So k_depth_gate only lists them
 // (warp-aggregated append) and k_depth_bounds deals the list out evenly, one warp per particle, lanes = tiles.
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, DepthParams dp, const uint4* __restrict__ splat_b,
+__global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, const GridParams* __restrict__ gp, DepthParams dp, const uint4* __restrict__ splat_b,
 													const uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ list,
 													uint32_t* __restrict__ n_list)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool take = false;
-	if (i < n)
+	if (i < sorted_count(gp, n))
 	{
 		uint4 const b = __ldg(splat_b + i);
 		int const x0 = (int)(b.z & 0xffffu), x1 = (int)(b.z >> 16), y0 = (int)(b.w & 0xffffu), y1 = (int)(b.w >> 16);
@@ -303,13 +315,13 @@ __global__ void __launch_bounds__(256) k_depth_coarse(const uint32_t* __restrict
 // pass 3: keep the particles that can still win a pixel of some tile they overlap (compacted, warp-aggregated).
 // Interior particles -- almost all of them -- are settled by the few coarse blocks their box touches.
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, DepthParams dp, const uint4* __restrict__ splat_b,
+__global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, const GridParams* __restrict__ gp, DepthParams dp, const uint4* __restrict__ splat_b,
 													const uint32_t* __restrict__ tile_bound, const uint32_t* __restrict__ coarse,
 													int coarse_x, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool wins = false;
-	if (i < n)
+	if (i < sorted_count(gp, n))
 	{
 		uint4 const b = __ldg(splat_b + i);
 		int const x0 = (int)(b.z & 0xffffu), x1 = (int)(b.z >> 16), y0 = (int)(b.w & 0xffffu), y1 = (int)(b.w >> 16);
@@ -440,19 +452,19 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	uint4* const splat_b = (uint4*)(ctx->d_splat + 4 * (size_t)n);
 	uint32_t* const n_surv = ctx->d_survivors;
 	uint32_t* const surv = ctx->d_survivors + 4;
-	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, dp, splat_a, splat_b, ctx->d_tile_bound);
+	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, f.d_gp, dp, splat_a, splat_b, ctx->d_tile_bound);
 	uint32_t const want = (n + 7u) / 8u;
 	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	if (refine_bounds)
 	{
 		// the gate's list shares the survivor array (it is consumed before k_depth_cull writes there); its count is word 2
-		k_depth_gate<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2);
+		k_depth_gate<T><<<blocks, 256, 0, st>>>(n, f.d_gp, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2);
 		k_depth_bounds<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv + 2, ctx->d_tile_bound);
 	}
 	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
 	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
 	k_depth_coarse<<<(cx * cy + 255) / 256, 256, 0, st>>>(ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy);
-	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv);
+	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, f.d_gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv);
 	k_depth_splat<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
 															 (uint32_t*)ctx->d_depth);
 	ctx->kernel_launches += refine_bounds ? 6 : 4;
@@ -497,6 +509,10 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	while ((1 << dp.part_sw) < ctx->part_tw) dp.part_sw++;
 	while ((1 << dp.part_sh) < ctx->part_th) dp.part_sh++;
 	dp.part_tiles_x = (ctx->width + ctx->part_tw - 1) / ctx->part_tw;
+	bool const region = ctx->region[2] > ctx->region[0];
+	dp.rx0 = region ? ctx->region[0] : 0; dp.ry0 = region ? ctx->region[1] : 0;
+	dp.rx1 = region ? ctx->region[2] : 0; dp.ry1 = region ? ctx->region[3] : 0;
+	if (region) dp.part_world = 1;
 
 	// tile size from the projected disc radius at the centre of the particle AABB (a tuning choice only:
 	// every T gives the same image)
@@ -516,8 +532,12 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	if ((rc = ensure_capacity(&ctx->d_splat, &ctx->cap_splat, 8 * f.n))) return rc;            // 2 x 16 B per particle
 	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
 
-	uint32_t const npix = (uint32_t)ctx->width * (uint32_t)ctx->height;
-	k_depth_clear<<<(npix + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, ctx->d_tile_bound, ntiles, ctx->d_survivors,
+	// (under a region partition only the region's pixels are cleared -- and only they are valid afterwards)
+	uint32_t const rw = region ? (uint32_t)(dp.rx1 - dp.rx0) : (uint32_t)ctx->width, rh = region ? (uint32_t)(dp.ry1 - dp.ry0) : (uint32_t)ctx->height;
+	uint32_t const npix = rw * rh;
+	uint32_t const clear_threads = npix > ntiles ? npix : ntiles;
+	k_depth_clear<<<(clear_threads + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
+																		  ctx->d_tile_bound, ntiles, ctx->d_survivors,
 																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u);
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)

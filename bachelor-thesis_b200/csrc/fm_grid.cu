@@ -195,6 +195,8 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	g.gcells = status ? 0u : (uint32_t)gcells;
 	g.status = status;
 	g.max_cell = 0u;
+	g.n_sorted = 0u;
+	g.pad = 0u;
 	*gp = g;
 }
 
@@ -256,8 +258,10 @@ __device__ __forceinline__ uint32_t centre_box_mask(float p, float mn, int c, in
 // switch (fr_set_count_mode): FR_COUNT_CENTRE_BOX (default) = the half-open box of half-width r/2 around the query
 // point, which is what the reference build under oracle/_ref does; FR_COUNT_CELL_EXACT = the node
 // QueryDensityGrid(particle) returns.  The two differ only for particles within an ulp of a cell face.
+constexpr uint32_t kKeyExcluded = 0xffffffffu;        // a particle the region filter left out
+
 __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, const GridParams* __restrict__ gp,
-														float half, int count_mode,
+														float half, int count_mode, RegionFilter rf,
 														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
 														uint32_t* __restrict__ grid_counts)
 {
@@ -265,6 +269,15 @@ __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict_
 	if (i >= n || gp->status) return;
 	BuildView const b = load_build_view(gp, half, count_mode);
 	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
+	if (rf.on)
+	{
+		// (a conservative test: the answer only decides whether the particle is carried along, never a pixel)
+		float const rx = x - rf.cam[0], ry = y - rf.cam[1], rz = z - rf.cam[2];
+		bool keep = true;
+#pragma unroll
+		for (int k = 0; k < 4; k++) keep = keep && (rf.plane[k][0] * rx + rf.plane[k][1] * ry + rf.plane[k][2] * rz <= rf.margin);
+		if (!keep) { keys[i] = kKeyExcluded; return; }
+	}
 	uint32_t const key = search_key(b, x, y, z);
 	keys[i] = key;
 	atomicAdd(cell_count + key, 1u);
@@ -398,7 +411,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_flags(GridParams* __restr
 			{
 				if (tile != 0) atomicExch(tile_state + tile, kTilePrefix | (unsigned long long)(prefix + total));
 				s_prefix = prefix;
-				if (tile == ntiles - 1) cell_start[m] = prefix + total;
+				if (tile == ntiles - 1) { cell_start[m] = prefix + total; gp->n_sorted = prefix + total; }
 			}
 		}
 		__syncthreads();
@@ -434,6 +447,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const GridPara
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || gp->status) return;
 	uint32_t const key = keys[i];
+	if (key == kKeyExcluded) return;
 	uint32_t const left = atomicSub(cursor + key, 1u);       // count .. 1
 	slot_index[cell_start[key] + (left - 1u)] = i;
 }
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_order(const float* __restrict
 														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
 {
 	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n || gp->status) return;
+	if (s >= n || gp->status || s >= gp->n_sorted) return;
 	if (gp->max_cell > kMaxCellParticles)
 	{
 		if (s == 0) atomicOr(&gp->status, (uint32_t)FM_GRID_CROWDED);     // (read by the host only: the march of this frame sees stale slots)
@@ -690,6 +704,45 @@ static float spline_sig_d(float h)
 	return 8.0f / t;
 }
 
+// the view frustum of the context's pixel rectangle as 4 planes through the camera position (see RegionFilter)
+static RegionFilter region_filter(const Context* ctx, float h)
+{
+	RegionFilter rf;
+	memset(&rf, 0, sizeof rf);
+	if (ctx->region[2] <= ctx->region[0] || !ctx->have_camera) return rf;
+	const float* m = ctx->camera.inv_projection_view;
+	double const W = ctx->width, H = ctx->height;
+	// far-plane points of the rectangle's corners (pixel corners, as the ray generation uses them; +-1 pixel of slack)
+	double c[4][3];
+	double const xs[2] = { (ctx->region[0] - 1) * 2.0 / W - 1.0, (ctx->region[2] + 1) * 2.0 / W - 1.0 };
+	double const ys[2] = { (ctx->region[1] - 1) * 2.0 / H - 1.0, (ctx->region[3] + 1) * 2.0 / H - 1.0 };
+	int const order[4][2] = { { 0, 0 }, { 1, 0 }, { 1, 1 }, { 0, 1 } };
+	for (int k = 0; k < 4; k++)
+	{
+		double const v[4] = { xs[order[k][0]], ys[order[k][1]], 1.0, 1.0 };
+		double o[4];
+		for (int r = 0; r < 4; r++) o[r] = m[0 + r] * v[0] + m[4 + r] * v[1] + m[8 + r] * v[2] + m[12 + r] * v[3];
+		for (int a = 0; a < 3; a++) c[k][a] = o[a] / o[3] - ctx->camera.position[a];
+	}
+	double centre[3] = { 0, 0, 0 };
+	for (int k = 0; k < 4; k++) for (int a = 0; a < 3; a++) centre[a] += 0.25 * c[k][a];
+	for (int k = 0; k < 4; k++)
+	{
+		const double* a = c[k];
+		const double* b = c[(k + 1) & 3];
+		double nrm[3] = { a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0] };
+		double len = sqrt(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+		if (!(len > 0.0)) return rf;                               // degenerate camera: no filter (every particle is kept)
+		double const inward = nrm[0] * centre[0] + nrm[1] * centre[1] + nrm[2] * centre[2];
+		double const sgn = inward > 0.0 ? -1.0 : 1.0;              // outward normal
+		for (int q = 0; q < 3; q++) rf.plane[k][q] = (float)(sgn * nrm[q] / len);
+	}
+	for (int a = 0; a < 3; a++) rf.cam[a] = ctx->camera.position[a];
+	rf.margin = 3.6f * h;
+	rf.on = 1;
+	return rf;
+}
+
 // layout of ctx->d_scan_tmp for `cells` histogram entries: [cursor: cells, padded to even][tile states: 2 words per
 // tile][scan ticket][AABB ticket]
 static size_t scan_tmp_words(size_t cells) { return ((cells + 1) & ~(size_t)1) + 2 * ((cells + kScanTile - 1) / kScanTile + 1) + 2; }
@@ -834,7 +887,9 @@ int build_frame_finish(Context* ctx)
 
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	float const half = 0.5f * f->h;                   // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
-	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, ctx->d_keys, d_cursor, f->d_grid_counts);
+	RegionFilter const rf = region_filter(ctx, f->h);
+	f->filtered = rf.on != 0;
+	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, rf, ctx->d_keys, d_cursor, f->d_grid_counts);
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter); occupancy flags
 	uint32_t const flag_blocks = (ctx->build.flag_cells + kScanThreads - 1) / kScanThreads;
 	uint32_t const scan_grid = std::max(ctx->build.scan_blocks, std::min(flag_blocks, (uint32_t)ctx->sm_count * 4u));

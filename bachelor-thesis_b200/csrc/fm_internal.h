@@ -28,6 +28,22 @@ struct GridParams
 	uint32_t cells, gcells;      // kdim / gdim products; 0 when status != 0
 	uint32_t status;             // FM_GRID_* bits; != 0: the frame is unusable and every kernel of the build returns at once
 	uint32_t max_cell;           // largest number of particles in one search cell (k_scan_flags)
+	uint32_t n_sorted;           // particles in the sorted array: all of them, or those the region filter kept (k_scan_flags)
+	uint32_t pad;
+};
+
+// Region partition (tile-parallel multi-GPU, fr_set_region_partition): this context renders the pixel rectangle
+// [x0, x1) x [y0, y1) only and builds its search structures from the particles that can influence those pixels: the ones
+// within `margin` of the rectangle's view frustum (4 side planes through the camera position, unit normals pointing
+// outward).  A sample of a ray of the region reads the 27 search cells around it, i.e. particles up to 2 h away per axis
+// (2 sqrt(3) h in distance); the depth pre-pass needs the discs that overlap the rectangle (radius h).  With a margin of
+// 3.6 h every cell such a sample can touch holds exactly the particles of the unpartitioned build, in the same order.
+struct RegionFilter
+{
+	int on;
+	float margin;
+	float cam[3];
+	float plane[4][3];
 };
 
 enum
@@ -61,6 +77,7 @@ struct Frame
 	uint64_t build_serial = 0;        // process-wide number of this build
 	const float* src_xyz = nullptr;   // device particles of the queued build (must stay valid until the host next waits)
 	float src_mult = 0.0f;
+	bool filtered = false;            // built under a region partition: holds only the particles its pixel rectangle needs
 	uint64_t occupied = 0;
 	// device buffers (capacities in elements)
 	float4* d_sorted = nullptr;       size_t cap_sorted = 0;
@@ -129,6 +146,7 @@ struct Context
 	bool have_camera = false;
 	bool have_depth = false;
 	int part_rank = 0, part_world = 1, part_tw = 64, part_th = 64;
+	int region[4] = { 0, 0, 0, 0 };    // x0, y0, x1, y1 of fr_set_region_partition; x1 == 0: none
 	int count_mode = FR_COUNT_CENTRE_BOX;   // reading of find_neighbors_box (fr_set_count_mode)
 
 	std::vector<Frame> frames;

@@ -36,6 +36,10 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	mp.part_rank = ctx->part_rank; mp.part_world = ctx->part_world;
 	mp.part_tw = ctx->part_tw; mp.part_th = ctx->part_th;
 	mp.part_tiles_x = (ctx->width + ctx->part_tw - 1) / ctx->part_tw;
+	bool const region = ctx->region[2] > ctx->region[0];
+	mp.rx0 = region ? ctx->region[0] : 0; mp.ry0 = region ? ctx->region[1] : 0;
+	mp.rx1 = region ? ctx->region[2] : 0; mp.ry1 = region ? ctx->region[3] : 0;
+	if (region) mp.part_world = 1;
 	mp.do_march = do_march ? 1 : 0;
 	mp.do_shade = do_shade ? 1 : 0;
 	mp.k_n = ctx->settings.k_n; mp.k_r = ctx->settings.k_r; mp.k_s = ctx->settings.k_s;
@@ -55,7 +59,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 	if (!ctx->zero_counters_in_depth)
 		FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));      // counters + control words
 	ctx->zero_counters_in_depth = false;
-	dim3 const grid((ctx->width + 31) / 32, (ctx->height + 7) / 8);
+	dim3 const grid(((region ? mp.rx1 - mp.rx0 : ctx->width) + 31) / 32, ((region ? mp.ry1 - mp.ry0 : ctx->height) + 7) / 8);
 	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
 	ctx->kernel_launches += 1;
 	FM_TIME(ctx, ctx->ev[10], st);

@@ -56,6 +56,7 @@ struct MarchParams
 	int early_out;
 	float early_margin;               // cells a sample must lie beyond the grid before the ray is stopped
 	int part_rank, part_world, part_tw, part_th, part_tiles_x;
+	int rx0, ry0, rx1, ry1;           // region partition: the pixel rectangle this context renders (rx1 == 0: everything)
 	int do_march, do_shade;
 	int tiles_x;                      // 8x4 pixel tiles per image row
 	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
@@ -786,6 +787,7 @@ __device__ __forceinline__ uchar4 shade_pixel(const MarchParams& mp, int px, int
 __device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int py)
 {
 	bool active = px < mp.W && py < mp.H;
+	if (active && mp.rx1 > 0) active = px >= mp.rx0 && px < mp.rx1 && py >= mp.ry0 && py < mp.ry1;
 	if (active && mp.part_world > 1)
 	{
 		int const tile = (py / mp.part_th) * mp.part_tiles_x + (px / mp.part_tw);
@@ -803,7 +805,8 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 												  uint32_t* __restrict__ n_tiles)
 {
 	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int const tx = blockIdx.x * 4 + (warp & 3), ty = blockIdx.y * 2 + (warp >> 2);
+	// (under a region partition the grid covers the region only: its bounds are multiples of 64 pixels)
+	int const tx = (mp.rx0 >> 3) + blockIdx.x * 4 + (warp & 3), ty = (mp.ry0 >> 2) + blockIdx.y * 2 + (warp >> 2);
 	int const px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
 	bool const active = pixel_active(mp, px, py);
 	uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;

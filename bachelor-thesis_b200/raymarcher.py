@@ -155,6 +155,10 @@ class Context:
     def set_tile_partition(self, rank, world, tile_w=64, tile_h=64):
         check(self.lib.fr_set_tile_partition(self.h, rank, world, tile_w, tile_h), "fr_set_tile_partition")
 
+    def set_region_partition(self, x0=0, y0=0, x1=0, y1=0):
+        """render (and build frames for) the pixel rectangle [x0, x1) x [y0, y1) only; all zero = off"""
+        check(self.lib.fr_set_region_partition(self.h, x0, y0, x1, y1), "fr_set_region_partition")
+
     # render ----------------------------------------------------------------------------------------
     def render_async(self, passes: int = FR_PASS_ALL):
         check(self.lib.fr_render_async(self.h, passes), "fr_render_async")

@@ -185,6 +185,13 @@ int fr_set_depth(fr_context* ctx, const float* depth_host);
  * (tiles of tile_w x tile_h pixels, row-major tile index); world = 1 renders everything */
 int fr_set_tile_partition(fr_context* ctx, int rank, int world, int tile_w, int tile_h);
 
+/* multi-GPU region-parallel: this context renders the pixel rectangle [x0, x1) x [y0, y1) only (bounds multiples of 64
+ * or the image edge; all zero = off) AND builds the frames uploaded afterwards from the particles that can influence those
+ * pixels under the camera set at build time (fr_set_camera first; a camera change needs a new upload): the grid geometry
+ * is the whole frame's, so the pixels are bit-identical to an unpartitioned render, while build, pre-pass and march
+ * all shrink with the region.  Images are valid inside the rectangle only; fr_query_* see the kept particles only. */
+int fr_set_region_partition(fr_context* ctx, int x0, int y0, int x1, int y1);
+
 /* ---- render: RayMarcher::Start / IsDone (RayMarcher.cpp:102-112, RayMarcher.h:44) ---------------- */
 int fr_render_async(fr_context* ctx, int passes);
 int fr_is_done(fr_context* ctx);      /* 1 = done, 0 = still running, <0 = error */
