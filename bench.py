@@ -314,10 +314,34 @@ def host_ceiling(torch, dist, dev, world, h2d_bytes, d2h_bytes, reps=40):
                     "memory, two streams, max over ranks; the e2e arm cannot be faster than this per frame"}
 
 
-def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, tile, steps=12):
-    """BASELINE config C3 (4M particles, 3840x2160): ONE frame split into interleaved screen tiles over the ranks, every
-    rank's shading epilogue storing its tiles straight into the presenting GPU's image over NVLink peer memory
-    (fr_ipc_*); strong scaling against the same frame rendered by one GPU alone, and bit-identity of the assembled image"""
+def balanced_strips(xyz, cam, W, world):
+    """vertical strips [x0, x1) with bounds at multiples of 64 pixels that hold about the same number of projected
+    particles each (covered area and march work follow the particle count for this scene)"""
+    v = np.asarray(cam["view"], np.float64).reshape(4, 4).T          # column-major -> row-major maths
+    p = np.asarray(cam["proj"], np.float64).reshape(4, 4).T
+    pts = np.concatenate([xyz.astype(np.float64), np.ones((len(xyz), 1))], axis=1)
+    clip = pts @ (p @ v).T
+    px = (clip[:, 0] / clip[:, 3] + 1.0) * (W / 2.0)
+    nb = (W + 63) // 64
+    hist = np.bincount(np.clip((px // 64).astype(np.int64), 0, nb - 1), minlength=nb).astype(np.float64)
+    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    bounds = [0]
+    for k in range(1, world):
+        target = cum[-1] * k / world
+        b = int(np.argmin(np.abs(cum - target)))
+        b = max(b, bounds[-1] + 1)
+        b = min(b, nb - (world - k))
+        bounds.append(b)
+    bounds.append(nb)
+    return [(64 * bounds[k], min(64 * bounds[k + 1], W)) for k in range(world)]
+
+
+def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, tile, steps=12):
+    """BASELINE config C3 (4M particles, 3840x2160): ONE frame split over the ranks, every rank's shading epilogue storing
+    its pixels straight into the presenting GPU's image over NVLink peer memory (fr_ipc_*); strong scaling against the
+    same frame rendered by one GPU alone, and bit-identity of the assembled image.  Two partitions: `regions` -- each
+    rank owns a vertical strip and builds its frame from the particles that can influence it (fr_set_region_partition:
+    build, pre-pass and march all shrink) -- and, for comparison, interleaved tiles over replicated frames."""
     n, W, H, h, dx = CONFIGS["C3"]
     xyz = fm.scenes.dam_break(n, h=h, dx=dx, t=FRAME_T)
     npart = len(xyz)
@@ -351,21 +375,22 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, tile, st
                 e1.record(stream)
             ctx.wait()
             if world > 1:
-                dist.barrier()                  # every rank's tiles have landed in the presenter's image
+                dist.barrier()                  # every rank's pixels have landed in the presenter's image
             wall += time.perf_counter() - t0
             total += e0.elapsed_time(e1)
         ms = total / k
+        mine = ms
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, 1e3 * wall / k
+        return ms, 1e3 * wall / k, mine
 
     def step():
         ctx.build_frame_device(0, d_xyz.data_ptr(), npart, h, 2.0)
         ctx.render_async(fm.FR_PASS_ALL)
 
-    one_ms, _ = timed(step, steps)                     # this GPU alone, the whole frame
+    one_ms, _, _ = timed(step, steps)                     # this GPU alone, the whole frame
     rec = {"workload": workload_string("C3", npart, W, H), "n_gpus": world, "ms_per_frame_one_gpu": one_ms}
     if world == 1:
         ctx.close()
@@ -375,26 +400,50 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, tile, st
     dist.broadcast_object_list(handle, src=0)
     if rank != 0:
         ctx.ipc_open_color_target(handle[0])
-    else:
-        torch.as_tensor(_DevPtr(ctx.device_images()["rgba"], W * H * 4), device=dev).fill_(0x5a)      # stale pixels must not pass
-        torch.cuda.synchronize()
+
+    def poison():
+        if rank == 0:
+            torch.as_tensor(_DevPtr(ctx.device_images()["rgba"], W * H * 4), device=dev).fill_(0x5a)      # stale pixels must not pass
+            torch.cuda.synchronize()
+        dist.barrier()
+
+    def check():
+        same, differing = None, None
+        if rank == 0:
+            got = ctx.download(False, False, False, True)[3]
+            differing = int((got != want).any(-1).sum())
+            same = differing == 0
+        dist.barrier()
+        return same, differing
+
+    # (1) regions: vertical strips balanced by particle count, filtered frame builds
+    strips = balanced_strips(xyz, cam, W, world)
+    x0, x1 = strips[rank]
+    ctx.set_region_partition(x0, 0, x1, H)
+    poison()
+    n_ms, n_wall, my_ms = timed(step, steps)
+    same, differing = check()
+    per_rank = [None] * world
+    dist.all_gather_object(per_rank, round(my_ms, 4))
+    ctx.set_region_partition()
+    # (2) interleaved tiles over replicated frames (round 1's partition)
     ctx.set_tile_partition(rank, world, tile, tile)
-    dist.barrier()
-    n_ms, n_wall = timed(step, steps)
-    same, differing = None, None
-    if rank == 0:
-        got = ctx.download(False, False, False, True)[3]
-        differing = int((got != want).any(-1).sum())
-        same = differing == 0
-    dist.barrier()
+    poison()
+    t_ms, t_wall, _ = timed(step, max(4, steps // 2))
+    t_same, t_diff = check()
     if rank != 0:
         ctx.ipc_close_color_target()
     ctx.close()
     rec.update({"ms_per_frame": n_ms, "ms_per_frame_wall_with_barrier": n_wall, "scaling": "strong",
                 "efficiency_vs_one_gpu": one_ms / (world * n_ms), "speedup_vs_one_gpu": one_ms / n_ms,
-                "bit_identical": same, "pixels_differing": differing, "tile": tile,
-                "parallelism": f"tile-parallel {tile}x{tile} interleaved; each rank's march epilogue stores its pixels into the presenting "
-                               "GPU's image over NVLink peer memory (fr_ipc_export_color / fr_ipc_open_color_target), no gather",
+                "bit_identical": same, "pixels_differing": differing,
+                "partition": "regions", "strips_px": strips, "ms_per_rank": per_rank,
+                "parallelism": "region-parallel: vertical strips (bounds at multiples of 64 px, balanced by projected particle count); each rank "
+                               "builds its frame from the particles within 3.6 h of its strip's frustum (fr_set_region_partition) and its march "
+                               "epilogue stores the pixels into the presenting GPU's image over NVLink peer memory (fr_ipc_*), no gather",
+                "interleaved_tiles": {"tile": tile, "ms_per_frame": t_ms, "ms_per_frame_wall_with_barrier": t_wall,
+                                      "efficiency_vs_one_gpu": one_ms / (world * t_ms), "bit_identical": t_same, "pixels_differing": t_diff,
+                                      "parallelism": f"tile-parallel {tile}x{tile} interleaved over replicated frames, same peer-memory colour target"},
                 "timing": "CUDA events on each rank's context stream around build + pre-pass + march of its share, max over ranks; "
                           "L2 flushed between frames; ms_per_frame_wall_with_barrier adds the NCCL barrier that tells the presenter "
                           "the image is complete"})
@@ -605,7 +654,7 @@ def run_b200(args):
     if not tiles_mode:
         ceiling = host_ceiling(torch, dist, dev, world, 12 * n_actual[0], W * H * 4)
         if not args.no_tiles:
-            tiles_rec = tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, args.tile)
+            tiles_rec = tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, args.tile)
 
     units = W * H * (1 if tiles_mode else world)          # rays per step over all ranks
     value = units / (ms_step * 1e-3)
