@@ -112,6 +112,7 @@ SYMBOLS = [
     ("fr_measure_l2_bandwidth", C.c_int, [C.c_void_p, C.c_size_t, C.c_uint32, f32p]),
     ("fr_selftest_division", C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
     ("fr_import_vk_memory_fd", C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]),
+    ("fr_import_vk_images_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_size_t]),
     ("fr_import_vk_semaphores_fd", C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     ("fr_bgeo_probe", C.c_int, [C.c_char_p, C.POINTER(FrBgeoInfo)]),
     ("fr_bgeo_read", C.c_int, [C.c_char_p, f32p, C.c_uint64, C.POINTER(C.c_uint64)]),

@@ -98,18 +98,20 @@ static void free_frame(Frame& f)
 static void free_images(Context* c)
 {
 	if (c->d_depth) cudaFree(c->d_depth);
-	if (c->d_pos) cudaFree(c->d_pos);
-	if (c->d_nrm) cudaFree(c->d_nrm);
+	if (c->d_pos_own) cudaFree(c->d_pos_own);
+	if (c->d_nrm_own) cudaFree(c->d_nrm_own);
 	if (c->d_rgba) cudaFree(c->d_rgba);
-	c->d_depth = nullptr; c->d_pos = nullptr; c->d_nrm = nullptr; c->d_rgba = nullptr; c->d_rgba_target = nullptr;
+	c->d_depth = nullptr; c->d_pos = nullptr; c->d_nrm = nullptr; c->d_pos_own = nullptr; c->d_nrm_own = nullptr;
+	c->d_rgba = nullptr; c->d_rgba_target = nullptr;
 }
 
 static int alloc_images(Context* c, int w, int h)
 {
 	size_t const npix = (size_t)w * (size_t)h;
 	FM_CUDA(cudaMalloc((void**)&c->d_depth, npix * sizeof(float)));
-	FM_CUDA(cudaMalloc((void**)&c->d_pos, npix * sizeof(float4)));
-	FM_CUDA(cudaMalloc((void**)&c->d_nrm, npix * sizeof(float4)));
+	FM_CUDA(cudaMalloc((void**)&c->d_pos_own, npix * sizeof(float4)));
+	FM_CUDA(cudaMalloc((void**)&c->d_nrm_own, npix * sizeof(float4)));
+	c->d_pos = c->d_pos_own; c->d_nrm = c->d_nrm_own;
 	FM_CUDA(cudaMalloc((void**)&c->d_rgba, npix * sizeof(uchar4)));
 	FM_CUDA(cudaMemsetAsync(c->d_pos, 0, npix * sizeof(float4), c->stream));
 	FM_CUDA(cudaMemsetAsync(c->d_nrm, 0, npix * sizeof(float4), c->stream));
@@ -287,6 +289,8 @@ int fr_resize(fr_context* ctx, int width, int height)
 	{ int const src = stream_sync(ctx); if (src) return src; }
 	ctx->render_pending = false;
 	bool const external = ctx->d_rgba_target != ctx->d_rgba;
+	if (ctx->ext_mem_pos) { cudaDestroyExternalMemory(ctx->ext_mem_pos); ctx->ext_mem_pos = nullptr; }       // imported images are
+	if (ctx->ext_mem_nrm) { cudaDestroyExternalMemory(ctx->ext_mem_nrm); ctx->ext_mem_nrm = nullptr; }       // tied to the old size
 	free_images(ctx);
 	int rc = alloc_images(ctx, width, height);
 	if (external) ctx->d_rgba_target = ctx->d_rgba;   // an external target is tied to the old size
@@ -321,6 +325,8 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->ext_wait) cudaDestroyExternalSemaphore(ctx->ext_wait);
 	if (ctx->ext_signal) cudaDestroyExternalSemaphore(ctx->ext_signal);
 	if (ctx->ext_mem) cudaDestroyExternalMemory(ctx->ext_mem);
+	if (ctx->ext_mem_pos) cudaDestroyExternalMemory(ctx->ext_mem_pos);
+	if (ctx->ext_mem_nrm) cudaDestroyExternalMemory(ctx->ext_mem_nrm);
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
 	if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
@@ -972,6 +978,43 @@ int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, siz
 	void* ptr = nullptr;
 	FM_CUDA(cudaExternalMemoryGetMappedBuffer(&ptr, ctx->ext_mem, &bd));
 	ctx->d_rgba_target = (uchar4*)ptr;
+	return FR_OK;
+}
+
+static int import_fd_buffer(int fd, size_t allocation_bytes, size_t need, cudaExternalMemory_t* mem, void** ptr)
+{
+	cudaExternalMemoryHandleDesc hd;
+	memset(&hd, 0, sizeof hd);
+	hd.type = cudaExternalMemoryHandleTypeOpaqueFd;
+	hd.handle.fd = fd;                       // ownership of the fd passes to CUDA on success
+	hd.size = allocation_bytes;
+	FM_CUDA(cudaImportExternalMemory(mem, &hd));
+	cudaExternalMemoryBufferDesc bd;
+	memset(&bd, 0, sizeof bd);
+	bd.offset = 0;
+	bd.size = need;
+	FM_CUDA(cudaExternalMemoryGetMappedBuffer(ptr, *mem, &bd));
+	return FR_OK;
+}
+
+int fr_import_vk_images_fd(fr_context* ctx, int positions_fd, int normals_fd, size_t allocation_bytes)
+{
+	FR_CHECK_CTX(ctx);
+	size_t const need = (size_t)ctx->width * ctx->height * 16;
+	if (positions_fd < 0 || normals_fd < 0 || need > allocation_bytes)
+	{
+		set_error("fr_import_vk_images_fd: bad fd or the allocations are smaller than W*H*16 bytes");
+		return FR_ERR_INVALID;
+	}
+	int rc = finish_pending(ctx);
+	if (rc) return rc;
+	if (ctx->ext_mem_pos) { cudaDestroyExternalMemory(ctx->ext_mem_pos); ctx->ext_mem_pos = nullptr; ctx->d_pos = ctx->d_pos_own; }
+	if (ctx->ext_mem_nrm) { cudaDestroyExternalMemory(ctx->ext_mem_nrm); ctx->ext_mem_nrm = nullptr; ctx->d_nrm = ctx->d_nrm_own; }
+	void* p = nullptr;
+	if ((rc = import_fd_buffer(positions_fd, allocation_bytes, need, &ctx->ext_mem_pos, &p))) return rc;
+	ctx->d_pos = (float4*)p;
+	if ((rc = import_fd_buffer(normals_fd, allocation_bytes, need, &ctx->ext_mem_nrm, &p))) return rc;
+	ctx->d_nrm = (float4*)p;
 	return FR_OK;
 }
 

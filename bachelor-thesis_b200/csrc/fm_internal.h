@@ -154,8 +154,10 @@ struct Context
 
 	// images
 	float* d_depth = nullptr;
-	float4* d_pos = nullptr;
-	float4* d_nrm = nullptr;
+	float4* d_pos = nullptr;           // where the march writes positions / normals: the context's own images or imported
+	float4* d_nrm = nullptr;           // Vulkan memory (fr_import_vk_images_fd)
+	float4* d_pos_own = nullptr;
+	float4* d_nrm_own = nullptr;
 	uchar4* d_rgba = nullptr;
 	uchar4* d_rgba_target = nullptr;   // where the colour pass writes (internal or external)
 	void* peer_rgba = nullptr;         // another process's colour image opened through CUDA IPC (tile-parallel)
@@ -183,7 +185,7 @@ struct Context
 	fr_timings timings{};
 	uint64_t kernel_launches = 0;      // kernels of this library launched since fr_create
 	// external interop
-	cudaExternalMemory_t ext_mem = nullptr;
+	cudaExternalMemory_t ext_mem = nullptr, ext_mem_pos = nullptr, ext_mem_nrm = nullptr;
 	cudaExternalSemaphore_t ext_wait = nullptr, ext_signal = nullptr;
 };
 

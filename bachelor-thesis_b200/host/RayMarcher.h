@@ -89,6 +89,15 @@ public:
 	void SetSkipLastPixel(bool on) { m_SkipLastPixel = on; }           // ThreadPool.cpp:50 leaves pixel W*H-1 untouched
 	fr_context* Context() { return m_Ctx; }
 
+	// interop call (host/engine.patch): no host buffers at all -- Output::DeviceOnly with the GPU depth pre-pass
+	struct Float4 { float x, y, z, w; };
+	template <class Controller, class DatasetT>
+	void Prepare(const VisualizationSettings& settings, const Controller& camera, DatasetT* dataset, std::nullptr_t, std::nullptr_t,
+				 std::nullptr_t)
+	{
+		Prepare(settings, camera, dataset, static_cast<Float4*>(nullptr), static_cast<Float4*>(nullptr), static_cast<float*>(nullptr));
+	}
+
 	// RayMarcher::Prepare (RayMarcher.cpp:76-100).  Controller = CameraController3D, DatasetT = Dataset,
 	// Vec4 = glm::vec4 (any 16-byte POD of four floats).
 	template <class Controller, class DatasetT, class Vec4>

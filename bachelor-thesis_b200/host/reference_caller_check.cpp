@@ -46,3 +46,50 @@ struct CallerLikeAdvancedRenderer
 };
 
 void instantiate(CallerLikeAdvancedRenderer& r) { r.Render(); r.Exit(); }
+
+// the call block as host/engine.patch leaves it (no host round trip): the members engine.patch adds to BilateralBuffer are
+// stood in for by this stub -- no Vulkan headers exist in this image, so the Vulkan side of the patch is not compiled
+struct ExportableBufferStub
+{
+	bool Exportable = false;
+	size_t AllocationSize = 0;
+	int ExportFd() { return -1; }
+	void CopyToGPU() {}
+};
+
+struct PatchedAdvancedRenderer
+{
+	Camera3D Camera;
+	CameraController3D CameraController{ Camera };
+	::Dataset* Dataset = nullptr;
+	RayMarcher m_RayMarcher;
+	ExportableBufferStub PositionsBuffer, NormalsBuffer;
+	bool RayMarchFinished = true;
+
+	void Init()
+	{
+		PositionsBuffer.Exportable = true;
+		NormalsBuffer.Exportable = true;
+		m_RayMarcher.SetOutput(RayMarcher::Output::DeviceOnly);
+		m_RayMarcher.SetUseGpuDepthPrePass(true);
+		m_RayMarcher.Prepare(g_VisualizationSettings, CameraController, Dataset, nullptr, nullptr, nullptr);
+		if (fr_import_vk_images_fd(m_RayMarcher.Context(), PositionsBuffer.ExportFd(), NormalsBuffer.ExportFd(),
+								   PositionsBuffer.AllocationSize) != FR_OK)
+			SPDLOG_ERROR("fluidmarch: {}", fr_last_error());
+	}
+
+	void Render()
+	{
+		if (RayMarchFinished)
+		{
+			RayMarchFinished = false;
+			m_RayMarcher.Prepare(g_VisualizationSettings, CameraController, Dataset, nullptr, nullptr, nullptr);
+			m_RayMarcher.Start();
+		}
+		if (!RayMarchFinished && m_RayMarcher.IsDone()) RayMarchFinished = true;
+		PositionsBuffer.CopyToGPU();
+		NormalsBuffer.CopyToGPU();
+	}
+};
+
+void instantiate_patched(PatchedAdvancedRenderer& r) { r.Init(); r.Render(); }

@@ -449,6 +449,70 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
                           "the image is complete"})
     return rec
 
+
+def aniso_subrecord(fm, ctx, torch, stream, flush, xyz, d_ptr, npart, h, W, H, args, cam, settings, sm_mhz, steps=6):
+    """the reference's DEFAULT path (EnableAnisotropy = true, AdvancedRenderer.cpp:23): PerPixel_Anisotropic
+    (RayMarcher.cpp:346-423) on the same frame -- one frame at a time, per-stage device times, parity against the
+    reference's own TUs, its CPU time beside it"""
+    ctx.set_settings(fm.VisualizationSettings(EnableAnisotropy=True))
+    log = []
+    for k in range(steps + 2):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        ctx.build_frame_device(0, d_ptr, npart, h, 2.0)
+        ctx.render_async(fm.FR_PASS_ALL)
+        with torch.cuda.stream(stream):
+            e1.record(stream)
+        ctx.wait()
+        torch.cuda.synchronize()
+        if k >= 2:
+            t = ctx.timings()
+            t["frame_ms"] = e0.elapsed_time(e1)
+            log.append(t)
+    tim = {k: float(np.mean([t[k] for t in log])) for k in log[0]}
+    cnt = ctx.counters()
+    rec = {"workload": workload_string(args.config, npart, W, H).replace("isotropic", "anisotropic (k_n 0.5, k_r 2, k_s 2000, N_eps 1)"),
+           "ms_per_frame": tim["frame_ms"], "value": W * H / (tim["frame_ms"] * 1e-3), "unit": UNIT,
+           "stage_ms": {k: tim[k] for k in ("grid_ms", "depth_ms", "classify_ms", "march_first_ms", "march_long_ms")},
+           "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates", "neighbours", "queued_rays")}}
+    ncu = load_ncu_stats(args.config, "k_march_long_aniso")
+    if ncu.get("warp_instructions"):
+        ipeak = 148 * 4 * sm_mhz * 1e6 / 1e9
+        iach = ncu["warp_instructions"] / (tim["march_long_ms"] * 1e-3) / 1e9
+        rec["roofline"] = {"bound": "issue", "kernel": "k_march_long<ANISO>", "achieved": iach, "peak": ipeak, "unit": "Ginst/s", "frac": iach / ipeak,
+                           "traffic": ncu.get("dram_bytes"), "warp_instructions_per_launch": ncu["warp_instructions"],
+                           "warp_instructions_source": f"profiles/{ncu.get('source', 'ncu_stats.json')}"}
+    if not args.no_cpu_baseline:
+        oracle_lib = checker()
+        g_depth, g_pos, g_nrm, _ = ctx.download()
+        s = oracle_lib.Settings(anisotropic=1)
+        t0 = time.perf_counter()
+        if oracle_lib.ref_available():
+            ref = oracle_lib.Ref()
+            ds = ref.dataset(xyz, h, 2.0)
+            t1 = time.perf_counter()
+            pos, nrm, march_s = ds.march(W, H, s, cam["inv_proj_view"], cam["position"], g_depth, threads=ref.lib.ref_hardware_threads())
+            ds.close()
+            kind, cores = "reference", ref.lib.ref_hardware_threads()
+        else:
+            orc = oracle_lib.Oracle()
+            f = orc.frame(xyz, h, 2.0)
+            t1 = time.perf_counter()
+            pos, nrm, *_ = f.march(W, H, s, cam["inv_proj_view"], cam["position"], g_depth, want_band=False)
+            march_s = time.perf_counter() - t1
+            kind, cores = "port", orc.lib.fo_get_threads()
+        total = time.perf_counter() - t0
+        u = lambda a: np.ascontiguousarray(a, np.float32).view(np.uint32)
+        diff = (u(g_pos) != u(pos)).any(-1) | (u(g_nrm) != u(nrm)).any(-1)
+        rec["cpu_baseline"] = {"value": W * H / total, "unit": UNIT, "cores": cores, "kind": kind,
+                               "sample": f"one full frame: Frame::Frame build {1e3 * (t1 - t0):.0f} ms + PerPixel_Anisotropic march {1e3 * march_s:.0f} ms"}
+        rec["parity_checked"] = True
+        rec["pixels_differing"] = int(diff.sum())
+    ctx.set_settings(settings)
+    return rec
+
 # ---------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch
@@ -758,6 +822,10 @@ def run_b200(args):
                       "parity_against": f"{kind}: hit mask, positions and normals bit for bit ({'oracle/_ref = the reference TUs' if kind == 'reference' else 'oracle C port'}); "
                                         "depth image against the oracle's restatement of depth.vert/frag",
                       "image_sha256_16": image_digest(g_pos, g_nrm)}
+        aniso = None
+        if world == 1 and not args.no_aniso and not tiles_mode:
+            aniso = aniso_subrecord(fm, ctx, torch, stream, flush, frames[0], d_frames[0].data_ptr(), n_actual[0], h, W, H, args, cam, settings,
+                                    (clocks or {}).get("sm_mhz") or 1965.0)
         if tiles_mode:
             par = (f"tile-parallel {args.tile}x{args.tile} interleaved, every rank's shading epilogue stores its tiles into the presenting GPU's image "
                    "over NVLink peer memory (CUDA IPC), barrier" if peer_mode else f"tile-parallel {args.tile}x{args.tile} interleaved + NCCL gather")
@@ -802,6 +870,7 @@ def run_b200(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "tiles": tiles_rec,
+            "aniso": aniso,
         }
         print(json.dumps(out), flush=True)
     ctx.close()
@@ -824,6 +893,7 @@ def main():
                     help="--mode tiles: peer = ranks render into the presenter's image over NVLink peer memory; nccl = gather collective")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-tiles", action="store_true", help="skip the C3 tile-parallel sub-record")
+    ap.add_argument("--no-aniso", action="store_true", help="skip the anisotropic (reference default path) sub-record")
     ap.add_argument("--fast-normals", action="store_true", help="fr_settings.fast_normals (default: normals bit-exact)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

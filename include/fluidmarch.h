@@ -253,6 +253,10 @@ int fr_measure_l2_bandwidth(fr_context* ctx, size_t bytes, uint32_t reps, float*
 /* imports VkDeviceMemory exported with VK_KHR_external_memory_fd (opaque fd, linear W*H*4-byte
  * image or buffer at `offset`) and makes it the colour target */
 int fr_import_vk_memory_fd(fr_context* ctx, int fd, size_t allocation_bytes, size_t offset);
+/* the same for the two RGBA32F images the reference's composition pass samples (AdvancedRenderer.cpp:303-304,
+ * PositionsBuffer / NormalsBuffer): two exported linear W*H*16-byte buffers become the march's position and normal
+ * targets, so that BilateralBuffer::CopyToGPU is a device-local buffer -> image copy instead of a PCIe upload */
+int fr_import_vk_images_fd(fr_context* ctx, int positions_fd, int normals_fd, size_t allocation_bytes);
 /* VK_KHR_external_semaphore_fd binary semaphores: the render waits on `wait_fd` (image available)
  * before writing and signals `signal_fd` when the image is complete; -1 = none */
 int fr_import_vk_semaphores_fd(fr_context* ctx, int wait_fd, int signal_fd);

@@ -86,3 +86,18 @@ def test_cpp_shim_is_source_compatible_with_the_reference_caller():
     host = os.path.join(ROOT, "bachelor-thesis_b200", "host")
     r = subprocess.run(["make", "-C", host, "check-reference-caller"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_engine_patch_applies_to_the_reference_tree():
+    """host/engine.patch (device extensions, exportable BilateralBuffer staging memory, the
+    AdvancedRenderer call sites without host round trip) is a real patch: it applies cleanly to the reference tree"""
+    import shutil
+    import subprocess
+    ref = "/root/reference"
+    if not os.path.isdir(ref) or shutil.which("patch") is None:
+        pytest.skip("needs /root/reference and patch(1)")
+    patch = os.path.join(ROOT, "bachelor-thesis_b200", "host", "engine.patch")
+    r = subprocess.run(["patch", "-p1", "--dry-run", "-d", ref, "-i", patch], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for f in ("RendererInit.cpp", "BilateralBuffer.cpp", "BilateralBuffer.h", "AdvancedRenderer.cpp"):
+        assert f in r.stdout
