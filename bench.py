@@ -314,17 +314,13 @@ def host_ceiling(torch, dist, dev, world, h2d_bytes, d2h_bytes, reps=40):
                     "memory, two streams, max over ranks; the e2e arm cannot be faster than this per frame"}
 
 
-def balanced_strips(xyz, cam, W, world):
-    """vertical strips [x0, x1) with bounds at multiples of 64 pixels that hold about the same number of projected
-    particles each (covered area and march work follow the particle count for this scene)"""
-    v = np.asarray(cam["view"], np.float64).reshape(4, 4).T          # column-major -> row-major maths
-    p = np.asarray(cam["proj"], np.float64).reshape(4, 4).T
-    pts = np.concatenate([xyz.astype(np.float64), np.ones((len(xyz), 1))], axis=1)
-    clip = pts @ (p @ v).T
-    px = (clip[:, 0] / clip[:, 3] + 1.0) * (W / 2.0)
+def balanced_strips(weights, W, world):
+    """vertical strips [x0, x1) with bounds at multiples of 64 pixels and about equal cost: `weights` = covered pixels per
+    64-pixel column block of the frame (from the previous render of the sequence -- here the one-GPU render of the same
+    frame)"""
     nb = (W + 63) // 64
-    hist = np.bincount(np.clip((px // 64).astype(np.int64), 0, nb - 1), minlength=nb).astype(np.float64)
-    cum = np.concatenate([[0.0], np.cumsum(hist)])
+    w = np.asarray(weights, np.float64)[:nb]
+    cum = np.concatenate([[0.0], np.cumsum(w)])
     bounds = [0]
     for k in range(1, world):
         target = cum[-1] * k / world
@@ -395,7 +391,8 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
     if world == 1:
         ctx.close()
         return rec
-    want = ctx.download(False, False, False, True)[3].copy() if rank == 0 else None
+    full_depth, _, _, full_rgba = ctx.download(True, False, False, True)
+    want = full_rgba.copy() if rank == 0 else None
     handle = [ctx.ipc_export_color() if rank == 0 else None]
     dist.broadcast_object_list(handle, src=0)
     if rank != 0:
@@ -417,7 +414,9 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
         return same, differing
 
     # (1) regions: vertical strips balanced by particle count, filtered frame builds
-    strips = balanced_strips(xyz, cam, W, world)
+    covered_cols = (full_depth != 1.0).sum(axis=0).astype(np.float64)
+    pad = (-len(covered_cols)) % 64
+    strips = balanced_strips(np.pad(covered_cols, (0, pad)).reshape(-1, 64).sum(axis=1), W, world)
     x0, x1 = strips[rank]
     ctx.set_region_partition(x0, 0, x1, H)
     poison()
@@ -438,7 +437,7 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
                 "efficiency_vs_one_gpu": one_ms / (world * n_ms), "speedup_vs_one_gpu": one_ms / n_ms,
                 "bit_identical": same, "pixels_differing": differing,
                 "partition": "regions", "strips_px": strips, "ms_per_rank": per_rank,
-                "parallelism": "region-parallel: vertical strips (bounds at multiples of 64 px, balanced by projected particle count); each rank "
+                "parallelism": "region-parallel: vertical strips (bounds at multiples of 64 px, balanced by the covered pixels of the previous render); each rank "
                                "builds its frame from the particles within 3.6 h of its strip's frustum (fr_set_region_partition) and its march "
                                "epilogue stores the pixels into the presenting GPU's image over NVLink peer memory (fr_ipc_*), no gather",
                 "interleaved_tiles": {"tile": tile, "ms_per_frame": t_ms, "ms_per_frame_wall_with_barrier": t_wall,
