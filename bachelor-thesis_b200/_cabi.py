@@ -63,7 +63,8 @@ class FrSeqJob(C.Structure):
     _fields_ = [("xyz", C.c_void_p), ("n", C.c_uint64), ("h", C.c_float), ("h_ext_mult", C.c_float),
                 ("xyz_on_device", C.c_int32), ("passes", C.c_int32),
                 ("depth", C.c_void_p), ("positions", C.c_void_p), ("normals", C.c_void_p), ("rgba", C.c_void_p),
-                ("bgeo_path", C.c_char_p), ("bmp_path", C.c_char_p)]
+                ("bgeo_path", C.c_char_p), ("bmp_path", C.c_char_p),
+                ("rgba_device", C.c_void_p), ("done_flag_device", C.c_void_p), ("done_value", C.c_uint32)]
 
 
 class FrBgeoInfo(C.Structure):
@@ -101,6 +102,11 @@ SYMBOLS = [
     ("fr_ipc_export_color", C.c_int, [C.c_void_p, C.c_void_p]),
     ("fr_ipc_open_color_target", C.c_int, [C.c_void_p, C.c_void_p]),
     ("fr_ipc_close_color_target", C.c_int, [C.c_void_p]),
+    ("fr_device_alloc", C.c_int, [C.c_int, C.c_size_t, vpp]),
+    ("fr_device_free", C.c_int, [C.c_int, C.c_void_p]),
+    ("fr_ipc_export_buffer", C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    ("fr_ipc_open_buffer", C.c_int, [C.c_int, C.c_void_p, vpp]),
+    ("fr_ipc_close_buffer", C.c_int, [C.c_int, C.c_void_p]),
     ("fr_get_counters", C.c_int, [C.c_void_p, C.POINTER(FrCounters)]),
     ("fr_get_timings", C.c_int, [C.c_void_p, C.POINTER(FrTimings)]),
     ("fr_get_stream", C.c_int, [C.c_void_p, vpp]),

@@ -437,16 +437,33 @@ int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_pa
 }
 
 // the rest of the frame -- march, copies out -- is launches only: a lane captures it into its CUDA graph
+// (stream-ordered store of a frame's completion flag; the flag may live in another GPU's memory)
+__global__ void k_signal(uint32_t* flag, uint32_t value)
+{
+	__threadfence_system();
+	*reinterpret_cast<volatile uint32_t*>(flag) = value;
+}
+
 int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job)
 {
 	int rc;
-	if ((rc = render_march(ctx, job.passes ? job.passes : FR_PASS_ALL))) return rc;
+	uchar4* const own_target = ctx->d_rgba_target;
+	if (job.rgba_device) ctx->d_rgba_target = (uchar4*)job.rgba_device;         // this frame only
+	rc = render_march(ctx, job.passes ? job.passes : FR_PASS_ALL);
 	cudaStream_t const s = ctx->stream;
+	if (rc == FR_OK && job.done_flag_device)
+	{
+		k_signal<<<1, 1, 0, s>>>(job.done_flag_device, job.done_value);
+		ctx->kernel_launches += 1;
+		if (cudaGetLastError() != cudaSuccess) rc = FR_ERR_CUDA;
+	}
+	if (rc) { ctx->d_rgba_target = own_target; return rc; }
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	if (job.depth) FM_CUDA(cudaMemcpyAsync(job.depth, ctx->d_depth, npix * 4, cudaMemcpyDeviceToHost, s));
 	if (job.positions) FM_CUDA(cudaMemcpyAsync(job.positions, ctx->d_pos, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (job.normals) FM_CUDA(cudaMemcpyAsync(job.normals, ctx->d_nrm, npix * 16, cudaMemcpyDeviceToHost, s));
 	if (job.rgba) FM_CUDA(cudaMemcpyAsync(job.rgba, ctx->d_rgba_target, npix * 4, cudaMemcpyDeviceToHost, s));
+	ctx->d_rgba_target = own_target;
 	return FR_OK;
 }
 
@@ -813,6 +830,50 @@ int fr_ipc_close_color_target(fr_context* ctx)
 		ctx->peer_rgba = nullptr;
 		ctx->d_rgba_target = ctx->d_rgba;
 	}
+	return FR_OK;
+}
+
+int fr_device_alloc(int device, size_t bytes, void** out)
+{
+	if (!out || bytes == 0) { set_error("fr_device_alloc: bad arguments"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaSetDevice(device));
+	FM_CUDA(cudaMalloc(out, bytes));
+	FM_CUDA(cudaMemset(*out, 0, bytes));
+	return FR_OK;
+}
+
+int fr_device_free(int device, void* p)
+{
+	FM_CUDA(cudaSetDevice(device));
+	if (p) FM_CUDA(cudaFree(p));
+	return FR_OK;
+}
+
+int fr_ipc_export_buffer(int device, void* device_ptr, fr_ipc_handle* out)
+{
+	if (!device_ptr || !out) { set_error("fr_ipc_export_buffer: null argument"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaSetDevice(device));
+	cudaIpcMemHandle_t h;
+	FM_CUDA(cudaIpcGetMemHandle(&h, device_ptr));
+	memset(out, 0, sizeof *out);
+	memcpy(out->bytes, &h, sizeof h);
+	return FR_OK;
+}
+
+int fr_ipc_open_buffer(int device, const fr_ipc_handle* handle, void** out)
+{
+	if (!handle || !out) { set_error("fr_ipc_open_buffer: null argument"); return FR_ERR_INVALID; }
+	FM_CUDA(cudaSetDevice(device));
+	cudaIpcMemHandle_t h;
+	memcpy(&h, handle->bytes, sizeof h);
+	FM_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+	return FR_OK;
+}
+
+int fr_ipc_close_buffer(int device, void* p)
+{
+	FM_CUDA(cudaSetDevice(device));
+	if (p) FM_CUDA(cudaIpcCloseMemHandle(p));
 	return FR_OK;
 }
 

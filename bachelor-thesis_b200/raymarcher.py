@@ -300,6 +300,39 @@ class Context:
         return int(bad.value)
 
 
+class DeviceBuffer:
+    """a plain device allocation that other processes of the box can map (fr_device_alloc / fr_ipc_*): frame rings and
+    completion flags on the presenting GPU of a frame-parallel run"""
+
+    def __init__(self, nbytes: int = 0, device: int = 0, handle: bytes | None = None):
+        self.lib = abi.load()
+        self.device = device
+        self.owner = handle is None
+        p = C.c_void_p()
+        if self.owner:
+            check(self.lib.fr_device_alloc(device, nbytes, C.byref(p)), "fr_device_alloc")
+        else:
+            buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+            check(self.lib.fr_ipc_open_buffer(device, buf, C.byref(p)), "fr_ipc_open_buffer")
+        self.ptr = p.value
+        self.nbytes = nbytes
+
+    def export(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        check(self.lib.fr_ipc_export_buffer(self.device, C.c_void_p(self.ptr), buf), "fr_ipc_export_buffer")
+        return bytes(buf)
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            if self.owner:
+                self.lib.fr_device_free(self.device, C.c_void_p(self.ptr))
+            else:
+                self.lib.fr_ipc_close_buffer(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    __del__ = close
+
+
 def bgeo_probe(path: str) -> dict:
     """header of a classic .bgeo file (fr_bgeo_probe)"""
     info = abi.FrBgeoInfo()
@@ -379,10 +412,11 @@ class Sequence:
 
     def submit_ptrs(self, xyz_ptr: int, n: int, h: float = 0.1, h_ext_mult: float = 2.0, on_device: bool = False,
                     passes: int = FR_PASS_ALL, depth: int = 0, positions: int = 0, normals: int = 0, rgba: int = 0,
-                    bgeo_path: str | None = None, bmp_path: str | None = None) -> int:
+                    bgeo_path: str | None = None, bmp_path: str | None = None, rgba_device: int = 0,
+                    done_flag_device: int = 0, done_value: int = 0) -> int:
         job = abi.FrSeqJob(xyz_ptr or None, n, h, h_ext_mult, 1 if on_device else 0, passes, depth or None, positions or None,
                            normals or None, rgba or None, os.fsencode(bgeo_path) if bgeo_path else None,
-                           os.fsencode(bmp_path) if bmp_path else None)
+                           os.fsencode(bmp_path) if bmp_path else None, rgba_device or None, done_flag_device or None, done_value)
         t = self.lib.fr_seq_submit(self.h, C.byref(job))
         if t < 0:
             check(int(t), "fr_seq_submit")

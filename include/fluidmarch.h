@@ -214,6 +214,13 @@ typedef struct fr_ipc_handle { unsigned char bytes[64]; } fr_ipc_handle;
 int fr_ipc_export_color(fr_context* ctx, fr_ipc_handle* out);
 int fr_ipc_open_color_target(fr_context* ctx, const fr_ipc_handle* handle);
 int fr_ipc_close_color_target(fr_context* ctx);      /* back to the internal image */
+/* generic form of the above for frame rings and flags: plain device allocations (cudaMalloc, hence exportable), their
+ * 64-byte handles for the other processes of the box, and the mapping of such a handle into this process */
+int fr_device_alloc(int device, size_t bytes, void** out);
+int fr_device_free(int device, void* p);
+int fr_ipc_export_buffer(int device, void* device_ptr, fr_ipc_handle* out);
+int fr_ipc_open_buffer(int device, const fr_ipc_handle* handle, void** out);
+int fr_ipc_close_buffer(int device, void* p);
 int fr_get_counters(fr_context* ctx, fr_counters* out);
 int fr_get_timings(fr_context* ctx, fr_timings* out);
 /* the CUDA stream all work of this context is ordered on (a cudaStream_t) */
@@ -312,6 +319,13 @@ typedef struct fr_seq_job
 	const char* bgeo_path;       /* non-NULL: the frame is this particle file (fr_upload_frame_bgeo on the lane's worker:
 	                                files of different lanes are read and decoded in parallel); xyz / n are ignored */
 	const char* bmp_path;        /* non-NULL: the finished frame is also written there as fr_write_bmp does (recording) */
+	/* frame-parallel presentation (multi-GPU): the finished colour image of THIS frame goes straight into
+	 * device memory of the caller's choice -- typically a slot of a frame ring on the presenting GPU, opened with
+	 * fr_ipc_open_buffer: the shading epilogue's stores travel over NVLink, no gather, no host copy -- and, behind it
+	 * on the lane's stream, done_value is stored to *done_flag_device (same kind of memory; NULL = no flag) */
+	void* rgba_device;
+	uint32_t* done_flag_device;
+	uint32_t done_value;
 } fr_seq_job;
 
 int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** out);

@@ -111,3 +111,45 @@ def test_sequence_reports_job_errors(fm):
         assert out["rgba"].any()
     finally:
         seq.close()
+
+
+def test_frames_land_in_a_device_ring_with_completion_flags(fm):
+    """frame-parallel presentation path: every frame's colour image goes into the slot of a device ring its job names
+    (on a multi-GPU box: the presenting GPU's memory, opened through fr_ipc_*), and a flag is stored behind it"""
+    import torch
+    cam = golden_camera("camera_close_16x9")
+    fs = frames(fm, 6)
+    slots = 3
+    ring = fm.DeviceBuffer(slots * W * H * 4)
+    flags = fm.DeviceBuffer(256)
+    # the mapping another process of the box would use (here: this process opens its own export, which CUDA refuses for
+    # the exporting process itself -- so only the export call is exercised and the ring is addressed directly)
+    assert len(ring.export()) == 64
+    seq = fm.Sequence(W, H, lanes=2)
+    try:
+        setup(seq, cam, fm)
+        outs = []
+        for k, xyz in enumerate(fs):
+            xyz = np.ascontiguousarray(xyz, np.float32)
+            host = np.zeros((H, W, 4), np.uint8)
+            t = seq.submit_ptrs(xyz.ctypes.data, len(xyz), 0.1, 2.0, rgba=host.ctypes.data,
+                                rgba_device=ring.ptr + (k % slots) * W * H * 4,
+                                done_flag_device=flags.ptr + 4 * (k % slots), done_value=k + 1)
+            outs.append((t, xyz, host))
+            if k >= slots - 1:
+                seq.wait(outs[k - (slots - 1)][0])        # a slot is reused only after its previous frame is done
+        seq.drain()
+
+        class Ptr:
+            def __init__(self, p, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (p, False), "version": 2}
+        got_ring = torch.as_tensor(Ptr(ring.ptr, slots * W * H * 4), device="cuda").cpu().numpy().reshape(slots, H, W, 4)
+        got_flags = torch.as_tensor(Ptr(flags.ptr, 4 * slots), device="cuda").cpu().numpy().view(np.uint32)
+        for k in range(len(fs) - slots, len(fs)):
+            assert np.array_equal(got_ring[k % slots], outs[k][2]), k      # the host copy of the same frame
+            assert outs[k][2].any()
+            assert got_flags[k % slots] == k + 1
+    finally:
+        seq.close()
+        ring.close()
+        flags.close()
