@@ -416,9 +416,24 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
     # (1) regions: vertical strips balanced by particle count, filtered frame builds
     covered_cols = (full_depth != 1.0).sum(axis=0).astype(np.float64)
     pad = (-len(covered_cols)) % 64
-    strips = balanced_strips(np.pad(covered_cols, (0, pad)).reshape(-1, 64).sum(axis=1), W, world)
-    x0, x1 = strips[rank]
-    ctx.set_region_partition(x0, 0, x1, H)
+    weights = np.pad(covered_cols, (0, pad)).reshape(-1, 64).sum(axis=1) + 1.0
+    # feedback balancing, as a sequence renderer does from frame to frame: start from the covered pixels per 64-pixel
+    # column block, then rescale every strip's blocks by its rank's measured time and split again
+    balance_log = []
+    for it in range(4):
+        strips = balanced_strips(weights, W, world)
+        x0, x1 = strips[rank]
+        ctx.set_region_partition(x0, 0, x1, H)
+        dist.barrier()
+        _, _, my_try = timed(step, 3)
+        tries = [None] * world
+        dist.all_gather_object(tries, float(my_try))
+        balance_log.append([round(t, 4) for t in tries])
+        if it == 3:
+            break
+        mean_t = sum(tries) / world
+        for k, (a, b) in enumerate(strips):
+            weights[a // 64:(b + 63) // 64] *= (tries[k] / mean_t) ** 1.5
     poison()
     n_ms, n_wall, my_ms = timed(step, steps)
     same, differing = check()
@@ -436,8 +451,8 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
     rec.update({"ms_per_frame": n_ms, "ms_per_frame_wall_with_barrier": n_wall, "scaling": "strong",
                 "efficiency_vs_one_gpu": one_ms / (world * n_ms), "speedup_vs_one_gpu": one_ms / n_ms,
                 "bit_identical": same, "pixels_differing": differing,
-                "partition": "regions", "strips_px": strips, "ms_per_rank": per_rank,
-                "parallelism": "region-parallel: vertical strips (bounds at multiples of 64 px, balanced by the covered pixels of the previous render); each rank "
+                "partition": "regions", "strips_px": strips, "ms_per_rank": per_rank, "balancing_trials_ms_per_rank": balance_log,
+                "parallelism": "region-parallel: vertical strips (bounds at multiples of 64 px, balanced by feedback: covered pixels of the previous render, rescaled by the ranks' measured times over three trial frames); each rank "
                                "builds its frame from the particles within 3.6 h of its strip's frustum (fr_set_region_partition) and its march "
                                "epilogue stores the pixels into the presenting GPU's image over NVLink peer memory (fr_ipc_*), no gather",
                 "interleaved_tiles": {"tile": tile, "ms_per_frame": t_ms, "ms_per_frame_wall_with_barrier": t_wall,
