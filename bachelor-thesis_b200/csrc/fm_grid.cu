@@ -55,9 +55,7 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 														  uint32_t* __restrict__ ticket,
 														  uint32_t* __restrict__ zero_a, uint32_t words_a,
 														  uint32_t* __restrict__ zero_b, uint32_t words_b,
-														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied,
-														  RegionFilter rf, uint32_t* __restrict__ kept, uint32_t* __restrict__ n_kept,
-														  uint32_t* __restrict__ n_kept_next)
+														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied)
 {
 	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
@@ -67,35 +65,13 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	bool bad = false;
 	for (uint32_t i = gtid; i < n; i += gsize)
 	{
-		float p[3];
 #pragma unroll
 		for (int a = 0; a < 3; a++)
 		{
 			float const v = __ldg(xyz + 3ull * i + a);
-			p[a] = v;
 			bad |= !isfinite(v);                // fminf / fmaxf would silently drop a NaN
 			mn[a] = fminf(mn[a], v);
 			mx[a] = fmaxf(mx[a], v);
-		}
-		if (rf.on)
-		{
-			// region partition: the indices of the particles this context's pixel rectangle needs (any order: the
-			// in-cell ranking by original index makes the sorted array deterministic).  A conservative test: the
-			// answer only decides whether the particle is carried along, never a pixel
-			float const rx = p[0] - rf.cam[0], ry = p[1] - rf.cam[1], rz = p[2] - rf.cam[2];
-			bool keep = true;
-#pragma unroll
-			for (int k = 0; k < 4; k++) keep = keep && (rf.plane[k][0] * rx + rf.plane[k][1] * ry + rf.plane[k][2] * rz <= rf.margin);
-			uint32_t const act = __activemask();
-			uint32_t const m = __ballot_sync(act, keep);
-			if (keep)
-			{
-				int const leader = __ffs(m) - 1, lane_id = threadIdx.x & 31;
-				uint32_t base = 0;
-				if (lane_id == leader) base = atomicAdd(n_kept, (uint32_t)__popc(m));
-				base = __shfl_sync(m, base, leader);
-				kept[base + (uint32_t)__popc(m & ((1u << lane_id) - 1u))] = i;
-			}
 		}
 	}
 #pragma unroll
@@ -171,7 +147,6 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	__syncthreads();
 	if (threadIdx.x != 0) return;
 	*ticket = 0u;                                    // ready for the next build
-	*n_kept_next = 0u;
 	*occupied = 0ull;
 	uint32_t status = 0;
 	for (int w = 0; w < kThreads / 32; w++) status |= s_bad[w] ? (uint32_t)FM_GRID_NONFINITE : 0u;
@@ -283,21 +258,26 @@ __device__ __forceinline__ uint32_t centre_box_mask(float p, float mn, int c, in
 // switch (fr_set_count_mode): FR_COUNT_CENTRE_BOX (default) = the half-open box of half-width r/2 around the query
 // point, which is what the reference build under oracle/_ref does; FR_COUNT_CELL_EXACT = the node
 // QueryDensityGrid(particle) returns.  The two differ only for particles within an ulp of a cell face.
+constexpr uint32_t kKeyExcluded = 0xffffffffu;        // a particle the region filter left out
+
 __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict__ xyz, uint32_t n, const GridParams* __restrict__ gp,
-														float half, int count_mode, const uint32_t* __restrict__ kept, const uint32_t* __restrict__ n_kept,
+														float half, int count_mode, RegionFilter rf,
 														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
 														uint32_t* __restrict__ grid_counts)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || gp->status) return;
-	uint32_t src = i;                    // region partition: thread i handles the i-th kept particle
-	if (kept)
-	{
-		if (i >= *n_kept) return;
-		src = kept[i];
-	}
 	BuildView const b = load_build_view(gp, half, count_mode);
-	float const x = __ldg(xyz + 3ull * src), y = __ldg(xyz + 3ull * src + 1), z = __ldg(xyz + 3ull * src + 2);
+	float const x = __ldg(xyz + 3ull * i), y = __ldg(xyz + 3ull * i + 1), z = __ldg(xyz + 3ull * i + 2);
+	if (rf.on)
+	{
+		// (a conservative test: the answer only decides whether the particle is carried along, never a pixel)
+		float const rx = x - rf.cam[0], ry = y - rf.cam[1], rz = z - rf.cam[2];
+		bool keep = true;
+#pragma unroll
+		for (int k = 0; k < 4; k++) keep = keep && (rf.plane[k][0] * rx + rf.plane[k][1] * ry + rf.plane[k][2] * rz <= rf.margin);
+		if (!keep) { keys[i] = kKeyExcluded; return; }
+	}
 	uint32_t const key = search_key(b, x, y, z);
 	keys[i] = key;
 	atomicAdd(cell_count + key, 1u);
@@ -460,17 +440,16 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_flags(GridParams* __restr
 // counting-sort scatter of the particle INDICES.  cursor[] holds the per-cell counts and is consumed (atomicSub), so
 // no second table is needed; the slot order inside a cell is arbitrary here and fixed by k_cell_order.
 __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const GridParams* __restrict__ gp,
-													  const uint32_t* __restrict__ kept, const uint32_t* __restrict__ n_kept,
 													  const uint32_t* __restrict__ keys,
 													  const uint32_t* __restrict__ cell_start,
 													  uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_index)
 {
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || gp->status) return;
-	if (kept && i >= *n_kept) return;
 	uint32_t const key = keys[i];
+	if (key == kKeyExcluded) return;
 	uint32_t const left = atomicSub(cursor + key, 1u);       // count .. 1
-	slot_index[cell_start[key] + (left - 1u)] = kept ? kept[i] : i;
+	slot_index[cell_start[key] + (left - 1u)] = i;
 }
 
 // one thread per particle slot: the final place of a particle inside its cell is its rank by original index
@@ -783,14 +762,8 @@ static int launch_aabb_params(Context* ctx, Frame* f, const float* d_xyz, uint32
 	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->d_grid_counts ? f->cap_grid : 0;
 	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
 	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
-	// region partition: two counters of kept particles in turn (this build's, and the next one's which the last block zeroes)
-	RegionFilter const rf = region_filter(ctx, h);
-	f->filtered = rf.on != 0;
-	ctx->kept_parity ^= 1;
-	uint32_t* const n_kept = ticket + 1 + ctx->kept_parity, * const n_kept_next = ticket + 1 + (ctx->kept_parity ^ 1);
-	if (rf.on) { int const rc = ensure_capacity(&ctx->d_kept, &ctx->cap_kept, (size_t)n32); if (rc) return rc; }
 	k_aabb_params<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
-												  f->d_gp, f->d_occupied, rf, ctx->d_kept, n_kept, n_kept_next);
+												  f->d_gp, f->d_occupied);
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
@@ -914,16 +887,15 @@ int build_frame_finish(Context* ctx)
 
 	uint32_t const pblocks = (n32 + kThreads - 1) / kThreads;
 	float const half = 0.5f * f->h;                   // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
-	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
-	const uint32_t* const kept = f->filtered ? ctx->d_kept : nullptr;
-	const uint32_t* const n_kept = ticket + 1 + ctx->kept_parity;
-	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, kept, n_kept, ctx->d_keys, d_cursor, f->d_grid_counts);
+	RegionFilter const rf = region_filter(ctx, f->h);
+	f->filtered = rf.on != 0;
+	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, rf, ctx->d_keys, d_cursor, f->d_grid_counts);
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter); occupancy flags
 	uint32_t const flag_blocks = (ctx->build.flag_cells + kScanThreads - 1) / kScanThreads;
 	uint32_t const scan_grid = std::max(ctx->build.scan_blocks, std::min(flag_blocks, (uint32_t)ctx->sm_count * 4u));
 	k_scan_flags<<<scan_grid, kScanThreads, 0, s>>>(f->d_gp, d_cursor, f->d_cell_start, tile_state, scan_ticket, f->d_grid_counts,
 													   spline_sig_d(f->h), f->d_occ_bits, f->d_occupied);
-	k_scatter<<<pblocks, kThreads, 0, s>>>(n32, f->d_gp, kept, n_kept, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx);
+	k_scatter<<<pblocks, kThreads, 0, s>>>(n32, f->d_gp, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx);
 	k_cell_order<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted);
 	ctx->kernel_launches += 4;
 	FM_CUDA(cudaGetLastError());

@@ -170,8 +170,6 @@ struct Context
 	uint32_t* d_keys = nullptr;       size_t cap_keys = 0;
 	float4* d_sort_tmp = nullptr;     size_t cap_sort_tmp = 0;     // r = h_ext search: counting sort output before the in-cell ordering
 	uint32_t* d_tmp_idx = nullptr;    size_t cap_tmp_idx = 0;      // counting sort output (particle indices) before the in-cell ordering
-	uint32_t* d_kept = nullptr;       size_t cap_kept = 0;         // region partition: indices of the particles the region needs
-	int kept_parity = 0;
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
 	float* d_aabb_partial = nullptr;  size_t cap_aabb_partial = 0;  // per-block extrema of k_aabb_params (+ its block ticket)
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
