@@ -491,7 +491,7 @@ def aniso_subrecord(fm, ctx, torch, stream, flush, xyz, d_ptr, npart, h, W, H, a
            "ms_per_frame": tim["frame_ms"], "value": W * H / (tim["frame_ms"] * 1e-3), "unit": UNIT,
            "stage_ms": {k: tim[k] for k in ("grid_ms", "depth_ms", "classify_ms", "march_first_ms", "march_long_ms")},
            "counters": {k: cnt[k] for k in ("covered_rays", "hit_rays", "ray_steps", "candidates", "neighbours", "queued_rays")}}
-    ncu = load_ncu_stats(args.config, "k_march_long_aniso")
+    ncu = load_ncu_stats(args.config + "_aniso", "k_march_long")
     if ncu.get("warp_instructions"):
         ipeak = 148 * 4 * sm_mhz * 1e6 / 1e9
         iach = ncu["warp_instructions"] / (tim["march_long_ms"] * 1e-3) / 1e9
