@@ -5,9 +5,9 @@ The directory name has a hyphen: import it with ``importlib.import_module("bache
 from . import _cabi, camera, scenes
 from ._cabi import (FR_COUNT_CELL_EXACT, FR_COUNT_CENTRE_BOX, FR_PASS_ALL, FR_PASS_DEPTH, FR_PASS_MARCH, FR_PASS_SHADE, FluidMarchError, LIB_PATH, load)
 from .camera import Camera3D, CameraController3D
-from .raymarcher import (Context, Dataset, DeviceBuffer, RayMarcher, Sequence, VisualizationSettings, bgeo_probe, bgeo_read, bgeo_write,
+from .raymarcher import (Context, Dataset, DeviceBuffer, RayMarcher, Sequence, VisualizationSettings, bgeo_probe, bgeo_read, bgeo_write, gauss_kernel,
                          dataset_count)
 
-__all__ = ["Camera3D", "CameraController3D", "Context", "Dataset", "DeviceBuffer", "RayMarcher", "Sequence", "VisualizationSettings", "bgeo_probe", "bgeo_read", "bgeo_write", "dataset_count",
+__all__ = ["Camera3D", "CameraController3D", "Context", "Dataset", "DeviceBuffer", "RayMarcher", "Sequence", "VisualizationSettings", "gauss_kernel", "bgeo_probe", "bgeo_read", "bgeo_write", "dataset_count",
            "FR_COUNT_CELL_EXACT", "FR_COUNT_CENTRE_BOX", "FR_PASS_ALL", "FR_PASS_DEPTH", "FR_PASS_MARCH", "FR_PASS_SHADE", "FluidMarchError", "LIB_PATH",
            "load", "scenes", "camera"]

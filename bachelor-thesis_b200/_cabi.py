@@ -127,6 +127,8 @@ SYMBOLS = [
     ("fr_upload_frame_bgeo", C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_float, C.c_float]),
     ("fr_encode_bmp", C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     ("fr_write_bmp", C.c_int, [C.c_void_p, C.c_char_p]),
+    ("fr_gauss_kernel", C.c_int, [C.c_int, f32p]),
+    ("fr_smooth_depth", C.c_int, [C.c_void_p, C.c_int, f32p, f32p, f32p]),
     ("fr_seq_create", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, vpp]),
     ("fr_seq_destroy", None, [C.c_void_p]),
     ("fr_seq_lanes", C.c_int, [C.c_void_p]),

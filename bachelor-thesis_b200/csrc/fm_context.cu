@@ -320,6 +320,7 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->d_rayq) cudaFree(ctx->d_rayq);
 	if (ctx->d_survivors) cudaFree(ctx->d_survivors);
 	if (ctx->d_tmp_idx) cudaFree(ctx->d_tmp_idx);
+	if (ctx->d_smooth) cudaFree(ctx->d_smooth);
 	if (ctx->d_counters) cudaFree(ctx->d_counters);
 	if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
 	if (ctx->ext_wait) cudaDestroyExternalSemaphore(ctx->ext_wait);

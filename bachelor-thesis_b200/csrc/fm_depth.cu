@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ dept
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < 4u) n_survivors[i] = 0u;             // survivor count (+ padding) of k_depth_cull
 	if (i < counter_words) counters[i] = 0u;     // DeviceCounters + work-list control words of the march that follows
-	if (i < npix) depth_bits[(size_t)(ry0 + i / rw) * W + rx0 + i % rw] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
+	if (i < npix) depth_bits[rw == W ? (size_t)i : (size_t)(ry0 + i / rw) * W + rx0 + i % rw] = 0x3f800000u;   // 1.0f: DepthRenderPass.cpp:54
 	if (i < ntiles) tile_bound[i] = 0x3f800000u;
 }
 

@@ -172,6 +172,7 @@ struct Context
 	uint32_t* d_tmp_idx = nullptr;    size_t cap_tmp_idx = 0;      // counting sort output (particle indices) before the in-cell ordering
 	uint32_t* d_scan_tmp = nullptr;   size_t cap_scan_tmp = 0;
 	float* d_aabb_partial = nullptr;  size_t cap_aabb_partial = 0;  // per-block extrema of k_aabb_params (+ its block ticket)
+	float* d_smooth = nullptr;        size_t cap_smooth = 0;       // fr_smooth_depth: smoothed depth, screen normals, kernel weights
 	uint32_t* d_tile_bound = nullptr; size_t cap_tile_bound = 0;   // depth pre-pass: per-tile upper bounds
 	float* d_splat = nullptr;         size_t cap_splat = 0;        // depth pre-pass: per-particle splat parameters
 	uint32_t* d_survivors = nullptr;  size_t cap_survivors = 0;    // depth pre-pass: [0] count, [4..] particle indices

@@ -288,6 +288,16 @@ class Context:
         return rho, grad
 
 
+    def smooth_depth(self, gauss_n: int = 8, inv_projection=None):
+        """GaussRenderPass on the context's depth image (GaussN = 8 by default, GaussRenderPass.h:41); with
+        inv_projection (Camera3D::InvProjection) also the Sobel screen normals of composition.frag:87-104"""
+        H, W = self.height, self.width
+        sm = np.empty((H, W), np.float32)
+        nrm = np.empty((H, W, 4), np.float32) if inv_projection is not None else None
+        ip = None if inv_projection is None else np.ascontiguousarray(inv_projection, np.float32).reshape(16)
+        check(self.lib.fr_smooth_depth(self.h, gauss_n, _ptr(ip, abi.f32p), _ptr(sm, abi.f32p), _ptr(nrm, abi.f32p)), "fr_smooth_depth")
+        return sm, nrm
+
     def measure_l2_bandwidth(self, mbytes: int = 32, reps: int = 40) -> float:
         """GB/s of read-only streaming over an L2-resident buffer (the roofline denominator of the march's gathers)"""
         g = C.c_float()
@@ -331,6 +341,13 @@ class DeviceBuffer:
             self.ptr = None
 
     __del__ = close
+
+
+def gauss_kernel(gauss_n: int = 8) -> np.ndarray:
+    """ComputeGaussKernel (reference GaussRenderPass.cpp:25-66): (N+1, N+1) weights, [i, j]"""
+    out = np.zeros((gauss_n + 1) * (gauss_n + 1), np.float32)
+    check(abi.load().fr_gauss_kernel(gauss_n, _ptr(out, abi.f32p)), "fr_gauss_kernel")
+    return out.reshape(gauss_n + 1, gauss_n + 1)
 
 
 def bgeo_probe(path: str) -> dict:

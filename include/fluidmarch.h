@@ -297,6 +297,16 @@ int fr_upload_frame_bgeo(fr_context* ctx, int frame, const char* path, float h, 
 int fr_encode_bmp(fr_context* ctx, uint8_t* out, size_t capacity, size_t* bytes);   /* out may be NULL: *bytes only */
 int fr_write_bmp(fr_context* ctx, const char* path);
 
+/* ---- screen-space smoothing: GaussRenderPass (src/app/AdvancedRenderer/GaussRenderPass.cpp:15-66, assets/shaders/advanced/
+ *      gauss.frag:28-47; runs every UI frame in the reference) and the Sobel normal of the unprojected smoothed depth
+ *      (composition.frag:50-57,87-104, fullscreen.vert:30-42; `#if 0` in the reference) -----------------------------------
+ * ComputeGaussKernel: (N+1)^2 weights, out[j + i*(N+1)], 0 <= N <= 31 */
+int fr_gauss_kernel(int gauss_n, float* out);
+/* the context's depth image (last FR_PASS_DEPTH or fr_set_depth) blurred with that kernel, Spread = 1, clamp-to-edge:
+ * W*H floats to smoothed_host; and, if screen_normals_host != NULL, normalize(cross(dx, dy)) of the Sobel differences of
+ * smoothedPosition() over the 8 neighbours, W*H*4 floats (w = 1); inv_projection = Camera3D::InvProjection (glm order) */
+int fr_smooth_depth(fr_context* ctx, int gauss_n, const float* inv_projection, float* smoothed_host, float* screen_normals_host);
+
 /* ---- frame sequences: the autoplay loop of AdvancedRenderer::Render (src/app/AdvancedRenderer/AdvancedRenderer.cpp:
  *      275-298: wait for the march, then Frame++) with `lanes` frames in flight on one GPU -------------------------------
  * One fr_context (own stream, images, scratch) and one host worker thread per lane; frame k is rendered on lane

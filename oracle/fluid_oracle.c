@@ -995,3 +995,79 @@ void fo_shade(int32_t W, int32_t H, const float* pos4, const float* nrm4,
 					v3_make(cam_dir[0], cam_dir[1], cam_dir[2]), color4, rgba8 };
 	parallel_for(H, 8, shade_body, &c);
 }
+
+/* ------------------------------------------------------------------------------------- */
+/* screen-space smoothing (f5): GaussRenderPass.cpp:15-66, gauss.frag:28-47,             */
+/* composition.frag:50-57,87-104, fullscreen.vert:30-42                                  */
+
+void fo_gauss_kernel(int32_t n, float* out)
+{
+	float const E = (float)2.7182818284590452353602874713527;      /* powf(E, ...) with E a double macro: float args */
+	float sum = 0.0f;
+	for (int32_t i = 0; i <= n; i++)
+		for (int32_t j = 0; j <= n; j++)
+		{
+			float const x = sqrtf((float)i * (float)i + (float)j * (float)j);
+			float const y = powf(E, -0.5f * x * x);
+			out[j + i * (n + 1)] = y;
+			if (i == 0 && j == 0) sum += y;
+			else if (i != 0 && j != 0) sum += 4.0f * y;
+			else sum += 2.0f * y;
+		}
+	for (int32_t i = 0; i <= n; i++)
+		for (int32_t j = 0; j <= n; j++) out[j + i * (n + 1)] /= sum;
+}
+
+static inline int32_t clampi(int32_t v, int32_t lo, int32_t hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+void fo_gauss_depth(int32_t W, int32_t H, const float* depth, int32_t n, float* smoothed)
+{
+	float* k = (float*)malloc(sizeof(float) * (size_t)(n + 1) * (size_t)(n + 1));
+	fo_gauss_kernel(n, k);
+	for (int32_t y = 0; y < H; y++)
+		for (int32_t x = 0; x < W; x++)
+		{
+			float sum = 0.0f;
+			for (int32_t i = -n; i <= n; i++)
+				for (int32_t j = -n; j <= n; j++)
+				{
+					int32_t const index = abs(i) * (n + 1) + abs(j);
+					float const t = k[index] * depth[(size_t)clampi(y + j, 0, H - 1) * W + clampi(x + i, 0, W - 1)];
+					sum = sum + t;
+				}
+			smoothed[(size_t)y * W + x] = sum;
+		}
+	free(k);
+}
+
+static v3 smoothed_position(int32_t W, int32_t H, const float* smoothed, const float* inv_proj, float u, float v)
+{
+	/* the texel a linear sampler returns at a texel centre: floor(uv * extent), clamp-to-edge */
+	int32_t const tx = clampi((int32_t)floorf(u * (float)W), 0, W - 1), ty = clampi((int32_t)floorf(v * (float)H), 0, H - 1);
+	float const clip[4] = { 2.0f * u - 1.0f, 2.0f * v - 1.0f, smoothed[(size_t)ty * W + tx], 1.0f };
+	float h[4];
+	mat4_mul_vec4(inv_proj, clip, h);
+	return v3_divs(v3_make(h[0], h[1], h[2]), h[3]);
+}
+
+void fo_sobel_normals(int32_t W, int32_t H, const float* smoothed, const float inv_proj[16], float* nrm4)
+{
+	float const tw = 1.0f / (float)W, th = 1.0f / (float)H;
+	for (int32_t y = 0; y < H; y++)
+		for (int32_t x = 0; x < W; x++)
+		{
+			float const u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;
+			v3 const tl = smoothed_position(W, H, smoothed, inv_proj, u - tw, v - th), tm = smoothed_position(W, H, smoothed, inv_proj, u, v - th),
+				tr = smoothed_position(W, H, smoothed, inv_proj, u + tw, v - th), ml = smoothed_position(W, H, smoothed, inv_proj, u - tw, v),
+				mr = smoothed_position(W, H, smoothed, inv_proj, u + tw, v), bl = smoothed_position(W, H, smoothed, inv_proj, u - tw, v + th),
+				bm = smoothed_position(W, H, smoothed, inv_proj, u, v + th), br = smoothed_position(W, H, smoothed, inv_proj, u + tw, v + th);
+			v3 const dx = v3_sub(v3_sub(v3_sub(v3_add(v3_add(v3_scale(tr, 1.0f), v3_scale(mr, 2.0f)), v3_scale(br, 1.0f)), v3_scale(tl, 1.0f)),
+										v3_scale(ml, 2.0f)), v3_scale(bl, 1.0f));
+			v3 const dy = v3_sub(v3_sub(v3_sub(v3_add(v3_add(v3_scale(bl, 1.0f), v3_scale(bm, 2.0f)), v3_scale(br, 1.0f)), v3_scale(tl, 1.0f)),
+										v3_scale(tm, 2.0f)), v3_scale(tr, 1.0f));
+			v3 const c = v3_make(dx.y * dy.z - dy.y * dx.z, dx.z * dy.x - dy.z * dx.x, dx.x * dy.y - dy.x * dx.y);      /* glm / GLSL cross */
+			v3 const nrm = v3_normalize(c);
+			float* o = nrm4 + 4 * ((size_t)y * W + x);
+			o[0] = nrm.x; o[1] = nrm.y; o[2] = nrm.z; o[3] = 1.0f;
+		}
+}

@@ -124,6 +124,17 @@ void fo_shade(int32_t W, int32_t H, const float* pos4, const float* nrm4,
 			  const float inv_proj_view[16], const float cam_pos[3], const float cam_dir[3],
 			  float* color4, uint8_t* rgba8);
 
+/* ---- screen-space smoothing (runs in the reference, its consumer in composition.frag is `#if 0`) --------
+ * GaussRenderPass.cpp:15-66: kernel[j + i*(N+1)] = e^(-r^2/2) / sum over the (2N+1)^2 taps, r = sqrt(i^2 + j^2).
+ * gauss.frag:28-47: SmoothedDepth = sum over i, j in [-N, N] (i outer, j inner) of kernel[|i|*(N+1) + |j|] *
+ * Depth(x + i, y + j), clamp-to-edge (BilateralBuffer.cpp:248-250), TexelWidth = Spread / W with Spread = 1: exact texels.
+ * composition.frag:50-57,87-104 + fullscreen.vert:30-42: smoothedPosition(uv) = unproject(InvProjection, 2uv - 1,
+ * SmoothedDepth(uv)); dx, dy = Sobel over the 8 neighbours (one texel away); screenNormal = normalize(cross(dx, dy)).
+ * FP32, one rounding per operation (GLSL may contract a*b+c: unpinned, like the rest of the GLSL restatements). */
+void fo_gauss_kernel(int32_t n, float* out);      /* (n+1)^2 floats */
+void fo_gauss_depth(int32_t W, int32_t H, const float* depth, int32_t n, float* smoothed);
+void fo_sobel_normals(int32_t W, int32_t H, const float* smoothed, const float inv_proj[16], float* nrm4);
+
 #ifdef __cplusplus
 }
 #endif

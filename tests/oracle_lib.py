@@ -90,6 +90,9 @@ class Oracle:
         L.fo_march.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(FoSettings), f32p, f32p, f32p,
                                f32p, f32p, f32p, u32p, C.POINTER(FoCounters), C.c_int]
         L.fo_shade.argtypes = [C.c_int32, C.c_int32, f32p, f32p, f32p, f32p, f32p, f32p, u8p]
+        L.fo_gauss_kernel.argtypes = [C.c_int32, f32p]
+        L.fo_gauss_depth.argtypes = [C.c_int32, C.c_int32, f32p, C.c_int32, f32p]
+        L.fo_sobel_normals.argtypes = [C.c_int32, C.c_int32, f32p, f32p, f32p]
         L.fo_set_threads.argtypes = [C.c_int]
         L.fo_set_count_mode.argtypes = [C.c_int]
         L.fo_get_threads.restype = C.c_int
@@ -176,6 +179,26 @@ class Oracle:
             return OracleFrame(self, xyz, h, mult)
         finally:
             self.lib.fo_set_count_mode(0)
+
+    # screen-space smoothing (f5)
+    def gauss_kernel(self, n):
+        out = np.zeros((n + 1) * (n + 1), np.float32)
+        self.lib.fo_gauss_kernel(n, _fp(out))
+        return out.reshape(n + 1, n + 1)
+
+    def gauss_depth(self, depth, n):
+        depth = _f32(depth)
+        H, W = depth.shape
+        out = np.zeros((H, W), np.float32)
+        self.lib.fo_gauss_depth(W, H, _fp(depth), n, _fp(out))
+        return out
+
+    def sobel_normals(self, smoothed, inv_proj):
+        smoothed, inv_proj = _f32(smoothed), _f32(inv_proj)
+        H, W = smoothed.shape
+        out = np.zeros((H, W, 4), np.float32)
+        self.lib.fo_sobel_normals(W, H, _fp(smoothed), _fp(inv_proj), _fp(out))
+        return out
 
     def shade(self, W, H, pos4, nrm4, ipv, cam_pos, cam_dir, want_color=True):
         pos4, nrm4, ipv, cam_pos, cam_dir = map(_f32, (pos4, nrm4, ipv, cam_pos, cam_dir))

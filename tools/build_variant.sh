@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 NAME=$1; EXTRA=$2; SRC=${3:-bachelor-thesis_b200/csrc}
 D=build_variants/$NAME; mkdir -p $D
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC $EXTRA"
-for f in fm_context fm_grid fm_depth fm_march fm_query fm_sequence fm_bgeo fm_record; do
+for f in fm_context fm_grid fm_depth fm_march fm_query fm_sequence fm_bgeo fm_record fm_smooth; do
   /usr/local/cuda/bin/nvcc $FLAGS -c $SRC/$f.cu -o $D/$f.o &
 done
 /usr/local/cuda/bin/nvcc $FLAGS -fmad=false -DFM_NO_FMAD -c $SRC/fm_aniso.cu -o $D/fm_aniso.o &
