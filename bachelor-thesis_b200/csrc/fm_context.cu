@@ -250,8 +250,6 @@ int fr_create(int device, int width, int height, fr_context** out)
 		if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
-		if (cudaEventCreateWithFlags(&c->ev_k1, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
-		if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaHostAlloc((void**)&c->h_sync_flag, 64, cudaHostAllocMapped) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		*c->h_sync_flag = 0u;
 		if (cudaHostGetDevicePointer((void**)&c->d_sync_flag, (void*)c->h_sync_flag, 0) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
@@ -331,8 +329,6 @@ void fr_destroy(fr_context* ctx)
 	for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
 	if (ctx->ev_done) cudaEventDestroy(ctx->ev_done);
 	if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
-	if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
-	if (ctx->side_stream) { cudaStreamSynchronize(ctx->side_stream); cudaStreamDestroy(ctx->side_stream); }
 	if (ctx->h_sync_flag) cudaFreeHost((void*)ctx->h_sync_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);
 	delete ctx;
@@ -398,43 +394,65 @@ int fr_set_async_build(fr_context* ctx, int on)
 namespace fm
 {
 
-int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path)
+// A lane's frame in three steps.  (1) lane_frame_begin: whatever needs the host -- a particle file is read and staged;
+// decides whether the rest can be queued without a wait.  (2) lane_frame_stage_a: upload, frame build, depth pre-pass --
+// (the upload goes first, by itself) launches only when the build does not wait (every frame of a lane but its
+// first), so the lane captures it into a CUDA graph: one stream operation.  Then lane_frame_resolve picks the grid parameters up from mapped memory (no stream
+// operation at all).  (3) lane_frame_enqueue: march and copies out, the lane's second graph.
+int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path, bool* stage_a_is_launches_only)
 {
 	FM_CUDA(cudaSetDevice(ctx->device));
 	Frame* f;
 	int rc = frame_slot(ctx, 0, &f);
 	if (rc) return rc;
 	if ((rc = finish_pending(ctx))) return rc;
-	const float* d_xyz = nullptr;
-	size_t n = (size_t)job.n;
+	ctx->lane_d_xyz = nullptr;
+	ctx->lane_n = (size_t)job.n;
+	ctx->lane_h2d = false;
 	if (bgeo_path)
 	{
-		if ((rc = stage_bgeo(ctx, bgeo_path, &n))) return rc;
-		d_xyz = ctx->d_xyz;
+		if ((rc = stage_bgeo(ctx, bgeo_path, &ctx->lane_n))) return rc;
+		ctx->lane_d_xyz = ctx->d_xyz;
 	}
-	else if (job.xyz_on_device) d_xyz = job.xyz;
+	else if (job.xyz_on_device) ctx->lane_d_xyz = job.xyz;
 	else
 	{
-		if (!job.xyz || n == 0) { set_error("sequence job without particles"); return FR_ERR_INVALID; }
-		if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, n * 3))) return rc;
-		FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, job.xyz, n * 12, cudaMemcpyHostToDevice, ctx->stream));
-		d_xyz = ctx->d_xyz;
+		if (!job.xyz || ctx->lane_n == 0) { set_error("sequence job without particles"); return FR_ERR_INVALID; }
+		if ((rc = ensure_capacity(&ctx->d_xyz, &ctx->cap_xyz, ctx->lane_n * 3))) return rc;
+		ctx->lane_d_xyz = ctx->d_xyz;
+		ctx->lane_h2d = true;
 	}
 	ctx->build_timed = 0;
 	if (!ctx->have_camera) { set_error("sequence: fr_seq_set_camera has not been called"); return FR_ERR_STATE; }
-	// Everything that does not need the frame's grid parameters on the host is queued here, without a wait: the build
-	// and the depth pre-pass.  Then the parameters are picked up from the side stream (they left right behind the
-	// first build kernel; a first frame of the lane waits inside build_frame instead)
-	if ((rc = build_frame(ctx, f, d_xyz, n, job.h, job.h_ext_mult, true))) return rc;
-	ctx->pending_frames.push_back(0);
 	int const passes = job.passes ? job.passes : FR_PASS_ALL;
 	if ((passes & FR_PASS_MARCH) && !(passes & FR_PASS_DEPTH) && !ctx->have_depth)
 	{
 		set_error("sequence: march without a depth image");
 		return FR_ERR_STATE;
 	}
-	if ((rc = render_depth(ctx, passes, false))) return rc;
-	return render_resolve(ctx, passes);
+	*stage_a_is_launches_only = build_will_not_wait(ctx, f, true);
+	return FR_OK;
+}
+
+// (the upload stays outside the lane's graph: the job's particles may sit in pageable memory)
+int lane_frame_upload(fr_context* ctx, const fr_seq_job& job)
+{
+	if (ctx->lane_h2d) FM_CUDA(cudaMemcpyAsync(ctx->d_xyz, job.xyz, ctx->lane_n * 12, cudaMemcpyHostToDevice, ctx->stream));
+	return FR_OK;
+}
+
+int lane_frame_stage_a(fr_context* ctx, const fr_seq_job& job)
+{
+	Frame* const f = &ctx->frames[0];
+	int rc;
+	if ((rc = build_frame(ctx, f, ctx->lane_d_xyz, ctx->lane_n, job.h, job.h_ext_mult, true))) return rc;
+	ctx->pending_frames.push_back(0);
+	return render_depth(ctx, job.passes ? job.passes : FR_PASS_ALL, false);
+}
+
+int lane_frame_resolve(fr_context* ctx, const fr_seq_job& job)
+{
+	return render_resolve(ctx, job.passes ? job.passes : FR_PASS_ALL);
 }
 
 // the rest of the frame -- march, copies out -- is launches only: a lane captures it into its CUDA graph

@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 														  uint32_t* __restrict__ ticket,
 														  uint32_t* __restrict__ zero_a, uint32_t words_a,
 														  uint32_t* __restrict__ zero_b, uint32_t words_b,
-														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied)
+														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied,
+														  GridParams* __restrict__ gp_host, uint32_t seq)
 {
 	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
@@ -196,8 +197,16 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 	g.status = status;
 	g.max_cell = 0u;
 	g.n_sorted = 0u;
-	g.pad = 0u;
+	g.seq = seq;
 	*gp = g;
+	if (gp_host)
+	{
+		// the host's copy, over PCIe: everything but the sequence number, a system-wide fence, then the number the host polls
+		g.seq = 0u;
+		*gp_host = g;
+		__threadfence_system();
+		*reinterpret_cast<volatile uint32_t*>(&gp_host->seq) = seq;
+	}
 }
 
 // what the particle kernels need of GridParams, loaded once per thread (every lane reads the same words: L1 broadcasts)
@@ -691,8 +700,7 @@ void free_frame_small(Frame& f)
 {
 	if (f.d_gp) cudaFree(f.d_gp);
 	if (f.h_gp) cudaFreeHost(f.h_gp);
-	if (f.ev_gp) cudaEventDestroy(f.ev_gp);
-	f.d_gp = nullptr; f.h_gp = nullptr; f.ev_gp = nullptr;
+	f.d_gp = nullptr; f.h_gp = nullptr; f.h_gp_dev = nullptr;
 }
 
 // CubicSplineKernel::sig_d = 8 / (pi h^3) (Kernel.cpp:8-14), evaluated in FP32 like the reference
@@ -747,6 +755,13 @@ static RegionFilter region_filter(const Context* ctx, float h)
 // tile][scan ticket][AABB ticket]
 static size_t scan_tmp_words(size_t cells) { return ((cells + 1) & ~(size_t)1) + 2 * ((cells + kScanTile - 1) / kScanTile + 1) + 2; }
 
+bool build_will_not_wait(const Context* ctx, const Frame* f, bool allow_async)
+{
+	// tables of an earlier build of this slot that the scan scratch also covers: no host round trip
+	return allow_async && ctx->async_build && f->cap_cells > 1 && f->cap_grid > 0 && f->cap_occ_words > 0 && ctx->d_scan_tmp &&
+		ctx->cap_scan_tmp >= scan_tmp_words(f->cap_cells - 1) && ctx->d_aabb_partial;
+}
+
 int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async)
 {
 	int const rc = build_frame_begin(ctx, f, d_xyz, n, h, h_ext_mult, allow_async);
@@ -763,7 +778,7 @@ static int launch_aabb_params(Context* ctx, Frame* f, const float* d_xyz, uint32
 	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
 	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
 	k_aabb_params<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
-												  f->d_gp, f->d_occupied);
+												  f->d_gp, f->d_occupied, f->h_gp_dev, f->gp_seq);
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
@@ -794,12 +809,17 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	f->h_ext = h_ext_mult * h;
 	static std::atomic<uint64_t> g_build_serial{ 0 };
 	f->build_serial = ++g_build_serial;        // process-wide: a Frame object may move (std::vector) and its address be reused
+	f->gp_seq = (uint32_t)(f->build_serial & 0x7fffffffu) + 1u;      // never 0
 
 	int rc;
 	if (!f->d_occupied) FM_CUDA(cudaMalloc((void**)&f->d_occupied, sizeof(unsigned long long)));
 	if (!f->d_gp) FM_CUDA(cudaMalloc((void**)&f->d_gp, sizeof(GridParams)));
-	if (!f->h_gp) FM_CUDA(cudaMallocHost((void**)&f->h_gp, 2 * sizeof(GridParams)));      // [0] early copy, [1] end of the build
-	if (!f->ev_gp) FM_CUDA(cudaEventCreateWithFlags(&f->ev_gp, cudaEventDisableTiming));
+	if (!f->h_gp)
+	{
+		FM_CUDA(cudaHostAlloc((void**)&f->h_gp, 2 * sizeof(GridParams), cudaHostAllocMapped));      // [0] zero-copy, [1] end of the build
+		memset(f->h_gp, 0, 2 * sizeof(GridParams));
+		FM_CUDA(cudaHostGetDevicePointer((void**)&f->h_gp_dev, f->h_gp, 0));
+	}
 	if (!ctx->d_aabb_partial)
 	{
 		if ((rc = ensure_capacity(&ctx->d_aabb_partial, &ctx->cap_aabb_partial, (size_t)kPartialStride * ctx->sm_count * 8 + 4))) return rc;
@@ -810,9 +830,7 @@ int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, floa
 	if ((rc = ensure_capacity(&ctx->d_keys, &ctx->cap_keys, n))) return rc;
 	if ((rc = ensure_capacity(&ctx->d_tmp_idx, &ctx->cap_tmp_idx, n))) return rc;
 
-	// tables of an earlier build of this slot that the scan scratch also covers: no host round trip
-	bool const async = allow_async && ctx->async_build && f->cap_cells > 1 && f->cap_grid > 0 && f->cap_occ_words > 0 &&
-		ctx->d_scan_tmp && ctx->cap_scan_tmp >= scan_tmp_words(f->cap_cells - 1);
+	bool const async = build_will_not_wait(ctx, f, allow_async);
 	ctx->build.f = f; ctx->build.d_xyz = d_xyz; ctx->build.n = n; ctx->build.h = h; ctx->build.h_ext_mult = h_ext_mult;
 	ctx->build.async = async;
 	f->src_xyz = d_xyz; f->src_mult = h_ext_mult;                  // for the rebuild after FM_GRID_OVERFLOW
@@ -873,12 +891,7 @@ int build_frame_finish(Context* ctx)
 		caps.occ_words = (uint32_t)std::min<size_t>(f->cap_occ_words, 0x7fffffffu);
 		caps.scan_tiles = ctx->build.scan_blocks;
 		if ((rc = launch_aabb_params(ctx, f, d_xyz, n32, ctx->build.h, caps))) return rc;
-		// the parameters leave for the host right away, beside the rest of the build (resolve_early)
-		FM_CUDA(cudaEventRecord(ctx->ev_k1, s));
-		FM_CUDA(cudaStreamWaitEvent(ctx->side_stream, ctx->ev_k1, 0));
-		FM_CUDA(cudaMemcpyAsync(f->h_gp, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, ctx->side_stream));
-		FM_CUDA(cudaEventRecord(f->ev_gp, ctx->side_stream));
-		f->gp_early_pending = true;
+		f->gp_early_pending = true;          // the kernel writes them into the host's mapped copy itself (resolve_early)
 	}
 	uint32_t* const d_cursor = ctx->d_scan_tmp;
 	size_t const state_off = (cursor_cells + 1) & ~(size_t)1;
@@ -907,25 +920,30 @@ int build_frame_finish(Context* ctx)
 	return FR_OK;
 }
 
-static int wait_event(Context* ctx, cudaEvent_t ev)
-{
-	if (!ctx->blocking_sync) { FM_CUDA(cudaEventSynchronize(ev)); return FR_OK; }
-	for (uint32_t spins = 0;; spins++)                 // oversubscribed hosts: give the core away between polls
-	{
-		cudaError_t const e = cudaEventQuery(ev);
-		if (e == cudaSuccess) return FR_OK;
-		if (e != cudaErrorNotReady) return cuda_fail(e, "cudaEventQuery", __FILE__, __LINE__);
-		if ((spins & 15u) == 15u) sched_yield(); else __builtin_ia32_pause();
-	}
-}
-
-// The host copy of the grid parameters of a frame whose build was queued without a host wait: waits for the early
-// side-stream copy only (k_aabb_params), not for the stream.  FR_RETRIED: the tables of the slot were too small, the
-// frame has been rebuilt (with a host wait) -- whatever was queued on it in between ran on an unusable frame.
+// The host copy of the grid parameters of a frame whose build was queued without a host wait: polls the sequence
+// number k_aabb_params stores, last, into mapped pinned memory -- not the stream.  FR_RETRIED: the tables of the slot
+// were too small, the frame has been rebuilt (with a host wait) -- whatever was queued on it in between ran on an
+// unusable frame.
 int resolve_early(Context* ctx, Frame* f)
 {
 	if (f->gp_host_valid || !f->gp_early_pending) return FR_OK;
-	{ int const rc = wait_event(ctx, f->ev_gp); if (rc) return rc; }
+	volatile uint32_t* const seq = &f->h_gp[0].seq;
+	for (uint32_t spins = 1; *seq != f->gp_seq; spins++)
+	{
+		if (ctx->blocking_sync && (spins & 15u) == 0u) sched_yield();      // oversubscribed hosts: give the core away between polls
+		else __builtin_ia32_pause();
+		if ((spins & 0xfffffu) == 0u)                                      // every ~million polls: has the stream failed?
+		{
+			cudaError_t const e = cudaStreamQuery(ctx->stream);
+			if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "cudaStreamQuery", __FILE__, __LINE__);
+			if (e == cudaSuccess && *seq != f->gp_seq)
+			{
+				set_error("frame build: the grid parameters never arrived");
+				return FR_ERR_STATE;
+			}
+		}
+	}
+	__sync_synchronize();
 	f->gp_early_pending = false;
 	GridParams const gp = f->h_gp[0];
 	if (gp.status & FM_GRID_OVERFLOW)

@@ -29,7 +29,7 @@ struct GridParams
 	uint32_t status;             // FM_GRID_* bits; != 0: the frame is unusable and every kernel of the build returns at once
 	uint32_t max_cell;           // largest number of particles in one search cell (k_scan_flags)
 	uint32_t n_sorted;           // particles in the sorted array: all of them, or those the region filter kept (k_scan_flags)
-	uint32_t pad;
+	uint32_t seq;                // number of the build that wrote this (the host polls it in the mapped copy, resolve_early)
 };
 
 // Region partition (tile-parallel multi-GPU, fr_set_region_partition): this context renders the pixel rectangle
@@ -69,9 +69,10 @@ struct Frame
 	float h = 0.0f, h_ext = 0.0f;
 	GridParams gp{};                  // host copy: valid once gp_pending is false (resolve_frame)
 	GridParams* d_gp = nullptr;       // device: written by k_aabb_params, read by the build kernels
-	GridParams* h_gp = nullptr;       // pinned, 2 entries: [0] leaves right behind k_aabb_params on the side stream, [1] at the end of the build
-	cudaEvent_t ev_gp = nullptr;      // behind the early copy
-	bool gp_early_pending = false;    // the early copy is on its way (resolve_early)
+	GridParams* h_gp = nullptr;       // pinned + mapped, 2 entries: [0] written by k_aabb_params itself (zero-copy), [1] copied at the end of the build
+	GridParams* h_gp_dev = nullptr;   // device address of h_gp[0]
+	uint32_t gp_seq = 0;              // GridParams::seq of the queued build
+	bool gp_early_pending = false;    // k_aabb_params of this build is queued: its parameters are on their way (resolve_early)
 	bool gp_pending = false;          // the build is queued: its end-of-build status has not been read yet (resolve_frame)
 	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (after resolve_early; at once after a build with a host wait)
 	uint64_t build_serial = 0;        // process-wide number of this build
@@ -111,8 +112,6 @@ struct Context
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
 	cudaEvent_t ev_copy = nullptr;     // behind the host -> device copy of fr_upload_frame
-	cudaStream_t side_stream = nullptr; // carries the early copy of a queued build's grid parameters to the host
-	cudaEvent_t ev_k1 = nullptr;       // behind k_aabb_params (the side stream waits for it)
 	// Host waits.  By default a thread waits inside the driver (cudaStreamSynchronize spins: lowest latency, best
 	// throughput while every waiting thread has a core of its own -- 0.296 ms per C2 frame at 6 lanes).  When the host
 	// is oversubscribed (8 ranks x 6 lanes on a 32-core box: 0.47 ms) the lanes of a sequence can instead append a
@@ -151,6 +150,7 @@ struct Context
 
 	std::vector<Frame> frames;
 	std::vector<int> pending_frames;   // frames built since the last host wait (resolve_frame at the next one)
+	const float* lane_d_xyz = nullptr; size_t lane_n = 0; bool lane_h2d = false;      // a sequence lane's frame between its steps
 
 	// images
 	float* d_depth = nullptr;
@@ -220,6 +220,7 @@ int build_frame(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, f
 // half: launches only, so a sequence lane can capture it into a CUDA graph
 int build_frame_begin(Context* ctx, Frame* f, const float* d_xyz, size_t n, float h, float h_ext_mult, bool allow_async = true);
 int build_frame_finish(Context* ctx);
+bool build_will_not_wait(const Context* ctx, const Frame* f, bool allow_async);      // the decision build_frame_begin takes
 // the host copy of the frame's grid parameters (waits for the build if it is still queued); FR_RETRIED: the tables
 // were too small, the frame has been rebuilt -- work queued behind the first build ran on an unusable frame
 constexpr int FR_RETRIED = 1;
@@ -240,7 +241,10 @@ int march_occupancy_aniso(int* blocks_per_sm);
 int query_aniso(Context* ctx, const Frame& f, const fr_settings& s, const float* points_host, size_t m, float* density,
 				float* grad, float* g9);
 // fm_context.cu: the two halves of a sequence lane's frame
-int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path);
+int lane_frame_begin(fr_context* ctx, const fr_seq_job& job, const char* bgeo_path, bool* stage_a_is_launches_only);
+int lane_frame_upload(fr_context* ctx, const fr_seq_job& job);
+int lane_frame_stage_a(fr_context* ctx, const fr_seq_job& job);
+int lane_frame_resolve(fr_context* ctx, const fr_seq_job& job);
 int lane_frame_enqueue(fr_context* ctx, const fr_seq_job& job);
 int lane_frame_wait(fr_context* ctx);
 int render_depth(fr_context* ctx, int passes, bool again);

@@ -43,10 +43,11 @@ struct Lane
 	// ask for ticket t after ticket t + lanes has already finished here (fr_seq_wait; cleared by wait and drain)
 	std::vector<std::pair<int64_t, std::pair<int, std::string>>> failed;
 	cudaEvent_t ev_end = nullptr;
-	// the part of a frame behind its one host wait (rest of the grid build, depth pre-pass, march, copies out) as a
-	// CUDA graph, re-captured every frame and patched into the instantiated graph: one launch instead of ~16 stream
-	// operations, which is what a host -> host sequence is short of while bulk copies keep PCIe busy
-	cudaGraphExec_t exec = nullptr;
+	// A frame as two CUDA graphs, each re-captured every frame and patched into its instantiated graph: (a) upload,
+	// frame build, depth pre-pass; (b) march, copies out.  Between them the worker polls the grid parameters in mapped
+	// memory.  Two launches instead of ~30 stream operations, which is what a host -> host sequence is short of while
+	// bulk copies keep PCIe busy (every stream operation gets slower then, tools/e2e_probe2.py)
+	cudaGraphExec_t exec = nullptr, exec_a = nullptr;
 	bool graph_ok = true;
 };
 
@@ -68,41 +69,43 @@ struct fr_sequence
 namespace
 {
 
-// second half of the frame through a CUDA graph (see Lane::exec).  Any failure of the capture machinery switches the
-// lane back to plain launches; the frame itself is then enqueued directly.
-int enqueue_as_graph(Lane* ln, const fr_seq_job& job)
+// one part of the frame through a CUDA graph (see Lane::exec).  Any failure of the capture machinery switches the lane
+// back to plain launches; the part itself is then enqueued directly.
+template <typename Fn>
+int enqueue_as_graph(Lane* ln, cudaGraphExec_t* exec, Fn&& enqueue)
 {
 	fr_context* const c = ln->ctx;
 	if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess)
 	{
 		cudaGetLastError();
 		ln->graph_ok = false;
-		return lane_frame_enqueue(c, job);
+		return enqueue();
 	}
-	int const rc = lane_frame_enqueue(c, job);
+	int const rc = enqueue();
 	cudaGraph_t g = nullptr;
 	cudaError_t e = cudaStreamEndCapture(c->stream, &g);
 	if (rc != FR_OK) { if (g) cudaGraphDestroy(g); cudaGetLastError(); return rc; }      // a real error of the frame
-	if (e == cudaSuccess && ln->exec)
+	if (e == cudaSuccess && *exec)
 	{
 		cudaGraphExecUpdateResultInfo info;
-		if (cudaGraphExecUpdate(ln->exec, g, &info) != cudaSuccess)       // topology changed (kernel variant, an extra memset)
+		if (cudaGraphExecUpdate(*exec, g, &info) != cudaSuccess)       // topology changed (kernel variant, an extra memset)
 		{
 			cudaGetLastError();
-			cudaGraphExecDestroy(ln->exec);
-			ln->exec = nullptr;
+			cudaGraphExecDestroy(*exec);
+			*exec = nullptr;
 		}
 	}
-	if (e == cudaSuccess && !ln->exec) e = cudaGraphInstantiate(&ln->exec, g, 0);
-	if (e == cudaSuccess) e = cudaGraphLaunch(ln->exec, c->stream);
+	if (e == cudaSuccess && !*exec) e = cudaGraphInstantiate(exec, g, 0);
+	if (e == cudaSuccess) e = cudaGraphLaunch(*exec, c->stream);
 	if (g) cudaGraphDestroy(g);
 	if (e != cudaSuccess)
 	{
+		// (nothing of this part has reached the stream: the capture only recorded it)
 		cudaGetLastError();
 		ln->graph_ok = false;
-		if (ln->exec) { cudaGraphExecDestroy(ln->exec); ln->exec = nullptr; }
+		if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
 		c->render_pending = false;
-		return lane_frame_enqueue(c, job);
+		return enqueue();
 	}
 	return FR_OK;
 }
@@ -126,8 +129,17 @@ void lane_main(fr_sequence* seq, Lane* ln)
 			ln->has_job = false;
 			ln->busy = true;
 		}
-		int rc = lane_frame_begin(ln->ctx, job, job.bgeo_path ? path.c_str() : nullptr);
-		if (rc == FR_OK) rc = seq->graphs && ln->graph_ok ? enqueue_as_graph(ln, job) : lane_frame_enqueue(ln->ctx, job);
+		bool launches_only = false;
+		int rc = lane_frame_begin(ln->ctx, job, job.bgeo_path ? path.c_str() : nullptr, &launches_only);
+		if (rc == FR_OK) rc = lane_frame_upload(ln->ctx, job);
+		if (rc == FR_OK)
+			rc = seq->graphs && ln->graph_ok && launches_only
+				? enqueue_as_graph(ln, &ln->exec_a, [&] { return lane_frame_stage_a(ln->ctx, job); })
+				: lane_frame_stage_a(ln->ctx, job);
+		if (rc == FR_OK) rc = lane_frame_resolve(ln->ctx, job);
+		if (rc == FR_OK)
+			rc = seq->graphs && ln->graph_ok ? enqueue_as_graph(ln, &ln->exec, [&] { return lane_frame_enqueue(ln->ctx, job); })
+											 : lane_frame_enqueue(ln->ctx, job);
 		if (rc == FR_OK) rc = lane_frame_wait(ln->ctx);       // the whole stream: build, render and copies
 		if (rc == FR_OK && job.bmp_path) rc = fr_write_bmp(ln->ctx, bmp.c_str());      // recording (Renderer.cpp:400-409)
 		std::string err;
@@ -202,6 +214,7 @@ void fr_seq_destroy(fr_sequence* seq)
 		cudaSetDevice(seq->device);
 		if (ln->ev_end) cudaEventDestroy(ln->ev_end);
 		if (ln->exec) cudaGraphExecDestroy(ln->exec);
+		if (ln->exec_a) cudaGraphExecDestroy(ln->exec_a);
 		if (ln->ctx) fr_destroy(ln->ctx);
 		delete ln;
 	}

@@ -90,3 +90,30 @@ def test_partition_rules():
         mg.tile_owner_map(100, 100, 2, tile_w=48)
     with pytest.raises(ValueError):
         mg.frames_of_rank(4, 4, 4)
+
+
+def test_balanced_strips_partition_the_image():
+    """bench.py's region partition for the tile-parallel record: strips cover [0, W) without gaps, bounds are multiples of
+    64 pixels (fr_set_region_partition's rule), every rank gets at least one block, the weights are split about evenly"""
+    import importlib
+    import sys
+    from conftest import ROOT
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    rng = np.random.default_rng(2)
+    for W in (3840, 1920, 1000):
+        nb = (W + 63) // 64
+        w = np.zeros(nb)
+        w[nb // 5: nb // 2] = rng.uniform(1.0, 5.0, nb // 2 - nb // 5)       # the fluid covers part of the image only
+        w += 1e-3
+        for world in (1, 2, 3, 4, 8):
+            strips = bench.balanced_strips(w, W, world)
+            assert len(strips) == world and strips[0][0] == 0 and strips[-1][1] == W
+            for (a0, a1), (b0, b1) in zip(strips, strips[1:]):
+                assert a1 == b0
+            for x0, x1 in strips:
+                assert x1 > x0 and x0 % 64 == 0 and (x1 % 64 == 0 or x1 == W)
+            if world in (2, 4):
+                loads = [w[x0 // 64:(x1 + 63) // 64].sum() for x0, x1 in strips]
+                assert max(loads) <= w.sum() / world + w.max() * 1.01        # within one block of the ideal split
