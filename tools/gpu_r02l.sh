@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=r02l
+TAG=r02m
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -6 > gpurun_out/${TAG}_tests.log
 cat gpurun_out/${TAG}_tests.log
@@ -7,7 +7,7 @@ timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/${TAG}_bench_C2.j
 tail -3 gpurun_out/${TAG}_bench.err
 python - <<'PY'
 import json
-d=json.loads([l for l in open("gpurun_out/r02l_bench_C2.json") if l.startswith("{")][-1])
+d=json.loads([l for l in open("gpurun_out/r02m_bench_C2.json") if l.startswith("{")][-1])
 print("ms/step", d["ms_per_step"], "value G", d["value"]/1e9, "latency", d["config"]["latency_ms_per_frame"], "e2e", d["e2e"]["ms_per_step"], "launches", d["gpu_launches"])
 print(d["config"]["stage_ms"]); print({k: d[k] for k in ("parity_checked","pixels_differing")}); print(d["cpu_baseline"]["value"], d["cpu_baseline"]["sample"][:120])
 r=d["roofline"]; print({k: r[k] for k in ("bound","achieved","peak","frac","traffic")}, r["hbm_algorithmic"]["frac"])
