@@ -85,6 +85,7 @@ SYMBOLS = [
     ("fr_build_frame_device", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_float, C.c_float]),
     ("fr_set_count_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_set_async_build", C.c_int, [C.c_void_p, C.c_int]),
+    ("fr_set_stage_timing", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_get_frame_info", C.c_int, [C.c_void_p, C.c_int, C.POINTER(FrFrameInfo)]),
     ("fr_release_frame", C.c_int, [C.c_void_p, C.c_int]),
     ("fr_download_frame", C.c_int, [C.c_void_p, C.c_int, f32p, u32p, u32p, u8p]),

@@ -16,6 +16,13 @@
 namespace fm
 {
 
+bool pdl_enabled()
+{
+	static int const on = [] { const char* e = getenv("FLUIDMARCH_PDL"); return (e && e[0] == '0') ? 0 : 1; }();
+	return on != 0;
+}
+
+
 static thread_local std::string g_error;
 
 void set_error(const std::string& msg) { g_error = msg; }
@@ -384,6 +391,16 @@ int fr_set_async_build(fr_context* ctx, int on)
 {
 	FR_CHECK_CTX(ctx);
 	ctx->async_build = on != 0;
+	return FR_OK;
+}
+
+int fr_set_stage_timing(fr_context* ctx, int on)
+{
+	FR_CHECK_CTX(ctx);
+	int const rc = fm::finish_pending(ctx);
+	if (rc) return rc;
+	ctx->stage_timing = on != 0;
+	if (!ctx->stage_timing) { ctx->build_timed = 0; ctx->march_timed = false; ctx->timings = fr_timings{}; }
 	return FR_OK;
 }
 
@@ -919,6 +936,12 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->queued_rays = d.ctl[2];          // slots of the ray queue that were filled
 	out->first_examined = d.first_examined;
 	out->first_fallbacks = d.first_fallbacks;
+#ifdef FM_LONG_PROFILE
+	// profiling build (tools/build_variant.sh x -DFM_LONG_PROFILE): k_march_long's per-ray maxima -- cycles of the slowest
+	// ray | cycles walking, cycles evaluating | windows << 16 + skips
+	out->first_examined = ((uint64_t)d.ctl[4] << 32) | d.ctl[5];
+	out->first_fallbacks = ((uint64_t)d.ctl[6] << 32) | d.ctl[7];
+#endif
 	return FR_OK;
 }
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ dept
 													 uint32_t* __restrict__ tile_bound, uint32_t ntiles,
 													 uint32_t* __restrict__ n_survivors, uint32_t* __restrict__ counters, uint32_t counter_words)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < 4u) n_survivors[i] = 0u;             // survivor count (+ padding) of k_depth_cull
 	if (i < counter_words) counters[i] = 0u;     // DeviceCounters + work-list control words of the march that follows
@@ -166,6 +167,7 @@ __global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ s
 													float4* __restrict__ splat_a, uint4* __restrict__ splat_b,
 													uint32_t* __restrict__ tile_bound)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= sorted_count(gp, n)) return;
 	Splat s;
@@ -240,6 +242,7 @@ __global__ void __launch_bounds__(256) k_depth_gate(uint32_t n, const GridParams
 													const uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ list,
 													uint32_t* __restrict__ n_list)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool take = false;
 	if (i < sorted_count(gp, n))
@@ -261,6 +264,7 @@ __global__ void __launch_bounds__(256) k_depth_bounds(DepthParams dp, const floa
 													  const uint4* __restrict__ splat_b, const uint32_t* __restrict__ list,
 													  const uint32_t* __restrict__ n_list, uint32_t* __restrict__ tile_bound)
 {
+	pdl_enter();
 	int const lane = threadIdx.x & 31;
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
 	uint32_t const count = __ldcg(n_list);
@@ -303,6 +307,7 @@ constexpr int kCoarse = 4;
 __global__ void __launch_bounds__(256) k_depth_coarse(const uint32_t* __restrict__ tile_bound, int tiles_x, int tiles_y,
 													  uint32_t* __restrict__ coarse, int cx, int cy)
 {
+	pdl_enter();
 	int const b = blockIdx.x * blockDim.x + threadIdx.x;
 	if (b >= cx * cy) return;
 	int const bx = b % cx, by = b / cx;
@@ -319,6 +324,7 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, const GridParams
 													const uint32_t* __restrict__ tile_bound, const uint32_t* __restrict__ coarse,
 													int coarse_x, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	bool wins = false;
 	if (i < sorted_count(gp, n))
@@ -356,6 +362,7 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 													 const uint32_t* __restrict__ survivors, const uint32_t* __restrict__ n_survivors,
 													 const uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ depth_bits)
 {
+	pdl_enter();
 	constexpr int PIX = T * T;                       // pixels per tile
 	constexpr int LPT = PIX < 32 ? PIX : 32;         // lanes working on one tile
 	constexpr int TPR = 32 / LPT;                    // tiles per round
@@ -452,21 +459,21 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	uint4* const splat_b = (uint4*)(ctx->d_splat + 4 * (size_t)n);
 	uint32_t* const n_surv = ctx->d_survivors;
 	uint32_t* const surv = ctx->d_survivors + 4;
-	k_depth_seed<T><<<blocks, 256, 0, st>>>(f.d_sorted, n, f.d_gp, dp, splat_a, splat_b, ctx->d_tile_bound);
+	FM_CUDA(launch_pdl(k_depth_seed<T>, dim3(blocks), dim3(256), 0, st, f.d_sorted, n, f.d_gp, dp, splat_a, splat_b, ctx->d_tile_bound));
 	uint32_t const want = (n + 7u) / 8u;
 	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	if (refine_bounds)
 	{
 		// the gate's list shares the survivor array (it is consumed before k_depth_cull writes there); its count is word 2
-		k_depth_gate<T><<<blocks, 256, 0, st>>>(n, f.d_gp, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2);
-		k_depth_bounds<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv + 2, ctx->d_tile_bound);
+		FM_CUDA(launch_pdl(k_depth_gate<T>, dim3(blocks), dim3(256), 0, st, n, f.d_gp, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2));
+		FM_CUDA(launch_pdl(k_depth_bounds<T>, dim3(want < cap ? want : cap), dim3(256), 0, st, dp, splat_a, splat_b, surv, n_surv + 2, ctx->d_tile_bound));
 	}
 	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
 	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
-	k_depth_coarse<<<(cx * cy + 255) / 256, 256, 0, st>>>(ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy);
-	k_depth_cull<T><<<blocks, 256, 0, st>>>(n, f.d_gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv);
-	k_depth_splat<T><<<want < cap ? want : cap, 256, 0, st>>>(dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
-															 (uint32_t*)ctx->d_depth);
+	FM_CUDA(launch_pdl(k_depth_coarse, dim3((cx * cy + 255) / 256), dim3(256), 0, st, ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy));
+	FM_CUDA(launch_pdl(k_depth_cull<T>, dim3(blocks), dim3(256), 0, st, n, f.d_gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv));
+	FM_CUDA(launch_pdl(k_depth_splat<T>, dim3(want < cap ? want : cap), dim3(256), 0, st, dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
+															 (uint32_t*)ctx->d_depth));
 	ctx->kernel_launches += refine_bounds ? 6 : 4;
 	return FR_OK;
 }
@@ -536,9 +543,9 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	uint32_t const rw = region ? (uint32_t)(dp.rx1 - dp.rx0) : (uint32_t)ctx->width, rh = region ? (uint32_t)(dp.ry1 - dp.ry0) : (uint32_t)ctx->height;
 	uint32_t const npix = rw * rh;
 	uint32_t const clear_threads = npix > ntiles ? npix : ntiles;
-	k_depth_clear<<<(clear_threads + 255) / 256, 256, 0, ctx->stream>>>((uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
+	FM_CUDA(launch_pdl(k_depth_clear, dim3((clear_threads + 255) / 256), dim3(256), 0, ctx->stream, (uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
 																		  ctx->d_tile_bound, ntiles, ctx->d_survivors,
-																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u);
+																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u));
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(kThreads) k_aabb_params(const float* __restric
 														  float h, BuildCaps caps, GridParams* __restrict__ gp, unsigned long long* __restrict__ occupied,
 														  GridParams* __restrict__ gp_host, uint32_t seq)
 {
+	pdl_enter();
 	uint32_t const gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
 	for (uint32_t i = gtid; i < words_a; i += gsize) zero_a[i] = 0u;
 	for (uint32_t i = gtid; i < words_b; i += gsize) zero_b[i] = 0u;
@@ -274,6 +275,7 @@ __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict_
 														uint32_t* __restrict__ keys, uint32_t* __restrict__ cell_count,
 														uint32_t* __restrict__ grid_counts)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || gp->status) return;
 	BuildView const b = load_build_view(gp, half, count_mode);
@@ -372,6 +374,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_flags(GridParams* __restr
 															 uint32_t* __restrict__ ticket, const uint32_t* __restrict__ grid_counts, float W0,
 															 uint32_t* __restrict__ occ_bits, unsigned long long* __restrict__ occupied)
 {
+	pdl_enter();
 	if (gp->status) return;
 	uint32_t const m = gp->cells, gcells = gp->gcells;
 	uint32_t const ntiles = (m + kScanTile - 1) / kScanTile;
@@ -453,6 +456,7 @@ __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const GridPara
 													  const uint32_t* __restrict__ cell_start,
 													  uint32_t* __restrict__ cursor, uint32_t* __restrict__ slot_index)
 {
+	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n || gp->status) return;
 	uint32_t const key = keys[i];
@@ -471,6 +475,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_order(const float* __restrict
 														 const uint32_t* __restrict__ slot_index,
 														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
 {
+	pdl_enter();
 	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= n || gp->status || s >= gp->n_sorted) return;
 	if (gp->max_cell > kMaxCellParticles)
@@ -777,8 +782,8 @@ static int launch_aabb_params(Context* ctx, Frame* f, const float* d_xyz, uint32
 	uint32_t* const zero_b = f->d_grid_counts; size_t const cap_b = f->d_grid_counts ? f->cap_grid : 0;
 	uint32_t const words_a = (uint32_t)(cap_a < 0xffffffffull ? cap_a : 0), words_b = (uint32_t)(cap_b < 0xffffffffull ? cap_b : 0);
 	uint32_t* const ticket = (uint32_t*)(ctx->d_aabb_partial + (size_t)kPartialStride * ctx->sm_count * 8);
-	k_aabb_params<<<aabb_blocks, kThreads, 0, s>>>(d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
-												  f->d_gp, f->d_occupied, f->h_gp_dev, f->gp_seq);
+	FM_CUDA(launch_pdl(k_aabb_params, dim3(aabb_blocks), dim3(kThreads), 0, s, d_xyz, n32, ctx->d_aabb_partial, ticket, zero_a, words_a, zero_b, words_b, h, caps,
+												  f->d_gp, f->d_occupied, f->h_gp_dev, f->gp_seq));
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
 	return FR_OK;
@@ -902,14 +907,14 @@ int build_frame_finish(Context* ctx)
 	float const half = 0.5f * f->h;                   // CompactNSearch: half = Real(0.5) * m_r, m_r = ParticleRadius
 	RegionFilter const rf = region_filter(ctx, f->h);
 	f->filtered = rf.on != 0;
-	k_key_count<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, half, ctx->count_mode, rf, ctx->d_keys, d_cursor, f->d_grid_counts);
+	FM_CUDA(launch_pdl(k_key_count, dim3(pblocks), dim3(kThreads), 0, s, d_xyz, n32, f->d_gp, half, ctx->count_mode, rf, ctx->d_keys, d_cursor, f->d_grid_counts));
 	// cell_start <- exclusive scan of the counts (counts stay in d_cursor for the scatter); occupancy flags
 	uint32_t const flag_blocks = (ctx->build.flag_cells + kScanThreads - 1) / kScanThreads;
 	uint32_t const scan_grid = std::max(ctx->build.scan_blocks, std::min(flag_blocks, (uint32_t)ctx->sm_count * 4u));
-	k_scan_flags<<<scan_grid, kScanThreads, 0, s>>>(f->d_gp, d_cursor, f->d_cell_start, tile_state, scan_ticket, f->d_grid_counts,
-													   spline_sig_d(f->h), f->d_occ_bits, f->d_occupied);
-	k_scatter<<<pblocks, kThreads, 0, s>>>(n32, f->d_gp, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx);
-	k_cell_order<<<pblocks, kThreads, 0, s>>>(d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted);
+	FM_CUDA(launch_pdl(k_scan_flags, dim3(scan_grid), dim3(kScanThreads), 0, s, f->d_gp, d_cursor, f->d_cell_start, tile_state, scan_ticket, f->d_grid_counts,
+													   spline_sig_d(f->h), f->d_occ_bits, f->d_occupied));
+	FM_CUDA(launch_pdl(k_scatter, dim3(pblocks), dim3(kThreads), 0, s, n32, f->d_gp, ctx->d_keys, f->d_cell_start, d_cursor, ctx->d_tmp_idx));
+	FM_CUDA(launch_pdl(k_cell_order, dim3(pblocks), dim3(kThreads), 0, s, d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted));
 	ctx->kernel_launches += 4;
 	FM_CUDA(cudaGetLastError());
 	// the status bits of the later kernels (FM_GRID_CROWDED) come back with the frame's results

@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <utility>
 #include <stdint.h>
 #include <stddef.h>
 
@@ -196,6 +197,28 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define FM_TIME(ctx, event, stream)                                              \
 	do { if ((ctx)->stage_timing) FM_CUDA(cudaEventRecord((event), (stream))); } while (0)
+
+// Programmatic dependent launch (sm_90+): the kernels of a frame are queued with the programmatic-stream-serialization
+// attribute and begin with fm::pdl_enter() (fm_common.cuh) -- `griddepcontrol.launch_dependents` lets the next kernel's
+// CTAs be scheduled as soon as every CTA of this one is resident, `griddepcontrol.wait` holds them until the previous
+// grid has completed and its writes are visible.  What overlaps is launch latency and CTA scheduling (2-3 us per kernel
+// boundary, 15 kernels per frame); the data dependences are unchanged.  FLUIDMARCH_PDL=0 launches them plainly.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = st;
+	cudaLaunchAttribute at[1];
+	at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = at;
+	cfg.numAttrs = pdl_enabled() ? 1u : 0u;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 #define FM_CUDA(expr)                                                            \
 	do {                                                                         \

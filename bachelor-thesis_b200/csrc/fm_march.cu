@@ -9,6 +9,29 @@
 namespace fm
 {
 
+// k_march_long's launch shape: when the frame's occupancy bitmap fits next to the warps' lists it is staged in shared
+// memory (the empty-space walk is a chain of dependent bitmap lookups, see advance) and the resident CTAs per SM follow
+// from what is left.  Returns the CTA count.
+constexpr size_t kLongSmemMax = 200 * 1024;
+static uint32_t long_launch_shape(Context* ctx, const Frame& f, const void*, size_t base_smem, int base_ctas_per_sm, uint32_t* occ_words,
+								  size_t* smem)
+{
+	*occ_words = 0;
+	*smem = base_smem;
+	int per_sm = base_ctas_per_sm > 0 ? base_ctas_per_sm : 1;
+	static int const allow = [] { const char* e = getenv("FLUIDMARCH_OCC_SMEM"); return (e && e[0] == '0') ? 0 : 1; }();
+	size_t const words = ((size_t)f.gp.gcells + 31u) / 32u;
+	size_t const bytes = ((words * 4u) + 15u) & ~(size_t)15u;
+	if (allow && f.gp_host_valid && words != 0 && base_smem + bytes <= kLongSmemMax)
+	{
+		*occ_words = (uint32_t)words;
+		*smem = base_smem + bytes;
+		int const fit = (int)((size_t)(228 * 1024) / (*smem + 1024u));
+		if (fit < per_sm) per_sm = fit > 0 ? fit : 1;
+	}
+	return (uint32_t)(ctx->sm_count * per_sm);
+}
+
 int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 {
 	bool const aniso = ctx->settings.enable_anisotropy != 0;
@@ -60,7 +83,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 		FM_CUDA(cudaMemsetAsync(ctx->d_counters, 0, sizeof(DeviceCounters), st));      // counters + control words
 	ctx->zero_counters_in_depth = false;
 	dim3 const grid(((region ? mp.rx1 - mp.rx0 : ctx->width) + 31) / 32, ((region ? mp.ry1 - mp.ry0 : ctx->height) + 7) / 8);
-	k_classify<<<grid, 256, 0, st>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl);
+	FM_CUDA(launch_pdl(k_classify, dim3(grid), dim3(256), 0, st, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl));
 	ctx->kernel_launches += 1;
 	FM_TIME(ctx, ctx->ev[10], st);
 	if (do_march)
@@ -82,6 +105,8 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			if (ctas > max_ctas) ctas = max_ctas;
 			MarchLaunch ml;
 			ml.fv = make_view(f); ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
+			ml.occ_words = 0; ml.smem_long = kAnisoSmem;
+			ml.ctas_long = std::min(long_launch_shape(ctx, f, nullptr, kAnisoSmem, per_sm, &ml.occ_words, &ml.smem_long), max_ctas);
 			if ((rc = launch_march_kernels_aniso(ctx, ml))) return rc;
 		}
 		else
@@ -98,8 +123,8 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
 				int nb = 0, nl = 0;
 				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, kFirstThreads, smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
-				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmem));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemMax));
+				FM_CUDA(cudaFuncSetAttribute(k_march_long<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemMax));
 				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nl, k_march_long<false, false>, 256, kLongSmem));
 				if (const char* e = getenv("FR_MARCH_CTAS_PER_SM")) { int const v = atoi(e); if (v > 0 && v < nb) nb = v; }   // tuning switch
 				ctx->march_ctas_per_sm = nb > 0 ? nb : 1;
@@ -108,11 +133,13 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			uint32_t const ntiles = (uint32_t)(tiles_x * tiles_y);
 			uint32_t ctas_first = (uint32_t)(ctx->sm_count * ctx->march_ctas_per_sm);
 			ctas_first = std::min(ctas_first, (ntiles + first_warps - 1) / first_warps);
-			uint32_t ctas_long = (uint32_t)(ctx->sm_count * ctx->march_long_ctas_per_sm);
+			uint32_t occ_words = 0;
+			size_t smem_long = kLongSmem;
+			uint32_t ctas_long = long_launch_shape(ctx, f, (const void*)k_march_long<false, false>, kLongSmem, ctx->march_long_ctas_per_sm, &occ_words, &smem_long);
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
-			first<<<ctas_first, kFirstThreads, smem_first, st>>>(fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters);
+			FM_CUDA(launch_pdl(first, dim3(ctas_first), dim3(kFirstThreads), smem_first, st, fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters));
 			FM_TIME(ctx, ctx->ev[11], st);
-			longk<<<ctas_long, 256, kLongSmem, st>>>(fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters);
+			FM_CUDA(launch_pdl(longk, dim3(ctas_long), dim3(256), smem_long, st, fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters, occ_words));
 		}
 		ctx->kernel_launches += 2;
 	}

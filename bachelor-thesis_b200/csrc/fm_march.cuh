@@ -76,6 +76,9 @@ struct MarchLaunch
 	RayQueues rq;
 	const uint32_t* tiles;
 	uint32_t ctas;
+	uint32_t ctas_long;          // k_march_long: CTAs, bitmap words staged in shared memory (0: read from global), dynamic bytes
+	uint32_t occ_words;
+	size_t smem_long;
 	bool fast_normals;
 };
 
@@ -92,6 +95,9 @@ struct LaneCounters
 	uint32_t fallbacks;      // samples whose tile did not fit the shared-memory stage (walked out of global memory)
 };
 
+#ifndef FM_LONG_MINBLOCKS
+#define FM_LONG_MINBLOCKS 2               // resident 256-thread CTAs per SM k_march_long (isotropic) is compiled for
+#endif
 #ifndef FM_MARCH_MINBLOCKS
 #define FM_MARCH_MINBLOCKS 3              // resident 256-thread CTAs per SM k_march_first is compiled for (<= 85 registers; r02b: 4 CTAs
                                           // at 64 registers and a 32-entry list: C2 0.139 ms, C3 0.450; 3 CTAs with 48 entries: 0.138 / 0.419)
@@ -115,6 +121,17 @@ constexpr int kWalkUnroll = FM_WALK_UNROLL;   // candidates per iteration of the
 #endif
 constexpr int kListCap = FM_LIST_CAP;
 constexpr int kListWords = kListCap * 32;  // shared-memory words per warp: list[k * 32 + lane]
+// the anisotropic march: one candidate list per warp (aniso_list_build)
+#ifndef FM_ANISO_LIST_CAP
+#define FM_ANISO_LIST_CAP 1024
+#endif
+#ifndef FM_ANISO_FIRST_LIST
+#define FM_ANISO_FIRST_LIST 0             // k_march_first<ANISO> with the warp's list: measured loss (r02o: 1.01 -> 1.30 ms at C2) -- the lanes
+                                          // of a tile sit in the same cells, their plain walks already share every load and skip the
+                                          // weight arithmetic for the candidates out of everyone's range
+#endif
+constexpr uint32_t kAnisoListCap = FM_ANISO_LIST_CAP;                       // entries per warp (u32: sorted index | h-flag << 31)
+constexpr size_t kAnisoSmem = (size_t)8 * kAnisoListCap * 4;               // 8 warps per CTA
 
 // 32-bit shared-window addressing for the per-lane list (a generic uint16_t* is carried as a 64-bit pair with carries)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -125,6 +142,12 @@ __device__ __forceinline__ void sts_u16(uint32_t a, uint32_t v)
 __device__ __forceinline__ void sts_u32(uint32_t a, uint32_t v)
 {
 	asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a)
+{
+	uint32_t v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
 }
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 {
@@ -660,6 +683,238 @@ __device__ __forceinline__ f3 aniso_gradient(const FrameView& f, f3 p, const Ani
 	});
 	return g;
 }
+
+// ---- the anisotropic sample with a candidate list shared by the warp ---------------------------------------------------
+// The 32 samples a warp evaluates together are close to each other -- the first samples of an 8x4 pixel tile
+// (k_march_first), or 32 consecutive samples of one ray (k_march_long) -- while a query's 27 cells of size h_ext hold
+// 6-7x the particles within h_ext of it: walking them per lane tests every candidate 32 times, and since nearly every
+// candidate is in range of SOME lane the weight / covariance arithmetic runs for all of them at ~15 % lane utilisation.
+// Here the warp first lists, lanes = candidates, the particles of the union of the lanes' cell blocks that lie within
+// h_ext (+ margin) of the segment the samples sit on (a capsule; for a tile the segment is its diagonal), in
+// ascending order of their position in the sorted array.  That order restricted to one lane's 27 cells IS the
+// reference's list order (ascending cell key, ascending index inside a cell), and the in-range test each lane then
+// applies to every list entry is the reference's own, so sums and truncation see the same particles in the same order:
+// bit-identical.  Two things the reference's cell lookup decides rather than the distance are guarded: a particle
+// whose distance test passes within rounding of h_ext on one axis could sit two cells away (outside the 27) -- such a
+// sample is re-evaluated by the plain walk (`redo`); and a list that does not fit sends the whole warp there.
+constexpr int kAnisoListMaxColumns = 400;                                  // larger unions (a window across a long gap) walk plainly
+
+struct SegmentFilter
+{
+	f3 a, v;
+	float inv_vv;
+	__device__ __forceinline__ float dist2(float x, float y, float z) const
+	{
+		float const wx = x - a.x, wy = y - a.y, wz = z - a.z;
+		float t = (wx * v.x + wy * v.y + wz * v.z) * inv_vv;
+		t = fminf(fmaxf(t, 0.0f), 1.0f);
+		float const cx = wx - t * v.x, cy = wy - t * v.y, cz = wz - t * v.z;
+		return cx * cx + cy * cy + cz * cz;
+	}
+};
+
+// returns false when the warp has to fall back to the plain walk; n = entries listed
+__device__ __forceinline__ bool aniso_list_build(const FrameView& f, f3 p, bool on, uint32_t* __restrict__ e, uint32_t& n)
+{
+	uint32_t const FULL = 0xffffffffu;
+	uint32_t const lane = threadIdx.x & 31u;
+	n = 0;
+	if (!(f.h_ext >= 1.02f * f.kernel.h)) return false;                    // the h-subset must lie well inside the list's reach
+	CellBox const bx = ext_box_full(f, p);
+	bool const has = on && bx.x0 <= bx.x1 && bx.y0 <= bx.y1 && bx.z0 <= bx.z1;
+	uint32_t const m_on = __ballot_sync(FULL, has);
+	if (m_on == 0u) return true;                                           // nothing in reach of any sample
+	int const big = 0x7fffffff;
+	int const ux0 = __reduce_min_sync(FULL, has ? bx.x0 : big), ux1 = __reduce_max_sync(FULL, has ? bx.x1 : -big);
+	int const uy0 = __reduce_min_sync(FULL, has ? bx.y0 : big), uy1 = __reduce_max_sync(FULL, has ? bx.y1 : -big);
+	int const uz0 = __reduce_min_sync(FULL, has ? bx.z0 : big), uz1 = __reduce_max_sync(FULL, has ? bx.z1 : -big);
+	if ((ux1 - ux0 + 1) * (uy1 - uy0 + 1) > kAnisoListMaxColumns) return false;
+	int const la = __ffs(m_on) - 1, lb = 31 - __clz(m_on);
+	SegmentFilter sf;
+	sf.a = mk3(__shfl_sync(FULL, p.x, la), __shfl_sync(FULL, p.y, la), __shfl_sync(FULL, p.z, la));
+	f3 const b = mk3(__shfl_sync(FULL, p.x, lb), __shfl_sync(FULL, p.y, lb), __shfl_sync(FULL, p.z, lb));
+	sf.v = mk3(b.x - sf.a.x, b.y - sf.a.y, b.z - sf.a.z);
+	float const vv = sf.v.x * sf.v.x + sf.v.y * sf.v.y + sf.v.z * sf.v.z;
+	sf.inv_vv = vv > 0.0f ? 1.0f / vv : 0.0f;
+	// how far the samples themselves are from the segment (a ray's samples: rounding only; a tile: half its height)
+	float const own = has ? sqrtf(sf.dist2(p.x, p.y, p.z)) : 0.0f;
+	float const rho = __uint_as_float(__reduce_max_sync(FULL, __float_as_uint(own)));
+	float const tol = 1e-3f * f.h_ext + 4e-6f * (fabsf(sf.a.x) + fabsf(sf.a.y) + fabsf(sf.a.z) + fabsf(b.x) + fabsf(b.y) + fabsf(b.z) + 1.0f);
+	float const R = f.h_ext + rho + tol, Rh = f.kernel.h + rho + tol;
+	float const R2 = R * R * 1.0001f, Rh2 = Rh * Rh * 1.0001f;
+	uint32_t const lt = (1u << lane) - 1u;
+#pragma unroll 1
+	for (int x = ux0; x <= ux1; x++)
+	{
+#pragma unroll 1
+		for (int y = uy0; y <= uy1; y++)
+		{
+			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim_ext.y + (uint32_t)y) * (uint32_t)f.kdim_ext.z;
+			uint32_t const jb = __ldg(f.cell_start_ext + base + uz0);
+			uint32_t const je = __ldg(f.cell_start_ext + base + uz1 + 1);
+#pragma unroll 1
+			for (uint32_t j0 = jb; j0 < je; j0 += 32u)
+			{
+				uint32_t const j = j0 + lane;
+				bool keep = false;
+				uint32_t hflag = 0u;
+				if (j < je)
+				{
+					float4 const q = __ldg(f.sorted_ext + j);
+					float const d2 = sf.dist2(q.x, q.y, q.z);
+					keep = d2 <= R2;
+					hflag = d2 <= Rh2 ? 0x80000000u : 0u;
+				}
+				uint32_t const bal = __ballot_sync(FULL, keep);
+				if (keep)
+				{
+					uint32_t const pos = n + (uint32_t)__popc(bal & lt);
+					if (pos < kAnisoListCap) e[pos] = j | hflag;
+				}
+				n += (uint32_t)__popc(bal);
+			}
+		}
+	}
+	__syncwarp();
+	return n <= kAnisoListCap;
+}
+
+// the number of particles in the query's 27 cells (what walk_ext reports as visited)
+__device__ __forceinline__ uint32_t ext_box_count(const FrameView& f, const CellBox& b)
+{
+	uint32_t visited = 0;
+	if (b.z0 > b.z1) return 0;
+	for (int x = b.x0; x <= b.x1; x++)
+		for (int y = b.y0; y <= b.y1; y++)
+		{
+			uint32_t const base = ((uint32_t)x * (uint32_t)f.kdim_ext.y + (uint32_t)y) * (uint32_t)f.kdim_ext.z;
+			visited += __ldg(f.cell_start_ext + base + b.z1 + 1) - __ldg(f.cell_start_ext + base + b.z0);
+		}
+	return visited;
+}
+
+// aniso_density over the warp's list: same three passes, same operations.  All lanes run the loops (uniform trip
+// count); `on` gates the arithmetic.  `redo` = this lane's sample must be re-evaluated by the plain walk.
+__device__ __forceinline__ float aniso_density_list(const FrameView& f, const MarchParams& mp, f3 p, bool on, AnisoSample& as,
+													LaneCounters& lc, const uint32_t* __restrict__ e, uint32_t n, bool& redo)
+{
+	float const edge = f.h_ext * 0.999f - 8e-6f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + f.h_ext);
+	float wsum = 0.0f;
+	f3 mean = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t n_ext = 0;
+	redo = false;
+#pragma unroll (kAnisoWalkUnroll)
+	for (uint32_t i = 0; i < n; i++)
+	{
+		float4 const q = __ldg(f.sorted_ext + (e[i] & 0x7fffffffu));
+		float const d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
+		float const l2 = d0 * d0 + d1 * d1 + d2 * d2;
+		if (on && l2 < f.h_ext_squared)
+		{
+			if (fmaxf(fmaxf(fabsf(d0), fabsf(d1)), fabsf(d2)) > edge) redo = true;
+			if (n_ext < (uint32_t)kMaxNeighbors)
+			{
+				float const w = aniso::cubic_W(f.h_ext, f.search_inv_ext, l2);
+				wsum += w;
+				mean.x += w * q.x; mean.y += w * q.y; mean.z += w * q.z;
+			}
+			n_ext++;
+		}
+	}
+	bool const over = n_ext > (uint32_t)kMaxNeighbors;
+	if (over) n_ext = (uint32_t)kMaxNeighbors;
+	float const inv_wsum = 1.0f / wsum;
+	mean.x *= inv_wsum; mean.y *= inv_wsum; mean.z *= inv_wsum;
+	aniso::Sym3 C = { 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f };
+	uint32_t n2 = 0;
+#pragma unroll (kAnisoWalkUnroll)
+	for (uint32_t i = 0; i < n; i++)
+	{
+		float4 const q = __ldg(f.sorted_ext + (e[i] & 0x7fffffffu));
+		float const d0 = p.x - q.x, d1 = p.y - q.y, d2 = p.z - q.z;
+		float const l2 = d0 * d0 + d1 * d1 + d2 * d2;
+		if (on && l2 < f.h_ext_squared)
+		{
+			if (n2 < (uint32_t)kMaxNeighbors)
+			{
+				float const w = aniso::cubic_W(f.h_ext, f.search_inv_ext, l2);
+				float const x0 = q.x - mean.x, x1 = q.y - mean.y, x2 = q.z - mean.z;
+				float const w0 = w * x0, w1 = w * x1, w2 = w * x2;
+				C.m00 += w0 * x0;
+				C.m10 += w1 * x0; C.m11 += w1 * x1;
+				C.m20 += w2 * x0; C.m21 += w2 * x1; C.m22 += w2 * x2;
+			}
+			n2++;
+		}
+	}
+	C.m00 *= inv_wsum; C.m10 *= inv_wsum; C.m11 *= inv_wsum; C.m20 *= inv_wsum; C.m21 *= inv_wsum; C.m22 *= inv_wsum;
+	aniso::Settings st;
+	st.k_n = mp.k_n; st.k_r = mp.k_r; st.k_s = mp.k_s; st.n_eps = mp.n_eps;
+	aniso::wpca_G(C, n_ext, st, f.kernel.h_inv, as.G);
+	as.detG = aniso::det3(as.G);
+	aniso::Kernel const ak = aniso_kernel_of(f);
+	bool const on3 = on && n_ext != 0u;        // no 2h neighbour, hence no h neighbour: the kernel sum is empty
+	float density = 0.0f;
+	uint32_t nn = 0;
+#pragma unroll 1
+	for (uint32_t i = 0; i < n; i++)
+	{
+		uint32_t const ei = e[i];
+		if (!(ei >> 31)) continue;                                           // (uniform) not within h of any sample of the warp
+		float4 const q = __ldg(f.sorted_ext + (ei & 0x7fffffffu));
+		f3 const r = mk3(q.x - p.x, q.y - p.y, q.z - p.z);
+		float const rr = (r.x * r.x + r.y * r.y) + r.z * r.z;           // glm::dot(r, r) (RayMarcher.cpp:392)
+		if (on3 && rr < f.kernel.h_squared)
+		{
+			density += aniso::W(ak, as.G, as.detG, r);
+			nn++;
+		}
+	}
+	if (on && !redo)
+	{
+		lc.candidates += ext_box_count(f, ext_box_full(f, p));
+		lc.neighbours += nn;
+		if (over) lc.overflow++;
+	}
+	return on ? density : 0.0f;
+}
+
+// aniso_gradient over the same list, for the lanes whose sample is a hit
+__device__ __forceinline__ f3 aniso_gradient_list(const FrameView& f, f3 p, bool on, const AnisoSample& as, const uint32_t* __restrict__ e,
+												  uint32_t n)
+{
+	aniso::Kernel const ak = aniso_kernel_of(f);
+	f3 g = mk3(0.0f, 0.0f, 0.0f);
+#pragma unroll 1
+	for (uint32_t i = 0; i < n; i++)
+	{
+		uint32_t const ei = e[i];
+		if (!(ei >> 31)) continue;
+		float4 const q = __ldg(f.sorted_ext + (ei & 0x7fffffffu));
+		f3 const r = mk3(q.x - p.x, q.y - p.y, q.z - p.z);
+		float const rr = (r.x * r.x + r.y * r.y) + r.z * r.z;
+		if (on && rr < f.kernel.h_squared)
+		{
+			f3 const t = aniso::gradW(ak, as.G, as.detG, r);
+			g.x += t.x; g.y += t.y; g.z += t.z;
+		}
+	}
+	return g;
+}
+
+// the warp's 32 samples (lanes with `on`): density, and G / det G left in `as`.  listed = the list in `e` (n entries) is
+// valid for these samples afterwards (the gradient pass of the hits can use it).
+__device__ __forceinline__ float aniso_density_warp(const FrameView& f, const MarchParams& mp, f3 p, bool on, AnisoSample& as,
+													LaneCounters& lc, uint32_t* __restrict__ e, uint32_t& n, bool& listed)
+{
+	__syncwarp();
+	listed = aniso_list_build(f, p, on, e, n);
+	if (!listed) return on ? aniso_density(f, mp, p, as, lc) : 0.0f;
+	bool redo;
+	float density = aniso_density_list(f, mp, p, on, as, lc, e, n, redo);
+	if (redo) density = aniso_density(f, mp, p, as, lc);
+	return density;
+}
 #endif   // FM_NO_FMAD
 
 // ---- one sample of either flavour ------------------------------------------------------------------------------------
@@ -667,7 +922,7 @@ __device__ __forceinline__ f3 aniso_gradient(const FrameView& f, f3 p, const Ani
 template <bool ANISO> struct SampleState;
 template <> struct SampleState<false> { f3 grad; bool have_grad; };
 #ifdef FM_NO_FMAD
-template <> struct SampleState<true> { AnisoSample as; };
+template <> struct SampleState<true> { AnisoSample as; f3 grad; bool have_grad; };
 #endif
 
 // WITH_GRAD (isotropic only): accumulate the gradient sum together with the density
@@ -678,6 +933,7 @@ __device__ __forceinline__ float sample_density(const FrameView& f, const MarchP
 	if constexpr (ANISO)
 	{
 #ifdef FM_NO_FMAD
+		st.have_grad = false;
 		return on ? aniso_density(f, mp, p, st.as, lc) : 0.0f;
 #else
 		return 0.0f;
@@ -697,7 +953,7 @@ __device__ __forceinline__ f3 sample_gradient(const FrameView& f, f3 p, SampleSt
 	if constexpr (ANISO)
 	{
 #ifdef FM_NO_FMAD
-		return aniso_gradient(f, p, st.as);
+		return st.have_grad ? st.grad : aniso_gradient(f, p, st.as);
 #else
 		return mk3(0.0f, 0.0f, 0.0f);
 #endif
@@ -804,6 +1060,7 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 												  uchar4* __restrict__ rgba_out, uint32_t* __restrict__ tiles,
 												  uint32_t* __restrict__ n_tiles)
 {
+	pdl_enter();
 	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	// (under a region partition the grid covers the region only: its bounds are multiples of 64 pixels)
 	int const tx = (mp.rx0 >> 3) + blockIdx.x * 4 + (warp & 3), ty = (mp.ry0 >> 2) + blockIdx.y * 2 + (warp >> 2);
@@ -853,25 +1110,107 @@ __device__ __forceinline__ void add_counts(LaneCounters& a, const LaneCounters& 
 	a.candidates += b.candidates; a.neighbours += b.neighbours; a.overflow += b.overflow;
 }
 
+// Per ray: what the empty-space skip needs of the (constant) step.  rcp = the refined reciprocal div2_shared derives
+// from a divisor (same three operations, so the quotients below are div2_shared's bit for bit); ok = every component
+// is a normal number in div2_shared's range (no zero, NaN, infinity).
+struct StepInfo
+{
+	f3 rcp;
+	bool ok;
+};
+__device__ __forceinline__ float refined_rcp(float s)
+{
+	float r0;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(s));
+	return fmaf(r0, fmaf(-s, r0, 1.0f), r0);
+}
+__device__ __forceinline__ StepInfo step_info(f3 step)
+{
+	StepInfo si;
+	float const ax = fabsf(step.x), ay = fabsf(step.y), az = fabsf(step.z);
+	si.ok = ax >= 0x1p-60f && ax <= 0x1p60f && ay >= 0x1p-60f && ay <= 0x1p60f && az >= 0x1p-60f && az <= 0x1p60f;
+	si.rcp = mk3(refined_rcp(step.x), refined_rcp(step.y), refined_rcp(step.z));
+	return si;
+}
+
+// the general intersectAABB, kept out of line: the walk below takes it only for degenerate steps and samples that
+// rounding put outside their own cell
+__device__ __noinline__ f3 skip_cell_general(f3 o, f3 d, f3 nmin, float cw)
+{
+	f3 const nmax = add3(nmin, mk3(cw, cw, cw));
+	return add3(intersect_aabb(o, d, nmin, nmax), d);
+}
+
 // one `position += step` with the empty-space skip of RayMarcher.cpp:279-306 (skips do not consume MaxSteps).
 // Returns true when the ray has left the density grid for good, i.e. this and all later samples are misses:
 // outside the grid every particle is farther than h (the grid is the particle AABB padded by h), so the
 // density is 0 there; each coordinate moves monotonically, so a ray that is outside on an axis and moving
 // away on it can never come back.  Stopping there leaves the result unchanged.
-__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, f3& position, f3& prev,
-										uint32_t& skips)
+//
+// The skip is a serial chain -- each exit point is computed from the previous one in FP32 -- and the longest such
+// chain is what k_march_long takes.  intersectAABB (RayMarcher.cpp:51-62) forms six quotients, but for a sample inside
+// its cell only three can win: with d > 0 on an axis (boxMax - o)/d >= (boxMin - o)/d (RN subtraction and division
+// are monotone), so t2 on that axis is the quotient of the FAR plane, and t1 <= 0 on every axis whose near plane
+// is not ahead of the sample.  Then tNear <= 0, and whenever tFar > 0, max(tNear, tFar) = tFar = the smallest of
+// the three far quotients, value and bits (equal positive values have equal bits).  Anything else -- a zero / non-finite
+// step component, a sample rounding put outside its box, tFar <= 0, a numerator outside div2_shared's range -- takes
+// the general function.
+//
+// occ_s != 0: the occupancy bitmap has been staged in shared memory at that (shared-window) address.  Every iteration
+// of the chain needs its cell's bit before it can go on; out of L2 that load IS the chain (ncu / clock64 r02o: ~900
+// cycles per skipped cell at C3, 72 of the kernel's 85 us in the walk of its slowest ray).
+__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, const StepInfo& si, f3& position,
+										f3& prev, uint32_t& skips, uint32_t occ_s = 0u)
 {
 	prev = position;
 	position = add3(position, step);
-	int gx, gy, gz;
+	bool const px = step.x > 0.0f, py = step.y > 0.0f, pz = step.z > 0.0f;
 	bool inside;
-	while ((inside = density_cell_of(f, position, gx, gy, gz)) && !density_cell_flag(f, gx, gy, gz))
+	for (;;)
 	{
-		// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133)
-		f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z), scale3(mk3((float)gx, (float)gy, (float)gz), f.cell_width));
+		// Frame::QueryDensityGrid (Dataset.cpp:26-47), as density_cell_of
+		float const fx = floorf(mulr(subr(position.x, f.mn.x), f.inv_cell_width.x));
+		float const fy = floorf(mulr(subr(position.y, f.mn.y), f.inv_cell_width.y));
+		float const fz = floorf(mulr(subr(position.z, f.mn.z), f.inv_cell_width.z));
+		inside = fx >= 0.0f && fx < (float)f.gdim.x && fy >= 0.0f && fy < (float)f.gdim.y && fz >= 0.0f && fz < (float)f.gdim.z;
+		if (!inside) break;
+		{
+			uint32_t const c = (uint32_t)(int)fx + (uint32_t)f.gdim.x * ((uint32_t)(int)fy + (uint32_t)f.gdim.y * (uint32_t)(int)fz);
+			uint32_t const word = occ_s ? lds_u32(occ_s + ((c >> 5) << 2)) : __ldg(f.occ_bits + (c >> 5));
+			if ((word >> (c & 31u)) & 1u) break;
+		}
+		// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133); fx is the
+		// integer the reference converts back to float
+		f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z), scale3(mk3(fx, fy, fz), f.cell_width));
 		f3 const nmax = add3(nmin, mk3(f.cell_width, f.cell_width, f.cell_width));
 		prev = position;
-		position = add3(intersect_aabb(position, step, nmin, nmax), step);
+		bool done = false;
+		if (si.ok)
+		{
+			float const nfx = subr(px ? nmax.x : nmin.x, position.x);
+			float const nfy = subr(py ? nmax.y : nmin.y, position.y);
+			float const nfz = subr(pz ? nmax.z : nmin.z, position.z);
+			bool const near_behind = (px ? nmin.x <= position.x : nmax.x >= position.x) &&
+				(py ? nmin.y <= position.y : nmax.y >= position.y) && (pz ? nmin.z <= position.z : nmax.z >= position.z);
+			float const lo = fminf(fminf(fabsf(nfx), fabsf(nfy)), fabsf(nfz));
+			float const hi = fmaxf(fmaxf(fabsf(nfx), fabsf(nfy)), fabsf(nfz));
+			if (near_behind && lo >= 0x1p-60f && hi <= 0x1p60f)
+			{
+				float q0 = mulr(nfx, si.rcp.x);
+				float const qx = fmaf(si.rcp.x, fmaf(-step.x, q0, nfx), q0);
+				q0 = mulr(nfy, si.rcp.y);
+				float const qy = fmaf(si.rcp.y, fmaf(-step.y, q0, nfy), q0);
+				q0 = mulr(nfz, si.rcp.z);
+				float const qz = fmaf(si.rcp.z, fmaf(-step.z, q0, nfz), q0);
+				float const t_far = fminf(fminf(qx, qy), qz);
+				if (t_far > 0.0f)
+				{
+					position = add3(add3(position, scale3(step, t_far)), step);
+					done = true;
+				}
+			}
+		}
+		if (!done) position = skip_cell_general(position, step, nmin, f.cell_width);
 		skips++;
 	}
 	if (!inside && mp.early_out)
@@ -986,6 +1325,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
 														 RayQueues rq, DeviceCounters* __restrict__ counters)
 {
+	pdl_enter();
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -1034,7 +1374,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 			prev = position;
 			if (mp.max_steps > 0)
 			{
-				if (advance(f, mp, step, position, prev, lc.skips)) lc.early_exits++;
+				if (advance(f, mp, step, step_info(step), position, prev, lc.skips)) lc.early_exits++;
 				else sample = true;
 			}
 		}
@@ -1058,7 +1398,24 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 				__syncwarp();
 			}
 		}
-		if (!staged)
+		if constexpr (ANISO && FM_ANISO_FIRST_LIST)
+		{
+#ifdef FM_NO_FMAD
+			// the tile's first samples share one candidate list (aniso_list_build); the hits' gradient pass reuses it
+			uint32_t* const wl = reinterpret_cast<uint32_t*>(s_dyn) + (threadIdx.x >> 5) * kAnisoListCap;
+			uint32_t wn;
+			bool listed;
+			st.have_grad = false;
+			density = aniso_density_warp(f, mp, position, sample, st.as, lc, wl, wn, listed);
+			bool const hit = sample && density >= mp.iso && mp.bisection_steps == 0;
+			if (listed && __any_sync(0xffffffffu, hit))
+			{
+				st.grad = aniso_gradient_list(f, position, hit, st.as, wl, wn);
+				st.have_grad = hit;
+			}
+#endif
+		}
+		else if (!staged)
 			density = (!ANISO && mp.bisection_steps == 0)
 				? sample_density<ANISO, true, FAST, true>(f, mp, position, st, lc, list, sample)
 				: sample_density<ANISO, false, false, true>(f, mp, position, st, lc, list, sample);
@@ -1072,7 +1429,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 				// most rays that miss here are silhouette rays about to leave the grid: settle them now
 				f3 p2 = position, prev2 = position;
 				uint32_t skips2 = 0;
-				if (advance(f, mp, step, p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
+				if (advance(f, mp, step, step_info(step), p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
 				else more = true;      // (the queue keeps the state before this advance)
 			}
 		}
@@ -1224,16 +1581,29 @@ __device__ __forceinline__ void coop_eval(const FrameView& f, f3 p, CoopWarp& cw
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
 template <bool FAST, bool ANISO>
-__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
+__global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINBLOCKS) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
-														RayQueues rq, DeviceCounters* __restrict__ counters)
+														RayQueues rq, DeviceCounters* __restrict__ counters, uint32_t occ_words)
 {
+	pdl_enter();
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
-	extern __shared__ __align__(16) unsigned char s_dyn[];       // isotropic: 8 warps x kListWords words (kLongSmem)
+	extern __shared__ __align__(16) unsigned char s_dyn[];       // the warps' lists (kLongSmem / kAnisoSmem), then the bitmap
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 2);
+	// the occupancy bitmap of the frame, staged once per CTA when the host found room for it (see advance)
+	uint32_t occ_s = 0u;
+	if (occ_words != 0u && count != 0u)
+	{
+		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoSmem : kLongSmem));
+		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);        // (cudaMalloc'ed: 256-byte aligned)
+		uint32_t const quads = occ_words >> 2;
+		for (uint32_t i = threadIdx.x; i < quads; i += blockDim.x) reinterpret_cast<uint4*>(occ)[i] = __ldg(src + i);
+		for (uint32_t i = (quads << 2) + threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = __ldg(f.occ_bits + i);
+		__syncthreads();
+		occ_s = smem_addr(occ);
+	}
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
 	bool first = true;
 	for (;;)
@@ -1249,11 +1619,21 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_l
 		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
 		f3 cur = mk3(a.x, a.y, a.z);
 		f3 const rstep = mk3(b.x, b.y, b.z);
+		StepInfo const rsi = step_info(rstep);
 		uint32_t const index = __float_as_uint(a.w);
 		int ri = __float_as_int(b.w);
 		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
+#ifdef FM_LONG_PROFILE
+		// profiling build: per-ray cycle counts land in the spare control words (read back through fr_get_counters)
+		long long const prof_t0 = clock64();
+		long long prof_walk = 0, prof_eval = 0;
+		uint32_t prof_windows = 0, prof_skips = 0;
+#endif
 		for (;;)
 		{
+#ifdef FM_LONG_PROFILE
+			long long const prof_w0 = clock64();
+#endif
 			// every lane walks the same 32 positions and keeps its own (uniform control flow)
 			f3 my_pos = cur, my_prev = cur, prv = cur;
 			uint32_t skips = 0, my_skips = 0;
@@ -1262,13 +1642,35 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_l
 			for (int k = 0; k < 32; k++)
 			{
 				if (ri + k >= mp.max_steps) { n_valid = k; break; }
-				if (advance(f, mp, rstep, cur, prv, skips)) { n_valid = k; gone = true; break; }
+				if (advance(f, mp, rstep, rsi, cur, prv, skips, occ_s)) { n_valid = k; gone = true; break; }
 				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
 			}
 			LaneCounters tc = {};
 			SampleState<ANISO> st;
-			float const density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
+#ifdef FM_LONG_PROFILE
+			long long const prof_e0 = clock64();
+			prof_walk += prof_e0 - prof_w0;
+			prof_windows++; prof_skips += skips;
+#endif
+			float density;
+			if constexpr (ANISO)
+			{
+#ifdef FM_NO_FMAD
+				// the window's samples lie on one segment: one candidate list for the warp (aniso_list_build)
+				uint32_t* const wl = reinterpret_cast<uint32_t*>(s_dyn) + (threadIdx.x >> 5) * kAnisoListCap;
+				uint32_t wn;
+				bool listed;
+				st.have_grad = false;
+				density = aniso_density_warp(f, mp, my_pos, lane < n_valid, st.as, tc, wl, wn, listed);
+#else
+				density = 0.0f;
+#endif
+			}
+			else density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
 			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
+#ifdef FM_LONG_PROFILE
+			prof_eval += clock64() - prof_e0;
+#endif
 			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
 			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
 			if (hits)
@@ -1315,6 +1717,15 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : 3) k_march_l
 			if (gone || ri >= mp.max_steps) break;
 		}
 		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+#ifdef FM_LONG_PROFILE
+		if (lane == 0)
+		{
+			atomicMax(rq.ctl + 4, (uint32_t)(clock64() - prof_t0));
+			atomicMax(rq.ctl + 5, (uint32_t)prof_walk);
+			atomicMax(rq.ctl + 6, (uint32_t)prof_eval);
+			atomicMax(rq.ctl + 7, (prof_windows << 16) | (prof_skips > 0xffffu ? 0xffffu : prof_skips));
+		}
+#endif
 	}
 	flush_counters(lc, counters);
 }

@@ -199,6 +199,7 @@ private:
 		else if (!m_Ctx)
 		{
 			if (fr_create(m_Device, (int)w, (int)h, &m_Ctx) != FR_OK) { m_Ctx = nullptr; Fail(fr_last_error()); return false; }
+			fr_set_stage_timing(m_Ctx, 0);      // nobody reads fr_get_timings here: no events between the kernels of a frame
 		}
 		m_CtxW = w; m_CtxH = h;
 		return true;

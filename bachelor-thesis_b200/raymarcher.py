@@ -106,6 +106,10 @@ class Context:
         build surface at the next wait"""
         check(self.lib.fr_set_async_build(self.h, 1 if on else 0), "fr_set_async_build")
 
+    def set_stage_timing(self, on: bool):
+        """per-stage CUDA events (timings()); off: the frame's kernels chain by programmatic dependent launch"""
+        check(self.lib.fr_set_stage_timing(self.h, 1 if on else 0), "fr_set_stage_timing")
+
     def frame_info(self, frame: int) -> dict:
         fi = abi.FrFrameInfo()
         check(self.lib.fr_get_frame_info(self.h, frame, C.byref(fi)), "fr_get_frame_info")

@@ -145,14 +145,19 @@ void fr_host_free(void* p);
  * Returns once xyz_host has been consumed; the build stays queued on the context's stream.
  * The first build of a frame slot waits once for the device (the table sizes depend on the particle bounds) and
  * reports an unusable frame at once.  Later builds into the same slot reuse its tables and do not wait: the build
- * kernels read the grid parameters from device memory, a copy travels to the host on a side stream and is picked up by
- * the next fr_render_async of the frame (its depth pre-pass is queued first, so the GPU never idles), which then
+ * kernels read the grid parameters from device memory, the first of them also stores them into mapped host memory, and
+ * the next fr_render_async of the frame picks them up (its depth pre-pass is queued first, so the GPU never idles) and
  * reports non-finite coordinates (FR_ERR_INVALID) or, if the tables are too small for the new bounds, rebuilds the
  * frame transparently.  More than 2048 particles in one h-cell (FR_ERR_UNSUPPORTED) is reported by the next call that
  * waits for the context (fr_wait, fr_download, fr_get_frame_info, ...). */
 int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult);
 /* 0: every frame build waits for the device once and reports its errors immediately (round-1 behaviour); default 1 */
 int fr_set_async_build(fr_context* ctx, int on);
+/* 1 (default): CUDA events between the stages of a frame feed fr_get_timings.  0: no events -- the kernels of a frame
+ * then form one chain of programmatic dependent launches (each kernel's CTAs are scheduled while the previous kernel
+ * drains), the lowest latency for a host that marches one frame at a time as AdvancedRenderer.cpp:257-298 does;
+ * fr_get_timings reports zeros.  Sequence lanes always run without the events. */
+int fr_set_stage_timing(fr_context* ctx, int on);
 /* same, particles already resident in device memory (n packed float3); the build is left on the context's stream:
  * xyz_device must stay valid and unchanged until the host next waits for the context (fr_wait, fr_download, ...) */
 int fr_build_frame_device(fr_context* ctx, int frame, const float* xyz_device, size_t n, float h, float h_ext_mult);
