@@ -42,7 +42,7 @@ struct DevBuf
 
 int march_occupancy_aniso(int* blocks_per_sm)
 {
-	FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_march_first<false, true>, 256, kAnisoSmem));
+	FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, k_march_first<false, true>, 256, kAnisoFirstSmem));
 	return FR_OK;
 }
 
@@ -52,16 +52,16 @@ int launch_march_kernels_aniso(Context* ctx, const MarchLaunch& ml)
 	static bool attr_done = false;
 	if (!attr_done)
 	{
-		FM_CUDA(cudaFuncSetAttribute(k_march_first<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnisoSmem));
-		FM_CUDA(cudaFuncSetAttribute(k_march_first<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAnisoSmem));
+		FM_CUDA(cudaFuncSetAttribute(k_march_first<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		FM_CUDA(cudaFuncSetAttribute(k_march_first<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		FM_CUDA(cudaFuncSetAttribute(k_march_long<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		FM_CUDA(cudaFuncSetAttribute(k_march_long<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 		attr_done = true;
 	}
 	if (ml.fast_normals)
-		k_march_first<true, true><<<ml.ctas, 256, kAnisoSmem, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
+		k_march_first<true, true><<<ml.ctas, 256, ml.smem_first, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters, ml.occ_words_first);
 	else
-		k_march_first<false, true><<<ml.ctas, 256, kAnisoSmem, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters);
+		k_march_first<false, true><<<ml.ctas, 256, ml.smem_first, st>>>(ml.fv, ml.mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.tiles, ml.rq, ctx->d_counters, ml.occ_words_first);
 	FM_TIME(ctx, ctx->ev[11], st);
 	if (ml.fast_normals)
 		k_march_long<true, true><<<ml.ctas_long, 256, ml.smem_long, st>>>(ml.fv, ml.mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, ml.rq, ctx->d_counters, ml.occ_words);

@@ -14,7 +14,7 @@ namespace fm
 // from what is left.  Returns the CTA count.
 constexpr size_t kLongSmemMax = 200 * 1024;
 static uint32_t long_launch_shape(Context* ctx, const Frame& f, const void*, size_t base_smem, int base_ctas_per_sm, uint32_t* occ_words,
-								  size_t* smem)
+								  size_t* smem, bool keep_ctas = false)
 {
 	*occ_words = 0;
 	*smem = base_smem;
@@ -22,12 +22,19 @@ static uint32_t long_launch_shape(Context* ctx, const Frame& f, const void*, siz
 	static int const allow = [] { const char* e = getenv("FLUIDMARCH_OCC_SMEM"); return (e && e[0] == '0') ? 0 : 1; }();
 	size_t const words = ((size_t)f.gp.gcells + 31u) / 32u;
 	size_t const bytes = ((words * 4u) + 15u) & ~(size_t)15u;
-	if (allow && f.gp_host_valid && words != 0 && base_smem + bytes <= kLongSmemMax)
+	bool const fits = base_smem + bytes <= kLongSmemMax && (!keep_ctas || (base_smem + bytes + 1024u) * (size_t)per_sm <= (size_t)(228 * 1024));
+	if (allow && f.gp_host_valid && words != 0 && fits)
 	{
 		*occ_words = (uint32_t)words;
 		*smem = base_smem + bytes;
 		int const fit = (int)((size_t)(228 * 1024) / (*smem + 1024u));
 		if (fit < per_sm) per_sm = fit > 0 ? fit : 1;
+		// one resident CTA per SM serialises the rays (r02s, C3: 69 KB of bitmap next to 48 KB of lists: 0.072 -> 0.084 ms)
+		if (per_sm < 2 && base_ctas_per_sm >= 2)
+		{
+			*occ_words = 0; *smem = base_smem;
+			per_sm = base_ctas_per_sm;
+		}
 	}
 	return (uint32_t)(ctx->sm_count * per_sm);
 }
@@ -107,6 +114,8 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			ml.fv = make_view(f); ml.mp = mp; ml.rq = rq; ml.tiles = tiles; ml.ctas = ctas; ml.fast_normals = fast;
 			ml.occ_words = 0; ml.smem_long = kAnisoSmem;
 			ml.ctas_long = std::min(long_launch_shape(ctx, f, nullptr, kAnisoSmem, per_sm, &ml.occ_words, &ml.smem_long), max_ctas);
+			ml.occ_words_first = 0; ml.smem_first = kAnisoFirstSmem;
+			long_launch_shape(ctx, f, nullptr, kAnisoFirstSmem, per_sm, &ml.occ_words_first, &ml.smem_first, true);
 			if ((rc = launch_march_kernels_aniso(ctx, ml))) return rc;
 		}
 		else
@@ -119,8 +128,8 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			auto const longk = fast ? k_march_long<true, false> : k_march_long<false, false>;
 			if (ctx->march_ctas_per_sm == 0)
 			{
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
-				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_first));
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemMax));
+				FM_CUDA(cudaFuncSetAttribute(k_march_first<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemMax));
 				int nb = 0, nl = 0;
 				FM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_first<false, false>, kFirstThreads, smem_first));
 				FM_CUDA(cudaFuncSetAttribute(k_march_long<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLongSmemMax));
@@ -137,7 +146,10 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 			size_t smem_long = kLongSmem;
 			uint32_t ctas_long = long_launch_shape(ctx, f, (const void*)k_march_long<false, false>, kLongSmem, ctx->march_long_ctas_per_sm, &occ_words, &smem_long);
 			ctas_long = std::min(ctas_long, (ntiles + 7) / 8);
-			FM_CUDA(launch_pdl(first, dim3(ctas_first), dim3(kFirstThreads), smem_first, st, fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters));
+			uint32_t occ_first = 0;
+			size_t smem_first_occ = smem_first;
+			long_launch_shape(ctx, f, nullptr, smem_first, ctx->march_ctas_per_sm, &occ_first, &smem_first_occ, true);
+			FM_CUDA(launch_pdl(first, dim3(ctas_first), dim3(kFirstThreads), smem_first_occ, st, fv, mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq, ctx->d_counters, occ_first));
 			FM_TIME(ctx, ctx->ev[11], st);
 			FM_CUDA(launch_pdl(longk, dim3(ctas_long), dim3(256), smem_long, st, fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters, occ_words));
 		}

@@ -79,6 +79,8 @@ struct MarchLaunch
 	uint32_t ctas_long;          // k_march_long: CTAs, bitmap words staged in shared memory (0: read from global), dynamic bytes
 	uint32_t occ_words;
 	size_t smem_long;
+	uint32_t occ_words_first;    // k_march_first: the same, only when it costs no resident CTA
+	size_t smem_first;
 	bool fast_normals;
 };
 
@@ -122,16 +124,17 @@ constexpr int kWalkUnroll = FM_WALK_UNROLL;   // candidates per iteration of the
 constexpr int kListCap = FM_LIST_CAP;
 constexpr int kListWords = kListCap * 32;  // shared-memory words per warp: list[k * 32 + lane]
 // the anisotropic march: one candidate list per warp (aniso_list_build)
-#ifndef FM_ANISO_LIST_CAP
-#define FM_ANISO_LIST_CAP 1024
-#endif
 #ifndef FM_ANISO_FIRST_LIST
 #define FM_ANISO_FIRST_LIST 0             // k_march_first<ANISO> with the warp's list: measured loss (r02o: 1.01 -> 1.30 ms at C2) -- the lanes
                                           // of a tile sit in the same cells, their plain walks already share every load and skip the
                                           // weight arithmetic for the candidates out of everyone's range
 #endif
+#ifndef FM_ANISO_LIST_CAP
+#define FM_ANISO_LIST_CAP 1024
+#endif
 constexpr uint32_t kAnisoListCap = FM_ANISO_LIST_CAP;                       // entries per warp (u32: sorted index | h-flag << 31)
 constexpr size_t kAnisoSmem = (size_t)8 * kAnisoListCap * 4;               // 8 warps per CTA
+constexpr size_t kAnisoFirstSmem = FM_ANISO_FIRST_LIST ? kAnisoSmem : 0;   // k_march_first<ANISO> (lists off by default, see below)
 
 // 32-bit shared-window addressing for the per-lane list (a generic uint16_t* is carried as a 64-bit pair with carries)
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -1113,10 +1116,18 @@ __device__ __forceinline__ void add_counts(LaneCounters& a, const LaneCounters& 
 // Per ray: what the empty-space skip needs of the (constant) step.  rcp = the refined reciprocal div2_shared derives
 // from a divisor (same three operations, so the quotients below are div2_shared's bit for bit); ok = every component
 // is a normal number in div2_shared's range (no zero, NaN, infinity).
+#ifdef FM_LONG_PROFILE
+#define FM_PROF_GENERAL() (skips += 0x10000u)      // profiling build: general-path skips ride in the high half of `skips`
+#else
+#define FM_PROF_GENERAL() ((void)0)
+#endif
 struct StepInfo
 {
 	f3 rcp;
-	bool ok;
+	bool ok;              // every component is +-0 or a normal number in div2_shared's range
+	bool px, py, pz;      // the component is > 0: the far plane of a cell on that axis is its Max
+	bool zx, zy, zz;      // the component is exactly +-0 (the ray through the image centre line of a symmetric camera)
+	bool any_zero;
 };
 __device__ __forceinline__ float refined_rcp(float s)
 {
@@ -1128,7 +1139,11 @@ __device__ __forceinline__ StepInfo step_info(f3 step)
 {
 	StepInfo si;
 	float const ax = fabsf(step.x), ay = fabsf(step.y), az = fabsf(step.z);
-	si.ok = ax >= 0x1p-60f && ax <= 0x1p60f && ay >= 0x1p-60f && ay <= 0x1p60f && az >= 0x1p-60f && az <= 0x1p60f;
+	si.px = step.x > 0.0f; si.py = step.y > 0.0f; si.pz = step.z > 0.0f;
+	si.zx = step.x == 0.0f; si.zy = step.y == 0.0f; si.zz = step.z == 0.0f;
+	si.any_zero = si.zx | si.zy | si.zz;
+	si.ok = (si.zx | ((ax >= 0x1p-60f) & (ax <= 0x1p60f))) & (si.zy | ((ay >= 0x1p-60f) & (ay <= 0x1p60f))) &
+		(si.zz | ((az >= 0x1p-60f) & (az <= 0x1p60f)));
 	si.rcp = mk3(refined_rcp(step.x), refined_rcp(step.y), refined_rcp(step.z));
 	return si;
 }
@@ -1152,19 +1167,57 @@ __device__ __noinline__ f3 skip_cell_general(f3 o, f3 d, f3 nmin, float cw)
 // its cell only three can win: with d > 0 on an axis (boxMax - o)/d >= (boxMin - o)/d (RN subtraction and division
 // are monotone), so t2 on that axis is the quotient of the FAR plane, and t1 <= 0 on every axis whose near plane
 // is not ahead of the sample.  Then tNear <= 0, and whenever tFar > 0, max(tNear, tFar) = tFar = the smallest of
-// the three far quotients, value and bits (equal positive values have equal bits).  Anything else -- a zero / non-finite
-// step component, a sample rounding put outside its box, tFar <= 0, a numerator outside div2_shared's range -- takes
-// the general function.
+// the three far quotients, value and bits (equal positive values have equal bits).  An axis with d = +-0 (the centre
+// column / row of a symmetric camera: r02q, 88 general-path skips at ~1500 cycles each were C3's slowest ray) has
+// quotients -inf / +inf strictly between its planes and constrains nothing.  Anything else -- a subnormal or
+// non-finite step component, a sample rounding put outside its box or exactly on a plane of a d = 0 axis, tFar <= 0,
+// a numerator outside div2_shared's range -- takes the general function.
 //
 // occ_s != 0: the occupancy bitmap has been staged in shared memory at that (shared-window) address.  Every iteration
 // of the chain needs its cell's bit before it can go on; out of L2 that load IS the chain (ncu / clock64 r02o: ~900
 // cycles per skipped cell at C3, 72 of the kernel's 85 us in the walk of its slowest ray).
-__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, const StepInfo& si, f3& position,
-										f3& prev, uint32_t& skips, uint32_t occ_s = 0u)
+// The skip of one cell without a branch: writes the exit point + step into `next` and returns whether the shortcut
+// applies (else the caller takes the general function).  ZERO = the step may have +-0 components.
+template <bool ZERO>
+__device__ __forceinline__ bool skip_cell_fast(const StepInfo& si, f3 step, f3 nmin, f3 nmax, f3 p, f3& next)
+{
+	float const nfx = subr(si.px ? nmax.x : nmin.x, p.x);
+	float const nfy = subr(si.py ? nmax.y : nmin.y, p.y);
+	float const nfz = subr(si.pz ? nmax.z : nmin.z, p.z);
+	// the near plane is not ahead of the sample:  d > 0: Min <= p;  d < 0: p <= Max
+	bool ok = ((si.px ? nmin.x : p.x) <= (si.px ? p.x : nmax.x)) & ((si.py ? nmin.y : p.y) <= (si.py ? p.y : nmax.y)) &
+		((si.pz ? nmin.z : p.z) <= (si.pz ? p.z : nmax.z));
+	float q0 = mulr(nfx, si.rcp.x);
+	float qx = fmaf(si.rcp.x, fmaf(-step.x, q0, nfx), q0);
+	q0 = mulr(nfy, si.rcp.y);
+	float qy = fmaf(si.rcp.y, fmaf(-step.y, q0, nfy), q0);
+	q0 = mulr(nfz, si.rcp.z);
+	float qz = fmaf(si.rcp.z, fmaf(-step.z, q0, nfz), q0);
+	float mx = fabsf(nfx), my = fabsf(nfy), mz = fabsf(nfz);
+	float const inf = __int_as_float(0x7f800000);
+	if (ZERO)
+	{
+		// an axis the ray does not move on (d = +-0): strictly between the planes both quotients are -inf / +inf,
+		// t1 = -inf, t2 = +inf, the axis constrains nothing; ON a plane 0/0 = NaN enters glm's min / max: general path
+		ok = ok & si.ok & (!si.zx | ((nmin.x < p.x) & (p.x < nmax.x))) & (!si.zy | ((nmin.y < p.y) & (p.y < nmax.y))) &
+			(!si.zz | ((nmin.z < p.z) & (p.z < nmax.z)));
+		qx = si.zx ? inf : qx; qy = si.zy ? inf : qy; qz = si.zz ? inf : qz;
+		mx = si.zx ? 1.0f : mx; my = si.zy ? 1.0f : my; mz = si.zz ? 1.0f : mz;
+	}
+	float const lo = fminf(fminf(mx, my), mz), hi = fmaxf(fmaxf(mx, my), mz);
+	float const t_far = fminf(fminf(qx, qy), qz);
+	ok = ok & (lo >= 0x1p-60f) & (hi <= 0x1p60f) & (t_far > 0.0f);
+	if (ZERO) ok = ok & (t_far < inf);
+	next = add3(add3(p, scale3(step, t_far)), step);
+	return ok;
+}
+
+template <bool ZERO>
+__device__ __forceinline__ bool advance_t(const FrameView& f, const MarchParams& mp, f3 step, const StepInfo& si, f3& position,
+										  f3& prev, uint32_t& skips, uint32_t occ_s)
 {
 	prev = position;
 	position = add3(position, step);
-	bool const px = step.x > 0.0f, py = step.y > 0.0f, pz = step.z > 0.0f;
 	bool inside;
 	for (;;)
 	{
@@ -1172,45 +1225,21 @@ __device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& m
 		float const fx = floorf(mulr(subr(position.x, f.mn.x), f.inv_cell_width.x));
 		float const fy = floorf(mulr(subr(position.y, f.mn.y), f.inv_cell_width.y));
 		float const fz = floorf(mulr(subr(position.z, f.mn.z), f.inv_cell_width.z));
-		inside = fx >= 0.0f && fx < (float)f.gdim.x && fy >= 0.0f && fy < (float)f.gdim.y && fz >= 0.0f && fz < (float)f.gdim.z;
+		// (NaN -> outside, as the reference's int conversion)
+		inside = (fx >= 0.0f) & (fy >= 0.0f) & (fz >= 0.0f) & (fx < (float)f.gdim.x) & (fy < (float)f.gdim.y) & (fz < (float)f.gdim.z);
 		if (!inside) break;
-		{
-			uint32_t const c = (uint32_t)(int)fx + (uint32_t)f.gdim.x * ((uint32_t)(int)fy + (uint32_t)f.gdim.y * (uint32_t)(int)fz);
-			uint32_t const word = occ_s ? lds_u32(occ_s + ((c >> 5) << 2)) : __ldg(f.occ_bits + (c >> 5));
-			if ((word >> (c & 31u)) & 1u) break;
-		}
+		uint32_t const c = (uint32_t)(int)fx + (uint32_t)f.gdim.x * ((uint32_t)(int)fy + (uint32_t)f.gdim.y * (uint32_t)(int)fz);
+		uint32_t const word = occ_s ? lds_u32(occ_s + ((c >> 5) << 2)) : __ldg(f.occ_bits + (c >> 5));
 		// node->Min = m_Min + vec3(x,y,z)*cellWidth; node->Max = Min + vec3(cellWidth) (Dataset.cpp:132-133); fx is the
-		// integer the reference converts back to float
+		// integer the reference converts back to float.  (The exit point is computed while the bitmap word is on its way.)
 		f3 const nmin = add3(mk3(f.mn.x, f.mn.y, f.mn.z), scale3(mk3(fx, fy, fz), f.cell_width));
 		f3 const nmax = add3(nmin, mk3(f.cell_width, f.cell_width, f.cell_width));
+		f3 next;
+		bool const fast = skip_cell_fast<ZERO>(si, step, nmin, nmax, position, next);
+		if ((word >> (c & 31u)) & 1u) break;
 		prev = position;
-		bool done = false;
-		if (si.ok)
-		{
-			float const nfx = subr(px ? nmax.x : nmin.x, position.x);
-			float const nfy = subr(py ? nmax.y : nmin.y, position.y);
-			float const nfz = subr(pz ? nmax.z : nmin.z, position.z);
-			bool const near_behind = (px ? nmin.x <= position.x : nmax.x >= position.x) &&
-				(py ? nmin.y <= position.y : nmax.y >= position.y) && (pz ? nmin.z <= position.z : nmax.z >= position.z);
-			float const lo = fminf(fminf(fabsf(nfx), fabsf(nfy)), fabsf(nfz));
-			float const hi = fmaxf(fmaxf(fabsf(nfx), fabsf(nfy)), fabsf(nfz));
-			if (near_behind && lo >= 0x1p-60f && hi <= 0x1p60f)
-			{
-				float q0 = mulr(nfx, si.rcp.x);
-				float const qx = fmaf(si.rcp.x, fmaf(-step.x, q0, nfx), q0);
-				q0 = mulr(nfy, si.rcp.y);
-				float const qy = fmaf(si.rcp.y, fmaf(-step.y, q0, nfy), q0);
-				q0 = mulr(nfz, si.rcp.z);
-				float const qz = fmaf(si.rcp.z, fmaf(-step.z, q0, nfz), q0);
-				float const t_far = fminf(fminf(qx, qy), qz);
-				if (t_far > 0.0f)
-				{
-					position = add3(add3(position, scale3(step, t_far)), step);
-					done = true;
-				}
-			}
-		}
-		if (!done) position = skip_cell_general(position, step, nmin, f.cell_width);
+		if (fast) position = next;
+		else { position = skip_cell_general(position, step, nmin, f.cell_width); FM_PROF_GENERAL(); }
 		skips++;
 	}
 	if (!inside && mp.early_out)
@@ -1224,6 +1253,13 @@ __device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& m
 			   (rz < -m && step.z <= 0.0f) || (rz >= (float)f.gdim.z + m && step.z >= 0.0f);
 	}
 	return false;
+}
+
+__device__ __forceinline__ bool advance(const FrameView& f, const MarchParams& mp, f3 step, const StepInfo& si, f3& position,
+										f3& prev, uint32_t& skips, uint32_t occ_s = 0u)
+{
+	return (si.ok & !si.any_zero) ? advance_t<false>(f, mp, step, si, position, prev, skips, occ_s)
+								  : advance_t<true>(f, mp, step, si, position, prev, skips, occ_s);
 }
 
 // the sample at `position` reached the threshold (RayMarcher.cpp:327-341 / :405-417): optional bisection, normal
@@ -1323,7 +1359,7 @@ template <bool FAST, bool ANISO>
 __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 														 uchar4* __restrict__ rgba_out, const uint32_t* __restrict__ tiles,
-														 RayQueues rq, DeviceCounters* __restrict__ counters)
+														 RayQueues rq, DeviceCounters* __restrict__ counters, uint32_t occ_words)
 {
 	pdl_enter();
 	constexpr uint32_t FULL = 0xffffffffu;
@@ -1334,6 +1370,18 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (kFirstWarpBytes / 4) + lane);
 	LaneCounters lc = {};
 	uint32_t const count = __ldcg(rq.ctl + 0);
+	// the occupancy bitmap, staged when it fits without costing a resident CTA (see advance, k_march_long)
+	uint32_t occ_s = 0u;
+	if (occ_words != 0u && count != 0u)
+	{
+		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoFirstSmem : kFirstSmem));
+		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);
+		uint32_t const quads = occ_words >> 2;
+		for (uint32_t i = threadIdx.x; i < quads; i += blockDim.x) reinterpret_cast<uint4*>(occ)[i] = __ldg(src + i);
+		for (uint32_t i = (quads << 2) + threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = __ldg(f.occ_bits + i);
+		__syncthreads();
+		occ_s = smem_addr(occ);
+	}
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
 
 	// the first tile of a warp is the one with its own number: thousands of warps drawing their first ticket from one
@@ -1374,7 +1422,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 			prev = position;
 			if (mp.max_steps > 0)
 			{
-				if (advance(f, mp, step, step_info(step), position, prev, lc.skips)) lc.early_exits++;
+				if (advance(f, mp, step, step_info(step), position, prev, lc.skips, occ_s)) lc.early_exits++;
 				else sample = true;
 			}
 		}
@@ -1429,7 +1477,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 				// most rays that miss here are silhouette rays about to leave the grid: settle them now
 				f3 p2 = position, prev2 = position;
 				uint32_t skips2 = 0;
-				if (advance(f, mp, step, step_info(step), p2, prev2, skips2)) { lc.skips += skips2; lc.early_exits++; }
+				if (advance(f, mp, step, step_info(step), p2, prev2, skips2, occ_s)) { lc.skips += skips2; lc.early_exits++; }
 				else more = true;      // (the queue keeps the state before this advance)
 			}
 		}
@@ -1627,7 +1675,7 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 		// profiling build: per-ray cycle counts land in the spare control words (read back through fr_get_counters)
 		long long const prof_t0 = clock64();
 		long long prof_walk = 0, prof_eval = 0;
-		uint32_t prof_windows = 0, prof_skips = 0;
+		uint32_t prof_windows = 0, prof_skips = 0, prof_steps = 0, prof_general = 0;
 #endif
 		for (;;)
 		{
@@ -1650,7 +1698,7 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 #ifdef FM_LONG_PROFILE
 			long long const prof_e0 = clock64();
 			prof_walk += prof_e0 - prof_w0;
-			prof_windows++; prof_skips += skips;
+			prof_windows++; prof_skips += skips & 0xffffu; prof_steps += (uint32_t)n_valid; prof_general += skips >> 16;
 #endif
 			float density;
 			if constexpr (ANISO)
@@ -1720,10 +1768,13 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 #ifdef FM_LONG_PROFILE
 		if (lane == 0)
 		{
-			atomicMax(rq.ctl + 4, (uint32_t)(clock64() - prof_t0));
-			atomicMax(rq.ctl + 5, (uint32_t)prof_walk);
-			atomicMax(rq.ctl + 6, (uint32_t)prof_eval);
-			atomicMax(rq.ctl + 7, (prof_windows << 16) | (prof_skips > 0xffffu ? 0xffffu : prof_skips));
+			// the ray with the longest walk: cycles << 32 | samples walked << 22 | skips << 10 | general-path skips
+			unsigned long long const a = ((unsigned long long)(uint32_t)prof_walk << 32) | ((unsigned long long)(prof_steps & 0x3ffu) << 22) |
+				((unsigned long long)(prof_skips & 0xfffu) << 10) | (unsigned long long)(prof_general & 0x3ffu);
+			atomicMax(reinterpret_cast<unsigned long long*>(rq.ctl + 4), a);
+			// the slowest ray: cycles << 32 | cycles evaluating
+			unsigned long long const b = ((unsigned long long)(uint32_t)(clock64() - prof_t0) << 32) | (uint32_t)prof_eval;
+			atomicMax(reinterpret_cast<unsigned long long*>(rq.ctl + 6), b);
 		}
 #endif
 	}

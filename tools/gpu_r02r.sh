@@ -1,0 +1,11 @@
+#!/bin/bash
+TAG=r02s
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -5 > gpurun_out/${TAG}_tests.log
+cat gpurun_out/${TAG}_tests.log
+for occ in 0 1; do
+  export FLUIDMARCH_OCC_SMEM=$occ
+  echo "== OCC_SMEM=$occ" | tee -a gpurun_out/${TAG}_ab.log
+  timeout 600 python tools/ab_probe.py C2 2>&1 | tee -a gpurun_out/${TAG}_ab.log
+  timeout 600 python tools/ab_probe.py C3 2>&1 | tee -a gpurun_out/${TAG}_ab.log
+done
