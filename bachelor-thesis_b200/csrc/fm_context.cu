@@ -936,12 +936,9 @@ int fr_get_counters(fr_context* ctx, fr_counters* out)
 	out->queued_rays = d.ctl[2];          // slots of the ray queue that were filled
 	out->first_examined = d.first_examined;
 	out->first_fallbacks = d.first_fallbacks;
-#ifdef FM_LONG_PROFILE
-	// profiling build (tools/build_variant.sh x -DFM_LONG_PROFILE): k_march_long's ray with the longest walk (cycles << 32 |
-	// samples << 22 | skips << 10 | general-path skips) and its slowest ray (cycles << 32 | cycles evaluating)
-	out->first_examined = ((uint64_t)d.ctl[5] << 32) | d.ctl[4];
-	out->first_fallbacks = ((uint64_t)d.ctl[7] << 32) | d.ctl[6];
-#endif
+	// (profiling builds, tools/build_variant.sh x -DFM_LONG_PROFILE: first_examined = long_ray's ray with the longest walk
+	// (cycles << 32 | samples << 22 | skips << 10 | general-path skips), first_fallbacks = its slowest ray (cycles << 32 |
+	// cycles evaluating))
 	return FR_OK;
 }
 

@@ -77,12 +77,16 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 
 	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
 	mp.tiles_x = tiles_x;
+	mp.tiles_total = tiles_x * tiles_y;
+	static int const fuse = [] { const char* e = getenv("FLUIDMARCH_FUSE"); return (e && e[0] == '0') ? 0 : 1; }();
+	mp.fuse_long = fuse;
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	int rc;
 	if ((rc = ensure_capacity(&ctx->d_tiles, &ctx->cap_tiles, (size_t)tiles_x * tiles_y + 8))) return rc;
 	if (do_march && (rc = ensure_capacity(&ctx->d_rayq, &ctx->cap_rayq, 2 * npix))) return rc;   // 32 B per pixel
 	RayQueues rq;
 	rq.ctl = ctx->d_counters->ctl;
+	rq.prof = reinterpret_cast<uint32_t*>(&ctx->d_counters->first_examined);
 	rq.q1 = ctx->d_rayq;
 	uint32_t* const tiles = ctx->d_tiles;
 	cudaStream_t const st = ctx->stream;
@@ -161,3 +165,12 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 }
 
 }  // namespace fm
+
+#ifdef FM_FIRST_PROFILE
+// profiling build only (not in include/fluidmarch.h): the per-warp records of the last k_march_first launch
+extern "C" int fr_debug_first_profile(unsigned long long* out, int words)
+{
+	if (words > 4 * 16384) words = 4 * 16384;
+	return cudaMemcpyFromSymbol(out, fm::g_first_prof, (size_t)words * 8u) == cudaSuccess ? 0 : -1;
+}
+#endif

@@ -59,14 +59,19 @@ struct MarchParams
 	int rx0, ry0, rx1, ry1;           // region partition: the pixel rectangle this context renders (rx1 == 0: everything)
 	int do_march, do_shade;
 	int tiles_x;                      // 8x4 pixel tiles per image row
+	int tiles_total;                  // slots of the tile list (edge tiles fill it from the front, full tiles from the back)
+	int fuse_long;                    // k_march_first marches queued rays between its tiles (isotropic; FLUIDMARCH_FUSE=0 switches it off)
 	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
 	uint32_t n_eps;
 };
 
 struct RayQueues
 {
-	float4* q1;              // rays left after the first sample -> k_march_long
-	uint32_t* ctl;           // [0] tiles listed [1] tile cursor [2] |q1| [3] q1 cursor
+	float4* q1;              // rays left after the first sample -> long_ray (k_march_first between its tiles, then k_march_long)
+	uint32_t* ctl;           // [0] edge tiles listed (front of the list) [1] tile cursor [2] |q1|: slots reserved [3] q1 cursor
+	                         // [4] published slots not yet claimed (semaphore) [5] k_march_long's cursor [6] full tiles listed (back
+	                         // of the list) [7] published prefix of q1
+	uint32_t* prof;          // FM_LONG_PROFILE builds: four spare words (DeviceCounters::first_examined / first_fallbacks)
 };
 
 struct MarchLaunch
@@ -97,6 +102,12 @@ struct LaneCounters
 	uint32_t fallbacks;      // samples whose tile did not fit the shared-memory stage (walked out of global memory)
 };
 
+#ifndef FM_FUSE_LONG
+#define FM_FUSE_LONG 0                    // k_march_first marches the rays it queues between its tiles (edge tiles first, claim_ray):
+                                          // a measured loss, r02w-y -- a queued ray's serial walk runs ~4x slower among the 24
+                                          // resident tile warps of an SM (190 us instead of 43 us for the slowest ray at C2) than
+                                          // in k_march_long's 16 mostly idle ones: C2 0.124 + 0.052 -> 0.33 + 0.04 ms
+#endif
 #ifndef FM_LONG_MINBLOCKS
 #define FM_LONG_MINBLOCKS 2               // resident 256-thread CTAs per SM k_march_long (isotropic) is compiled for
 #endif
@@ -1087,24 +1098,30 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
 	}
 	if (!mp.do_march) return;
-	__shared__ uint32_t s_any[8];
-	__shared__ uint32_t s_base;
+	// FM_FUSE_LONG builds: edge tiles -- not every pixel covered: the fluid's silhouette, where the rays are that miss on
+	// their first sample and go to the queue -- are listed from the front, full tiles from the back of the array, and
+	// the march draws its tickets front to back: the queued rays, whose walks are the longest serial chains of the
+	// frame, become known in the first wave of tiles (k_march_first, FUSE).  Otherwise every tile counts as an edge tile.
+	__shared__ uint32_t s_kind[8];       // 0: nothing covered, 1: edge tile, 2: full tile
+	__shared__ uint32_t s_base[2];
 	bool const any = __any_sync(0xffffffffu, covered);
-	if (lane == 0) s_any[warp] = any ? 1u : 0u;
+	bool const all = FM_FUSE_LONG && __all_sync(0xffffffffu, covered || !active);      // (one list, front to back, unless FM_FUSE_LONG)
+	if (lane == 0) s_kind[warp] = any ? (all ? 2u : 1u) : 0u;
 	__syncthreads();
-	if (threadIdx.x == 0)
+	if (threadIdx.x < 2)
 	{
 		uint32_t c = 0;
 #pragma unroll
-		for (int w = 0; w < 8; w++) c += s_any[w];
-		s_base = c ? atomicAdd(n_tiles, c) : 0u;
+		for (int w = 0; w < 8; w++) c += s_kind[w] == threadIdx.x + 1u ? 1u : 0u;
+		s_base[threadIdx.x] = c ? atomicAdd(n_tiles + (threadIdx.x == 0 ? 0 : 6), c) : 0u;
 	}
 	__syncthreads();
 	if (any && lane == 0)
 	{
-		uint32_t slot = s_base;
-		for (int w = 0; w < warp; w++) slot += s_any[w];
-		tiles[slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
+		uint32_t const kind = all ? 2u : 1u;
+		uint32_t slot = s_base[kind - 1u];
+		for (int w = 0; w < warp; w++) slot += s_kind[w] == kind ? 1u : 0u;
+		tiles[all ? (uint32_t)mp.tiles_total - 1u - slot : slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
 	}
 }
 
@@ -1294,20 +1311,38 @@ __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams
 
 // ---- ray queues between the three march phases -----------------------------------------------------------
 // A ray that is not finished by a phase is handed on as 32 bytes: (position.xyz, pixel index) (step.xyz, samples taken)
+// publish != nullptr (= RayQueues::ctl): the slots are handed to the warps that march queued rays while k_march_first
+// is still running (claim_ray).  Commits are ordered -- a warp publishes its slots once every slot below them has been
+// published (ctl[7] = the published prefix; the wait is the few instructions another warp spends between its
+// reservation and its commit) -- and each published slot adds one to the semaphore ctl[4].
 __device__ __forceinline__ void push_rays(bool want, float4* __restrict__ q, uint32_t* __restrict__ n, uint32_t index,
-										  f3 position, f3 step, int i)
+										  f3 position, f3 step, int i, uint32_t* __restrict__ publish = nullptr)
 {
 	uint32_t const m = __ballot_sync(0xffffffffu, want);
 	if (m == 0u) return;
 	int const lane = threadIdx.x & 31;
+	int const leader = __ffs(m) - 1;
 	uint32_t base = 0;
-	if (lane == __ffs(m) - 1) base = atomicAdd(n, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+	if (lane == leader) base = atomicAdd(n, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, leader);
 	if (want)
 	{
 		uint32_t const slot = base + __popc(m & ((1u << lane) - 1u));
 		q[2 * (size_t)slot] = make_float4(position.x, position.y, position.z, __uint_as_float(index));
 		q[2 * (size_t)slot + 1] = make_float4(step.x, step.y, step.z, __int_as_float(i));
+		if (publish) __threadfence();
+	}
+	if (publish)
+	{
+		__syncwarp();
+		if (lane == leader)
+		{
+			uint32_t seen;
+			do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(publish + 7) : "memory"); } while (seen != base);
+			__threadfence();
+			atomicExch(publish + 7, base + (uint32_t)__popc(m));
+			atomicAdd(publish + 4, (uint32_t)__popc(m));
+		}
 	}
 }
 
@@ -1355,6 +1390,19 @@ static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's lis
 // from device memory instead -- which would let the march be queued before the host knows the frame's grid parameters
 // -- was measured, r02c-e: through a __constant__ table indexed per context k_march_first +20 %, through a shared-memory
 // copy +12 %, k_march_long +9 %.  The host gets the parameters early on a side stream instead, fm_grid.cu.)
+// (defined behind coop_eval, below)
+template <bool FAST, bool ANISO>
+__device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& mp, uint32_t t, const RayQueues& rq, unsigned char* s_dyn,
+										 uint32_t occ_s, LaneCounters& lc, float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+										 uchar4* __restrict__ rgba_out);
+__device__ __forceinline__ uint32_t claim_ray(uint32_t* __restrict__ ctl);
+
+#ifdef FM_FIRST_PROFILE
+// profiling build (tools/build_variant.sh x -DFM_FIRST_PROFILE, read by tools/first_profile.py through fr_debug_first_profile):
+// per warp: start, finish (globaltimer ns), duration of its longest tile, (max skips of a lane on that tile << 32 | tiles done)
+__device__ unsigned long long g_first_prof[4 * 16384];
+__device__ __forceinline__ unsigned long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 template <bool FAST, bool ANISO>
 __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_MINBLOCKS : (FM_FIRST_STAGED ? FM_FIRST_MINBLOCKS : FM_MARCH_MINBLOCKS)) k_march_first(FrameView f, MarchParams mp, const float* __restrict__ depth,
 														 float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
@@ -1369,7 +1417,13 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	// samples) keeps its list at the start of the warp's share
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (kFirstWarpBytes / 4) + lane);
 	LaneCounters lc = {};
-	uint32_t const count = __ldcg(rq.ctl + 0);
+	uint32_t const n_edge = __ldcg(rq.ctl + 0), count = n_edge + __ldcg(rq.ctl + 6);
+	// k_march_first also marches the rays it queues (long_ray): a warp that finds a queued ray ready takes it before its
+	// next tile, so the serial walks of those rays run underneath the tiles instead of behind them in k_march_long,
+	// and the warps that run out of tiles towards the end of the kernel (r02u: they finish between 82 and 117 us of a
+	// 127 us launch at C2, a tile takes 28 us) have something to do.  Nobody waits: what is not ready is left for k_march_long.
+	constexpr bool FUSE = FM_FUSE_LONG && !ANISO && !FM_FIRST_STAGED;
+	bool const fuse = FUSE && mp.fuse_long != 0;
 	// the occupancy bitmap, staged when it fits without costing a resident CTA (see advance, k_march_long)
 	uint32_t occ_s = 0u;
 	if (occ_words != 0u && count != 0u)
@@ -1387,11 +1441,24 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	// the first tile of a warp is the one with its own number: thousands of warps drawing their first ticket from one
 	// counter at the same moment queue up at that address for longer than a tile takes to launch; afterwards the
 	// tickets are spread in time
+	// (r02z: tiles cost about the same -- C2: p50 27.8 us, p90 30.1 us -- and a warp gets only 3.67 of them, so the kernel
+	// lasts 4 tiles while the SMs drain for the last quarter of it.  Letting only ceil(tiles / 4) warps take part, so that
+	// every round of tiles is full, does not help: a tile takes as long among 22 warps as among 24 -- 0.1249 -> 0.1268 ms.)
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
+	uint32_t const my_first = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
 	bool first = true;
+#ifdef FM_FIRST_PROFILE
+	unsigned long long const prof_start = prof_now();
+	unsigned long long prof_longest = 0, prof_info = 0;
+	uint32_t prof_tiles = 0;
+#endif
 	for (;;)
 	{
-		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+#ifdef FM_FIRST_PROFILE
+		unsigned long long const prof_t0 = prof_now();
+		uint32_t const prof_s0 = lc.skips;
+#endif
+		uint32_t t = my_first;
 		if (!first)
 		{
 			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 1, 1u);
@@ -1399,7 +1466,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 		}
 		first = false;
 		if (t >= count) break;
-		uint32_t const txy = __ldg(tiles + t);
+		uint32_t const txy = __ldg(tiles + (t < n_edge ? t : (uint32_t)mp.tiles_total - 1u - (t - n_edge)));
 		int const px = (int)(txy & 0xffffu) * 8 + (lane & 7), py = (int)(txy >> 16) * 4 + (lane >> 3);
 		uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
 		bool covered = pixel_active(mp, px, py);
@@ -1482,9 +1549,54 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 			}
 		}
 		__syncwarp();
-		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
+		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1, fuse ? rq.ctl : nullptr);
 		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+		if constexpr (FUSE)
+		{
+			// a queued ray before the next tile: their chains are long, the sooner they start the better they hide.  ONE
+			// per tile -- the rays must spread over the warps (a warp that keeps claiming marches them one after the other)
+			if (fuse)
+			{
+				uint32_t r = 0xffffffffu;
+				if (lane == 0) r = claim_ray(rq.ctl);
+				r = __shfl_sync(FULL, r, 0);
+				if (r != 0xffffffffu) long_ray<FAST, ANISO>(f, mp, r, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
+			}
+		}
+#ifdef FM_FIRST_PROFILE
+		{
+			__syncwarp();
+			unsigned long long const dt = prof_now() - prof_t0;
+			uint32_t sk = lc.skips - prof_s0;
+			for (int o = 16; o; o >>= 1) sk = max(sk, __shfl_xor_sync(FULL, sk, o));
+			prof_tiles++;
+			if (dt > prof_longest) { prof_longest = dt; prof_info = ((unsigned long long)sk << 32) | ((unsigned long long)(txy >> 16) << 16) | (txy & 0xffffu); }
+		}
+#endif
 	}
+	if constexpr (FUSE)
+	{
+		// out of tiles: up to two more rays (more would march them one after the other; k_march_long takes them all at once)
+		for (int k = 0; fuse && k < 2; k++)
+		{
+			uint32_t r = 0xffffffffu;
+			if (lane == 0) r = claim_ray(rq.ctl);
+			r = __shfl_sync(FULL, r, 0);
+			if (r == 0xffffffffu) break;
+			long_ray<FAST, ANISO>(f, mp, r, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
+		}
+	}
+#ifdef FM_FIRST_PROFILE
+	if (lane == 0)
+	{
+		uint32_t const w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		if (w < 16384u)
+		{
+			g_first_prof[4 * w + 0] = prof_start; g_first_prof[4 * w + 1] = prof_now();
+			g_first_prof[4 * w + 2] = (prof_longest << 16) | prof_tiles; g_first_prof[4 * w + 3] = prof_info;
+		}
+	}
+#endif
 	flush_counters<true>(lc, counters);
 }
 
@@ -1628,6 +1740,147 @@ __device__ __forceinline__ void coop_eval(const FrameView& f, f3 p, CoopWarp& cw
 // 32 consecutive samples of the ray are evaluated at once -- the sample positions do not depend on the
 // densities; the first sample at or above the threshold is the reference's hit; samples behind it are discarded
 // and not counted.
+//
+// long_ray marches queue slot t with the whole warp.  s_dyn = the CTA's dynamic shared memory (the warps' lists first).
+template <bool FAST, bool ANISO>
+__device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& mp, uint32_t t, const RayQueues& rq, unsigned char* s_dyn,
+										 uint32_t occ_s, LaneCounters& lc, float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
+										 uchar4* __restrict__ rgba_out)
+{
+	constexpr uint32_t FULL = 0xffffffffu;
+	int const lane = threadIdx.x & 31;
+	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
+	float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
+	f3 cur = mk3(a.x, a.y, a.z);
+	f3 const rstep = mk3(b.x, b.y, b.z);
+	StepInfo const rsi = step_info(rstep);
+	uint32_t const index = __float_as_uint(a.w);
+	int ri = __float_as_int(b.w);
+	float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
+#ifdef FM_LONG_PROFILE
+	// profiling build: per-ray cycle counts land in the spare control words (read back through fr_get_counters)
+	long long const prof_t0 = clock64();
+	long long prof_walk = 0, prof_eval = 0;
+	uint32_t prof_windows = 0, prof_skips = 0, prof_steps = 0, prof_general = 0;
+#endif
+	for (;;)
+	{
+#ifdef FM_LONG_PROFILE
+		long long const prof_w0 = clock64();
+#endif
+		// every lane walks the same 32 positions and keeps its own (uniform control flow)
+		f3 my_pos = cur, my_prev = cur, prv = cur;
+		uint32_t skips = 0, my_skips = 0;
+		int n_valid = 32;
+		bool gone = false;
+		for (int k = 0; k < 32; k++)
+		{
+			if (ri + k >= mp.max_steps) { n_valid = k; break; }
+			if (advance(f, mp, rstep, rsi, cur, prv, skips, occ_s)) { n_valid = k; gone = true; break; }
+			if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
+		}
+		LaneCounters tc = {};
+		SampleState<ANISO> st;
+#ifdef FM_LONG_PROFILE
+		long long const prof_e0 = clock64();
+		prof_walk += prof_e0 - prof_w0;
+		prof_windows++; prof_skips += skips & 0xffffu; prof_steps += (uint32_t)n_valid; prof_general += skips >> 16;
+#endif
+		float density;
+		if constexpr (ANISO)
+		{
+#ifdef FM_NO_FMAD
+			// the window's samples lie on one segment: one candidate list for the warp (aniso_list_build)
+			uint32_t* const wl = reinterpret_cast<uint32_t*>(s_dyn) + (threadIdx.x >> 5) * kAnisoListCap;
+			uint32_t wn;
+			bool listed;
+			st.have_grad = false;
+			density = aniso_density_warp(f, mp, my_pos, lane < n_valid, st.as, tc, wl, wn, listed);
+#else
+			density = 0.0f;
+#endif
+		}
+		else density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
+		uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
+#ifdef FM_LONG_PROFILE
+		prof_eval += clock64() - prof_e0;
+#endif
+		int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
+		if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
+		if (hits)
+		{
+			bool coop = false;
+			if constexpr (!ANISO)
+			{
+				if (mp.bisection_steps == 0)
+				{
+					// the normal of the hit: gradient sum at the hit sample, the whole warp on it (the warp's list area is free)
+					coop = true;
+					f3 const hp = mk3(__shfl_sync(FULL, my_pos.x, kstar), __shfl_sync(FULL, my_pos.y, kstar), __shfl_sync(FULL, my_pos.z, kstar));
+					CoopWarp& cw = *reinterpret_cast<CoopWarp*>(s_dyn + (threadIdx.x >> 5) * (size_t)kListWords * 4);
+					float rho;
+					f3 g;
+					uint32_t cand, nn;
+					__syncwarp();
+					coop_eval<FAST>(f, hp, cw, rho, g, cand, nn);
+					if (lane == kstar)
+					{
+						lc.skips += my_skips;
+						lc.candidates += cand; lc.neighbours += nn;
+						if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
+						f3 const n = normalize3(g);                                   // glm::normalize(normal) (RayMarcher.cpp:338)
+						P = make_float4(hp.x, hp.y, hp.z, 1.0f);
+						N = make_float4(n.x, n.y, n.z, 1.0f);
+						lc.hits++;
+					}
+				}
+			}
+			if (!coop && lane == kstar)
+			{
+				lc.skips += my_skips;
+				finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, list, P, N);
+			}
+			P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
+			P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
+			N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
+			N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
+			break;
+		}
+		if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
+		ri += n_valid;
+		if (gone || ri >= mp.max_steps) break;
+	}
+	if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
+#ifdef FM_LONG_PROFILE
+	if (lane == 0)
+	{
+		// the ray with the longest walk: cycles << 32 | samples walked << 22 | skips << 10 | general-path skips
+		unsigned long long const pa = ((unsigned long long)(uint32_t)prof_walk << 32) | ((unsigned long long)(prof_steps & 0x3ffu) << 22) |
+			((unsigned long long)(prof_skips & 0xfffu) << 10) | (unsigned long long)(prof_general & 0x3ffu);
+		atomicMax(reinterpret_cast<unsigned long long*>(rq.prof), pa);
+		// the slowest ray: cycles << 32 | cycles evaluating
+		unsigned long long const pb = ((unsigned long long)(uint32_t)(clock64() - prof_t0) << 32) | (uint32_t)prof_eval;
+		atomicMax(reinterpret_cast<unsigned long long*>(rq.prof + 2), pb);
+	}
+#endif
+	__syncwarp();
+}
+
+// A warp of k_march_first claims a queued ray (lane 0 calls this): ctl[4] counts the published slots nobody has
+// claimed yet -- a semaphore; a claim that finds it empty puts its unit back -- and a successful claim draws the next
+// slot from the cursor ctl[3], which therefore never passes the published prefix.  Returns 0xffffffff when no ray is
+// ready: nobody ever waits for a ray; k_march_long marches what is left in the queue when k_march_first ends.
+__device__ __forceinline__ uint32_t claim_ray(uint32_t* __restrict__ ctl)
+{
+	uint32_t avail;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(avail) : "l"(ctl + 4) : "memory");
+	if ((int)avail <= 0) return 0xffffffffu;
+	if ((int)atomicSub(ctl + 4, 1u) <= 0) { atomicAdd(ctl + 4, 1u); return 0xffffffffu; }
+	uint32_t const r = atomicAdd(ctl + 3, 1u);
+	__threadfence();
+	return r;
+}
+
 template <bool FAST, bool ANISO>
 __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINBLOCKS) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
@@ -1637,12 +1890,12 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 	constexpr uint32_t FULL = 0xffffffffu;
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];       // the warps' lists (kLongSmem / kAnisoSmem), then the bitmap
-	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * kListWords + lane);
 	LaneCounters lc = {};
-	uint32_t const count = __ldcg(rq.ctl + 2);
+	// the rays k_march_first did not march itself: slots [start, count) of the queue
+	uint32_t const count = __ldcg(rq.ctl + 2), start = __ldcg(rq.ctl + 3);
 	// the occupancy bitmap of the frame, staged once per CTA when the host found room for it (see advance)
 	uint32_t occ_s = 0u;
-	if (occ_words != 0u && count != 0u)
+	if (occ_words != 0u && count > start)
 	{
 		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoSmem : kLongSmem));
 		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);        // (cudaMalloc'ed: 256-byte aligned)
@@ -1656,127 +1909,15 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 	bool first = true;
 	for (;;)
 	{
-		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // first ray: the warp's own number (see k_march_first)
+		uint32_t t = start + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);     // first ray: the warp's own number (see k_march_first)
 		if (!first)
 		{
-			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 3, 1u);
+			if (lane == 0) t = start + nwarps + atomicAdd(rq.ctl + 5, 1u);
 			t = __shfl_sync(FULL, t, 0);
 		}
 		first = false;
 		if (t >= count) break;
-		float4 const a = __ldcg(rq.q1 + 2 * (size_t)t), b = __ldcg(rq.q1 + 2 * (size_t)t + 1);
-		f3 cur = mk3(a.x, a.y, a.z);
-		f3 const rstep = mk3(b.x, b.y, b.z);
-		StepInfo const rsi = step_info(rstep);
-		uint32_t const index = __float_as_uint(a.w);
-		int ri = __float_as_int(b.w);
-		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = P;
-#ifdef FM_LONG_PROFILE
-		// profiling build: per-ray cycle counts land in the spare control words (read back through fr_get_counters)
-		long long const prof_t0 = clock64();
-		long long prof_walk = 0, prof_eval = 0;
-		uint32_t prof_windows = 0, prof_skips = 0, prof_steps = 0, prof_general = 0;
-#endif
-		for (;;)
-		{
-#ifdef FM_LONG_PROFILE
-			long long const prof_w0 = clock64();
-#endif
-			// every lane walks the same 32 positions and keeps its own (uniform control flow)
-			f3 my_pos = cur, my_prev = cur, prv = cur;
-			uint32_t skips = 0, my_skips = 0;
-			int n_valid = 32;
-			bool gone = false;
-			for (int k = 0; k < 32; k++)
-			{
-				if (ri + k >= mp.max_steps) { n_valid = k; break; }
-				if (advance(f, mp, rstep, rsi, cur, prv, skips, occ_s)) { n_valid = k; gone = true; break; }
-				if (k == lane) { my_pos = cur; my_prev = prv; my_skips = skips; }
-			}
-			LaneCounters tc = {};
-			SampleState<ANISO> st;
-#ifdef FM_LONG_PROFILE
-			long long const prof_e0 = clock64();
-			prof_walk += prof_e0 - prof_w0;
-			prof_windows++; prof_skips += skips & 0xffffu; prof_steps += (uint32_t)n_valid; prof_general += skips >> 16;
-#endif
-			float density;
-			if constexpr (ANISO)
-			{
-#ifdef FM_NO_FMAD
-				// the window's samples lie on one segment: one candidate list for the warp (aniso_list_build)
-				uint32_t* const wl = reinterpret_cast<uint32_t*>(s_dyn) + (threadIdx.x >> 5) * kAnisoListCap;
-				uint32_t wn;
-				bool listed;
-				st.have_grad = false;
-				density = aniso_density_warp(f, mp, my_pos, lane < n_valid, st.as, tc, wl, wn, listed);
-#else
-				density = 0.0f;
-#endif
-			}
-			else density = lane < n_valid ? sample_density<ANISO, false, false>(f, mp, my_pos, st, tc, list) : 0.0f;
-			uint32_t const hits = __ballot_sync(FULL, lane < n_valid && density >= mp.iso);
-#ifdef FM_LONG_PROFILE
-			prof_eval += clock64() - prof_e0;
-#endif
-			int const kstar = hits ? __ffs(hits) - 1 : n_valid - 1;     // last sample that counts
-			if (lane <= kstar) { add_counts(lc, tc); lc.steps++; }
-			if (hits)
-			{
-				bool coop = false;
-				if constexpr (!ANISO)
-				{
-					if (mp.bisection_steps == 0)
-					{
-						// the normal of the hit: gradient sum at the hit sample, the whole warp on it (the warp's list area is free)
-						coop = true;
-						f3 const hp = mk3(__shfl_sync(FULL, my_pos.x, kstar), __shfl_sync(FULL, my_pos.y, kstar), __shfl_sync(FULL, my_pos.z, kstar));
-						CoopWarp& cw = *reinterpret_cast<CoopWarp*>(s_dyn + (threadIdx.x >> 5) * (size_t)kListWords * 4);
-						float rho;
-						f3 g;
-						uint32_t cand, nn;
-						__syncwarp();
-						coop_eval<FAST>(f, hp, cw, rho, g, cand, nn);
-						if (lane == kstar)
-						{
-							lc.skips += my_skips;
-							lc.candidates += cand; lc.neighbours += nn;
-							if (nn > (uint32_t)kMaxNeighbors) lc.overflow++;
-							f3 const n = normalize3(g);                                   // glm::normalize(normal) (RayMarcher.cpp:338)
-							P = make_float4(hp.x, hp.y, hp.z, 1.0f);
-							N = make_float4(n.x, n.y, n.z, 1.0f);
-							lc.hits++;
-						}
-					}
-				}
-				if (!coop && lane == kstar)
-				{
-					lc.skips += my_skips;
-					finish_hit<ANISO, FAST>(f, mp, my_prev, my_pos, st, lc, list, P, N);
-				}
-				P.x = __shfl_sync(FULL, P.x, kstar); P.y = __shfl_sync(FULL, P.y, kstar);
-				P.z = __shfl_sync(FULL, P.z, kstar); P.w = __shfl_sync(FULL, P.w, kstar);
-				N.x = __shfl_sync(FULL, N.x, kstar); N.y = __shfl_sync(FULL, N.y, kstar);
-				N.z = __shfl_sync(FULL, N.z, kstar); N.w = __shfl_sync(FULL, N.w, kstar);
-				break;
-			}
-			if (lane == 0) { lc.skips += skips; if (gone) lc.early_exits++; }
-			ri += n_valid;
-			if (gone || ri >= mp.max_steps) break;
-		}
-		if (lane == 0) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
-#ifdef FM_LONG_PROFILE
-		if (lane == 0)
-		{
-			// the ray with the longest walk: cycles << 32 | samples walked << 22 | skips << 10 | general-path skips
-			unsigned long long const a = ((unsigned long long)(uint32_t)prof_walk << 32) | ((unsigned long long)(prof_steps & 0x3ffu) << 22) |
-				((unsigned long long)(prof_skips & 0xfffu) << 10) | (unsigned long long)(prof_general & 0x3ffu);
-			atomicMax(reinterpret_cast<unsigned long long*>(rq.ctl + 4), a);
-			// the slowest ray: cycles << 32 | cycles evaluating
-			unsigned long long const b = ((unsigned long long)(uint32_t)(clock64() - prof_t0) << 32) | (uint32_t)prof_eval;
-			atomicMax(reinterpret_cast<unsigned long long*>(rq.ctl + 6), b);
-		}
-#endif
+		long_ray<FAST, ANISO>(f, mp, t, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
 	}
 	flush_counters(lc, counters);
 }
