@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(256) k_depth_clear(uint32_t* __restrict__ dept
 // particles in the sorted array: the frame's, or fewer under a region partition (k_scan_flags); none of an unusable frame
 __device__ __forceinline__ uint32_t sorted_count(const GridParams* __restrict__ gp, uint32_t n)
 {
+	if (!gp) return n;                  // particles straight from the input array (pre-pass beside the build)
 	return gp->status ? 0u : min(n, gp->n_sorted);
 }
 
@@ -163,7 +164,7 @@ __device__ __forceinline__ bool splat_setup(const DepthParams& dp, float4 p, Spl
 // pass 1: per-particle splat parameters -> scratch, and the cheapest useful bound: the tile that contains the
 // disc centre (fully covered whenever the disc radius exceeds the tile diagonal, which is how T is chosen)
 template <int T>
-__global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, uint32_t n, const GridParams* __restrict__ gp, DepthParams dp,
+__global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, const float* __restrict__ raw, uint32_t n, const GridParams* __restrict__ gp, DepthParams dp,
 													float4* __restrict__ splat_a, uint4* __restrict__ splat_b,
 													uint32_t* __restrict__ tile_bound)
 {
@@ -171,7 +172,8 @@ __global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ s
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= sorted_count(gp, n)) return;
 	Splat s;
-	bool live = splat_setup(dp, __ldg(sorted + i), s);
+	float4 const p = raw ? make_float4(__ldg(raw + 3ull * i), __ldg(raw + 3ull * i + 1), __ldg(raw + 3ull * i + 2), 0.0f) : __ldg(sorted + i);
+	bool live = splat_setup(dp, p, s);
 	if (live && !box_owned(dp, s.x0, s.y0, s.x1, s.y1)) live = false;      // cannot touch a pixel this rank renders
 	splat_a[i] = make_float4(s.z_c, s.ax, s.bx, s.ay);
 	splat_b[i] = make_uint4(__float_as_uint(s.by), s.near_bits, live ? ((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)) : 0xffffu,
@@ -450,28 +452,28 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 }
 
 template <int T>
-int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bounds)
+int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bounds, cudaStream_t st, const float* raw)
 {
 	uint32_t const n = (uint32_t)f.n;
 	uint32_t const blocks = (n + 255u) / 256u;
-	cudaStream_t const st = ctx->stream;
+	const GridParams* const gp = raw ? nullptr : f.d_gp;
 	float4* const splat_a = (float4*)ctx->d_splat;
 	uint4* const splat_b = (uint4*)(ctx->d_splat + 4 * (size_t)n);
 	uint32_t* const n_surv = ctx->d_survivors;
 	uint32_t* const surv = ctx->d_survivors + 4;
-	FM_CUDA(launch_pdl(k_depth_seed<T>, dim3(blocks), dim3(256), 0, st, f.d_sorted, n, f.d_gp, dp, splat_a, splat_b, ctx->d_tile_bound));
+	FM_CUDA(launch_pdl(k_depth_seed<T>, dim3(blocks), dim3(256), 0, st, (const float4*)f.d_sorted, raw, n, gp, dp, splat_a, splat_b, ctx->d_tile_bound));
 	uint32_t const want = (n + 7u) / 8u;
 	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	if (refine_bounds)
 	{
 		// the gate's list shares the survivor array (it is consumed before k_depth_cull writes there); its count is word 2
-		FM_CUDA(launch_pdl(k_depth_gate<T>, dim3(blocks), dim3(256), 0, st, n, f.d_gp, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2));
+		FM_CUDA(launch_pdl(k_depth_gate<T>, dim3(blocks), dim3(256), 0, st, n, gp, dp, splat_b, ctx->d_tile_bound, surv, n_surv + 2));
 		FM_CUDA(launch_pdl(k_depth_bounds<T>, dim3(want < cap ? want : cap), dim3(256), 0, st, dp, splat_a, splat_b, surv, n_surv + 2, ctx->d_tile_bound));
 	}
 	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
 	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
 	FM_CUDA(launch_pdl(k_depth_coarse, dim3((cx * cy + 255) / 256), dim3(256), 0, st, ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy));
-	FM_CUDA(launch_pdl(k_depth_cull<T>, dim3(blocks), dim3(256), 0, st, n, f.d_gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv));
+	FM_CUDA(launch_pdl(k_depth_cull<T>, dim3(blocks), dim3(256), 0, st, n, gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv));
 	FM_CUDA(launch_pdl(k_depth_splat<T>, dim3(want < cap ? want : cap), dim3(256), 0, st, dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
 															 (uint32_t*)ctx->d_depth));
 	ctx->kernel_launches += refine_bounds ? 6 : 4;
@@ -480,7 +482,7 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 
 }  // namespace
 
-int launch_depth_prepass(Context* ctx, const Frame& f)
+int launch_depth_prepass(Context* ctx, const Frame& f, cudaStream_t st, const float* raw_xyz)
 {
 	const fr_camera& cam = ctx->camera;
 	// only the perspective structure glm::perspectiveLH_ZO scaled by (1,-1,1) produces is supported
@@ -543,16 +545,16 @@ int launch_depth_prepass(Context* ctx, const Frame& f)
 	uint32_t const rw = region ? (uint32_t)(dp.rx1 - dp.rx0) : (uint32_t)ctx->width, rh = region ? (uint32_t)(dp.ry1 - dp.ry0) : (uint32_t)ctx->height;
 	uint32_t const npix = rw * rh;
 	uint32_t const clear_threads = npix > ntiles ? npix : ntiles;
-	FM_CUDA(launch_pdl(k_depth_clear, dim3((clear_threads + 255) / 256), dim3(256), 0, ctx->stream, (uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
+	FM_CUDA(launch_pdl(k_depth_clear, dim3((clear_threads + 255) / 256), dim3(256), 0, st, (uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
 																		  ctx->d_tile_bound, ntiles, ctx->d_survivors,
 																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u));
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{
-	case 2: launch_tiles<2>(ctx, f, dp, refine); break;
-	case 4: launch_tiles<4>(ctx, f, dp, refine); break;
-	case 8: launch_tiles<8>(ctx, f, dp, refine); break;
-	default: launch_tiles<16>(ctx, f, dp, refine); break;
+	case 2: launch_tiles<2>(ctx, f, dp, refine, st, raw_xyz); break;
+	case 4: launch_tiles<4>(ctx, f, dp, refine, st, raw_xyz); break;
+	case 8: launch_tiles<8>(ctx, f, dp, refine, st, raw_xyz); break;
+	default: launch_tiles<16>(ctx, f, dp, refine, st, raw_xyz); break;
 	}
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());

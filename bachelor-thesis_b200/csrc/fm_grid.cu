@@ -888,6 +888,13 @@ int build_frame_finish(Context* ctx)
 	uint32_t const n32 = (uint32_t)ctx->build.n;
 	int rc;
 	size_t const cursor_cells = f->cap_cells - 1;                  // histogram capacity in cells
+	// whatever is queued behind this event has the particles (the pre-pass of a render may start here: render_depth)
+	if (ctx->ev_fork)
+	{
+		FM_CUDA(cudaEventRecord(ctx->ev_fork, s));
+		ctx->fork_serial = f->build_serial;
+		f->src_epoch = ctx->wait_epoch;
+	}
 	if (ctx->build.async)
 	{
 		BuildCaps caps;

@@ -78,6 +78,7 @@ struct Frame
 	bool gp_host_valid = false;       // `gp` holds THIS build's parameters (after resolve_early; at once after a build with a host wait)
 	uint64_t build_serial = 0;        // process-wide number of this build
 	const float* src_xyz = nullptr;   // device particles of the queued build (must stay valid until the host next waits)
+	uint64_t src_epoch = 0;           // Context::wait_epoch when the build was queued
 	float src_mult = 0.0f;
 	bool filtered = false;            // built under a region partition: holds only the particles its pixel rectangle needs
 	uint64_t occupied = 0;
@@ -113,6 +114,16 @@ struct Context
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev_done = nullptr;
 	cudaEvent_t ev_copy = nullptr;     // behind the host -> device copy of fr_upload_frame
+	// The depth pre-pass needs the particles, not the grid: with stage timing off (fr_set_stage_timing(ctx, 0): the
+	// RayMarcher shim, latency measurements) a render queued behind a frame build runs it on a second stream, from the
+	// raw particle array, while the build's kernels run on the first (render_depth).  ev_fork is recorded in front of
+	// a build's kernels, ev_join behind the pre-pass.  wait_epoch counts the host waits of the context: the raw array
+	// of a queued build is only guaranteed until the next one (fr_build_frame_device's contract).
+	cudaStream_t stream_depth = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	uint64_t fork_serial = 0;          // Frame::build_serial of the build ev_fork belongs to
+	uint64_t wait_epoch = 0;
+	bool overlap_depth = true;         // FLUIDMARCH_OVERLAP=0 switches it off; sequence lanes: off (other lanes' frames fill the GPU)
 	// Host waits.  By default a thread waits inside the driver (cudaStreamSynchronize spins: lowest latency, best
 	// throughput while every waiting thread has a core of its own -- 0.296 ms per C2 frame at 6 lanes).  When the host
 	// is oversubscribed (8 ranks x 6 lanes on a 32-core box: 0.47 ms) the lanes of a sequence can instead append a
@@ -254,7 +265,9 @@ FrameView make_view(const Frame& f);              // needs resolve_frame
 void free_frame_small(Frame& f);
 
 // fm_depth.cu
-int launch_depth_prepass(Context* ctx, const Frame& f);
+// st / raw_xyz: the context's stream and nullptr (particles from the frame's sorted array), or the side stream and the
+// packed float3 array the frame is being built from (same image: it is a minimum over all fragments)
+int launch_depth_prepass(Context* ctx, const Frame& f, cudaStream_t st, const float* raw_xyz);
 // fm_march.cu
 int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade);
 // fm_aniso.cu (the one translation unit compiled with -fmad=false)

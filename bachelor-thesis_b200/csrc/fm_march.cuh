@@ -1069,6 +1069,8 @@ __device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int 
 }
 
 // every pixel: background + work list of the 8x4 tiles that hold covered pixels.  CTA = 4x2 tiles = 32x8 pixels.
+// (r03b: writing the outputs of the uncovered pixels from a second kernel on a side stream, beside the march, gains
+// nothing -- C2 0.3026 -> 0.3011 ms per frame, C3 0.908 -> 0.934 ms: it competes with k_march_first for the SMs.)
 __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* __restrict__ depth,
 												  float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 												  uchar4* __restrict__ rgba_out, uint32_t* __restrict__ tiles,

@@ -192,6 +192,7 @@ int fr_seq_create(int device, int width, int height, int lanes, fr_sequence** ou
 		int const rc = fr_create(device, width, height, &ln->ctx);
 		if (rc != FR_OK) { fr_seq_destroy(seq); return rc; }
 		ln->ctx->stage_timing = false;       // no per-stage events in a sequence (see Context::stage_timing)
+		{ const char* e = getenv("FLUIDMARCH_OVERLAP_LANES"); ln->ctx->overlap_depth = e && e[0] == '1'; }   // (the other lanes' frames fill the GPU)
 		if (cudaEventCreate(&ln->ev_end) != cudaSuccess) { fr_seq_destroy(seq); return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__); }
 	}
 	if (cudaEventCreate(&seq->ev_begin) != cudaSuccess) { fr_seq_destroy(seq); return cuda_fail(cudaGetLastError(), "cudaEventCreate", __FILE__, __LINE__); }

@@ -226,3 +226,35 @@ def test_region_partition_is_bit_identical_and_filters_particles(fm, gpu_ctx_fac
         assert np.array_equal(bits(a), bits(b))
     with pytest.raises(fm.FluidMarchError, match="multiples of 64"):
         part.set_region_partition(10, 0, 200, 100)
+
+
+@pytest.mark.parametrize("shuffle", [False, True])
+def test_prepass_beside_the_build_is_bit_identical(fm, gpu_ctx_factory, shuffle):
+    """With stage timing off a render queued behind a frame build runs the depth pre-pass on a second stream from the
+    raw particle array (render_depth): same depth image, same march, whatever the particle order."""
+    cam = golden_camera("camera_close_16x9")
+    xyz = scenes.dam_break(30000, t=0.6)
+    if shuffle:
+        xyz = xyz[np.random.default_rng(5).permutation(len(xyz))]
+    want, _, want_counters = render_fresh(fm, xyz, cam)               # stage timing on: one stream
+    c = gpu_ctx_factory(W, H)
+    set_cam(c, cam)
+    c.set_stage_timing(False)
+    for k in range(3):                                                # first build (host-sized), then builds that do not wait
+        c.upload_frame(0, xyz, 0.1, 2.0)
+        c.render_async(fm.FR_PASS_ALL)
+        got = c.download()
+        for name, g, w in zip(("depth", "positions", "normals", "rgba"), got, want):
+            assert np.array_equal(bits(g), bits(w)), (name, k)
+    assert c.counters()["hit_rays"] == want_counters["hit_rays"]
+    # a second render of the same frame (camera moved, no new build): the pre-pass reads the sorted array again
+    cam2 = golden_camera("camera_default_16x9")
+    set_cam(c, cam2)
+    c.render_async(fm.FR_PASS_ALL)
+    got2 = c.download()
+    c2 = gpu_ctx_factory(W, H)
+    set_cam(c2, cam2)
+    c2.upload_frame(0, xyz, 0.1, 2.0)
+    c2.render(fm.FR_PASS_ALL)
+    for name, g, w in zip(("depth", "positions", "normals", "rgba"), got2, c2.download()):
+        assert np.array_equal(bits(g), bits(w)), name
