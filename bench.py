@@ -299,11 +299,15 @@ def host_ceiling(torch, dist, dev, world, h2d_bytes, d2h_bytes, reps=40):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        pair()
-    torch.cuda.synchronize()
-    ms = (time.perf_counter() - t0) / reps * 1e3
+    ms = float("inf")
+    for _ in range(5):                   # a capability: the best of five rounds (other host threads disturb single rounds)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            pair()
+        torch.cuda.synchronize()
+        ms = min(ms, (time.perf_counter() - t0) / reps * 1e3)
     if world > 1:
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -551,7 +555,10 @@ def run_b200(args):
     # frames in flight per GPU; every lane has a host worker thread (see --wait)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     cores = os.cpu_count() or 8
-    lanes = 1 if tiles_mode else max(1, args.lanes)
+    # frames in flight per GPU: 8 on one GPU (r03d/e: host -> host 0.257-0.268 ms per frame against 0.28-0.29 with 5 or 6 and
+    # 0.265-0.279 with 9 or 10; the device-resident rate does not care: 0.225-0.229 from 4 to 12); 6 with several ranks
+    # on one host, where the lane threads outnumber the cores
+    lanes = 1 if tiles_mode else (args.lanes if args.lanes > 0 else (8 if world == 1 else 6))
     # Every step renders THE SAME synthetic frame (FRAME_T) -- the one the reference arm, the cpu_baseline leg and
     # tests/test_gpu_fullsize.py march -- out of n_frames separate device / pinned-host buffers, enough of them that
     # the particle INPUTS alone exceed the 126 MB L2 (the pipelined arm does not flush).  Frame-parallel: rank r
@@ -660,8 +667,10 @@ def run_b200(args):
     cnt = ctx.counters()                                        # counters of the last step
     serial_launches = timed_serial.launches
     tim = {k: float(np.mean([t[k] for t in stage_log])) for k in stage_log[0]}
-    # the same frames without the per-stage events (fr_set_stage_timing(0), what the RayMarcher shim runs): the 15
-    # kernels of a frame then form one chain of programmatic dependent launches
+    # the same frames without the per-stage events (fr_set_stage_timing(0), what the RayMarcher shim runs): the
+    # kernels of a frame then form chains of programmatic dependent launches, and the depth pre-pass runs on a second
+    # stream beside the frame build (so latency_ms_per_frame is below the sum of stage_ms, which are timed one stage
+    # after the other)
     serial_with_events_ms = serial_ms
     if not tiles_mode:
         ctx.set_stage_timing(False)
@@ -947,7 +956,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default="frames", choices=["frames", "tiles"])
-    ap.add_argument("--lanes", type=int, default=6, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time")
+    ap.add_argument("--lanes", type=int, default=0, help="frames in flight per GPU (fr_seq_create); 1 = one frame at a time; 0 = 8 on one GPU, 6 per rank otherwise")
     ap.add_argument("--wait", default="auto", choices=["auto", "spin", "yield"], help="how lane workers wait for the GPU (fr_seq_set_yielding)")
     ap.add_argument("--tile", type=int, default=128, help="--mode tiles: partition tile size in pixels (multiple of 64)")
     ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
