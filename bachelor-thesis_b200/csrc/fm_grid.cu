@@ -465,47 +465,115 @@ __global__ void __launch_bounds__(kThreads) k_scatter(uint32_t n, const GridPara
 	slot_index[cell_start[key] + (left - 1u)] = i;
 }
 
+// In-place ascending sort of a[0, n) by key(a[i]) with the whole CTA: the bitonic network in its normalised form --
+// every comparator points the same way, the first step of a merge of size k pairs i with i ^ (k - 1), the others i with
+// i ^ j -- which sorts any n: a partner beyond n is an element at +infinity that no comparator would move.
+// n log^2 n / 4 compare-exchanges on global memory: the ordering of a CROWDED cell only (below).
+template <typename T, typename Key>
+__device__ void cta_sort_in_place(T* __restrict__ a, uint32_t n, Key key)
+{
+	for (uint32_t k = 2; (k >> 1) < n; k <<= 1)
+	{
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			uint32_t const mask = (j == (k >> 1)) ? k - 1u : j;
+			__syncthreads();
+			for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+			{
+				uint32_t const l = i ^ mask;
+				if (l > i && l < n)
+				{
+					T const x = a[i], y = a[l];
+					if (key(x) > key(y)) { a[i] = y; a[l] = x; }
+				}
+			}
+		}
+	}
+	__syncthreads();
+}
+
 // one thread per particle slot: the final place of a particle inside its cell is its rank by original index
 // (number of cell mates with a smaller index), so that every FP32 sum over a cell runs in the reference's order
 // (ascending point id) and results are reproducible from run to run and from GPU to GPU.  `slot_index` holds the
 // cell's particles in arrival order of the scatter atomics; the positions are gathered from the input array.
-// The ranking is quadratic in the cell population: a cell with more than kMaxCellParticles particles (a collapsed
-// simulation) marks the frame FM_GRID_CROWDED instead of occupying the GPU for seconds.
+// The ranking is quadratic in the cell population.  A CROWDED cell -- more than kMaxCellParticles particles: a collapsed
+// simulation, or h far too large for the particle spacing -- is ordered by one CTA instead, the one that
+// holds the cell's first slot: it sorts the cell's stretch of slot_index in place and gathers the positions; the
+// threads of the cell's other slots do nothing.  (A crowded cell has more slots than a CTA has threads, so at most
+// one starts inside a CTA.)  Frames without such a cell (k_scan_flags keeps the maximum) never reach that code.
 __global__ void __launch_bounds__(kThreads) k_cell_order(const float* __restrict__ xyz, uint32_t n, GridParams* __restrict__ gp,
-														 const uint32_t* __restrict__ slot_index,
+														 uint32_t* __restrict__ slot_index,
 														 const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
 {
 	pdl_enter();
 	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n || gp->status || s >= gp->n_sorted) return;
-	if (gp->max_cell > kMaxCellParticles)
+	if (gp->status) return;
+	bool const crowded_frame = gp->max_cell > kMaxCellParticles;       // (uniform)
+	bool const valid = s < n && s < gp->n_sorted;
+	if (!crowded_frame && !valid) return;
+	__shared__ uint32_t s_own[2];
+	if (crowded_frame)
 	{
-		if (s == 0) atomicOr(&gp->status, (uint32_t)FM_GRID_CROWDED);     // (read by the host only: the march of this frame sees stale slots)
-		return;
+		if (threadIdx.x == 0) s_own[0] = s_own[1] = 0u;
+		__syncthreads();
 	}
-	uint32_t const id = __ldg(slot_index + s);
-	float const x = __ldg(xyz + 3ull * id), y = __ldg(xyz + 3ull * id + 1), z = __ldg(xyz + 3ull * id + 2);
-	BuildView const b = load_build_view(gp, 0.0f, 0);
-	uint32_t const key = search_key(b, x, y, z);
-	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
-	uint32_t rank = 0;
-	for (uint32_t t = cb; t < ce; t++) rank += __ldg(slot_index + t) < id ? 1u : 0u;
-	sorted[cb + rank] = make_float4(x, y, z, __uint_as_float(id));
+	if (valid)
+	{
+		// (non-coherent loads: only a crowded cell's stretch is ever written, and whatever a thread of such a cell reads
+		// from it while its owner sorts is still one of the cell's indices, which is all it is used for)
+		uint32_t const id = __ldg(slot_index + s);
+		float const x = __ldg(xyz + 3ull * id), y = __ldg(xyz + 3ull * id + 1), z = __ldg(xyz + 3ull * id + 2);
+		BuildView const b = load_build_view(gp, 0.0f, 0);
+		uint32_t const key = search_key(b, x, y, z);
+		uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
+		if (ce - cb <= kMaxCellParticles)
+		{
+			uint32_t rank = 0;
+			for (uint32_t t = cb; t < ce; t++) rank += __ldg(slot_index + t) < id ? 1u : 0u;
+			sorted[cb + rank] = make_float4(x, y, z, __uint_as_float(id));
+		}
+		else if (s == cb) { s_own[0] = cb; s_own[1] = ce; }
+	}
+	if (!crowded_frame) return;
+	__syncthreads();
+	uint32_t const cb = s_own[0], ce = s_own[1];
+	if (ce == cb) return;                                              // (uniform) no crowded cell starts in this CTA
+	cta_sort_in_place(slot_index + cb, ce - cb, [](uint32_t v) { return v; });
+	for (uint32_t t = cb + threadIdx.x; t < ce; t += blockDim.x)
+	{
+		uint32_t const id = slot_index[t];
+		sorted[t] = make_float4(__ldg(xyz + 3ull * id), __ldg(xyz + 3ull * id + 1), __ldg(xyz + 3ull * id + 2), __uint_as_float(id));
+	}
 }
 
-// the r = h_ext search orders float4 records (k_scatter4): same ranking
+// the r = h_ext search orders float4 records (k_scatter4): same ranking; a crowded cell's records are copied to their
+// stretch of `sorted` and sorted there by original index
 __global__ void __launch_bounds__(kThreads) k_cell_order4(const float4* __restrict__ unordered, uint32_t n, BuildView b,
 														  const uint32_t* __restrict__ cell_start, float4* __restrict__ sorted)
 {
 	uint32_t const s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= n) return;
-	float4 const v = __ldg(unordered + s);
-	uint32_t const id = __float_as_uint(v.w);
-	uint32_t const key = search_key(b, v.x, v.y, v.z);
-	uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
-	uint32_t rank = 0;
-	for (uint32_t t = cb; t < ce; t++) rank += __float_as_uint(__ldg(&unordered[t].w)) < id ? 1u : 0u;
-	sorted[cb + rank] = v;
+	__shared__ uint32_t s_own[2];
+	if (threadIdx.x == 0) s_own[0] = s_own[1] = 0u;
+	__syncthreads();
+	if (s < n)
+	{
+		float4 const v = __ldg(unordered + s);
+		uint32_t const id = __float_as_uint(v.w);
+		uint32_t const key = search_key(b, v.x, v.y, v.z);
+		uint32_t const cb = __ldg(cell_start + key), ce = __ldg(cell_start + key + 1);
+		if (ce - cb <= kMaxCellParticles)
+		{
+			uint32_t rank = 0;
+			for (uint32_t t = cb; t < ce; t++) rank += __float_as_uint(__ldg(&unordered[t].w)) < id ? 1u : 0u;
+			sorted[cb + rank] = v;
+		}
+		else if (s == cb) { s_own[0] = cb; s_own[1] = ce; }
+	}
+	__syncthreads();
+	uint32_t const cb = s_own[0], ce = s_own[1];
+	if (ce == cb) return;
+	for (uint32_t t = cb + threadIdx.x; t < ce; t += blockDim.x) sorted[t] = __ldg(unordered + t);
+	cta_sort_in_place(sorted + cb, ce - cb, [](float4 v) { return __float_as_uint(v.w); });
 }
 
 // two-kernel scan of the r = h_ext build (host-sized, not on the per-frame path)
@@ -793,7 +861,6 @@ static const char* grid_status_text(uint32_t status)
 {
 	if (status & FM_GRID_NONFINITE) return "frame build: a particle coordinate is NaN or infinite";
 	if (status & FM_GRID_DEGENERATE) return "frame build: degenerate particle bounds (extent / h exceeds 2^31 cells)";
-	if (status & FM_GRID_CROWDED) return "frame build: more than 2048 particles in one search cell (collapsed simulation or h far too large)";
 	return "frame build failed";
 }
 
@@ -924,7 +991,7 @@ int build_frame_finish(Context* ctx)
 	FM_CUDA(launch_pdl(k_cell_order, dim3(pblocks), dim3(kThreads), 0, s, d_xyz, n32, f->d_gp, ctx->d_tmp_idx, f->d_cell_start, f->d_sorted));
 	ctx->kernel_launches += 4;
 	FM_CUDA(cudaGetLastError());
-	// the status bits of the later kernels (FM_GRID_CROWDED) come back with the frame's results
+	// the status word at the end of the build comes back with the frame's results
 	FM_CUDA(cudaMemcpyAsync(f->h_gp + 1, f->d_gp, sizeof(GridParams), cudaMemcpyDeviceToHost, s));
 	f->gp_pending = true;
 	FM_TIME(ctx, ctx->ev[3], s);
@@ -989,7 +1056,7 @@ int resolve_frame(Context* ctx, Frame* f, bool synced)
 	{
 		f->valid = false;
 		set_error(grid_status_text(gp.status));
-		return (gp.status & FM_GRID_CROWDED) ? FR_ERR_UNSUPPORTED : FR_ERR_INVALID;
+		return FR_ERR_INVALID;
 	}
 	return erc;
 }

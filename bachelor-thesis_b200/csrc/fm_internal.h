@@ -51,10 +51,9 @@ enum
 {
 	FM_GRID_NONFINITE = 1,       // a particle coordinate is NaN or infinite
 	FM_GRID_DEGENERATE = 2,      // empty / non-finite bounds, or extent / h beyond 2^31 cells
-	FM_GRID_OVERFLOW = 4,        // the tables sized for an earlier frame are too small: rebuild with a host round trip
-	FM_GRID_CROWDED = 8          // more than kMaxCellParticles particles in one search cell
+	FM_GRID_OVERFLOW = 4         // the tables sized for an earlier frame are too small: rebuild with a host round trip
 };
-constexpr uint32_t kMaxCellParticles = 2048;     // in-cell ordering is quadratic in the cell population (k_cell_order)
+constexpr uint32_t kMaxCellParticles = 2048;     // above: the cell is sorted by one CTA instead of ranked quadratically (k_cell_order)
 
 // table capacities the device checks the grid parameters against (all 0xffffffff: no check, the host sizes the tables
 // after reading the parameters back)

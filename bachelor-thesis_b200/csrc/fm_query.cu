@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(128) k_query_density(FrameView f, const float*
 	int const z0 = max(kz - 1, 0), z1 = min(kz + 1, f.kdim.z - 1);
 	float rho = 0.0f;
 	f3 g = mk3(0.0f, 0.0f, 0.0f);
+	uint32_t nn = 0;
 	if (z0 <= z1)
 		for (int dx = -1; dx <= 1; dx++)
 		{
@@ -87,8 +88,13 @@ __global__ void __launch_bounds__(128) k_query_density(FrameView f, const float*
 					float const l2 = addr(addr(mulr(d0, d0), mulr(d1, d1)), mulr(d2, d2));
 					if (l2 < f.kernel.h_squared)
 					{
-						rho = addr(rho, spline_W_inrange(f.kernel, l2));
-						g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+						// `NumNeighbors = min(neighbors.size(), MAX_NEIGHBORS)` (RayMarcher.cpp:14, :312): the sums stop there
+						if (nn < 8192u)
+						{
+							rho = addr(rho, spline_W_inrange(f.kernel, l2));
+							g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
+						}
+						nn++;
 					}
 				}
 			}

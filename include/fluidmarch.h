@@ -148,8 +148,8 @@ void fr_host_free(void* p);
  * kernels read the grid parameters from device memory, the first of them also stores them into mapped host memory, and
  * the next fr_render_async of the frame picks them up (its depth pre-pass is queued first, so the GPU never idles) and
  * reports non-finite coordinates (FR_ERR_INVALID) or, if the tables are too small for the new bounds, rebuilds the
- * frame transparently.  More than 2048 particles in one h-cell (FR_ERR_UNSUPPORTED) is reported by the next call that
- * waits for the context (fr_wait, fr_download, fr_get_frame_info, ...). */
+ * frame transparently.  (A collapsed simulation -- thousands to millions of particles in one h-cell -- builds too: such a
+ * cell is ordered by a sort instead of the quadratic ranking.) */
 int fr_upload_frame(fr_context* ctx, int frame, const float* xyz_host, size_t n, float h, float h_ext_mult);
 /* 0: every frame build waits for the device once and reports its errors immediately (round-1 behaviour); default 1 */
 int fr_set_async_build(fr_context* ctx, int on);
@@ -240,7 +240,8 @@ int fr_get_stream(fr_context* ctx, void** stream);
 int fr_query_neighbors(fr_context* ctx, int frame, const float* points_host, size_t m,
 					   uint32_t* counts, uint32_t* ids, size_t cap);
 /* density = sum_j W(x_j - p_i) (RayMarcher.cpp:322-325) and, if grad != NULL, the un-normalised
- * sum_j gradW(x_j - p_i) (RayMarcher.cpp:333-336), m*3 floats */
+ * sum_j gradW(x_j - p_i) (RayMarcher.cpp:333-336), m*3 floats; over the first MAX_NEIGHBORS = 8192 neighbours in the
+ * reference's list order, as the march (RayMarcher.cpp:312) */
 int fr_query_density(fr_context* ctx, int frame, const float* points_host, size_t m, float* density, float* grad);
 
 /* ---- anisotropic path probes (parity of Dataset::GetNeighborsExt, RayMarcher::WPCA, AnisotropicKernel) ------ */

@@ -123,18 +123,50 @@ def test_non_finite_particles_are_rejected(fm, gpu_ctx_factory, poison, tmp_path
         other.upload_frame_bgeo(0, path, 0.1, 2.0)
 
 
-def test_collapsed_cell_is_refused_not_ranked(fm, gpu_ctx_factory):
-    """the in-cell ordering is quadratic; a collapsed simulation must not occupy the GPU for seconds"""
-    xyz = np.concatenate([scenes.dam_break(8000), np.full((5000, 3), 0.01234, np.float32)])
+@pytest.mark.parametrize("crowd", [1500, 5000, 40000])
+def test_collapsed_cell_is_ordered_by_a_sort(fm, oracle, gpu_ctx_factory, crowd):
+    """the in-cell ranking is quadratic; a cell with more than 2048 particles (a collapsed simulation) is
+    sorted by one CTA instead -- same order (ascending original index inside every cell, both searches), same sums"""
+    rng = np.random.default_rng(crowd)
+    blob = (np.float32(0.01234) + rng.uniform(0.0, 0.02, (crowd, 3))).astype(np.float32)      # inside one h-cell
+    xyz = np.concatenate([scenes.dam_break(8000), blob])
+    xyz = xyz[rng.permutation(len(xyz))]
     ctx = gpu_ctx_factory(64, 64)
-    ctx.upload_frame(0, xyz, 0.1, 2.0)
-    with pytest.raises(fm.FluidMarchError, match="2048 particles in one search cell"):
-        ctx.frame_info(0)
-    ok = np.concatenate([scenes.dam_break(8000), np.full((1500, 3), 0.01234, np.float32)])
-    ctx.upload_frame(0, ok, 0.1, 2.0)
-    g = ctx.download_frame(0)
-    idx = g["sorted_index"].astype(np.int64)
-    assert np.array_equal(np.sort(idx), np.arange(len(ok)))
+    for _ in range(2):                                   # host-sized tables, then a build that does not wait
+        ctx.upload_frame(0, xyz, 0.1, 2.0)
+        g = ctx.download_frame(0)
+        idx = g["sorted_index"].astype(np.int64)
+        assert np.array_equal(np.sort(idx), np.arange(len(xyz)))
+        cs = g["cell_start"].astype(np.int64)
+        assert (np.diff(cs) > 2048).any() == (crowd > 2048)
+        inner = np.ones(len(idx), bool)
+        inner[cs[1:-1][cs[1:-1] < len(idx)]] = False     # first slot of every later cell
+        inner[0] = False
+        assert (np.diff(idx)[inner[1:]] > 0).all(), "indices ascend inside every cell"
+        assert np.array_equal(xyz[idx], g["sorted_xyz"])
+    # the ordered sums over the blob (up to MAX_NEIGHBORS = 8192 of its particles) against the oracle
+    pts = np.array([[0.02, 0.02, 0.02], [0.05, 0.0, 0.03], [-0.3, -0.8, 0.1]], np.float32)
+    rho, grad = ctx.query_density(0, pts)
+    f = oracle.frame(xyz, 0.1, 2.0)
+    perm = f.particles()
+    for i, p in enumerate(pts):
+        want, gw = np.float32(0), np.zeros(3, np.float32)
+        for j in f.neighbors(p, cap=8192):               # MAX_NEIGHBORS (RayMarcher.cpp:14): the list is cut there
+            r = (perm[j] - p).astype(np.float32)
+            want = np.float32(want + oracle.W(0.1, r))
+            gw = (gw + oracle.gradW(0.1, r)).astype(np.float32)
+        assert bits(rho[i:i + 1])[0] == bits(np.array([want]))[0], (i, rho[i], want)
+        assert np.array_equal(bits(grad[i]), bits(gw)), i
+    # the r = 2h search
+    srt, cs_ext, _, _ = ctx.download_frame_ext(0)
+    ids = srt[:, 3].view(np.uint32).astype(np.int64)
+    assert np.array_equal(np.sort(ids), np.arange(len(xyz)))
+    cs_ext = cs_ext.astype(np.int64)
+    inner = np.ones(len(ids), bool)
+    inner[cs_ext[1:-1][cs_ext[1:-1] < len(ids)]] = False
+    inner[0] = False
+    assert (np.diff(ids)[inner[1:]] > 0).all()
+    assert np.array_equal(xyz[ids], srt[:, :3])
 
 
 def test_many_search_cells_scan_in_one_pass(fm, oracle, gpu_ctx_factory):
