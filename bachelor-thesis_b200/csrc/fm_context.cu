@@ -57,6 +57,7 @@ static StreamWriteValue32Fn stream_write_value32()
 
 int stream_sync(Context* c)
 {
+	c->wait_epoch++;                     // a host wait: the raw particle array of a queued build is the caller's again (render_depth)
 	// the lanes of a sequence: a word in mapped pinned memory, written behind everything on the stream, polled
 	// without entering the driver
 	if (c->blocking_sync && c->h_sync_flag)
@@ -157,7 +158,7 @@ static int render_passes(fr_context* ctx, int passes);
 // of its slot too small and has been rebuilt.
 static int finish_pending_ex(Context* c)
 {
-	c->wait_epoch++;                     // (the raw particle array of a queued build is the caller's again: render_depth)
+	c->wait_epoch++;                     // (as stream_sync: whoever calls this may have waited)
 	bool const rendered = c->render_pending;
 	if (c->render_pending)
 	{
