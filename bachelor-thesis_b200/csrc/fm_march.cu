@@ -77,9 +77,6 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 
 	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
 	mp.tiles_x = tiles_x;
-	mp.tiles_total = tiles_x * tiles_y;
-	static int const fuse = [] { const char* e = getenv("FLUIDMARCH_FUSE"); return (e && e[0] == '0') ? 0 : 1; }();
-	mp.fuse_long = fuse;
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	int rc;
 	if ((rc = ensure_capacity(&ctx->d_tiles, &ctx->cap_tiles, (size_t)tiles_x * tiles_y + 8))) return rc;

@@ -59,18 +59,14 @@ struct MarchParams
 	int rx0, ry0, rx1, ry1;           // region partition: the pixel rectangle this context renders (rx1 == 0: everything)
 	int do_march, do_shade;
 	int tiles_x;                      // 8x4 pixel tiles per image row
-	int tiles_total;                  // slots of the tile list (edge tiles fill it from the front, full tiles from the back)
-	int fuse_long;                    // k_march_first marches queued rays between its tiles (isotropic; FLUIDMARCH_FUSE=0 switches it off)
 	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
 	uint32_t n_eps;
 };
 
 struct RayQueues
 {
-	float4* q1;              // rays left after the first sample -> long_ray (k_march_first between its tiles, then k_march_long)
-	uint32_t* ctl;           // [0] edge tiles listed (front of the list) [1] tile cursor [2] |q1|: slots reserved [3] q1 cursor
-	                         // [4] published slots not yet claimed (semaphore) [5] k_march_long's cursor [6] full tiles listed (back
-	                         // of the list) [7] published prefix of q1
+	float4* q1;              // rays left after the first sample -> k_march_long
+	uint32_t* ctl;           // [0] tiles listed [1] tile cursor [2] |q1| [3] q1 cursor
 	uint32_t* prof;          // FM_LONG_PROFILE builds: four spare words (DeviceCounters::first_examined / first_fallbacks)
 };
 
@@ -102,12 +98,6 @@ struct LaneCounters
 	uint32_t fallbacks;      // samples whose tile did not fit the shared-memory stage (walked out of global memory)
 };
 
-#ifndef FM_FUSE_LONG
-#define FM_FUSE_LONG 0                    // k_march_first marches the rays it queues between its tiles (edge tiles first, claim_ray):
-                                          // a measured loss, r02w-y -- a queued ray's serial walk runs ~4x slower among the 24
-                                          // resident tile warps of an SM (190 us instead of 43 us for the slowest ray at C2) than
-                                          // in k_march_long's 16 mostly idle ones: C2 0.124 + 0.052 -> 0.33 + 0.04 ms
-#endif
 #ifndef FM_LONG_MINBLOCKS
 #define FM_LONG_MINBLOCKS 2               // resident 256-thread CTAs per SM k_march_long (isotropic) is compiled for
 #endif
@@ -1100,30 +1090,24 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
 	}
 	if (!mp.do_march) return;
-	// FM_FUSE_LONG builds: edge tiles -- not every pixel covered: the fluid's silhouette, where the rays are that miss on
-	// their first sample and go to the queue -- are listed from the front, full tiles from the back of the array, and
-	// the march draws its tickets front to back: the queued rays, whose walks are the longest serial chains of the
-	// frame, become known in the first wave of tiles (k_march_first, FUSE).  Otherwise every tile counts as an edge tile.
-	__shared__ uint32_t s_kind[8];       // 0: nothing covered, 1: edge tile, 2: full tile
-	__shared__ uint32_t s_base[2];
+	__shared__ uint32_t s_any[8];
+	__shared__ uint32_t s_base;
 	bool const any = __any_sync(0xffffffffu, covered);
-	bool const all = FM_FUSE_LONG && __all_sync(0xffffffffu, covered || !active);      // (one list, front to back, unless FM_FUSE_LONG)
-	if (lane == 0) s_kind[warp] = any ? (all ? 2u : 1u) : 0u;
+	if (lane == 0) s_any[warp] = any ? 1u : 0u;
 	__syncthreads();
-	if (threadIdx.x < 2)
+	if (threadIdx.x == 0)
 	{
 		uint32_t c = 0;
 #pragma unroll
-		for (int w = 0; w < 8; w++) c += s_kind[w] == threadIdx.x + 1u ? 1u : 0u;
-		s_base[threadIdx.x] = c ? atomicAdd(n_tiles + (threadIdx.x == 0 ? 0 : 6), c) : 0u;
+		for (int w = 0; w < 8; w++) c += s_any[w];
+		s_base = c ? atomicAdd(n_tiles, c) : 0u;
 	}
 	__syncthreads();
 	if (any && lane == 0)
 	{
-		uint32_t const kind = all ? 2u : 1u;
-		uint32_t slot = s_base[kind - 1u];
-		for (int w = 0; w < warp; w++) slot += s_kind[w] == kind ? 1u : 0u;
-		tiles[all ? (uint32_t)mp.tiles_total - 1u - slot : slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
+		uint32_t slot = s_base;
+		for (int w = 0; w < warp; w++) slot += s_any[w];
+		tiles[slot] = ((uint32_t)ty << 16) | (uint32_t)tx;
 	}
 }
 
@@ -1327,38 +1311,20 @@ __device__ __forceinline__ void finish_hit(const FrameView& f, const MarchParams
 
 // ---- ray queues between the three march phases -----------------------------------------------------------
 // A ray that is not finished by a phase is handed on as 32 bytes: (position.xyz, pixel index) (step.xyz, samples taken)
-// publish != nullptr (= RayQueues::ctl): the slots are handed to the warps that march queued rays while k_march_first
-// is still running (claim_ray).  Commits are ordered -- a warp publishes its slots once every slot below them has been
-// published (ctl[7] = the published prefix; the wait is the few instructions another warp spends between its
-// reservation and its commit) -- and each published slot adds one to the semaphore ctl[4].
 __device__ __forceinline__ void push_rays(bool want, float4* __restrict__ q, uint32_t* __restrict__ n, uint32_t index,
-										  f3 position, f3 step, int i, uint32_t* __restrict__ publish = nullptr)
+										  f3 position, f3 step, int i)
 {
 	uint32_t const m = __ballot_sync(0xffffffffu, want);
 	if (m == 0u) return;
 	int const lane = threadIdx.x & 31;
-	int const leader = __ffs(m) - 1;
 	uint32_t base = 0;
-	if (lane == leader) base = atomicAdd(n, (uint32_t)__popc(m));
-	base = __shfl_sync(0xffffffffu, base, leader);
+	if (lane == __ffs(m) - 1) base = atomicAdd(n, (uint32_t)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
 	if (want)
 	{
 		uint32_t const slot = base + __popc(m & ((1u << lane) - 1u));
 		q[2 * (size_t)slot] = make_float4(position.x, position.y, position.z, __uint_as_float(index));
 		q[2 * (size_t)slot + 1] = make_float4(step.x, step.y, step.z, __int_as_float(i));
-		if (publish) __threadfence();
-	}
-	if (publish)
-	{
-		__syncwarp();
-		if (lane == leader)
-		{
-			uint32_t seen;
-			do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(publish + 7) : "memory"); } while (seen != base);
-			__threadfence();
-			atomicExch(publish + 7, base + (uint32_t)__popc(m));
-			atomicAdd(publish + 4, (uint32_t)__popc(m));
-		}
 	}
 }
 
@@ -1406,13 +1372,6 @@ static_assert(sizeof(WarpStage) >= kListWords * 4, "the global-memory walk's lis
 // from device memory instead -- which would let the march be queued before the host knows the frame's grid parameters
 // -- was measured, r02c-e: through a __constant__ table indexed per context k_march_first +20 %, through a shared-memory
 // copy +12 %, k_march_long +9 %.  The host gets the parameters early on a side stream instead, fm_grid.cu.)
-// (defined behind coop_eval, below)
-template <bool FAST, bool ANISO>
-__device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& mp, uint32_t t, const RayQueues& rq, unsigned char* s_dyn,
-										 uint32_t occ_s, LaneCounters& lc, float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
-										 uchar4* __restrict__ rgba_out);
-__device__ __forceinline__ uint32_t claim_ray(uint32_t* __restrict__ ctl);
-
 #ifdef FM_FIRST_PROFILE
 // profiling build (tools/build_variant.sh x -DFM_FIRST_PROFILE, read by tools/first_profile.py through fr_debug_first_profile):
 // per warp: start, finish (globaltimer ns), duration of its longest tile, (max skips of a lane on that tile << 32 | tiles done)
@@ -1433,13 +1392,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	// samples) keeps its list at the start of the warp's share
 	uint32_t* const list = reinterpret_cast<uint32_t*>(s_dyn) + (ANISO ? 0 : (threadIdx.x >> 5) * (kFirstWarpBytes / 4) + lane);
 	LaneCounters lc = {};
-	uint32_t const n_edge = __ldcg(rq.ctl + 0), count = n_edge + __ldcg(rq.ctl + 6);
-	// k_march_first also marches the rays it queues (long_ray): a warp that finds a queued ray ready takes it before its
-	// next tile, so the serial walks of those rays run underneath the tiles instead of behind them in k_march_long,
-	// and the warps that run out of tiles towards the end of the kernel (r02u: they finish between 82 and 117 us of a
-	// 127 us launch at C2, a tile takes 28 us) have something to do.  Nobody waits: what is not ready is left for k_march_long.
-	constexpr bool FUSE = FM_FUSE_LONG && !ANISO && !FM_FIRST_STAGED;
-	bool const fuse = FUSE && mp.fuse_long != 0;
+	uint32_t const count = __ldcg(rq.ctl + 0);
 	// the occupancy bitmap, staged when it fits without costing a resident CTA (see advance, k_march_long)
 	uint32_t occ_s = 0u;
 	if (occ_words != 0u && count != 0u)
@@ -1457,6 +1410,10 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	// the first tile of a warp is the one with its own number: thousands of warps drawing their first ticket from one
 	// counter at the same moment queue up at that address for longer than a tile takes to launch; afterwards the
 	// tickets are spread in time
+	// (r02w-y: this kernel marching the rays it queues between its tiles -- edge tiles first, a semaphore-published queue,
+	// k_march_long for what is left; the code is in the history at d55db80 -- loses: a queued ray's serial walk runs ~4x
+	// slower among the 24 busy warps of an SM than among k_march_long's 16 mostly idle ones, C2 0.124 + 0.052 -> 0.33 +
+	// 0.04 ms.)
 	// (r02z: tiles cost about the same -- C2: p50 27.8 us, p90 30.1 us -- and a warp gets only 3.67 of them, so the kernel
 	// lasts 4 tiles while the SMs drain for the last quarter of it.  Letting only ceil(tiles / 4) warps take part, so that
 	// every round of tiles is full, does not help: a tile takes as long among 22 warps as among 24 -- 0.1249 -> 0.1268 ms.)
@@ -1482,7 +1439,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 		}
 		first = false;
 		if (t >= count) break;
-		uint32_t const txy = __ldg(tiles + (t < n_edge ? t : (uint32_t)mp.tiles_total - 1u - (t - n_edge)));
+		uint32_t const txy = __ldg(tiles + t);
 		int const px = (int)(txy & 0xffffu) * 8 + (lane & 7), py = (int)(txy >> 16) * 4 + (lane >> 3);
 		uint32_t const index = (uint32_t)py * (uint32_t)mp.W + (uint32_t)px;
 		bool covered = pixel_active(mp, px, py);
@@ -1565,20 +1522,8 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 			}
 		}
 		__syncwarp();
-		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1, fuse ? rq.ctl : nullptr);
+		push_rays(more, rq.q1, rq.ctl + 2, index, position, step, 1);
 		if (covered && !more) write_pixel(mp, index, P, N, pos_out, nrm_out, rgba_out);
-		if constexpr (FUSE)
-		{
-			// a queued ray before the next tile: their chains are long, the sooner they start the better they hide.  ONE
-			// per tile -- the rays must spread over the warps (a warp that keeps claiming marches them one after the other)
-			if (fuse)
-			{
-				uint32_t r = 0xffffffffu;
-				if (lane == 0) r = claim_ray(rq.ctl);
-				r = __shfl_sync(FULL, r, 0);
-				if (r != 0xffffffffu) long_ray<FAST, ANISO>(f, mp, r, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
-			}
-		}
 #ifdef FM_FIRST_PROFILE
 		{
 			__syncwarp();
@@ -1589,18 +1534,6 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 			if (dt > prof_longest) { prof_longest = dt; prof_info = ((unsigned long long)sk << 32) | ((unsigned long long)(txy >> 16) << 16) | (txy & 0xffffu); }
 		}
 #endif
-	}
-	if constexpr (FUSE)
-	{
-		// out of tiles: up to two more rays (more would march them one after the other; k_march_long takes them all at once)
-		for (int k = 0; fuse && k < 2; k++)
-		{
-			uint32_t r = 0xffffffffu;
-			if (lane == 0) r = claim_ray(rq.ctl);
-			r = __shfl_sync(FULL, r, 0);
-			if (r == 0xffffffffu) break;
-			long_ray<FAST, ANISO>(f, mp, r, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
-		}
 	}
 #ifdef FM_FIRST_PROFILE
 	if (lane == 0)
@@ -1910,21 +1843,6 @@ __device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& 
 	__syncwarp();
 }
 
-// A warp of k_march_first claims a queued ray (lane 0 calls this): ctl[4] counts the published slots nobody has
-// claimed yet -- a semaphore; a claim that finds it empty puts its unit back -- and a successful claim draws the next
-// slot from the cursor ctl[3], which therefore never passes the published prefix.  Returns 0xffffffff when no ray is
-// ready: nobody ever waits for a ray; k_march_long marches what is left in the queue when k_march_first ends.
-__device__ __forceinline__ uint32_t claim_ray(uint32_t* __restrict__ ctl)
-{
-	uint32_t avail;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(avail) : "l"(ctl + 4) : "memory");
-	if ((int)avail <= 0) return 0xffffffffu;
-	if ((int)atomicSub(ctl + 4, 1u) <= 0) { atomicAdd(ctl + 4, 1u); return 0xffffffffu; }
-	uint32_t const r = atomicAdd(ctl + 3, 1u);
-	__threadfence();
-	return r;
-}
-
 template <bool FAST, bool ANISO>
 __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINBLOCKS) k_march_long(FrameView f, MarchParams mp, float4* __restrict__ pos_out,
 														float4* __restrict__ nrm_out, uchar4* __restrict__ rgba_out,
@@ -1935,11 +1853,10 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 	int const lane = threadIdx.x & 31;
 	extern __shared__ __align__(16) unsigned char s_dyn[];       // the warps' lists (kLongSmem / kAnisoSmem), then the bitmap
 	LaneCounters lc = {};
-	// the rays k_march_first did not march itself: slots [start, count) of the queue
-	uint32_t const count = __ldcg(rq.ctl + 2), start = __ldcg(rq.ctl + 3);
+	uint32_t const count = __ldcg(rq.ctl + 2);
 	// the occupancy bitmap of the frame, staged once per CTA when the host found room for it (see advance)
 	uint32_t occ_s = 0u;
-	if (occ_words != 0u && count > start)
+	if (occ_words != 0u && count != 0u)
 	{
 		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoSmem : kLongSmem));
 		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);        // (cudaMalloc'ed: 256-byte aligned)
@@ -1953,10 +1870,10 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 	bool first = true;
 	for (;;)
 	{
-		uint32_t t = start + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);     // first ray: the warp's own number (see k_march_first)
+		uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;     // first ray: the warp's own number (see k_march_first)
 		if (!first)
 		{
-			if (lane == 0) t = start + nwarps + atomicAdd(rq.ctl + 5, 1u);
+			if (lane == 0) t = nwarps + atomicAdd(rq.ctl + 3, 1u);
 			t = __shfl_sync(FULL, t, 0);
 		}
 		first = false;
