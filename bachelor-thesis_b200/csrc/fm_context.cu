@@ -262,6 +262,8 @@ int fr_create(int device, int width, int height, fr_context** out)
 		if (cudaStreamCreateWithFlags(&c->stream_depth, cudaStreamNonBlocking) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaEventCreateWithFlags(&c->ev_fork2, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
+		if (cudaEventCreateWithFlags(&c->ev_join2, cudaEventDisableTiming) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		if (const char* e = getenv("FLUIDMARCH_OVERLAP")) c->overlap_depth = e[0] != '0';
 		if (cudaHostAlloc((void**)&c->h_sync_flag, 64, cudaHostAllocMapped) != cudaSuccess) { rc = FR_ERR_CUDA; break; }
 		*c->h_sync_flag = 0u;
@@ -344,6 +346,8 @@ void fr_destroy(fr_context* ctx)
 	if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
 	if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
 	if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+	if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+	if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
 	if (ctx->stream_depth) cudaStreamDestroy(ctx->stream_depth);
 	if (ctx->h_sync_flag) cudaFreeHost((void*)ctx->h_sync_flag);
 	if (ctx->stream) cudaStreamDestroy(ctx->stream);

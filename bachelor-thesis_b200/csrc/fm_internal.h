@@ -120,6 +120,7 @@ struct Context
 	// of a queued build is only guaranteed until the next one (fr_build_frame_device's contract).
 	cudaStream_t stream_depth = nullptr;
 	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+	cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;      // the same around the uncovered pixels' outputs beside k_march_long (launch_march)
 	uint64_t fork_serial = 0;          // Frame::build_serial of the build ev_fork belongs to
 	uint64_t wait_epoch = 0;
 	bool overlap_depth = true;         // FLUIDMARCH_OVERLAP=0 switches it off; sequence lanes: off (other lanes' frames fill the GPU)

@@ -1059,12 +1059,12 @@ __device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int 
 }
 
 // every pixel: background + work list of the 8x4 tiles that hold covered pixels.  CTA = 4x2 tiles = 32x8 pixels.
-// (r03b: writing the outputs of the uncovered pixels from a second kernel on a side stream, beside the march, gains
-// nothing -- C2 0.3026 -> 0.3011 ms per frame, C3 0.908 -> 0.934 ms: it competes with k_march_first for the SMs.)
+// what: 1 = the tile list, 2 = the outputs of the uncovered pixels, 3 = both.  With stage timing off the second half runs
+// on the context's side stream beside k_march_long (launch_march).
 __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* __restrict__ depth,
 												  float4* __restrict__ pos_out, float4* __restrict__ nrm_out,
 												  uchar4* __restrict__ rgba_out, uint32_t* __restrict__ tiles,
-												  uint32_t* __restrict__ n_tiles)
+												  uint32_t* __restrict__ n_tiles, int what)
 {
 	pdl_enter();
 	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1079,7 +1079,7 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 		if (mp.do_march)
 		{
 			covered = depth[index] != 1.0f;     // `if (z == 1.0f) return;` (RayMarcher.cpp:264)
-			if (!covered)
+			if (!covered && (what & 2))
 			{
 				float4 const zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // RayMarcher.cpp:262-263
 				pos_out[index] = zero;
@@ -1089,7 +1089,7 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 		}
 		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
 	}
-	if (!mp.do_march) return;
+	if (!mp.do_march || !(what & 1)) return;
 	__shared__ uint32_t s_any[8];
 	__shared__ uint32_t s_base;
 	bool const any = __any_sync(0xffffffffu, covered);

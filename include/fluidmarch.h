@@ -156,10 +156,11 @@ int fr_set_async_build(fr_context* ctx, int on);
 /* 1 (default): CUDA events between the stages of a frame feed fr_get_timings.  0: no events -- the kernels of a frame
  * then form one chain of programmatic dependent launches (each kernel's CTAs are scheduled while the previous kernel
  * drains), and the depth pre-pass of a render queued behind a frame build runs on a second stream beside the build's
- * kernels (from the same particle array: see fr_build_frame_device for how long that array must stay unchanged) -- the
+ * kernels (from the same particle array: see fr_build_frame_device for how long that array must stay unchanged), the
+ * outputs of the uncovered pixels are written on that stream while the long rays march -- the
  * lowest latency for a host that marches one frame at a time as AdvancedRenderer.cpp:257-298 does; fr_get_timings
- * reports zeros.  Sequence lanes always run without the events.  Environment: FLUIDMARCH_OVERLAP=0 keeps the pre-pass on
- * the one stream, FLUIDMARCH_PDL=0 switches the programmatic launches off. */
+ * reports zeros.  Sequence lanes always run without the events.  Environment: FLUIDMARCH_OVERLAP=0 keeps everything on
+ * the one stream (FLUIDMARCH_BG=0: only the uncovered pixels), FLUIDMARCH_PDL=0 switches the programmatic launches off. */
 int fr_set_stage_timing(fr_context* ctx, int on);
 /* same, particles already resident in device memory (n packed float3); the build is left on the context's stream:
  * xyz_device must stay valid and unchanged until the host next waits for the context (fr_wait, fr_download, ...) */

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 fm = importlib.import_module("bachelor-thesis_b200")
 
-CONFIGS = {"C2": (1_000_000, 1920, 1080, 0.1, None), "C3": (4_000_000, 3840, 2160, 0.063, 0.0315)}
+CONFIGS = {"C1": (64_000, 1280, 720, 0.1, None), "C2": (1_000_000, 1920, 1080, 0.1, None), "C3": (4_000_000, 3840, 2160, 0.063, 0.0315)}
 
 
 def main():
