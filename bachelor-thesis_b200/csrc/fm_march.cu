@@ -165,6 +165,7 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 				FM_CUDA(cudaStreamWaitEvent(ctx->stream_depth, ctx->ev_fork2, 0));
 				k_classify<<<grid, 256, 0, ctx->stream_depth>>>(mp, ctx->d_depth, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, tiles, rq.ctl, 2);
 				FM_CUDA(cudaEventRecord(ctx->ev_join2, ctx->stream_depth));
+				ctx->kernel_launches += 1;
 			}
 			FM_CUDA(launch_pdl(longk, dim3(ctas_long), dim3(256), smem_long, st, fv, mp, ctx->d_pos, ctx->d_nrm, ctx->d_rgba_target, rq, ctx->d_counters, occ_words));
 		}
