@@ -153,6 +153,48 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a)
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 	return v;
 }
+
+// ---- the occupancy bitmap into shared memory: one bulk asynchronous copy (TMA, cp.async.bulk) per CTA ------------------
+// One thread arms an mbarrier with the byte count and issues the copy; the CTA goes on -- control words, the first tile
+// or ray, its depth and step -- and every thread waits on the barrier's phase 0 right before its first look-up.  The
+// copy moves the bitmap's 16-byte multiple; the up to three words behind it are stored by plain loads.
+__device__ __forceinline__ void bitmap_stage_begin(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t words,
+												   unsigned long long* bar)
+{
+	uint32_t const bar_s = smem_addr(bar), dst_s = smem_addr(dst);
+	uint32_t const bulk_words = words & ~3u;
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s) : "memory");
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (threadIdx.x < (words & 3u)) dst[bulk_words + threadIdx.x] = __ldg(src + bulk_words + threadIdx.x);
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		if (bulk_words != 0u)
+		{
+			asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bulk_words * 4u) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_s), "l"(src),
+						 "r"(bulk_words * 4u), "r"(bar_s)
+						 : "memory");
+		}
+		else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_s) : "memory");
+	}
+}
+
+__device__ __forceinline__ void bitmap_stage_wait(unsigned long long* bar)
+{
+	uint32_t const bar_s = smem_addr(bar);
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"BITMAP_WAIT:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+		"@p bra BITMAP_DONE;\n\t"
+		"bra BITMAP_WAIT;\n\t"
+		"BITMAP_DONE:\n\t}" ::"r"(bar_s)
+		: "memory");
+}
 __device__ __forceinline__ uint32_t lds_u16(uint32_t a)
 {
 	unsigned short v;
@@ -1395,14 +1437,13 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 	uint32_t const count = __ldcg(rq.ctl + 0);
 	// the occupancy bitmap, staged when it fits without costing a resident CTA (see advance, k_march_long)
 	uint32_t occ_s = 0u;
+	__shared__ __align__(8) unsigned long long s_bitmap_bar;
+	bool bitmap_pending = false;
 	if (occ_words != 0u && count != 0u)
 	{
 		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoFirstSmem : kFirstSmem));
-		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);
-		uint32_t const quads = occ_words >> 2;
-		for (uint32_t i = threadIdx.x; i < quads; i += blockDim.x) reinterpret_cast<uint4*>(occ)[i] = __ldg(src + i);
-		for (uint32_t i = (quads << 2) + threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = __ldg(f.occ_bits + i);
-		__syncthreads();
+		bitmap_stage_begin(occ, f.occ_bits, occ_words, &s_bitmap_bar);
+		bitmap_pending = true;
 		occ_s = smem_addr(occ);
 	}
 	f3 const cam = mk3(mp.cam[0], mp.cam[1], mp.cam[2]);
@@ -1449,6 +1490,7 @@ __global__ void __launch_bounds__(ANISO ? 256 : kFirstThreads, ANISO ? FM_ANISO_
 		float4 P = make_float4(0.0f, 0.0f, 0.0f, 0.0f), N = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 		f3 position = mk3(0.0f, 0.0f, 0.0f), step = position, prev = position;
 		bool more = false, sample = false;
+		if (bitmap_pending) { bitmap_stage_wait(&s_bitmap_bar); bitmap_pending = false; }
 		if (covered)
 		{
 			lc.covered++;
@@ -1858,14 +1900,13 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 	uint32_t const count = __ldcg(rq.ctl + 2);
 	// the occupancy bitmap of the frame, staged once per CTA when the host found room for it (see advance)
 	uint32_t occ_s = 0u;
+	__shared__ __align__(8) unsigned long long s_bitmap_bar;
+	bool bitmap_pending = false;
 	if (occ_words != 0u && count != 0u)
 	{
 		uint32_t* const occ = reinterpret_cast<uint32_t*>(s_dyn + (ANISO ? kAnisoSmem : kLongSmem));
-		uint4 const* const src = reinterpret_cast<uint4 const*>(f.occ_bits);        // (cudaMalloc'ed: 256-byte aligned)
-		uint32_t const quads = occ_words >> 2;
-		for (uint32_t i = threadIdx.x; i < quads; i += blockDim.x) reinterpret_cast<uint4*>(occ)[i] = __ldg(src + i);
-		for (uint32_t i = (quads << 2) + threadIdx.x; i < occ_words; i += blockDim.x) occ[i] = __ldg(f.occ_bits + i);
-		__syncthreads();
+		bitmap_stage_begin(occ, f.occ_bits, occ_words, &s_bitmap_bar);        // (cudaMalloc'ed: 256-byte aligned)
+		bitmap_pending = true;
 		occ_s = smem_addr(occ);
 	}
 	uint32_t const nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -1880,6 +1921,7 @@ __global__ void __launch_bounds__(256, ANISO ? FM_ANISO_MINBLOCKS : FM_LONG_MINB
 		}
 		first = false;
 		if (t >= count) break;
+		if (bitmap_pending) { bitmap_stage_wait(&s_bitmap_bar); bitmap_pending = false; }
 		long_ray<FAST, ANISO>(f, mp, t, rq, s_dyn, occ_s, lc, pos_out, nrm_out, rgba_out);
 	}
 	flush_counters(lc, counters);
