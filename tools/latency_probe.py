@@ -22,6 +22,8 @@ def main():
     frames = int(sys.argv[2]) if len(sys.argv) > 2 else 40
     n, W, H, h, dx = CONFIGS[cfg]
     xyz = fm.scenes.dam_break(n, h=h, dx=dx, t=0.6)
+    if os.environ.get("SHUFFLE") == "1":                      # particle order as a simulation leaves it: arbitrary
+        xyz = xyz[np.random.default_rng(0).permutation(len(xyz))]
     cam = fm.camera.reference_default_camera()
     dev = torch.device("cuda:0")
     d_xyz = torch.from_numpy(np.ascontiguousarray(xyz)).to(dev)
