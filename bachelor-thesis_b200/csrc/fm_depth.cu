@@ -14,7 +14,7 @@
 // is order-independent, so ANY superset of the winning fragments gives the same bits.  The kernels below
 // only decide which (particle, pixel) pairs are worth evaluating:
 //
-//   k_depth_clear    depth <- 1.0 (DepthRenderPass.cpp:54); tile bounds <- 1.0; survivor count and march counters <- 0
+//   k_depth_clear    tile bounds <- 1.0; survivor count and march counters <- 0 (depth <- 1.0, DepthRenderPass.cpp:54: k_depth_seed)
 //   k_depth_seed     per particle: projection, splat record (32 B), and the cheapest useful bound -- the tile under
 //                    the disc centre.  Screen tiles of T x T pixels.  A particle whose disc contains all pixel
 //                    centres of a tile bounds the final depth of every pixel of that tile from above by its own
@@ -166,10 +166,17 @@ __device__ __forceinline__ bool splat_setup(const DepthParams& dp, float4 p, Spl
 template <int T>
 __global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ sorted, const float* __restrict__ raw, uint32_t n, const GridParams* __restrict__ gp, DepthParams dp,
 													float4* __restrict__ splat_a, uint4* __restrict__ splat_b,
-													uint32_t* __restrict__ tile_bound)
+													uint32_t* __restrict__ tile_bound, uint32_t* __restrict__ depth_bits, uint32_t npix)
 {
 	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
+	// depth <- 1.0 (DepthRenderPass.cpp:54) rides along here: nothing reads the image before k_depth_splat, and the 8 MB of
+	// stores overlap the projection arithmetic instead of standing at the head of the chain in k_depth_clear
+	{
+		uint32_t const rw = dp.rx1 > 0 ? (uint32_t)(dp.rx1 - dp.rx0) : (uint32_t)dp.W;
+		for (uint32_t p = i; p < npix; p += gridDim.x * blockDim.x)
+			depth_bits[rw == (uint32_t)dp.W ? (size_t)p : (size_t)((uint32_t)dp.ry0 + p / rw) * (uint32_t)dp.W + (uint32_t)dp.rx0 + p % rw] = 0x3f800000u;
+	}
 	if (i >= sorted_count(gp, n)) return;
 	Splat s;
 	float4 const p = raw ? make_float4(__ldg(raw + 3ull * i), __ldg(raw + 3ull * i + 1), __ldg(raw + 3ull * i + 2), 0.0f) : __ldg(sorted + i);
@@ -452,7 +459,7 @@ __global__ void __launch_bounds__(256) k_depth_splat(DepthParams dp, const float
 }
 
 template <int T>
-int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bounds, cudaStream_t st, const float* raw)
+int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bounds, cudaStream_t st, const float* raw, uint32_t npix)
 {
 	uint32_t const n = (uint32_t)f.n;
 	uint32_t const blocks = (n + 255u) / 256u;
@@ -461,7 +468,8 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	uint4* const splat_b = (uint4*)(ctx->d_splat + 4 * (size_t)n);
 	uint32_t* const n_surv = ctx->d_survivors;
 	uint32_t* const surv = ctx->d_survivors + 4;
-	FM_CUDA(launch_pdl(k_depth_seed<T>, dim3(blocks), dim3(256), 0, st, (const float4*)f.d_sorted, raw, n, gp, dp, splat_a, splat_b, ctx->d_tile_bound));
+	FM_CUDA(launch_pdl(k_depth_seed<T>, dim3(blocks), dim3(256), 0, st, (const float4*)f.d_sorted, raw, n, gp, dp, splat_a, splat_b, ctx->d_tile_bound,
+					   (uint32_t*)ctx->d_depth, npix));
 	uint32_t const want = (n + 7u) / 8u;
 	uint32_t const cap = (uint32_t)ctx->sm_count * 8u;
 	if (refine_bounds)
@@ -544,17 +552,22 @@ int launch_depth_prepass(Context* ctx, const Frame& f, cudaStream_t st, const fl
 	// (under a region partition only the region's pixels are cleared -- and only they are valid afterwards)
 	uint32_t const rw = region ? (uint32_t)(dp.rx1 - dp.rx0) : (uint32_t)ctx->width, rh = region ? (uint32_t)(dp.ry1 - dp.ry0) : (uint32_t)ctx->height;
 	uint32_t const npix = rw * rh;
-	uint32_t const clear_threads = npix > ntiles ? npix : ntiles;
-	FM_CUDA(launch_pdl(k_depth_clear, dim3((clear_threads + 255) / 256), dim3(256), 0, st, (uint32_t*)ctx->d_depth, npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
+	// the image itself is cleared by k_depth_seed's threads (one per particle) unless they are too few for it
+	bool const seed_clears = (size_t)f.n * 16u >= (size_t)npix;
+	uint32_t const counter_threads = ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 4u;
+	uint32_t const small_threads = ntiles > counter_threads ? ntiles : counter_threads;
+	uint32_t const clear_threads = seed_clears ? small_threads : (npix > small_threads ? npix : small_threads);
+	uint32_t const npix_seed = seed_clears ? npix : 0u;
+	FM_CUDA(launch_pdl(k_depth_clear, dim3((clear_threads + 255) / 256), dim3(256), 0, st, (uint32_t*)ctx->d_depth, seed_clears ? 0u : npix, rw, (uint32_t)dp.rx0, (uint32_t)dp.ry0, (uint32_t)ctx->width,
 																		  ctx->d_tile_bound, ntiles, ctx->d_survivors,
 																	  (uint32_t*)ctx->d_counters, ctx->zero_counters_in_depth ? (uint32_t)(sizeof(DeviceCounters) / 4) : 0u));
 	bool const refine = ctx->depth_refine_bounds;
 	switch (T)
 	{
-	case 2: launch_tiles<2>(ctx, f, dp, refine, st, raw_xyz); break;
-	case 4: launch_tiles<4>(ctx, f, dp, refine, st, raw_xyz); break;
-	case 8: launch_tiles<8>(ctx, f, dp, refine, st, raw_xyz); break;
-	default: launch_tiles<16>(ctx, f, dp, refine, st, raw_xyz); break;
+	case 2: launch_tiles<2>(ctx, f, dp, refine, st, raw_xyz, npix_seed); break;
+	case 4: launch_tiles<4>(ctx, f, dp, refine, st, raw_xyz, npix_seed); break;
+	case 8: launch_tiles<8>(ctx, f, dp, refine, st, raw_xyz, npix_seed); break;
+	default: launch_tiles<16>(ctx, f, dp, refine, st, raw_xyz, npix_seed); break;
 	}
 	ctx->kernel_launches += 1;
 	FM_CUDA(cudaGetLastError());
