@@ -308,6 +308,22 @@ __global__ void __launch_bounds__(kThreads) k_key_count(const float* __restrict_
 	// floor() of a coordinate relative to m_Min lies in [-1, dim] for every particle (m_Min = min - h); clamp for safety
 	int const cx = (int)fminf(fmaxf(fx, -2.0f), (float)b.gdim.x + 1.0f), cy = (int)fminf(fmaxf(fy, -2.0f), (float)b.gdim.y + 1.0f),
 		cz = (int)fminf(fmaxf(fz, -2.0f), (float)b.gdim.z + 1.0f);
+	// The boxes of neighbouring cells meet at the cell faces up to a few ulps of the coordinates, so a particle that is not
+	// within `eps` cells of a face -- eps = 64 ulps of the largest coordinate of the frame, in cells, at least 1e-4 -- is
+	// counted for its own cell and no other without evaluating the nine boxes (99 % of the particles: 250 -> ~160
+	// instructions per particle).
+	{
+		float const big = fmaxf(fmaxf(fabsf(b.mn.x), fabsf(b.mn.y)), fabsf(b.mn.z)) + fmaxf(fmaxf((float)b.gdim.x, (float)b.gdim.y), (float)b.gdim.z) * b.cw;
+		float const eps = fmaxf(1e-4f, 64.0f * 1.1920929e-7f * big * b.inv_cw);
+		float const rx = mulr(subr(x, b.mn.x), b.inv_cw) - fx, ry = mulr(subr(y, b.mn.y), b.inv_cw) - fy, rz = mulr(subr(z, b.mn.z), b.inv_cw) - fz;
+		bool const interior = eps < 0.25f && rx > eps && rx < 1.0f - eps && ry > eps && ry < 1.0f - eps && rz > eps && rz < 1.0f - eps &&
+			cx >= 0 && cx < b.gdim.x && cy >= 0 && cy < b.gdim.y && cz >= 0 && cz < b.gdim.z;
+		if (interior)
+		{
+			atomicAdd(grid_counts + ((uint32_t)cx + (uint32_t)b.gdim.x * ((uint32_t)cy + (uint32_t)b.gdim.y * (uint32_t)cz)), 1u);
+			return;
+		}
+	}
 	uint32_t const mx = centre_box_mask(x, b.mn.x, cx, b.gdim.x, b.cw, b.half);
 	uint32_t const my = centre_box_mask(y, b.mn.y, cy, b.gdim.y, b.cw, b.half);
 	uint32_t const mz = centre_box_mask(z, b.mn.z, cz, b.gdim.z, b.cw, b.half);
