@@ -313,17 +313,43 @@ __global__ void __launch_bounds__(256) k_depth_bounds(DepthParams dp, const floa
 // depth is not in front of that maximum cannot win any tile of the block.
 constexpr int kCoarse = 4;
 
+// One CTA per 16 x 16 block of tiles: thread t holds tile (t % 16, t / 16) of the block; the 4 x 4 maxima go to
+// `coarse`, the maximum of the whole block to `coarse2` -- the level that settles a particle deep inside the fluid
+// with one to four loads (k_depth_cull).
+constexpr int kCoarse2 = 4 * kCoarse;
+
 __global__ void __launch_bounds__(256) k_depth_coarse(const uint32_t* __restrict__ tile_bound, int tiles_x, int tiles_y,
-													  uint32_t* __restrict__ coarse, int cx, int cy)
+													  uint32_t* __restrict__ coarse, int cx, uint32_t* __restrict__ coarse2, int c2x)
 {
 	pdl_enter();
-	int const b = blockIdx.x * blockDim.x + threadIdx.x;
-	if (b >= cx * cy) return;
-	int const bx = b % cx, by = b / cx;
+	int const bx2 = blockIdx.x % c2x, by2 = blockIdx.x / c2x;
+	int const lx = threadIdx.x & 15, ly = threadIdx.x >> 4;
+	int const tx = bx2 * kCoarse2 + lx, ty = by2 * kCoarse2 + ly;
 	uint32_t m = 0u;
-	for (int y = by * kCoarse; y < min((by + 1) * kCoarse, tiles_y); y++)
-		for (int x = bx * kCoarse; x < min((bx + 1) * kCoarse, tiles_x); x++) m = max(m, __ldg(tile_bound + (size_t)y * tiles_x + x));
-	coarse[b] = m;
+	if (tx < tiles_x && ty < tiles_y) m = __ldg(tile_bound + (size_t)ty * tiles_x + tx);
+	// 4 x 4 maxima: over lx within groups of 4 (lanes 0..3 | 4..7 | ...), then over ly within groups of 4 through shared memory
+	m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+	m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+	__shared__ uint32_t s_row[16][4];
+	__shared__ uint32_t s_blk[16];
+	if ((lx & 3) == 0) s_row[ly][lx >> 2] = m;
+	__syncthreads();
+	if (threadIdx.x < 16)
+	{
+		int const gx = threadIdx.x & 3, gy = threadIdx.x >> 2;
+		uint32_t v = max(max(s_row[4 * gy][gx], s_row[4 * gy + 1][gx]), max(s_row[4 * gy + 2][gx], s_row[4 * gy + 3][gx]));
+		int const ccx = bx2 * 4 + gx, ccy = by2 * 4 + gy;
+		if (ccx < cx && ccy * kCoarse < tiles_y) coarse[(size_t)ccy * cx + ccx] = v;
+		s_blk[threadIdx.x] = v;
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t v = 0u;
+#pragma unroll
+		for (int k = 0; k < 16; k++) v = max(v, s_blk[k]);
+		coarse2[blockIdx.x] = v;
+	}
 }
 
 // pass 3: keep the particles that can still win a pixel of some tile they overlap (compacted, warp-aggregated).
@@ -331,7 +357,8 @@ __global__ void __launch_bounds__(256) k_depth_coarse(const uint32_t* __restrict
 template <int T>
 __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, const GridParams* __restrict__ gp, DepthParams dp, const uint4* __restrict__ splat_b,
 													const uint32_t* __restrict__ tile_bound, const uint32_t* __restrict__ coarse,
-													int coarse_x, uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
+													int coarse_x, const uint32_t* __restrict__ coarse2, int c2x,
+													uint32_t* __restrict__ survivors, uint32_t* __restrict__ n_survivors)
 {
 	pdl_enter();
 	uint32_t const i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,6 +370,11 @@ __global__ void __launch_bounds__(256) k_depth_cull(uint32_t n, const GridParams
 		if (x1 >= x0)
 		{
 			int const tx0 = x0 / T, ty0 = y0 / T, tx1 = x1 / T, ty1 = y1 / T;
+			// the 16 x 16-tile blocks first: a particle behind the bound of every one it touches (nearly all particles) is done
+			bool maybe = false;
+			for (int by2 = ty0 / kCoarse2; by2 <= ty1 / kCoarse2; by2++)
+				for (int bx2 = tx0 / kCoarse2; bx2 <= tx1 / kCoarse2; bx2++) maybe = maybe || b.y < __ldg(coarse2 + (size_t)by2 * c2x + bx2);
+			if (maybe)
 			for (int by = ty0 / kCoarse; by <= ty1 / kCoarse && !wins; by++)
 				for (int bx = tx0 / kCoarse; bx <= tx1 / kCoarse && !wins; bx++)
 				{
@@ -480,8 +512,10 @@ int launch_tiles(Context* ctx, const Frame& f, DepthParams dp, bool refine_bound
 	}
 	int const cx = (dp.tiles_x + kCoarse - 1) / kCoarse, cy = (dp.tiles_y + kCoarse - 1) / kCoarse;
 	uint32_t* const coarse = ctx->d_tile_bound + (size_t)dp.tiles_x * dp.tiles_y;
-	FM_CUDA(launch_pdl(k_depth_coarse, dim3((cx * cy + 255) / 256), dim3(256), 0, st, ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, cy));
-	FM_CUDA(launch_pdl(k_depth_cull<T>, dim3(blocks), dim3(256), 0, st, n, gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, surv, n_surv));
+	int const c2x = (dp.tiles_x + kCoarse2 - 1) / kCoarse2, c2y = (dp.tiles_y + kCoarse2 - 1) / kCoarse2;
+	uint32_t* const coarse2 = coarse + (size_t)cx * cy;
+	FM_CUDA(launch_pdl(k_depth_coarse, dim3(c2x * c2y), dim3(256), 0, st, ctx->d_tile_bound, dp.tiles_x, dp.tiles_y, coarse, cx, coarse2, c2x));
+	FM_CUDA(launch_pdl(k_depth_cull<T>, dim3(blocks), dim3(256), 0, st, n, gp, dp, splat_b, ctx->d_tile_bound, coarse, cx, coarse2, c2x, surv, n_surv));
 	FM_CUDA(launch_pdl(k_depth_splat<T>, dim3(want < cap ? want : cap), dim3(256), 0, st, dp, splat_a, splat_b, surv, n_surv, ctx->d_tile_bound,
 															 (uint32_t*)ctx->d_depth));
 	ctx->kernel_launches += refine_bounds ? 6 : 4;
@@ -545,7 +579,8 @@ int launch_depth_prepass(Context* ctx, const Frame& f, cudaStream_t st, const fl
 	uint32_t const ntiles = (uint32_t)dp.tiles_x * (uint32_t)dp.tiles_y;
 	int rc;
 	size_t const ncoarse = (size_t)((dp.tiles_x + kCoarse - 1) / kCoarse) * ((dp.tiles_y + kCoarse - 1) / kCoarse);
-	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles + ncoarse))) return rc;   // tiles + coarse blocks
+	size_t const ncoarse2 = (size_t)((dp.tiles_x + kCoarse2 - 1) / kCoarse2) * ((dp.tiles_y + kCoarse2 - 1) / kCoarse2);
+	if ((rc = ensure_capacity(&ctx->d_tile_bound, &ctx->cap_tile_bound, (size_t)ntiles + ncoarse + ncoarse2))) return rc;   // tiles + both coarse levels
 	if ((rc = ensure_capacity(&ctx->d_splat, &ctx->cap_splat, 8 * f.n))) return rc;            // 2 x 16 B per particle
 	if ((rc = ensure_capacity(&ctx->d_survivors, &ctx->cap_survivors, f.n + 4))) return rc;     // [0] = count
 
