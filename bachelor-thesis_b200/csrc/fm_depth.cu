@@ -58,6 +58,7 @@ struct DepthParams
 	// region partition (fr_set_region_partition): only the pixel rectangle [rx0, rx1) x [ry0, ry1) is needed; its bounds are
 	// multiples of 64 (or the image edge), so a hi-Z tile or coarse block lies inside or outside as a whole.  rx1 == 0: none
 	int rx0, ry0, rx1, ry1;
+	int affine_view;             // the view matrix' last row is 0 0 0 1: w = 1 exactly
 };
 
 __device__ __forceinline__ bool tile_owned(const DepthParams& dp, int tx, int ty)
@@ -132,16 +133,21 @@ __device__ __forceinline__ bool splat_setup(const DepthParams& dp, float4 p, Spl
 	// depth.vert:20-27: viewPosition = View * vec4(p, 1); ViewPosition = xyz / w
 	float vc[4];
 	mat4_mul_vec4(dp.view, p.x, p.y, p.z, 1.0f, vc);
-	float const x_c = divr(vc[0], vc[3]), y_c = divr(vc[1], vc[3]), z_c = divr(vc[2], vc[3]);
+	// (an affine view matrix -- last row 0 0 0 1, every camera of the reference -- makes w exactly 1 and x / 1 = x)
+	float const x_c = dp.affine_view ? vc[0] : divr(vc[0], vc[3]), y_c = dp.affine_view ? vc[1] : divr(vc[1], vc[3]),
+		z_c = dp.affine_view ? vc[2] : divr(vc[2], vc[3]);
 	if (!(z_c > 0.0f)) return false;
 	float const quad_depth = divr(addr(mulr(dp.P22, z_c), dp.P32), z_c);
 	if (!(quad_depth >= 0.0f && quad_depth <= 1.0f)) return false;   // quad clipped by near / far
 
-	// conservative pixel box of the disc (any superset yields the same image)
-	float const cx = mulr(addr(divr(mulr(dp.P00, x_c), z_c), 1.0f), dp.half_w);
-	float const cy = mulr(addr(divr(mulr(dp.P11, y_c), z_c), 1.0f), dp.half_h);
-	float const rx = addr(mulr(divr(mulr(fabsf(dp.P00), dp.h), z_c), dp.half_w), 1.0f);
-	float const ry = addr(mulr(divr(mulr(fabsf(dp.P11), dp.h), z_c), dp.half_h), 1.0f);
+	// conservative pixel box of the disc (any superset yields the same image): one approximate reciprocal serves its
+	// four quotients -- their error, ~1e-3 of a pixel, disappears in the whole pixel of slack the radii carry
+	float inv_z;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv_z) : "f"(z_c));
+	float const cx = (dp.P00 * x_c * inv_z + 1.0f) * dp.half_w;
+	float const cy = (dp.P11 * y_c * inv_z + 1.0f) * dp.half_h;
+	float const rx = fabsf(dp.P00) * dp.h * inv_z * dp.half_w + 1.0f;
+	float const ry = fabsf(dp.P11) * dp.h * inv_z * dp.half_h + 1.0f;
 	float const fx0 = floorf(cx - rx - 0.5f), fx1 = ceilf(cx + rx - 0.5f);
 	float const fy0 = floorf(cy - ry - 0.5f), fy1 = ceilf(cy + ry - 0.5f);
 	if (!(fx1 >= 0.0f && fy1 >= 0.0f && fx0 <= (float)(dp.W - 1) && fy0 <= (float)(dp.H - 1))) return false;
@@ -186,9 +192,10 @@ __global__ void __launch_bounds__(256) k_depth_seed(const float4* __restrict__ s
 	splat_b[i] = make_uint4(__float_as_uint(s.by), s.near_bits, live ? ((uint32_t)s.x0 | ((uint32_t)s.x1 << 16)) : 0xffffu,
 							live ? ((uint32_t)s.y0 | ((uint32_t)s.y1 << 16)) : 0xffffu);
 	if (!live) return;
-	// tile under the disc centre: u = 0 at ndc_x = bx / ax  ->  pixel = (ndc + 1) * W/2 - 0.5
-	float const pcx = subr(mulr(addr(divr(s.bx, s.ax), 1.0f), dp.half_w), 0.5f);
-	float const pcy = subr(mulr(addr(divr(s.by, s.ay), 1.0f), dp.half_h), 0.5f);
+	// tile under the disc centre: u = 0 at ndc_x = bx / ax  ->  pixel = (ndc + 1) * W/2 - 0.5 (which tile gets the bound is a
+	// choice -- the bound itself is checked against the tile's corners below -- so approximate quotients do)
+	float const pcx = (__fdividef(s.bx, s.ax) + 1.0f) * dp.half_w - 0.5f;
+	float const pcy = (__fdividef(s.by, s.ay) + 1.0f) * dp.half_h - 0.5f;
 	if (!(pcx >= 0.0f && pcy >= 0.0f && pcx < (float)dp.W && pcy < (float)dp.H)) return;
 	int const tx = (int)pcx / T, ty = (int)pcy / T;
 	int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
@@ -537,6 +544,7 @@ int launch_depth_prepass(Context* ctx, const Frame& f, cudaStream_t st, const fl
 	DepthParams dp;
 	for (int k = 0; k < 16; k++) dp.view[k] = cam.view[k];
 	dp.P00 = cam.projection[0]; dp.P11 = cam.projection[5]; dp.P22 = cam.projection[10]; dp.P32 = cam.projection[14];
+	dp.affine_view = (cam.view[3] == 0.0f && cam.view[7] == 0.0f && cam.view[11] == 0.0f && cam.view[15] == 1.0f) ? 1 : 0;
 	dp.h = f.h;
 	dp.h_inv = 1.0f / f.h;
 	dp.W = ctx->width; dp.H = ctx->height;
