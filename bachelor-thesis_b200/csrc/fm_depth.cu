@@ -297,9 +297,13 @@ __global__ void __launch_bounds__(256) k_depth_bounds(DepthParams dp, const floa
 		if (s.y1 < dp.H - 1) ty1--;
 		if (tx1 < tx0 || ty1 < ty0) continue;
 		int const nx = tx1 - tx0 + 1, ntile = nx * (ty1 - ty0 + 1);
+		// t / nx by one multiplication: (t + 0.5) / nx is at least 0.5 / nx away from an integer and the product's error
+		// below 2^16 * 2^-22 / nx
+		float const inv_nx = 1.0f / (float)nx;
 		for (int t = lane; t < ntile; t += 32)
 		{
-			int const ty = ty0 + t / nx, tx = tx0 + t % nx;
+			int const row = ntile < (1 << 16) ? (int)(((float)t + 0.5f) * inv_nx) : t / nx;
+			int const ty = ty0 + row, tx = tx0 + (t - row * nx);
 			int const px0 = tx * T, px1 = min(px0 + T - 1, dp.W - 1);
 			int const py0 = ty * T, py1 = min(py0 + T - 1, dp.H - 1);
 			if (!pixel_owned(dp, px0, py0)) continue;

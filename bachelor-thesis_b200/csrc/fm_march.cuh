@@ -215,6 +215,16 @@ __device__ __forceinline__ void add_neighbour(const FrameView& f, float d0, floa
 {
 	if (nn < (uint32_t)kMaxNeighbors)   // list truncation of RayMarcher.cpp:312
 	{
+		if (DENS && GRAD && !FAST)
+		{
+			float W;
+			f3 gw;
+			spline_W_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2, W, gw);
+			g = add3(g, gw);
+			density = addr(density, W);
+			nn++;
+			return;
+		}
 		if (GRAD && !FAST) g = add3(g, spline_gradW_inrange(f.kernel, mk3(-d0, -d1, -d2), l2));
 		if (GRAD && FAST)
 		{

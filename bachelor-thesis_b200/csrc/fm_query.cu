@@ -157,6 +157,22 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t per_thread, 
 	if (bad) atomicAdd(mismatches, bad);
 }
 
+// every float in [2^-100, 2^100]: sqrt_rn_normal against __fsqrt_rn, rcp_rn_normal against __frcp_rn -- for the
+// reciprocal also the negative ones (the spline only takes it of lengths, but the function does not care)
+__global__ void __launch_bounds__(256) k_selftest_sqrt_rcp(unsigned long long* mismatches)
+{
+	uint32_t const lo = 0x0d800000u, hi = 0x71800000u;        // 2^-100 .. 2^100
+	unsigned long long bad = 0;
+	for (uint64_t b = (uint64_t)lo + blockIdx.x * blockDim.x + threadIdx.x; b <= (uint64_t)hi; b += (uint64_t)gridDim.x * blockDim.x)
+	{
+		float const x = __uint_as_float((uint32_t)b);
+		bad += __float_as_uint(sqrt_rn_normal(x)) != __float_as_uint(__fsqrt_rn(x)) ? 1 : 0;
+		bad += __float_as_uint(rcp_rn_normal(x)) != __float_as_uint(__frcp_rn(x)) ? 1 : 0;
+		bad += __float_as_uint(rcp_rn_normal(-x)) != __float_as_uint(__frcp_rn(-x)) ? 1 : 0;
+	}
+	if (bad) atomicAdd(mismatches, bad);
+}
+
 }  // namespace
 
 // read-only streaming over a buffer that fits the L2 but not the L1s: the L2 -> SM bandwidth the march's gathers are
@@ -210,7 +226,8 @@ int selftest_division(Context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatc
 	unsigned const blocks = (unsigned)ctx->sm_count * 8;
 	uint64_t const per_thread = (n + (uint64_t)blocks * 256 - 1) / ((uint64_t)blocks * 256);
 	k_selftest_division<<<blocks, 256, 0, s>>>(per_thread, seed, (unsigned long long*)dm.p);
-	ctx->kernel_launches += 1;
+	k_selftest_sqrt_rcp<<<blocks, 256, 0, s>>>((unsigned long long*)dm.p);
+	ctx->kernel_launches += 2;
 	FM_CUDA(cudaGetLastError());
 	unsigned long long h = 0;
 	FM_CUDA(cudaMemcpyAsync(&h, dm.p, 8, cudaMemcpyDeviceToHost, s));

@@ -258,8 +258,9 @@ int fr_query_anisotropic(fr_context* ctx, int frame, const float* points_host, s
 int fr_download_frame_ext(fr_context* ctx, int frame, float* sorted_xyzi, uint32_t* cell_start, int32_t search_min[3],
 						  int32_t search_dims[3]);
 
-/* device self-test of the shortcuts that claim bit-identity with IEEE division (shared-reciprocal quotients of
- * gradW, Kernel.cpp:43): n pseudo-random operand sets, *mismatches must come back 0 */
+/* device self-test of the shortcuts that claim bit-identity with IEEE arithmetic: the shared-reciprocal quotients of
+ * gradW (Kernel.cpp:43) on n pseudo-random operand sets, and the unguarded square root / reciprocal sequences of the
+ * spline on EVERY float in [2^-100, 2^100]; *mismatches must come back 0 */
 int fr_selftest_division(fr_context* ctx, uint64_t n, uint64_t seed, uint64_t* mismatches);
 /* roofline denominator the driver does not measure: read-only streaming over `bytes` of device memory that stay
  * resident in the L2 (pick 16-64 MB), `reps` passes, GB/s served by the L2 to the SMs */

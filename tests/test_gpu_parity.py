@@ -542,3 +542,10 @@ def test_full_size_properties(fm, gpu_ctx_factory):
     # hits lie on the far side of the seed depth: unprojected hit is never in front of the pre-pass surface
     hit = a[1][..., 3] == 1
     assert np.all(np.isfinite(a[1][hit])) and np.all(np.abs(np.linalg.norm(a[2][hit][:, :3], axis=1) - 1) < 1e-3)
+
+
+def test_ieee_shortcuts_selftest(fm, gpu_ctx_factory):
+    """the sequences that claim the bits of IEEE division / square root / reciprocal without the library's range checks:
+    shared-reciprocal quotients on random operands, sqrt_rn_normal / rcp_rn_normal on EVERY float in [2^-100, 2^100]"""
+    ctx = gpu_ctx_factory(64, 64)
+    assert ctx.selftest_division(1 << 22, 3) == 0
