@@ -290,3 +290,54 @@ def test_prepass_beside_the_build_is_bit_identical(fm, gpu_ctx_factory, shuffle)
     c2.render(fm.FR_PASS_ALL)
     for name, g, w in zip(("depth", "positions", "normals", "rgba"), got2, c2.download()):
         assert np.array_equal(bits(g), bits(w)), name
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_call_sequences_render_what_a_fresh_context_renders(fm, gpu_ctx_factory, seed):
+    """uploads into two frame slots, camera changes, renders with and without per-stage events (one stream / pre-pass
+    beside the build + uncovered pixels beside the long rays), host waits in between, in random order: every image that
+    is downloaded equals the one a fresh context renders for that (particles, camera)"""
+    rng = np.random.default_rng(seed)
+    second = scenes.dam_break(26000, t=0.65)
+    data = [scenes.dam_break(20000, t=0.5), second[rng.permutation(len(second))]]
+    cams = [golden_camera("camera_close_16x9"), golden_camera("camera_default_16x9")]
+    want = {}
+    for d in range(2):
+        for k in range(2):
+            c = gpu_ctx_factory(W, H)
+            set_cam(c, cams[k])
+            c.upload_frame(0, data[d], 0.1, 2.0)
+            c.render(fm.FR_PASS_ALL)
+            want[d, k] = c.download()
+    ctx = gpu_ctx_factory(W, H)
+    slot_data = {}
+    cam_now, frame_now = 0, 0
+    set_cam(ctx, cams[0])
+    checked = 0
+    for step in range(140):
+        op = rng.integers(0, 7)
+        if op == 0 or not slot_data:
+            slot, d = int(rng.integers(0, 2)), int(rng.integers(0, 2))
+            ctx.upload_frame(slot, data[d], 0.1, 2.0)
+            slot_data[slot] = d
+        elif op == 1:
+            cam_now = int(rng.integers(0, 2))
+            set_cam(ctx, cams[cam_now])
+        elif op == 2:
+            ctx.set_stage_timing(bool(rng.integers(0, 2)))
+        elif op == 3:
+            ctx.frame_info(int(rng.choice(list(slot_data))))            # a host wait between a build and its render
+        elif op == 4:
+            ctx.wait()
+        else:
+            frame_now = int(rng.choice(list(slot_data)))
+            s = fm.VisualizationSettings()
+            s.Frame = frame_now
+            ctx.set_settings(s)
+            ctx.render_async(fm.FR_PASS_ALL)
+            if rng.integers(0, 3):
+                got = ctx.download()
+                for name, g, w in zip(("depth", "positions", "normals", "rgba"), got, want[slot_data[frame_now], cam_now]):
+                    assert np.array_equal(bits(g), bits(w)), (name, step, slot_data[frame_now], cam_now)
+                checked += 1
+    assert checked > 15
