@@ -153,6 +153,27 @@ __global__ void __launch_bounds__(256) k_selftest_division(uint64_t per_thread, 
 		bad += (__float_as_uint(qb) != __float_as_uint(w.y) && !(isnan(qb) && isnan(w.y))) ? 1 : 0;
 		float const r1 = rcpr(d), r2 = divr(1.0f, d);
 		bad += (__float_as_uint(r1) != __float_as_uint(r2) && !(isnan(r1) && isnan(r2))) ? 1 : 0;
+		// the spline's one-guard evaluation against the separately guarded functions it replaces (finite, non-zero r:
+		// components of every magnitude, kernel radii from 2^-25 to 2^25)
+		if (mode != 2)
+		{
+			SplineKernel k;
+			k.h = __uint_as_float(((127u - 25u + (mix32(st) % 51u)) << 23) | (mix32(st) & 0x007fffffu));
+			k.h_squared = mulr(k.h, k.h); k.h_inv = divr(1.0f, k.h); k.sig_d = 2.5464790894703255f;
+			float const rn = addr(addr(mulr(a.x, a.x), mulr(a.y, a.y)), mulr(a.z, a.z));
+			if (rn > 0.0f && rn < 0x1p120f)
+			{
+				float W;
+				f3 g;
+				spline_W_gradW_inrange(k, a, rn, W, g);
+				float const W2 = spline_W_inrange(k, rn);
+				f3 const g2 = spline_gradW_inrange(k, a, rn);
+				bad += (__float_as_uint(W) != __float_as_uint(W2) && !(isnan(W) && isnan(W2))) ? 1 : 0;
+				bad += (__float_as_uint(g.x) != __float_as_uint(g2.x) && !(isnan(g.x) && isnan(g2.x))) ? 1 : 0;
+				bad += (__float_as_uint(g.y) != __float_as_uint(g2.y) && !(isnan(g.y) && isnan(g2.y))) ? 1 : 0;
+				bad += (__float_as_uint(g.z) != __float_as_uint(g2.z) && !(isnan(g.z) && isnan(g2.z))) ? 1 : 0;
+			}
+		}
 	}
 	if (bad) atomicAdd(mismatches, bad);
 }
