@@ -77,6 +77,19 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 
 	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
 	mp.tiles_x = tiles_x;
+	static int const bg_fast = [] { const char* e = getenv("FLUIDMARCH_BGFAST"); return (e && e[0] == '0') ? 0 : 1; }();
+	mp.bg_fast = bg_fast;
+	{
+		const float* m = mp.ipv;
+		float big = 0.0f;
+		for (int r = 0; r < 3; r++)
+		{
+			mp.bg_c[r] = m[8 + r] + m[12 + r];
+			big = std::max(big, std::fabs(m[r]) + std::fabs(m[4 + r]) + std::fabs(mp.bg_c[r]));
+		}
+		mp.bg_err = 64.0f * 1.1920929e-7f * big;
+		mp.bg_cam = std::fabs(mp.cam[0]) + std::fabs(mp.cam[2]) + 1.0f;
+	}
 	size_t const npix = (size_t)ctx->width * ctx->height;
 	int rc;
 	if ((rc = ensure_capacity(&ctx->d_tiles, &ctx->cap_tiles, (size_t)tiles_x * tiles_y + 8))) return rc;

@@ -59,6 +59,8 @@ struct MarchParams
 	int rx0, ry0, rx1, ry1;           // region partition: the pixel rectangle this context renders (rx1 == 0: everything)
 	int do_march, do_shade;
 	int tiles_x;                      // 8x4 pixel tiles per image row
+	int bg_fast;                      // k_classify settles the floor square of an uncovered pixel approximately when it can (FLUIDMARCH_BGFAST=0: never)
+	float bg_c[3], bg_err, bg_cam;    // background_fast: ipv[8 + r] + ipv[12 + r], the error bound of its ray, |cam.x| + |cam.z| + 1
 	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
 	uint32_t n_eps;
 };
@@ -1096,6 +1098,37 @@ __device__ __forceinline__ uchar4 shade_pixel(const MarchParams& mp, int px, int
 	return make_uchar4((unsigned char)r8, (unsigned char)g8, (unsigned char)b8, (unsigned char)unorm8(color[3]));
 }
 
+// The colour of an uncovered pixel is one of three greys -- 0.75 * sampleFloor(camera, viewRay), the checker of
+// composition.frag:37-46 -- decided by which square of the floor the view ray meets.  Four out of five pixels are such
+// pixels, and shade_pixel spends ~200 instructions on the reference's exact arithmetic to find that square.  Here the
+// meeting point is computed approximately (FMAs, no division by w: the point does not depend on the ray's scale) with a
+// bound on how far it can be from shade_pixel's: a point farther than that from every edge of its square lies in the
+// same square for both, and the pixel takes its grey from the table `codes` (the three values shade_pixel produces,
+// computed by it); a point near an edge, or anything not finite, returns false and shade_pixel decides.
+__device__ __forceinline__ bool background_fast(const MarchParams& mp, int px, int py, const uint32_t* codes, uchar4& out)
+{
+	float const nx = fmaf((float)px + 0.5f, mp.two_w_inv, -1.0f), ny = fmaf((float)py + 0.5f, mp.two_h_inv, -1.0f);
+	const float* m = mp.ipv;
+	// (mp.bg_c[r] = m[8 + r] + m[12 + r]: one rounding, the same one shade_pixel makes -- the cancellation of the z row is
+	// common to both)
+	float const wx = fmaf(m[0], nx, fmaf(m[4], ny, mp.bg_c[0]));
+	float const wy = fmaf(m[1], nx, fmaf(m[5], ny, mp.bg_c[1]));
+	float const wz = fmaf(m[2], nx, fmaf(m[6], ny, mp.bg_c[2]));
+	// mp.bg_err: how far wx, wy, wz can be from shade_pixel's -- 64 ulps of the largest |m[r]| + |m[4 + r]| + |bg_c[r]| cover
+	// the handful of roundings that differ; the quotient and the products add relative errors of a few ulps
+	float const ry = __fdividef(1.0f, wy);
+	float const t = (-1.0f - mp.cam[1]) * ry;
+	float const bx = fmaf(wx, t, mp.cam[0]), bz = fmaf(wz, t, mp.cam[2]);
+	float const e = mp.bg_err * fabsf(t) * (1.0f + (fabsf(wx) + fabsf(wz)) * fabsf(ry)) + 1e-5f * (fabsf(bx) + fabsf(bz) + mp.bg_cam);
+	float const mx = bx - 2.0f * floorf(bx * 0.5f), mz = bz - 2.0f * floorf(bz * 0.5f);       // mod(b, 2) in [0, 2)
+	float const d = fminf(fminf(fminf(mx, fabsf(mx - 1.0f)), 2.0f - mx), fminf(fminf(mz, fabsf(mz - 1.0f)), 2.0f - mz));
+	if (!(d > e && e < 0.25f)) return false;
+	uint32_t const k = (mx < 1.0f ? 1u : 0u) + (mz < 1.0f ? 1u : 0u);                        // step(m, 1) summed
+	uint32_t const c = codes[k];
+	out = make_uchar4((unsigned char)c, (unsigned char)c, (unsigned char)c, (unsigned char)codes[3]);
+	return true;
+}
+
 __device__ __forceinline__ bool pixel_active(const MarchParams& mp, int px, int py)
 {
 	bool active = px < mp.W && py < mp.H;
@@ -1120,6 +1153,17 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 {
 	pdl_enter();
 	int const warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	// the three greys of the floor + its alpha as shade_pixel encodes them (background_fast)
+	__shared__ uint32_t s_bg[4];
+	if ((what & 2) && mp.do_march && mp.do_shade)
+	{
+		if (threadIdx.x < 4)
+		{
+			float const g = 0.25f + (float)threadIdx.x * 0.25f;        // 0.25 + (fx + fy) / 4, exact
+			s_bg[threadIdx.x] = threadIdx.x < 3 ? unorm8(srgb_encode(mulr(0.75f, g))) : unorm8(mulr(0.75f, 0.5f));
+		}
+		__syncthreads();
+	}
 	// (under a region partition the grid covers the region only: its bounds are multiples of 64 pixels)
 	int const tx = (mp.rx0 >> 3) + blockIdx.x * 4 + (warp & 3), ty = (mp.ry0 >> 2) + blockIdx.y * 2 + (warp >> 2);
 	int const px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
@@ -1136,7 +1180,12 @@ __global__ void __launch_bounds__(256) k_classify(MarchParams mp, const float* _
 				float4 const zero = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // RayMarcher.cpp:262-263
 				pos_out[index] = zero;
 				nrm_out[index] = zero;
-				if (mp.do_shade) rgba_out[index] = shade_pixel(mp, px, py, zero, zero);
+				if (mp.do_shade)
+				{
+					uchar4 c;
+					if (!mp.bg_fast || !background_fast(mp, px, py, s_bg, c)) c = shade_pixel(mp, px, py, zero, zero);
+					rgba_out[index] = c;
+				}
 			}
 		}
 		else rgba_out[index] = shade_pixel(mp, px, py, pos_out[index], nrm_out[index]);   // shade-only pass
@@ -1634,13 +1683,14 @@ __device__ __forceinline__ void coop_flush(const FrameView& f, CoopWarp& cw, uin
 	for (uint32_t k = lane; k < cnt; k += 32)
 	{
 		float4 const e = cw.ent[k];
-		float const W = spline_W_inrange(f.kernel, e.w);
 		if (!FAST)
 		{
-			f3 const gw = spline_gradW_inrange(f.kernel, mk3(-e.x, -e.y, -e.z), e.w);
+			float W;
+			f3 gw;
+			spline_W_gradW_inrange(f.kernel, mk3(-e.x, -e.y, -e.z), e.w, W, gw);
 			cw.con[k] = make_float4(W, gw.x, gw.y, gw.z);
 		}
-		else cw.con[k] = make_float4(W, spline_gradW_coeff_fast(f.kernel, e.w, mulr(sqrtr(e.w), f.kernel.h_inv)), 0.0f, 0.0f);
+		else cw.con[k] = make_float4(spline_W_inrange(f.kernel, e.w), spline_gradW_coeff_fast(f.kernel, e.w, mulr(sqrtr(e.w), f.kernel.h_inv)), 0.0f, 0.0f);
 	}
 	__syncwarp();
 	// the sums, in list order (every lane runs the chain: the result is warp-uniform without a broadcast)
