@@ -77,8 +77,11 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 
 	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
 	mp.tiles_x = tiles_x;
-	static int const bg_fast = [] { const char* e = getenv("FLUIDMARCH_BGFAST"); return (e && e[0] == '0') ? 0 : 1; }();
-	mp.bg_fast = bg_fast;
+	{
+		// (read at every launch, not once: tests/test_gpu_parity.py switches it between two renders of one process)
+		const char* const e = getenv("FLUIDMARCH_BGFAST");
+		mp.bg_fast = (e && e[0] == '0') ? 0 : 1;
+	}
 	{
 		const float* m = mp.ipv;
 		float big = 0.0f;

@@ -549,3 +549,47 @@ def test_ieee_shortcuts_selftest(fm, gpu_ctx_factory):
     shared-reciprocal quotients on random operands, sqrt_rn_normal / rcp_rn_normal on EVERY float in [2^-100, 2^100]"""
     ctx = gpu_ctx_factory(64, 64)
     assert ctx.selftest_division(1 << 22, 3) == 0
+
+
+def _look_at(eye, target, fov_deg, aspect):
+    """the matrices the reference's camera classes produce (glm::lookAtLH-style view, perspectiveLH_ZO with y flipped)"""
+    eye, target = np.asarray(eye, np.float64), np.asarray(target, np.float64)
+    fwd = target - eye
+    fwd /= np.linalg.norm(fwd)
+    right = np.cross([0.0, 1.0, 0.0], fwd)
+    right /= np.linalg.norm(right)
+    up = np.cross(fwd, right)
+    view = np.eye(4)
+    view[0, :3], view[1, :3], view[2, :3] = right, up, fwd
+    view[:3, 3] = -view[:3, :3] @ eye
+    n, f_ = 0.1, 1000.0
+    t = 1.0 / np.tan(np.radians(fov_deg) / 2)
+    proj = np.zeros((4, 4))
+    proj[0, 0], proj[1, 1], proj[2, 2], proj[2, 3], proj[3, 2] = t / aspect, -t, f_ / (f_ - n), -(f_ * n) / (f_ - n), 1.0
+    ipv = np.linalg.inv(proj @ view)
+    colmajor = lambda m: np.ascontiguousarray(m.T, dtype=np.float32).reshape(-1)
+    return colmajor(view), colmajor(proj), colmajor(ipv), eye.astype(np.float32), fwd.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_floor_squares_found_approximately_equal_the_exact_ones(fm, gpu_ctx_factory, seed, monkeypatch):
+    """k_classify's background_fast (the checker square of an uncovered pixel from an approximate ray + error bound)
+    against shade_pixel everywhere (FLUIDMARCH_BGFAST=0), for cameras all around the scene, near the floor, looking up"""
+    rng = np.random.default_rng(seed)
+    xyz = scenes.dam_break(8000, t=0.6)
+    W, H = 640, 360
+    ctx = gpu_ctx_factory(W, H)
+    ctx.upload_frame(0, xyz, 0.1, 2.0)
+    for k in range(10):
+        ang, rad, hgt = rng.uniform(0, 2 * np.pi), rng.uniform(2.0, 40.0), rng.uniform(-0.9, 25.0)
+        eye = [rad * np.cos(ang), hgt, rad * np.sin(ang)]
+        target = [rng.uniform(-1, 1), rng.uniform(-1.5, 3.0), rng.uniform(-1, 1)]
+        cam = _look_at(eye, target, rng.uniform(25, 100), W / H)
+        ctx.set_camera(*cam)
+        images = []
+        for mode in ("0", "1"):
+            monkeypatch.setenv("FLUIDMARCH_BGFAST", mode)
+            ctx.render(fm.FR_PASS_ALL)
+            images.append(ctx.download()[3])
+        assert np.array_equal(images[0], images[1]), (k, eye, target)
+        assert len(np.unique(images[0].reshape(-1, 4), axis=0)) >= 2
