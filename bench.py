@@ -349,6 +349,7 @@ def tiles_subrecord(fm, torch, dist, dev, rank, world, local, cam_args, cam, til
     ctx = fm.Context(W, H, device=local)
     ctx.set_camera(*cam_args)
     ctx.set_settings(fm.VisualizationSettings())
+    ctx.set_stage_timing(False)       # one frame at a time, as the RayMarcher shim runs it: no per-stage events (latency mode)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 

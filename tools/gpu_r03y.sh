@@ -1,6 +1,6 @@
 #!/bin/bash
 # final 2-GPU check of the round: multi-GPU tests + the N = 2 bench line (frame-parallel, C3 regions / tiles)
-TAG=r03y
+TAG=r04w
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_tests_multi.log
 N=2
