@@ -1,6 +1,6 @@
 #!/bin/bash
 # 8-GPU box: frame-parallel + C3 region / tile-parallel records at N = 2, 4, 8
-TAG=r04t
+TAG=r04x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8; nproc; free -g | head -2
 timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -3 | tee gpurun_out/${TAG}_tests_multi.log
