@@ -77,6 +77,8 @@ int launch_march(Context* ctx, const Frame& f, bool do_march, bool do_shade)
 
 	int const tiles_x = (ctx->width + 7) / 8, tiles_y = (ctx->height + 3) / 4;
 	mp.tiles_x = tiles_x;
+	static int const skip_empty = [] { const char* e = getenv("FLUIDMARCH_ANISO_EMPTY"); return (e && e[0] == '0') ? 0 : 1; }();
+	mp.aniso_skip_empty = (skip_empty && ctx->settings.iso_density > 0.0f) ? 1 : 0;      // (density 0 must not be a hit)
 	{
 		// (read at every launch, not once: tests/test_gpu_parity.py switches it between two renders of one process)
 		const char* const e = getenv("FLUIDMARCH_BGFAST");

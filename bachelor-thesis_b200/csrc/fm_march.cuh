@@ -59,6 +59,7 @@ struct MarchParams
 	int rx0, ry0, rx1, ry1;           // region partition: the pixel rectangle this context renders (rx1 == 0: everything)
 	int do_march, do_shade;
 	int tiles_x;                      // 8x4 pixel tiles per image row
+	int aniso_skip_empty;             // anisotropic list evaluation: samples without a particle within h skip the WPCA (FLUIDMARCH_ANISO_EMPTY=0: no)
 	int bg_fast;                      // k_classify settles the floor square of an uncovered pixel approximately when it can (FLUIDMARCH_BGFAST=0: never)
 	float bg_c[3], bg_err, bg_cam;    // background_fast: ipv[8 + r] + ipv[12 + r], the error bound of its ray, |cam.x| + |cam.z| + 1
 	float k_n, k_r, k_s;              // WPCA eigenvalue clamps (RayMarcher.cpp:229-232)
@@ -856,6 +857,30 @@ __device__ __forceinline__ uint32_t ext_box_count(const FrameView& f, const Cell
 __device__ __forceinline__ float aniso_density_list(const FrameView& f, const MarchParams& mp, f3 p, bool on, AnisoSample& as,
 													LaneCounters& lc, const uint32_t* __restrict__ e, uint32_t n, bool& redo)
 {
+	// A sample without a particle within h has density exactly 0 -- the empty sum of RayMarcher.cpp:389-395 -- whatever G is:
+	// such a lane skips the weights, the covariance and the eigen-solve (`on` goes false), and a warp of such lanes (a window
+	// of a silhouette ray through the fringe of the fluid) skips the passes altogether.  (The 2h-list's overflow counter is
+	// not kept for those lanes.)
+	if (mp.aniso_skip_empty)
+	{
+		bool any_h = false;
+#pragma unroll 1
+		for (uint32_t i = 0; i < n; i++)
+		{
+			uint32_t const ei = e[i];
+			if (!(ei >> 31)) continue;
+			float4 const q = __ldg(f.sorted_ext + (ei & 0x7fffffffu));
+			f3 const r = mk3(q.x - p.x, q.y - p.y, q.z - p.z);
+			float const rr = (r.x * r.x + r.y * r.y) + r.z * r.z;
+			any_h = any_h || rr < f.kernel.h_squared;
+		}
+		if (on && !any_h)
+		{
+			lc.candidates += ext_box_count(f, ext_box_full(f, p));
+			on = false;
+		}
+		if (!__any_sync(0xffffffffu, on)) { redo = false; return 0.0f; }
+	}
 	float const edge = f.h_ext * 0.999f - 8e-6f * (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) + f.h_ext);
 	float wsum = 0.0f;
 	f3 mean = mk3(0.0f, 0.0f, 0.0f);
