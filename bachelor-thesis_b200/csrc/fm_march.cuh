@@ -101,6 +101,10 @@ struct LaneCounters
 	uint32_t fallbacks;      // samples whose tile did not fit the shared-memory stage (walked out of global memory)
 };
 
+#ifndef FM_ANISO_SPEC_WALK
+#define FM_ANISO_SPEC_WALK 0              // long_ray's runs of samples in the anisotropic kernel too: measured twice, 2.68 -> 2.90 ms (r03l) and,
+                                          // after the empty-neighbourhood skip, 2.02 -> 2.09 ms (r05d): off
+#endif
 #ifndef FM_LONG_MINBLOCKS
 #define FM_LONG_MINBLOCKS 2               // resident 256-thread CTAs per SM k_march_long (isotropic) is compiled for
 #endif
@@ -1864,7 +1868,7 @@ __device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& 
 		bool gone = false;
 		while (n_valid < limit)
 		{
-			if (!ANISO && serial == 0)
+			if ((!ANISO || FM_ANISO_SPEC_WALK) && serial == 0)
 			{
 				f3 q = cur, qp = cur;
 				for (int k = n_valid; k < limit; k++)
@@ -1880,7 +1884,7 @@ __device__ __forceinline__ void long_ray(const FrameView& f, const MarchParams& 
 				n_valid = b;
 				if (n_valid >= limit) break;
 			}
-			else if (!ANISO) serial--;
+			else if (!ANISO || FM_ANISO_SPEC_WALK) serial--;
 			if (advance(f, mp, rstep, rsi, cur, prv, skips, occ_s)) { gone = true; break; }
 			if (lane == n_valid) { my_pos = cur; my_prev = prv; my_skips = skips; }
 			n_valid++;
